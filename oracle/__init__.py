@@ -1,0 +1,288 @@
+"""TEST INFRASTRUCTURE ONLY - ctypes binding of the CPU oracle (oracle/ssb_oracle.cpp).
+
+The oracle restates, on the CPU, the algorithm the reference (jnibauer/streamsculptor)
+executes on its hot path; see the header of oracle/ssb_oracle.cpp for the file:line map and
+for its PARITY STATUS ("unpinned at 1e-10; pinned by the reference's notebook goldens").
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline leg / --impl reference) may
+import this package.  The product package `streamsculptor_b200` never does.
+
+The builder API below is deliberately independent of the product's potential classes and
+lowering code so that a parameter-order mistake in the product cannot cancel out.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+G_KPC_MYR_MSUN = 4.498502151469553e-12  # astropy G in kpc^3 Msun^-1 Myr^-2 (main.py:18,30; pinned by golden G1)
+
+NFW, HERNQUIST, MIYAMOTO, PLUMMER, ISOCHRONE, TRIAXNFW, UNIFORM_ACC, SUBHALOS = range(8)
+LINEAR, CUBIC = 0, 1
+PR_PLUMMER, PR_HERNQUIST, PR_NFW = 0, 1, 2
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_lp = C.POINTER(C.c_int64)
+
+
+def build(force=False):
+    """Compile oracle/_build/libssb_oracle.so with the committed Makefile."""
+    args = ["make", "-C", _HERE] + (["-B"] if force else [])
+    subprocess.run(args, check=True, stdout=subprocess.DEVNULL)
+    return os.path.join(_HERE, "_build", "libssb_oracle.so")
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = build()
+        L = C.CDLL(path)
+        L.orc_program_new.restype = C.c_void_p
+        L.orc_normal1.restype = C.c_double
+        L.orc_erfinv.restype = C.c_double
+        L.orc_erfinv.argtypes = [C.c_double]
+        L.orc_normal1.argtypes = [C.c_int64]
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+class Program:
+    """A sum of potential components (Potential_Combine, potential.py:1279-1296)."""
+
+    def __init__(self, G=G_KPC_MYR_MSUN):
+        self.G = float(G)
+        self._h = C.c_void_p(lib().orc_program_new())
+        self.n_sh = []
+
+    def __del__(self):
+        try:
+            lib().orc_program_free(self._h)
+        except Exception:
+            pass
+
+    # ---- builders -------------------------------------------------------------------------
+    def track(self, kind, t, y):
+        t, y = _d(t), _d(y)
+        y = y.reshape(len(t), -1)
+        return lib().orc_add_track(self._h, int(kind), len(t), _p(t), _p(y), y.shape[1])
+
+    def _comp(self, typ, params, track=-1):
+        p = np.zeros(8)
+        p[: len(params)] = params
+        lib().orc_add_comp(self._h, typ, _p(p), int(track))
+        return self
+
+    def nfw(self, m, r_s, track=-1):
+        return self._comp(NFW, [self.G * m, r_s], track)
+
+    def hernquist(self, m, r_s, soft=0.0, track=-1):
+        return self._comp(HERNQUIST, [self.G * m, r_s, soft], track)
+
+    def miyamoto(self, m, a, b, track=-1):
+        return self._comp(MIYAMOTO, [self.G * m, a, b], track)
+
+    def plummer(self, m, r_s, track=-1):
+        return self._comp(PLUMMER, [self.G * m, r_s], track)
+
+    def isochrone(self, m, a, track=-1):
+        return self._comp(ISOCHRONE, [self.G * m, a], track)
+
+    def triaxnfw(self, m, r_s, q1, q2, q3, track=-1):
+        return self._comp(TRIAXNFW, [self.G * m, r_s, q1, q2, q3], track)
+
+    def uniform_acc(self, t, vel):
+        return self._comp(UNIFORM_ACC, [], self.track(LINEAR, t, vel))
+
+    def subhalos(self, profile, m, r_s, x0, v, t0, t_window, dradius=False, track=-1):
+        m, r_s, x0, v, t0 = _d(m), _d(r_s), _d(x0), _d(v), _d(t0)
+        n = len(m)
+        tw = _d(np.broadcast_to(_d(t_window), (n,)))
+        idx = lib().orc_add_subhalos(self._h, int(profile), int(bool(dradius)), C.c_double(self.G), n, _p(m), _p(r_s),
+                                     _p(x0), _p(v), _p(t0), _p(tw), int(track))
+        self.n_sh.append(n)
+        self.last_sh = idx
+        return self
+
+    # ---- field evaluation -------------------------------------------------------------------
+    def _xt(self, xyz, t):
+        xyz = _d(xyz).reshape(-1, 3)
+        t = _d(np.broadcast_to(_d(t), (len(xyz),)))
+        return xyz, t
+
+    def potential(self, xyz, t=0.0):
+        xyz, t = self._xt(xyz, t)
+        out = np.empty(len(xyz))
+        lib().orc_potential(self._h, len(xyz), _p(xyz), _p(t), _p(out))
+        return out
+
+    def gradient(self, xyz, t=0.0):
+        xyz, t = self._xt(xyz, t)
+        out = np.empty((len(xyz), 3))
+        lib().orc_gradient(self._h, len(xyz), _p(xyz), _p(t), _p(out))
+        return out
+
+    def hessian(self, xyz, t=0.0):
+        xyz, t = self._xt(xyz, t)
+        out = np.empty((len(xyz), 3, 3))
+        lib().orc_hessian(self._h, len(xyz), _p(xyz), _p(t), _p(out))
+        return out
+
+    def third(self, xyz, t=0.0):
+        xyz, t = self._xt(xyz, t)
+        out = np.empty((len(xyz), 3, 3, 3))
+        lib().orc_third(self._h, len(xyz), _p(xyz), _p(t), _p(out))
+        return out
+
+    def per_sh(self, xyz, t, sh=0):
+        xyz = _d(xyz).reshape(3)
+        n = self.n_sh[sh]
+        phi, grad = np.empty(n), np.empty((n, 3))
+        lib().orc_per_sh(self._h, sh, _p(xyz), C.c_double(t), _p(phi), _p(grad))
+        return phi, grad
+
+    def track_eval(self, track, t):
+        t = _d(t).reshape(-1)
+        out, dout = np.empty((len(t), 3)), np.empty((len(t), 3))
+        lib().orc_track_eval(self._h, int(track), len(t), _p(t), _p(out), _p(dout))
+        return out, dout
+
+    # ---- integration ------------------------------------------------------------------------
+    def integrate_orbits(self, w0, t0, t1, ts=None, solver=8, rtol=1e-7, atol=1e-7, dtmin=0.3, dtmax=None,
+                         max_steps=10_000, threads=1):
+        """Batch of integrate_orbit calls (main.py:125-163).  ts: [M] or [N,M]; None -> [t1]."""
+        w0 = _d(w0).reshape(-1, 6)
+        N = len(w0)
+        t0 = _d(np.broadcast_to(_d(t0), (N,)))
+        t1 = _d(np.broadcast_to(_d(t1), (N,)))
+        if ts is None:
+            ts = t1[:, None]
+        ts = _d(ts)
+        if ts.ndim == 1:
+            ts = np.broadcast_to(ts, (N, len(ts)))
+        ts = _d(ts)
+        M = ts.shape[1]
+        ys = np.empty((N, M, 6))
+        status = np.empty(N, dtype=np.int32)
+        nsteps = np.empty((N, 3), dtype=np.int32)
+        lib().orc_integrate_orbits(self._h, N, _p(w0), _p(t0), _p(t1), _p(ts), M, int(solver), C.c_double(rtol),
+                                   C.c_double(atol), C.c_double(dtmin), C.c_double(np.inf if dtmax is None else dtmax),
+                                   int(max_steps), _p(ys), status.ctypes.data_as(_ip), nsteps.ctypes.data_as(_ip), int(threads))
+        return ys, status, nsteps
+
+    def orbit_steps(self, w0, t0, t1, solver=8, rtol=1e-7, atol=1e-7, dtmin=0.3, dtmax=None, max_steps=10_000):
+        cap = max_steps + 1
+        tg, yg = np.empty(cap + 1), np.empty((cap + 1, 6))
+        w0 = _d(w0)
+        n = lib().orc_orbit_steps(self._h, _p(w0), C.c_double(t0), C.c_double(t1), int(solver), C.c_double(rtol),
+                                  C.c_double(atol), C.c_double(dtmin), C.c_double(np.inf if dtmax is None else dtmax),
+                                  int(max_steps), cap, _p(tg), _p(yg))
+        return tg[: n + 1], yg[: n + 1]
+
+    # ---- release model ----------------------------------------------------------------------
+    def release(self, xv, Msat, idx, t, seed, kvals=None, normals=None, jacobian=False):
+        """release_model (main.py:209-280) for a batch; returns pos_lead, pos_trail, v_lead, v_trail [n,3]
+        (or dRel_dIC [n,2,6,6] when jacobian=True, perturbative.py:281-296)."""
+        xv = _d(xv).reshape(-1, 6)
+        n = len(xv)
+        Msat = _d(np.broadcast_to(_d(Msat), (n,)))
+        t = _d(np.broadcast_to(_d(t), (n,)))
+        idx = np.ascontiguousarray(idx, dtype=np.int64).reshape(n)
+        kv = _d([2.0, 0.3, 0.0, 0.0, 0.4, 0.4, 0.5, 0.5] if kvals is None else kvals)   # main.py:214
+        nr = None if normals is None else _d(normals).reshape(n, 4)
+        nrp = _p(nr) if nr is not None else None
+        if jacobian:
+            out = np.empty((n, 2, 6, 6))
+            lib().orc_release_jacobian(self._h, C.c_double(self.G), n, _p(xv), _p(Msat), idx.ctypes.data_as(_lp), _p(t),
+                                       C.c_int64(int(seed)), _p(kv), nrp, _p(out))
+            return out
+        out = np.empty((n, 12))
+        lib().orc_release(self._h, C.c_double(self.G), n, _p(xv), _p(Msat), idx.ctypes.data_as(_lp), _p(t),
+                          C.c_int64(int(seed)), _p(kv), nrp, _p(out))
+        return out[:, 0:3].copy(), out[:, 3:6].copy(), out[:, 6:9].copy(), out[:, 9:12].copy()
+
+    # ---- stream generation (main.py:287-368) ---------------------------------------------------
+    def gen_stream_ics(self, ts, prog_w0, Msat, seed, solver=5, kvals=None, normals=None, **ctl):
+        ts = _d(ts)
+        prog, _, _ = self.integrate_orbits(prog_w0, ts.min(), ts.max(), ts=ts, solver=solver, **ctl)   # main.py:289
+        return self.release(prog[0], Msat, np.arange(len(ts)), ts, seed, kvals, normals) + (prog[0],)
+
+    def gen_stream(self, ts, prog_w0, Msat, seed, solver=5, kvals=None, normals=None, threads=1, **ctl):
+        """gen_stream_vmapped / gen_stream_scan (main.py:312-368): returns lead[N-1,6], trail[N-1,6], nsteps."""
+        ts = _d(ts)
+        pl, pt, vl, vt, _ = self.gen_stream_ics(ts, prog_w0, Msat, seed, solver, kvals, normals, **ctl)
+        w0 = np.concatenate([np.hstack([pl, vl])[:-1], np.hstack([pt, vt])[:-1]])
+        t0 = np.concatenate([ts[:-1], ts[:-1]])
+        ys, status, nsteps = self.integrate_orbits(w0, t0, ts[-1], solver=solver, threads=threads, **ctl)
+        n = len(ts) - 1
+        return ys[:n, -1], ys[n:, -1], status, nsteps
+
+
+def linear_response(base, shprog, w0, t0, t1, D0=None, sh=0, solver=8, rtol=1e-6, atol=1e-6, dtmin=0.05, dtmax=None,
+                    max_steps=10_000, threads=1):
+    """compute_perturbation_OTF (perturbative.py:101-135, 726-755): returns w[N,6], D[N,nsh,12], status, nsteps."""
+    w0 = _d(w0).reshape(-1, 6)
+    N = len(w0)
+    nsh = shprog.n_sh[sh]
+    t0 = _d(np.broadcast_to(_d(t0), (N,)))
+    D0p = None
+    if D0 is not None:
+        D0 = _d(D0).reshape(N, nsh, 12)
+        D0p = _p(D0)
+    wout, Dout = np.empty((N, 6)), np.empty((N, nsh, 12))
+    status, nsteps = np.empty(N, dtype=np.int32), np.empty((N, 3), dtype=np.int32)
+    lib().orc_linear_response(base._h, shprog._h, sh, N, _p(w0), D0p, _p(t0), C.c_double(t1), int(solver), C.c_double(rtol),
+                              C.c_double(atol), C.c_double(dtmin), C.c_double(np.inf if dtmax is None else dtmax),
+                              int(max_steps), _p(wout), _p(Dout), status.ctypes.data_as(_ip), nsteps.ctypes.data_as(_ip),
+                              int(threads))
+    return wout, Dout, status, nsteps
+
+
+def response_term(base, shprog, t, y, sh=0):
+    y = _d(y)
+    dy = np.empty_like(y)
+    lib().orc_response_term(base._h, shprog._h, sh, C.c_double(t), _p(y), _p(dy))
+    return dy
+
+
+def threefry2x32(k0, k1, c0, c1):
+    out = (C.c_uint32 * 2)()
+    lib().orc_threefry(C.c_uint32(k0), C.c_uint32(k1), C.c_uint32(c0), C.c_uint32(c1), out)
+    return int(out[0]), int(out[1])
+
+
+def randint5(seed, lo=0, hi=1000):
+    out = np.empty(5, dtype=np.int64)
+    lib().orc_randint5(C.c_int64(seed), C.c_int64(lo), C.c_int64(hi), out.ctypes.data_as(_lp))
+    return out
+
+
+def normal1(seed):
+    return lib().orc_normal1(C.c_int64(seed))
+
+
+def erfinv(x):
+    return lib().orc_erfinv(C.c_double(x))
+
+
+def release_normals(seed, idx):
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    out = np.empty((len(idx), 4))
+    lib().orc_release_normals(C.c_int64(seed), len(idx), idx.ctypes.data_as(_lp), _p(out))
+    return out
+
+
+def num_threads():
+    return lib().orc_num_threads()
