@@ -1,0 +1,193 @@
+/*
+ * ssb200.h - C ABI of libssb200.so, the B200-native (sm_100a) hot path of streamsculptor.
+ *
+ * The reference (jnibauer/streamsculptor) has NO native boundary: its hot path is Python/JAX that funnels into
+ * diffrax.diffeqsolve inside one jitted XLA program.  The entry points below are therefore what
+ * an XLA-FFI custom call (or any ctypes / cgo / JNI binding) for that path binds to; each one cites the reference
+ * interface it replaces (paths relative to /root/reference/streamsculptor/).  INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, no torch / JAX types.  All array arguments of the *_f64 entry points are DEVICE pointers owned by the
+ *     caller; work is enqueued on `stream` (a cudaStream_t passed as void*) and the call returns without synchronising.
+ *     The *_host entry points take HOST pointers, do the H2D/D2H copies themselves and synchronise before returning.
+ *   - no global mutable state: entry points are re-entrant; potential descriptions are passed by value per call.
+ *   - return value: 0 = enqueued, <0 = ssb_status error (bad argument, unsupported potential, CUDA error).
+ *     NUMERICAL failure is per orbit in status[]: 0 ok, 1 max_steps reached, 2 non-finite; rows never saved are +inf
+ *     (diffrax throw=False semantics, main.py:136).
+ *   - units: kpc, Myr, Msun; all real data IEEE fp64.  Arrays are C-contiguous in the layout the reference's Python
+ *     API uses ([N,6] phase-space rows, [N,M,6] saved trajectories, [N,Nsh,12] responses).
+ */
+#ifndef SSB200_H
+#define SSB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_ABI_VERSION 1
+#define SSB_MAX_COMP 12
+#define SSB_MAX_TRACK 4
+#define SSB_MAX_SUBHALO_SETS 2
+
+typedef enum {
+    SSB_OK = 0,
+    SSB_ERR_ARG = -1,         /* null pointer / negative size / inconsistent shapes */
+    SSB_ERR_UNSUPPORTED = -2, /* component type, profile or solver this library does not implement */
+    SSB_ERR_CUDA = -3,        /* CUDA runtime error (ssb_last_error() has the text) */
+    SSB_ERR_SCRATCH = -4      /* scratch buffer too small (see ssb_scratch_bytes) */
+} ssb_status;
+
+/* ---- potential program: a flat sum of components (Potential_Combine, potential.py:1279-1296) ------------------- */
+typedef enum {
+    SSB_NFW = 0,          /* potential.py:74-84    p = {G*m, r_s}                      */
+    SSB_HERNQUIST = 1,    /* potential.py:132-138  p = {G*m, r_s, soft}                */
+    SSB_MIYAMOTO = 2,     /* potential.py:66-72    p = {G*m, a, b}                     */
+    SSB_PLUMMER = 3,      /* potential.py:124-130  p = {G*m, r_s}                      */
+    SSB_ISOCHRONE = 4,    /* potential.py:114-122  p = {G*m, a}                        */
+    SSB_TRIAXNFW = 5,     /* potential.py:86-97    p = {G*m, r_s, q1, q2, q3}          */
+    SSB_UNIFORM_ACC = 6,  /* potential.py:480-502  gradient = d(velocity track)/dt ; track = velocity table */
+    SSB_SUBHALOS = 7      /* potential.py:802-850, 1161-1213  sh = index into ssb_potential.sh              */
+} ssb_comp_type;
+
+typedef struct {
+    int32_t type;   /* ssb_comp_type */
+    int32_t track;  /* >= 0: evaluate at x - c(t), c = tracks[track] (TimeDepTranslatingPotential, potential.py:448-462); -1: static */
+    int32_t sh;     /* SSB_SUBHALOS: which subhalo set */
+    int32_t _pad;
+    double p[8];
+} ssb_component;
+
+typedef enum {
+    SSB_TRACK_LINEAR = 0, /* RegularGridInterpolator(method='linear', fill_value=None): potential.py:581-600 (linear extrapolation) */
+    SSB_TRACK_CUBIC = 1   /* interpax.Interpolator1D(method='cubic'): streamhelpers.py:520, perturbative.py:642 (NaN outside knots)  */
+} ssb_track_kind;
+
+typedef struct {
+    int32_t kind;     /* ssb_track_kind */
+    int32_t n;        /* knots */
+    const double* t;  /* [n] increasing (device) */
+    const double* y;  /* [n,3] (device) */
+    const double* s;  /* [n,3] knot slopes for SSB_TRACK_CUBIC (device; fill with ssb_track_slopes_f64), NULL for linear */
+} ssb_track;
+
+typedef enum { SSB_PROFILE_PLUMMER = 0, SSB_PROFILE_HERNQUIST = 1, SSB_PROFILE_NFW = 2 } ssb_profile;
+
+/* N_sh subhalos on straight lines x0 + v (t - t0), active iff |t - t0| < t_window (strict; potential.py:826). */
+typedef struct {
+    int32_t n;
+    int32_t profile;    /* ssb_profile: SubhaloLinePotential = Plummer; ..Custom_fromFunc = any func(m, r_s) - Hernquist in production */
+    double G;
+    const double* m;    /* [n]   (device) */
+    const double* rs;   /* [n]   */
+    const double* x0;   /* [n,3] */
+    const double* v;    /* [n,3] */
+    const double* t0;   /* [n]   */
+    const double* tw;   /* [n]   t_window per subhalo (broadcast a scalar on the host side) */
+} ssb_subhalos;
+
+typedef struct {
+    int32_t n_comp, n_track, n_sh, _pad;
+    ssb_component comp[SSB_MAX_COMP];
+    ssb_track track[SSB_MAX_TRACK];
+    ssb_subhalos sh[SSB_MAX_SUBHALO_SETS];
+} ssb_potential;
+
+/* ---- solver control: diffrax.PIDController(rtol, atol, dtmin, dtmax, force_dtmin=True) + max_steps (main.py:144-162) */
+typedef struct {
+    int32_t solver;     /* 5 = Dopri5, 8 = Dopri8 */
+    int32_t max_steps;  /* accepted + rejected */
+    double rtol, atol;
+    double dtmin;       /* steps at dt <= dtmin are always accepted */
+    double dtmax;       /* +inf = None */
+} ssb_ctrl;
+
+int ssb_abi_version(void);
+const char* ssb_last_error(void); /* thread-local text of the last SSB_ERR_CUDA / SSB_ERR_ARG */
+
+/* A1/A5  Potential.potential / gradient / jacobian_force (main.py:37-65) at n points.
+ * Any of phi[n], grad[n,3], hess[n,3,3] may be NULL.  SSB_UNIFORM_ACC contributes to grad only. */
+int ssb_potential_eval_f64(const ssb_potential* pot, int64_t n, const double* xyz, const double* t,
+                           double* phi, double* grad, double* hess, void* stream);
+
+/* per-subhalo values of one subhalo set at ONE point: potential_per_SH and its jacfwd (potential.py:832-850;
+ * perturbative.py:40-41, 695-696).  dradius != 0 evaluates d/dr_s of the profile (potential.py:852-904, 1215-1268).
+ * phi[n_sh], grad[n_sh,3]. */
+int ssb_subhalo_eval_f64(const ssb_subhalos* sh, int dradius, const double* xyz /*[3] host*/, double t,
+                         double* phi, double* grad, void* stream);
+
+/* knot slopes of a cubic track (interpax 'cubic' derivative rule).  t[n], y[n,3] -> s[n,3]. */
+int ssb_track_slopes_f64(int64_t n, const double* t, const double* y, double* s, void* stream);
+/* evaluate a track and its time derivative at nq times: out[nq,3], dout[nq,3] (dout may be NULL) */
+int ssb_track_eval_f64(const ssb_track* tr, int64_t nq, const double* tq, double* out, double* dout, void* stream);
+
+/* A3/A4  Potential.integrate_orbit / integrate_orbit_batch_vmapped (main.py:125-202): N independent adaptive solves.
+ *   w0[N,6]; t0[N], t1[N] (t1 < t0 integrates backwards); ts: save times, [N,M] if ts_per_orbit else [M] shared,
+ *   monotone from t0 towards t1; ys[N,M,6]; status[N]; nsteps[N,3] = {attempted, accepted, rejected}. */
+int ssb_orbit_integrate_f64(const ssb_potential* pot, int64_t N, const double* w0, const double* t0, const double* t1,
+                            const double* ts, int32_t M, int32_t ts_per_orbit, ssb_ctrl ctrl,
+                            double* ys, int32_t* status, int32_t* nsteps, void* stream);
+
+/* A7 (serial part)  ONE orbit saved at M times with dense output (main.py:289: the progenitor at every stripping time).
+ * Steps are taken by one thread and recorded; the M interpolations run in parallel.  scratch >= ssb_scratch_bytes(). */
+int ssb_orbit_dense_f64(const ssb_potential* pot, const double* w0 /*[6] device*/, double t0, double t1,
+                        const double* ts, int64_t M, ssb_ctrl ctrl, double* ys /*[M,6]*/, int32_t* status /*[1]*/,
+                        int32_t* nsteps /*[3]*/, void* scratch, size_t scratch_bytes, void* stream);
+size_t ssb_scratch_bytes(int32_t max_steps);
+
+/* A6  Potential.release_model vmapped over stripping times (main.py:209-306).
+ *   prog[N,6] progenitor phase-space at t[N]; Msat[N]; idx[N] the stripping index i that seeds jax.random
+ *   (main.py:223-228); kvals[8] (host) = {kr, kvphi, kz, kvz, sigma_kr, sigma_kvphi, sigma_kz, sigma_kvz};
+ *   normals[N,4] optional externally supplied standard normals (NULL = reproduce the jax threefry recipe);
+ *   outputs pos_lead, pos_trail, vel_lead, vel_trail each [N,3]. */
+int ssb_release_spray_f64(const ssb_potential* pot, double G, int64_t N, const double* prog, const double* Msat,
+                          const int64_t* idx, const double* t, int64_t seed, const double* kvals, const double* normals,
+                          double* pos_lead, double* pos_trail, double* vel_lead, double* vel_trail, void* stream);
+
+/* A8  Potential.gen_stream_vmapped (main.py:343-368) as one enqueue: progenitor orbit at ts[Nts] (dense), release at
+ * every ts[i], then 2 (Nts-1) independent solves from ts[i] to ts[Nts-1]; lead[Nts-1,6], trail[Nts-1,6].
+ * pot_release: potential used by release_model (== pot for gen_stream_vmapped; the base potential for
+ * gen_stream_vmapped_with_pert, streamhelpers.py:56-116).  Only particles [i_begin, i_end) are integrated (multi-GPU
+ * sharding); outputs are indexed from i_begin.  scratch >= ssb_stream_scratch_bytes(). */
+int ssb_gen_stream_f64(const ssb_potential* pot, const ssb_potential* pot_release, double G, int64_t Nts,
+                       const double* ts, const double* prog_w0 /*[6]*/, const double* Msat /*[Nts]*/, int64_t seed,
+                       const double* kvals /*host[8]*/, const double* normals /*[Nts,4] or NULL*/, ssb_ctrl ctrl,
+                       int64_t i_begin, int64_t i_end, double* lead, double* trail, int32_t* status /*[2,(i_end-i_begin)]*/,
+                       int32_t* nsteps /*[2,(i_end-i_begin),3]*/, void* scratch, size_t scratch_bytes, void* stream);
+size_t ssb_stream_scratch_bytes(int64_t Nts, int32_t max_steps);
+
+/* A12-A14  compute_perturbation_OTF (perturbative.py:101-135, 425-454, 726-755) with the field
+ * MassRadiusPerturbation_OTF (fields.py:159-206): per particle ONE coupled ODE [w(6), D(n_sh,12)] whose step-size
+ * controller sees the RMS error over all 6 + 12 n_sh components; final state kept.
+ *   w0[N,6]; D0[N,n_sh,12] or NULL (= zeros, perturbative.py:712); t0[N]; t1 common end time;
+ *   wout[N,6]; Dout[N,n_sh,12]; scratch >= ssb_response_scratch_bytes(n_sh). */
+int ssb_linear_response_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0,
+                            const double* D0, const double* t0, double t1, ssb_ctrl ctrl, double* wout, double* Dout,
+                            int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream);
+size_t ssb_response_scratch_bytes(int32_t n_sh);
+/* RHS of that field at one state (fields.py:175-206): y[6+12 n_sh] -> dy (device pointers), for unit tests */
+int ssb_response_term_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, double t, const double* y, double* dy,
+                          void* stream);
+
+/* ---- host-pointer conveniences (H2D, launch, D2H, synchronise) - what a CPU-side plugin call looks like ---------- */
+int ssb_orbit_integrate_host(const ssb_potential* pot_hostptrs, int64_t N, const double* w0, const double* t0,
+                             const double* t1, const double* ts, int32_t M, int32_t ts_per_orbit, ssb_ctrl ctrl,
+                             double* ys, int32_t* status, int32_t* nsteps);
+int ssb_gen_stream_host(const ssb_potential* pot_hostptrs, const ssb_potential* pot_release_hostptrs, double G, int64_t Nts,
+                        const double* ts, const double* prog_w0, const double* Msat, int64_t seed, const double* kvals,
+                        const double* normals, ssb_ctrl ctrl, int64_t i_begin, int64_t i_end, double* lead, double* trail,
+                        int32_t* status, int32_t* nsteps);
+int ssb_linear_response_host(const ssb_potential* pot_base_hostptrs, const ssb_subhalos* sh_hostptrs, int64_t N,
+                             const double* w0, const double* D0, const double* t0, double t1, ssb_ctrl ctrl,
+                             double* wout, double* Dout, int32_t* status, int32_t* nsteps);
+
+/* measured-peak helper for the roofline denominator: runs a dependent-chain-free DFMA loop on every SM and returns
+ * the achieved fp64 FLOP/s (2 flops per DFMA); used by bench.py, never by the product path. */
+int ssb_fp64_peak_probe(int iters, double* flops_per_s, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,295 @@
+"""Host-side plumbing between the Python API and libssb200 (device-pointer entry points).
+
+torch is used for what the task allows it for: device memory, streams and (in parallel.py) torch.distributed.
+All arithmetic happens in the CUDA library; there is no CPU fallback anywhere in this package.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .solvers import solver_id
+
+_F64 = None
+
+
+def torch():
+    return _lib.require_cuda()
+
+
+def device():
+    t = torch()
+    return t.device("cuda", t.cuda.current_device())
+
+
+def to_dev(a, dtype=None):
+    """numpy / list / torch (any device) -> contiguous CUDA tensor."""
+    t = torch()
+    dtype = dtype or t.float64
+    if isinstance(a, t.Tensor):
+        return a.to(device=device(), dtype=dtype).contiguous()
+    arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64 if dtype == t.float64 else None))
+    return t.from_numpy(arr).to(device=device(), dtype=dtype).contiguous()
+
+
+def is_dev(a):
+    t = torch()
+    return isinstance(a, t.Tensor) and a.is_cuda
+
+
+def out(x, like_device):
+    """Return type policy: CUDA tensors in -> CUDA tensors out; anything else -> numpy arrays."""
+    return x if like_device else x.cpu().numpy()
+
+
+def ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch().cuda.current_stream().cuda_stream)
+
+
+def empty(shape, dtype=None):
+    t = torch()
+    return t.empty(shape, dtype=dtype or t.float64, device=device())
+
+
+def make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps):
+    return _lib.Ctrl(solver=solver_id(solver), max_steps=int(max_steps), rtol=float(rtol), atol=float(atol),
+                     dtmin=float(dtmin), dtmax=float(np.inf if dtmax is None else dtmax))
+
+
+# ------------------------------------------------------------------------------------------------
+# lowering: Potential object tree -> flat potential program (walk potential_list
+# recursively and dispatch on component type; never call .potential of force-only components)
+# ------------------------------------------------------------------------------------------------
+class Track:
+    """A tabulated 3-vector function of time living on the device."""
+
+    def __init__(self, kind, t, y):
+        self.kind = int(kind)
+        self.t_host = np.ascontiguousarray(np.asarray(t, dtype=np.float64)).reshape(-1)
+        self.y_host = np.ascontiguousarray(np.asarray(y, dtype=np.float64)).reshape(len(self.t_host), 3)
+        if len(self.t_host) < 2:
+            raise ValueError("a track needs at least 2 knots")
+        self._dev = None
+
+    def dev(self):
+        if self._dev is None:
+            t, y = to_dev(self.t_host), to_dev(self.y_host)
+            s = None
+            if self.kind == _lib.TRACK_CUBIC:
+                s = empty((len(self.t_host), 3))
+                _lib.check(_lib.lib().ssb_track_slopes_f64(len(self.t_host), ptr(t), ptr(y), ptr(s), stream_ptr()))
+            self._dev = (t, y, s)
+        return self._dev
+
+    def struct(self):
+        t, y, s = self.dev()
+        return _lib.Track(kind=self.kind, n=len(self.t_host), t=t.data_ptr(), y=y.data_ptr(), s=0 if s is None else s.data_ptr())
+
+    def __call__(self, tq, derivative=False):
+        tq_dev = to_dev(np.atleast_1d(np.asarray(tq, dtype=np.float64)))
+        o, d = empty((len(tq_dev), 3)), empty((len(tq_dev), 3))
+        st = self.struct()
+        _lib.check(_lib.lib().ssb_track_eval_f64(C.byref(st), len(tq_dev), ptr(tq_dev), ptr(o), ptr(d), stream_ptr()))
+        res = (d if derivative else o).cpu().numpy()
+        return res[0] if np.ndim(tq) == 0 else res
+
+
+def as_track(obj, default_kind=None):
+    """Accept our Track objects or interpolator-like objects exposing knots (interpax.Interpolator1D: .x, .f, .method)."""
+    if isinstance(obj, Track):
+        return obj
+    if hasattr(obj, "x") and hasattr(obj, "f"):
+        method = getattr(obj, "method", "cubic")
+        if method == "linear":
+            kind = _lib.TRACK_LINEAR
+        elif method == "cubic":
+            kind = _lib.TRACK_CUBIC
+        else:
+            raise NotImplementedError(f"interpolation method {method!r} is not implemented on the device")
+        return Track(kind, np.asarray(obj.x), np.asarray(obj.f))
+    raise NotImplementedError(
+        "time-dependent centres must be tabulated tracks (streamsculptor_b200.LinearTrack / CubicTrack or an "
+        "interpax-like object with .x/.f); arbitrary Python callables cannot run inside the CUDA kernels")
+
+
+class SubhaloArrays:
+    def __init__(self, profile, G, m, rs, x0, v, t0, tw):
+        m = np.atleast_1d(np.asarray(m, dtype=np.float64))
+        n = len(m)
+        self.n, self.profile, self.G = n, int(profile), float(G)
+        self.host = dict(m=m, rs=np.broadcast_to(np.asarray(rs, dtype=np.float64), (n,)).copy(),
+                         x0=np.asarray(x0, dtype=np.float64).reshape(n, 3).copy(), v=np.asarray(v, dtype=np.float64).reshape(n, 3).copy(),
+                         t0=np.broadcast_to(np.asarray(t0, dtype=np.float64), (n,)).copy(),
+                         tw=np.broadcast_to(np.asarray(tw, dtype=np.float64), (n,)).copy())
+        self._dev = None
+
+    def struct(self):
+        if self._dev is None:
+            self._dev = {k: to_dev(v) for k, v in self.host.items()}
+        d = self._dev
+        return _lib.Subhalos(n=self.n, profile=self.profile, G=self.G, m=d["m"].data_ptr(), rs=d["rs"].data_ptr(), x0=d["x0"].data_ptr(),
+                             v=d["v"].data_ptr(), t0=d["t0"].data_ptr(), tw=d["tw"].data_ptr())
+
+
+class Program:
+    """Flat potential program under construction."""
+
+    def __init__(self):
+        self.comps, self.tracks, self.shs = [], [], []
+
+    def add_track(self, track):
+        for i, t in enumerate(self.tracks):
+            if t is track:
+                return i
+        if len(self.tracks) >= _lib.MAX_TRACK:
+            raise NotImplementedError(f"more than {_lib.MAX_TRACK} tabulated tracks in one potential")
+        self.tracks.append(track)
+        return len(self.tracks) - 1
+
+    def add(self, typ, params, track=-1, sh=-1):
+        if len(self.comps) >= _lib.MAX_COMP:
+            raise NotImplementedError(f"more than {_lib.MAX_COMP} components in one potential")
+        self.comps.append((int(typ), [float(p) for p in params], int(track), int(sh)))
+
+    def add_subhalos(self, arrays, track=-1):
+        if len(self.shs) >= _lib.MAX_SH:
+            raise NotImplementedError(f"more than {_lib.MAX_SH} subhalo sets in one potential")
+        self.shs.append(arrays)
+        self.add(_lib.SUBHALOS, [], track=track, sh=len(self.shs) - 1)
+
+    def struct(self):
+        P = _lib.Potential()
+        P.n_comp, P.n_track, P.n_sh = len(self.comps), len(self.tracks), len(self.shs)
+        for i, (typ, params, track, sh) in enumerate(self.comps):
+            P.comp[i].type, P.comp[i].track, P.comp[i].sh = typ, track, sh
+            for k, v in enumerate(params):
+                P.comp[i].p[k] = v
+        for i, t in enumerate(self.tracks):
+            P.track[i] = t.struct()
+        for i, s in enumerate(self.shs):
+            P.sh[i] = s.struct()
+        return P
+
+
+def lower(pot):
+    """Potential object -> (ctypes struct, keepalive).  Cached on the object (parameters are immutable by convention)."""
+    cached = getattr(pot, "_ssb_lowered", None)
+    if cached is not None:
+        return cached
+    prog = Program()
+    pot._lower(prog, -1)
+    res = (prog.struct(), prog)
+    try:
+        pot._ssb_lowered = res
+    except Exception:
+        pass
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# calls
+# ------------------------------------------------------------------------------------------------
+def potential_eval(pot, xyz, t, want):
+    dev_in = is_dev(xyz)
+    x = to_dev(xyz).reshape(-1, 3)
+    n = x.shape[0]
+    tt = to_dev(np.broadcast_to(np.asarray(t, dtype=np.float64), (n,)).copy()) if not is_dev(t) else t.reshape(-1).expand(n).contiguous()
+    P, _keep = lower(pot)
+    phi = empty((n,)) if "phi" in want else None
+    grad = empty((n, 3)) if "grad" in want else None
+    hess = empty((n, 3, 3)) if "hess" in want else None
+    _lib.check(_lib.lib().ssb_potential_eval_f64(C.byref(P), n, ptr(x), ptr(tt), ptr(phi), ptr(grad), ptr(hess), stream_ptr()))
+    return tuple(out(v, dev_in) for v in (phi, grad, hess) if v is not None)
+
+
+def orbit_integrate(pot, w0, t0, t1, ts, ctrl, ts_per_orbit):
+    """Device tensors in, device tensors out: ys[N,M,6], status[N], nsteps[N,3]."""
+    t = torch()
+    P, _keep = lower(pot)
+    N, M = w0.shape[0], ts.shape[-1]
+    ys = empty((N, M, 6))
+    status = empty((N,), t.int32)
+    nsteps = empty((N, 3), t.int32)
+    _lib.check(_lib.lib().ssb_orbit_integrate_f64(C.byref(P), N, ptr(w0), ptr(t0), ptr(t1), ptr(ts), M, int(ts_per_orbit), ctrl,
+                                                  ptr(ys), ptr(status), ptr(nsteps), stream_ptr()))
+    return ys, status, nsteps
+
+
+def orbit_dense(pot, w0, t0, t1, ts, ctrl):
+    """One orbit: returns ys[M,6], status[1], nsteps[3], scratch (kept for later dense evaluation)."""
+    t = torch()
+    P, _keep = lower(pot)
+    M = ts.shape[0]
+    nbytes = _lib.lib().ssb_scratch_bytes(ctrl.max_steps)
+    scratch = empty(((nbytes + 7) // 8,))
+    ys = empty((M, 6))
+    status = empty((1,), t.int32)
+    nsteps = empty((3,), t.int32)
+    _lib.check(_lib.lib().ssb_orbit_dense_f64(C.byref(P), ptr(w0), float(t0), float(t1), ptr(ts), M, ctrl, ptr(ys), ptr(status), ptr(nsteps),
+                                              ptr(scratch), nbytes, stream_ptr()))
+    return ys, status, nsteps, scratch
+
+
+def release_spray(pot, G, prog, Msat, idx, t, seed, kvals, normals):
+    tt = torch()
+    P, _keep = lower(pot)
+    N = prog.shape[0]
+    outs = [empty((N, 3)) for _ in range(4)]
+    kv = (C.c_double * 8)(*[float(k) for k in kvals])
+    _lib.check(_lib.lib().ssb_release_spray_f64(C.byref(P), float(G), N, ptr(prog), ptr(Msat), ptr(idx), ptr(t), int(seed), kv, ptr(normals),
+                                                ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), stream_ptr()))
+    return outs
+
+
+def gen_stream(pot, pot_release, G, ts, prog_w0, Msat, seed, kvals, normals, ctrl, i_begin=None, i_end=None):
+    tt = torch()
+    P, _k1 = lower(pot)
+    PR, _k2 = lower(pot_release)
+    Nts = ts.shape[0]
+    i_begin = 0 if i_begin is None else int(i_begin)
+    i_end = Nts - 1 if i_end is None else int(i_end)
+    n = i_end - i_begin
+    lead, trail = empty((n, 6)), empty((n, 6))
+    status, nsteps = empty((2, n), tt.int32), empty((2, n, 3), tt.int32)
+    nbytes = _lib.lib().ssb_stream_scratch_bytes(Nts, ctrl.max_steps)
+    scratch = empty(((nbytes + 7) // 8,))
+    kv = (C.c_double * 8)(*[float(k) for k in kvals])
+    _lib.check(_lib.lib().ssb_gen_stream_f64(C.byref(P), C.byref(PR), float(G), Nts, ptr(ts), ptr(prog_w0), ptr(Msat), int(seed), kv, ptr(normals),
+                                             ctrl, i_begin, i_end, ptr(lead), ptr(trail), ptr(status), ptr(nsteps), ptr(scratch), nbytes,
+                                             stream_ptr()))
+    return lead, trail, status, nsteps
+
+
+def linear_response(pot_base, sharrays, w0, D0, t0, t1, ctrl):
+    tt = torch()
+    P, _keep = lower(pot_base)
+    S = sharrays.struct()
+    N = w0.shape[0]
+    wout, Dout = empty((N, 6)), empty((N, sharrays.n, 12))
+    status, nsteps = empty((N,), tt.int32), empty((N, 3), tt.int32)
+    nbytes = _lib.lib().ssb_response_scratch_bytes(sharrays.n)
+    scratch = empty(((nbytes + 7) // 8,))
+    _lib.check(_lib.lib().ssb_linear_response_f64(C.byref(P), C.byref(S), N, ptr(w0), ptr(D0), ptr(t0), float(t1), ctrl, ptr(wout), ptr(Dout),
+                                                  ptr(status), ptr(nsteps), ptr(scratch), nbytes, stream_ptr()))
+    return wout, Dout, status, nsteps
+
+
+def response_term(pot_base, sharrays, t, y):
+    P, _keep = lower(pot_base)
+    S = sharrays.struct()
+    yd = to_dev(y).reshape(-1)
+    dy = empty(yd.shape)
+    _lib.check(_lib.lib().ssb_response_term_f64(C.byref(P), C.byref(S), float(t), ptr(yd), ptr(dy), stream_ptr()))
+    return dy
+
+
+def subhalo_eval(sharrays, dradius, xyz, t):
+    S = sharrays.struct()
+    x = (C.c_double * 3)(*[float(v) for v in np.asarray(xyz, dtype=np.float64).reshape(3)])
+    phi, grad = empty((sharrays.n,)), empty((sharrays.n, 3))
+    _lib.check(_lib.lib().ssb_subhalo_eval_f64(C.byref(S), int(bool(dradius)), x, float(t), ptr(phi), ptr(grad), stream_ptr()))
+    return phi, grad

@@ -1,0 +1,31 @@
+// Shared declarations of the libssb200 translation units.
+#ifndef SSB_COMMON_CUH
+#define SSB_COMMON_CUH
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ssb200.h"
+#include "ssb_potential.cuh"
+#include "ssb_rk.cuh"
+
+#define SSB_ORBIT_THREADS 128
+#define SSB_REC_STRIDE 64   // doubles per recorded step: ta, tb, x, p, x1, p1 (14) + up to 14 force stages (42)
+
+namespace ssb {
+
+// copy the by-value kernel parameter into shared memory so that non-inlined force calls can index it dynamically
+__device__ __forceinline__ void stage_potential(ssb_potential* dst, const ssb_potential* src) {
+    const int* s = reinterpret_cast<const int*>(src);
+    int* d = reinterpret_cast<int*>(dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(ssb_potential) / sizeof(int)); i += blockDim.x) d[i] = s[i];
+    __syncthreads();
+}
+
+}  // namespace ssb
+
+// error helpers shared by the host-side translation units (defined in ssb_kernels.cu)
+int ssb_set_error(int code, const char* msg);
+int ssb_cuda_check(cudaError_t e, const char* what);
+int ssb_validate_potential(const ssb_potential* p);
+int ssb_validate_ctrl(const ssb_ctrl& c);
+#endif

@@ -1,0 +1,682 @@
+// libssb200: sm_100a kernels + C ABI (include/ssb200.h) for the streamsculptor hot path.
+//
+//   K1 orbit_kernel        one thread per orbit, stepper state in registers        (main.py:125-202, A3/A4)
+//   K0 dense_step_kernel + dense_eval_kernel   one orbit saved at M times            (main.py:289, A7)
+//   K2 release_kernel      particle-spray ICs incl. jax threefry normals            (main.py:209-306, A6)
+//   potential_eval_kernel, subhalo_eval_kernel, track kernels                       (main.py:37-65, A1/A5/A10/A11)
+// The linear-response kernel lives in ssb_response.cu.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <limits>
+#include <vector>
+
+#include "ssb_common.cuh"
+
+using namespace ssb;
+
+// =============================================================================================
+// force functors
+// =============================================================================================
+// The force is a real function call (not inlined 13x into the unrolled stepper): the stepper body stays inside
+// the instruction cache and ptxas allocates the stage registers once.
+__device__ __noinline__ double3 accel_call(const ssb_potential* P, double x, double y, double z, double t) {
+    const double X[3] = {x, y, z};
+    double phi, g[3];
+    Sym3 H;
+    pot_eval<WANT_GRAD>(*P, X, t, phi, g, H);
+    return make_double3(-g[0], -g[1], -g[2]);
+}
+struct OrbitForce {                      // Potential.velocity_acceleration (main.py:116-120) in mirrored time
+    const ssb_potential* P;
+    double dir;
+    __device__ __forceinline__ void operator()(const double X[3], double tau, double A[3]) const {
+        const double3 a = accel_call(P, X[0], X[1], X[2], tau * dir);
+        A[0] = a.x; A[1] = a.y; A[2] = a.z;
+    }
+};
+
+// =============================================================================================
+// K1: batch of independent adaptive solves
+// =============================================================================================
+struct OrbitArgs {
+    int64_t N;
+    const double *w0, *t0, *t1, *ts;
+    int M, ts_per_orbit;
+    double* ys;
+    int32_t *status, *nsteps;
+    CtrlDev c;
+};
+
+// per-thread integration of one orbit; REC != nullptr records accepted steps (K0) instead of saving
+template <int SOLVER, bool RECORD>
+__device__ __forceinline__ void integrate_one(const ssb_potential* P, const double* w0, double t0_in, double t1_in,
+                                              const double* tsp, int M, double* ys, const CtrlDev& c, bool valid,
+                                              int& status, int& n_steps, int& n_acc, int& n_rej, double* rec, int rec_cap) {
+    typedef Tab<SOLVER> T;
+    constexpr int S = T::S;
+    const double dir = (t0_in < t1_in) ? 1.0 : -1.0;              // diffrax: direction = where(t0 < t1, 1, -1)
+    const double T0 = t0_in * dir, T1 = t1_in * dir;
+    OrbitForce force{P, dir};
+    double x[3], p[3], F[S][3];
+    status = 0; n_steps = 0; n_acc = 0; n_rej = 0;
+    double tprev = T0, tnext = T0, h = 0.0;
+    bool at_dtmin = false;
+    int save_idx = 0;
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { x[k] = w0[k]; p[k] = dir * w0[3 + k]; }
+        if (!RECORD) {
+            const double inf = __longlong_as_double(0x7ff0000000000000LL);
+            for (int m = 0; m < M; ++m)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) ys[(size_t)m * 6 + k] = inf;
+        }
+        // ---- PIDController.init: Hairer-Norsett-Wanner initial step ----
+        force(x, T0, F[0]);
+        double sx[3], sp[3], d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            sx[k] = fma(c.rtol, fabs(x[k]), c.atol); sp[k] = fma(c.rtol, fabs(p[k]), c.atol);
+            double q;
+            q = x[k] / sx[k]; d0 = fma(q, q, d0); q = p[k] / sp[k]; d0 = fma(q, q, d0);
+            q = p[k] / sx[k]; d1 = fma(q, q, d1); q = F[0][k] / sp[k]; d1 = fma(q, q, d1);
+        }
+        d0 = sqrt(d0 / 6.0); d1 = sqrt(d1 / 6.0);
+        const double h0 = hnw_h0(d0, d1);
+        double X1[3], F1[3], d2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) X1[k] = fma(h0, p[k], x[k]);
+        force(X1, T0 + h0, F1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double q;
+            q = (fma(h0, F[0][k], p[k]) - p[k]) / sx[k]; d2 = fma(q, q, d2);     // f1 - f0, position rows: p1 - p
+            q = (F1[k] - F[0][k]) / sp[k]; d2 = fma(q, q, d2);
+        }
+        d2 = sqrt(d2 / 6.0) / h0;
+        h = fmin(hnw_h1<T::ORDER>(h0, d1, d2), c.dtmax);
+        at_dtmin = h <= c.dtmin;
+        h = fmax(h, c.dtmin);
+        tnext = fmin(T0 + h, T1);
+    }
+    for (;;) {
+        bool active = valid && status == 0 && tprev < T1;
+        if (active && n_steps >= c.max_steps) { status = 1; active = false; }
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (!active) continue;
+        const double dt = tnext - tprev;
+        double x1[3], p1[3], ex[3], ep[3];
+        rk_stages<SOLVER>(force, x, p, tprev, dt, F);
+        rk_candidate<SOLVER>(x, p, dt, F, x1, p1);
+        force(x1, tprev + T::c(S - 1) * dt, F[S - 1]);
+        rk_error<SOLVER>(p, dt, F, ex, ep);
+        bool nan_cand = false, finite = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            nan_cand |= isnan(x1[k]) | isnan(p1[k]);
+            finite &= isfinite(x1[k]) & isfinite(p1[k]);
+        }
+        const double err = sqrt(err_sq6(x, p, x1, p1, ex, ep, c.rtol, c.atol, nan_cand) / 6.0);
+        double hn; bool bad;
+        const bool keep = pid_update<T::ORDER>(err, dt, c, at_dtmin, hn, bad);
+        n_steps++;
+        if (bad) { status = 2; n_rej++; continue; }
+        if (keep) {
+            n_acc++;
+            if (!finite) { status = 2; continue; }
+            if (RECORD) {
+                if (n_acc <= rec_cap) {
+                    double* r = rec + (size_t)(n_acc - 1) * SSB_REC_STRIDE;
+                    r[0] = tprev; r[1] = tnext;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { r[2 + k] = x[k]; r[5 + k] = p[k]; r[8 + k] = x1[k]; r[11 + k] = p1[k]; }
+#pragma unroll
+                    for (int l = 0; l < S; ++l)
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) r[14 + 3 * l + k] = F[l][k];
+                }
+            } else {
+                // SaveAt(ts): every ts[save_idx] <= tnext is interpolated inside this accepted step
+                while (save_idx < M) {
+                    const double tq = tsp[save_idx] * dir;
+                    if (!(tq <= tnext)) break;
+                    double xo[3], po[3];
+                    if (tq == tnext) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) { xo[k] = x1[k]; po[k] = p1[k]; }
+                    } else {
+                        rk_dense<SOLVER>(x, p, x1, p1, dt, F, (tq - tprev) / dt, xo, po);
+                    }
+                    double* o = ys + (size_t)save_idx * 6;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { o[k] = xo[k]; o[3 + k] = dir * po[k]; }
+                    save_idx++;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { x[k] = x1[k]; p[k] = p1[k]; F[0][k] = F[S - 1][k]; }    // FSAL
+            tprev = tnext;
+        } else {
+            n_rej++;
+        }
+        tprev = fmin(tprev, T1);
+        double tn = tprev + hn;
+        if (tn > T1 - 1e-10) tn = keep ? T1 : tprev + 0.5 * (T1 - tprev);     // diffrax _clip_to_end (f64)
+        tnext = tn;
+    }
+}
+
+template <int SOLVER>
+__global__ void __launch_bounds__(SSB_ORBIT_THREADS) orbit_kernel(const __grid_constant__ ssb_potential Pin, const OrbitArgs a) {
+    __shared__ ssb_potential sP;
+    stage_potential(&sP, &Pin);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < a.N;
+    const int64_t ii = valid ? i : 0;
+    int status, n_steps, n_acc, n_rej;
+    const double* tsp = a.ts + (a.ts_per_orbit ? ii * a.M : 0);
+    integrate_one<SOLVER, false>(&sP, a.w0 + ii * 6, a.t0[ii], a.t1[ii], tsp, a.M, a.ys + (size_t)ii * a.M * 6, a.c, valid,
+                                 status, n_steps, n_acc, n_rej, nullptr, 0);
+    if (valid) {
+        a.status[i] = status;
+        a.nsteps[3 * i] = n_steps; a.nsteps[3 * i + 1] = n_acc; a.nsteps[3 * i + 2] = n_rej;
+    }
+}
+
+// =============================================================================================
+// K0: one orbit with dense output at M save times (progenitor at all stripping times, main.py:289)
+//   scratch layout: hdr[8] doubles {n_acc, status, n_steps, n_rej, dir}, then rec[max_steps][SSB_REC_STRIDE]
+// =============================================================================================
+template <int SOLVER>
+__global__ void __launch_bounds__(32) dense_step_kernel(const __grid_constant__ ssb_potential Pin, const double* w0, double t0, double t1,
+                                                        const double* t0p, const double* t1p, CtrlDev c, double* scratch, int rec_cap,
+                                                        int32_t* status_out, int32_t* nsteps_out) {
+    __shared__ ssb_potential sP;
+    stage_potential(&sP, &Pin);
+    if (t0p) { t0 = *t0p; t1 = *t1p; }              // interval ends read on the device (no host round trip in gen_stream)
+    const bool valid = threadIdx.x == 0;
+    int status, n_steps, n_acc, n_rej;
+    integrate_one<SOLVER, true>(&sP, w0, t0, t1, nullptr, 0, nullptr, c, valid, status, n_steps, n_acc, n_rej, scratch + 8, rec_cap);
+    if (valid) {
+        scratch[0] = (double)min(n_acc, rec_cap); scratch[1] = (double)status; scratch[4] = (t0 < t1) ? 1.0 : -1.0;
+        if (status_out) *status_out = status;
+        if (nsteps_out) { nsteps_out[0] = n_steps; nsteps_out[1] = n_acc; nsteps_out[2] = n_rej; }
+    }
+}
+
+template <int SOLVER>
+__global__ void dense_eval_kernel(const double* scratch, const double* ts, int64_t M, double* ys) {
+    constexpr int S = Tab<SOLVER>::S;
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int n = (int)scratch[0];
+    const double dir = scratch[4];
+    const double* rec = scratch + 8;
+    const double tq = ts[m] * dir;
+    double* o = ys + m * 6;
+    // first accepted step whose end time >= tq (the step inside which diffrax saves this ts)
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (rec[(size_t)mid * SSB_REC_STRIDE + 1] < tq) lo = mid + 1; else hi = mid; }
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    if (lo >= n || n == 0 || tq < rec[0]) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o[k] = inf;
+        return;
+    }
+    const double* r = rec + (size_t)lo * SSB_REC_STRIDE;
+    const double ta = r[0], tb = r[1];
+    double x[3], p[3], x1[3], p1[3], F[S][3], xo[3], po[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { x[k] = r[2 + k]; p[k] = r[5 + k]; x1[k] = r[8 + k]; p1[k] = r[11 + k]; }
+#pragma unroll
+    for (int l = 0; l < S; ++l)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) F[l][k] = r[14 + 3 * l + k];
+    if (tq == tb) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { xo[k] = x1[k]; po[k] = p1[k]; }
+    } else {
+        rk_dense<SOLVER>(x, p, x1, p1, tb - ta, F, (tq - ta) / (tb - ta), xo, po);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[k] = xo[k]; o[3 + k] = dir * po[k]; }
+}
+
+// =============================================================================================
+// field evaluation kernels
+// =============================================================================================
+__global__ void potential_eval_kernel(const __grid_constant__ ssb_potential Pin, int64_t n, const double* xyz, const double* t,
+                                      double* phi, double* grad, double* hess) {
+    __shared__ ssb_potential sP;
+    stage_potential(&sP, &Pin);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double X[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+    double P, g[3];
+    Sym3 H;
+    pot_eval<WANT_PHI | WANT_GRAD | WANT_HESS>(sP, X, t[i], P, g, H);
+    if (phi) phi[i] = P;
+    if (grad) { grad[3 * i] = g[0]; grad[3 * i + 1] = g[1]; grad[3 * i + 2] = g[2]; }
+    if (hess) {
+        double* h = hess + 9 * i;
+        h[0] = H.xx; h[1] = H.xy; h[2] = H.xz; h[3] = H.xy; h[4] = H.yy; h[5] = H.yz; h[6] = H.xz; h[7] = H.yz; h[8] = H.zz;
+    }
+}
+
+__global__ void subhalo_eval_kernel(const ssb_subhalos S, int dradius, double x0, double x1, double x2, double t, double* phi, double* grad) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= S.n) return;
+    double ph = 0.0, g[3] = {0, 0, 0};
+    const double dt = t - S.t0[j];
+    if (fabs(dt) < S.tw[j]) {
+        const double X[3] = {x0, x1, x2};
+        double rel[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) rel[k] = X[k] - fma(S.v[3 * j + k], dt, S.x0[3 * j + k]);
+        const double r2 = fma(rel[0], rel[0], fma(rel[1], rel[1], rel[2] * rel[2]));
+        double q, w = 0;
+        if (dradius) profile_dradius(S.profile, S.G * S.m[j], S.rs[j], r2, ph, q);
+        else profile_terms<WANT_PHI | WANT_GRAD>(S.profile, S.G * S.m[j], S.rs[j], r2, ph, q, w);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g[k] = q * rel[k];
+    }
+    if (phi) phi[j] = ph;
+    if (grad) { grad[3 * j] = g[0]; grad[3 * j + 1] = g[1]; grad[3 * j + 2] = g[2]; }
+}
+
+__global__ void track_slopes_kernel(int64_t n, const double* t, const double* y, double* s) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto sec = [&](int64_t j, int k) {           // secant slope of segment j (interpax approx_df 'cubic')
+        const double dx = t[j + 1] - t[j];
+        const double dxi = dx == 0.0 ? 0.0 : 1.0 / dx;
+        return dxi * (y[3 * (j + 1) + k] - y[3 * j + k]);
+    };
+    for (int k = 0; k < 3; ++k) {
+        double v;
+        if (i == 0) v = sec(0, k);
+        else if (i == n - 1) v = sec(n - 2, k);
+        else v = 0.5 * (sec(i - 1, k) + sec(i, k));
+        s[3 * i + k] = v;
+    }
+}
+
+__global__ void track_eval_kernel(const ssb_track T, int64_t nq, const double* tq, double* out, double* dout) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    double c[3], dc[3];
+    track_eval<true>(T, tq[i], c, dc);
+    for (int k = 0; k < 3; ++k) { out[3 * i + k] = c[k]; if (dout) dout[3 * i + k] = dc[k]; }
+}
+
+// =============================================================================================
+// K2: release model (main.py:209-280) with jax.random threefry2x32 normals (main.py:220-228, 263-266)
+// =============================================================================================
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+__device__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t& o0, uint32_t& o1) {
+    const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+    const int R[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+    uint32_t x0 = c0 + ks[0], x1 = c1 + ks[1];
+#pragma unroll
+    for (int g = 0; g < 5; ++g) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { x0 += x1; x1 = rotl32(x1, R[g & 1][r]); x1 ^= x0; }
+        x0 += ks[(g + 1) % 3];
+        x1 += ks[(g + 2) % 3] + (uint32_t)(g + 1);
+    }
+    o0 = x0; o1 = x1;
+}
+// jax.random.normal(PRNGKey(seed), (1,), float64): bits64 = threefry(key, (0,1)); mantissa trick; sqrt(2) erfinv(u)
+__device__ double jax_normal1(int64_t seed) {
+    const uint64_t u64 = (uint64_t)seed;
+    uint32_t o0, o1;
+    threefry2x32((uint32_t)(u64 >> 32), (uint32_t)(u64 & 0xFFFFFFFFu), 0u, 1u, o0, o1);
+    const uint64_t bits = ((uint64_t)o0 << 32) | (uint64_t)o1;
+    const double f = __longlong_as_double((long long)((bits >> 12) | 0x3FF0000000000000ull)) - 1.0;
+    const double lo = -0.99999999999999989;          // nextafter(-1, 0)
+    const double u = fmax(lo, fma(f, 1.0 - lo, lo));
+    return 1.4142135623730951 * erfinv(u);
+}
+
+struct ReleaseArgs {
+    int64_t N;
+    const double *prog, *Msat, *t, *normals;
+    const int64_t* idx;
+    int64_t r[4];                 // jax.random.randint(PRNGKey(seed), (5,), 0, 1000)[:4], computed on the host
+    double kv[8];
+    double G;
+    double *pos_lead, *pos_trail, *vel_lead, *vel_trail;
+    double *w0_packed, *t0_packed;   // optional [2,N,6] / [2,N] in the orbit-kernel layout (lead block, trail block)
+};
+
+__global__ void release_kernel(const __grid_constant__ ssb_potential Pin, const ReleaseArgs a) {
+    __shared__ ssb_potential sP;
+    stage_potential(&sP, &Pin);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const double* w = a.prog + 6 * i;
+    const double x[3] = {w[0], w[1], w[2]}, v[3] = {w[3], w[4], w[5]};
+    const double t = a.t[i];
+    double nr[4];
+    if (a.normals) { for (int q = 0; q < 4; ++q) nr[q] = a.normals[4 * i + q]; }
+    else { const int64_t id = a.idx ? a.idx[i] : i; for (int q = 0; q < 4; ++q) nr[q] = jax_normal1(id * a.r[q]); }
+    // omega (main.py:88-96), d2phidr2 = rhat^T H rhat (main.py:76-85), tidal radius (main.py:104)
+    const double rad2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+    const double L[3] = {x[1] * v[2] - x[2] * v[1], x[2] * v[0] - x[0] * v[2], x[0] * v[1] - x[1] * v[0]};
+    const double Lmag = sqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+    const double omega = Lmag / rad2;
+    const double r = sqrt(rad2);
+    const double rhat[3] = {x[0] / r, x[1] / r, x[2] / r};
+    double P, g[3];
+    Sym3 H;
+    pot_eval<WANT_HESS>(sP, x, t, P, g, H);
+    const double d2 = rhat[0] * (H.xx * rhat[0] + H.xy * rhat[1] + H.xz * rhat[2]) + rhat[1] * (H.xy * rhat[0] + H.yy * rhat[1] + H.yz * rhat[2]) +
+                      rhat[2] * (H.xz * rhat[0] + H.yz * rhat[1] + H.zz * rhat[2]);
+    const double rt = pow((a.G * a.Msat[i]) / (omega * omega - d2), 1.0 / 3.0);
+    const double vcirc = omega * rt;                                   // main.py:238,242
+    const double zhat[3] = {L[0] / Lmag, L[1] / Lmag, L[2] / Lmag};
+    const double vr = v[0] * rhat[0] + v[1] * rhat[1] + v[2] * rhat[2];
+    const double pv[3] = {v[0] - vr * rhat[0], v[1] - vr * rhat[1], v[2] - vr * rhat[2]};
+    const double pn = sqrt(pv[0] * pv[0] + pv[1] * pv[1] + pv[2] * pv[2]);
+    const double phat[3] = {pv[0] / pn, pv[1] / pn, pv[2] / pn};
+    const double kr = a.kv[0] + nr[0] * a.kv[4];                       // main.py:263-266
+    const double kvphi = kr * (a.kv[1] + nr[1] * a.kv[5]);
+    const double kz = a.kv[2] + nr[2] * a.kv[6];
+    const double kvz = a.kv[3] + nr[3] * a.kv[7];
+    for (int k = 0; k < 3; ++k) {
+        double pt = x[k] + kr * rhat[k] * rt;                          // main.py:269-272 (trailing)
+        pt = pt + zhat[k] * kz * (rt / 1.0);
+        double vt = v[k] + (0.0 + kvphi * vcirc * 1.0) * phat[k];
+        vt = vt + (kvz * vcirc * 1.0) * zhat[k];
+        double pl = x[k] + kr * rhat[k] * (-rt);                       // main.py:275-278 (leading)
+        pl = pl + zhat[k] * kz * (-rt / 1.0);
+        double vl = v[k] + (0.0 + kvphi * vcirc * (-1.0)) * phat[k];
+        vl = vl + (kvz * vcirc * (-1.0)) * zhat[k];
+        if (a.pos_lead) { a.pos_lead[3 * i + k] = pl; a.pos_trail[3 * i + k] = pt; a.vel_lead[3 * i + k] = vl; a.vel_trail[3 * i + k] = vt; }
+        if (a.w0_packed) {
+            a.w0_packed[6 * i + k] = pl; a.w0_packed[6 * i + 3 + k] = vl;
+            a.w0_packed[6 * (a.N + i) + k] = pt; a.w0_packed[6 * (a.N + i) + 3 + k] = vt;
+        }
+    }
+    if (a.t0_packed) { a.t0_packed[i] = t; a.t0_packed[a.N + i] = t; }
+}
+
+// gather the [i_begin, i_end) slice of the packed release output into the orbit-kernel input of the stream
+__global__ void stream_pack_kernel(int64_t Nts, int64_t i_begin, int64_t n, const double* w0_packed, const double* ts,
+                                   double* w0, double* t0, double* t1) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= 2 * n) return;
+    const int arm = j >= n;
+    const int64_t i = i_begin + (arm ? j - n : j);
+    const double* src = w0_packed + 6 * ((int64_t)arm * Nts + i);
+    for (int k = 0; k < 6; ++k) w0[6 * j + k] = src[k];
+    t0[j] = ts[i];
+    t1[j] = ts[Nts - 1];
+}
+
+// fp64 peak probe: 8 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, double* sink) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000000001, b = 1e-12;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+            a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+        }
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[0] = s;
+}
+
+// =============================================================================================
+// host side: C ABI
+// =============================================================================================
+static thread_local char g_err[512] = "";
+int ssb_set_error(int code, const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); return code; }
+int ssb_cuda_check(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return SSB_ERR_CUDA;
+}
+#define CK(call) do { int _e = ssb_cuda_check((call), #call); if (_e) return _e; } while (0)
+#define CKL(what) do { int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
+
+int ssb_validate_potential(const ssb_potential* p) {
+    if (!p) return ssb_set_error(SSB_ERR_ARG, "potential is NULL");
+    if (p->n_comp < 0 || p->n_comp > SSB_MAX_COMP || p->n_track < 0 || p->n_track > SSB_MAX_TRACK || p->n_sh < 0 ||
+        p->n_sh > SSB_MAX_SUBHALO_SETS)
+        return ssb_set_error(SSB_ERR_ARG, "potential: component/track/subhalo-set count out of range");
+    for (int i = 0; i < p->n_comp; ++i) {
+        const ssb_component& c = p->comp[i];
+        if (c.type < SSB_NFW || c.type > SSB_SUBHALOS) return ssb_set_error(SSB_ERR_UNSUPPORTED, "potential: unknown component type");
+        if (c.track >= p->n_track) return ssb_set_error(SSB_ERR_ARG, "potential: component references a missing track");
+        if (c.type == SSB_UNIFORM_ACC && c.track < 0) return ssb_set_error(SSB_ERR_ARG, "uniform acceleration needs a velocity track");
+        if (c.type == SSB_SUBHALOS && (c.sh < 0 || c.sh >= p->n_sh)) return ssb_set_error(SSB_ERR_ARG, "subhalo component references a missing set");
+    }
+    for (int i = 0; i < p->n_track; ++i) {
+        const ssb_track& t = p->track[i];
+        if (t.n < 2 || !t.t || !t.y) return ssb_set_error(SSB_ERR_ARG, "track: needs >= 2 knots and t, y pointers");
+        if (t.kind == SSB_TRACK_CUBIC && !t.s) return ssb_set_error(SSB_ERR_ARG, "cubic track: slopes pointer is NULL (ssb_track_slopes_f64)");
+        if (t.kind != SSB_TRACK_LINEAR && t.kind != SSB_TRACK_CUBIC) return ssb_set_error(SSB_ERR_UNSUPPORTED, "track: unknown kind");
+    }
+    for (int i = 0; i < p->n_sh; ++i) {
+        const ssb_subhalos& s = p->sh[i];
+        if (s.n < 0 || (s.n > 0 && (!s.m || !s.rs || !s.x0 || !s.v || !s.t0 || !s.tw))) return ssb_set_error(SSB_ERR_ARG, "subhalo set: NULL array");
+        if (s.profile < SSB_PROFILE_PLUMMER || s.profile > SSB_PROFILE_NFW) return ssb_set_error(SSB_ERR_UNSUPPORTED, "subhalo set: unknown profile");
+    }
+    return 0;
+}
+int ssb_validate_ctrl(const ssb_ctrl& c) {
+    if (c.solver != 5 && c.solver != 8) return ssb_set_error(SSB_ERR_UNSUPPORTED, "solver must be 5 (Dopri5) or 8 (Dopri8)");
+    if (!(c.rtol >= 0) || !(c.atol >= 0) || !(c.dtmin >= 0) || c.max_steps < 0) return ssb_set_error(SSB_ERR_ARG, "ctrl: negative tolerance / dtmin / max_steps");
+    return 0;
+}
+static CtrlDev to_dev(const ssb_ctrl& c) { CtrlDev d; d.rtol = c.rtol; d.atol = c.atol; d.dtmin = c.dtmin; d.dtmax = c.dtmax; d.max_steps = c.max_steps; return d; }
+static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// jax.random.randint(PRNGKey(seed), (5,), 0, 1000) on the host (5 integers; main.py:220-221)
+static inline uint32_t h_rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+static void h_threefry(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t* o0, uint32_t* o1) {
+    static const int R[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+    uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+    uint32_t x0 = c0 + ks[0], x1 = c1 + ks[1];
+    for (int g = 0; g < 5; ++g) {
+        for (int r = 0; r < 4; ++r) { x0 += x1; x1 = h_rotl32(x1, R[g & 1][r]); x1 ^= x0; }
+        x0 += ks[(g + 1) % 3];
+        x1 += ks[(g + 2) % 3] + (uint32_t)(g + 1);
+    }
+    *o0 = x0; *o1 = x1;
+}
+static void host_randint5(int64_t seed, int64_t* out) {
+    const uint64_t u = (uint64_t)seed;
+    const uint32_t ka = (uint32_t)(u >> 32), kb = (uint32_t)(u & 0xFFFFFFFFu);
+    uint32_t a0, b0, a1, b1;
+    h_threefry(ka, kb, 0, 2, &a0, &b0);          // jax.random.split(key): counts iota(4) -> halves (0,1),(2,3)
+    h_threefry(ka, kb, 1, 3, &a1, &b1);
+    const uint32_t k1[2] = {a0, a1}, k2[2] = {b0, b1};
+    const uint64_t span = 1000, mult0 = (((uint64_t)1 << 32) % span), mult = (mult0 * mult0) % span;
+    for (int j = 0; j < 5; ++j) {
+        uint32_t h0, h1, l0, l1;
+        h_threefry(k1[0], k1[1], (uint32_t)j, (uint32_t)(5 + j), &h0, &h1);
+        h_threefry(k2[0], k2[1], (uint32_t)j, (uint32_t)(5 + j), &l0, &l1);
+        const uint64_t hi = ((uint64_t)h0 << 32) | h1, lo = ((uint64_t)l0 << 32) | l1;
+        out[j] = (int64_t)(((hi % span) * mult + (lo % span)) % span);
+    }
+}
+
+extern "C" {
+
+int ssb_abi_version(void) { return SSB_ABI_VERSION; }
+const char* ssb_last_error(void) { return g_err; }
+
+int ssb_potential_eval_f64(const ssb_potential* pot, int64_t n, const double* xyz, const double* t, double* phi, double* grad,
+                           double* hess, void* stream) {
+    if (int e = ssb_validate_potential(pot)) return e;
+    if (n < 0 || (n > 0 && (!xyz || !t))) return ssb_set_error(SSB_ERR_ARG, "potential_eval: bad n / NULL xyz, t");
+    if (n == 0) return 0;
+    potential_eval_kernel<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(*pot, n, xyz, t, phi, grad, hess);
+    CKL("potential_eval_kernel");
+    return 0;
+}
+
+int ssb_subhalo_eval_f64(const ssb_subhalos* sh, int dradius, const double* xyz, double t, double* phi, double* grad, void* stream) {
+    if (!sh || !xyz) return ssb_set_error(SSB_ERR_ARG, "subhalo_eval: NULL argument");
+    if (sh->n <= 0) return 0;
+    subhalo_eval_kernel<<<nblk(sh->n, 128), 128, 0, (cudaStream_t)stream>>>(*sh, dradius, xyz[0], xyz[1], xyz[2], t, phi, grad);
+    CKL("subhalo_eval_kernel");
+    return 0;
+}
+
+int ssb_track_slopes_f64(int64_t n, const double* t, const double* y, double* s, void* stream) {
+    if (n < 2 || !t || !y || !s) return ssb_set_error(SSB_ERR_ARG, "track_slopes: need n >= 2 and non-NULL arrays");
+    track_slopes_kernel<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(n, t, y, s);
+    CKL("track_slopes_kernel");
+    return 0;
+}
+
+int ssb_track_eval_f64(const ssb_track* tr, int64_t nq, const double* tq, double* out, double* dout, void* stream) {
+    if (!tr || nq < 0 || (nq > 0 && (!tq || !out))) return ssb_set_error(SSB_ERR_ARG, "track_eval: NULL argument");
+    if (nq == 0) return 0;
+    track_eval_kernel<<<nblk(nq, 128), 128, 0, (cudaStream_t)stream>>>(*tr, nq, tq, out, dout);
+    CKL("track_eval_kernel");
+    return 0;
+}
+
+int ssb_orbit_integrate_f64(const ssb_potential* pot, int64_t N, const double* w0, const double* t0, const double* t1, const double* ts,
+                            int32_t M, int32_t ts_per_orbit, ssb_ctrl ctrl, double* ys, int32_t* status, int32_t* nsteps, void* stream) {
+    if (int e = ssb_validate_potential(pot)) return e;
+    if (int e = ssb_validate_ctrl(ctrl)) return e;
+    if (N < 0 || M < 0) return ssb_set_error(SSB_ERR_ARG, "orbit_integrate: negative N or M");
+    if (N == 0) return 0;
+    if (!w0 || !t0 || !t1 || !status || !nsteps || (M > 0 && (!ts || !ys))) return ssb_set_error(SSB_ERR_ARG, "orbit_integrate: NULL array");
+    OrbitArgs a;
+    a.N = N; a.w0 = w0; a.t0 = t0; a.t1 = t1; a.ts = ts; a.M = M; a.ts_per_orbit = ts_per_orbit; a.ys = ys; a.status = status; a.nsteps = nsteps;
+    a.c = to_dev(ctrl);
+    const unsigned grid = nblk(N, SSB_ORBIT_THREADS);
+    if (ctrl.solver == 5) orbit_kernel<5><<<grid, SSB_ORBIT_THREADS, 0, (cudaStream_t)stream>>>(*pot, a);
+    else orbit_kernel<8><<<grid, SSB_ORBIT_THREADS, 0, (cudaStream_t)stream>>>(*pot, a);
+    CKL("orbit_kernel");
+    return 0;
+}
+
+size_t ssb_scratch_bytes(int32_t max_steps) { return sizeof(double) * (8 + (size_t)(max_steps > 0 ? max_steps : 1) * SSB_REC_STRIDE); }
+
+static int dense_launch(const ssb_potential* pot, const double* w0, double t0, double t1, const double* t0p, const double* t1p,
+                        const double* ts, int64_t M, const ssb_ctrl& ctrl, double* ys, int32_t* status, int32_t* nsteps, double* scratch,
+                        cudaStream_t st) {
+    const CtrlDev c = to_dev(ctrl);
+    if (ctrl.solver == 5) dense_step_kernel<5><<<1, 32, 0, st>>>(*pot, w0, t0, t1, t0p, t1p, c, scratch, ctrl.max_steps, status, nsteps);
+    else dense_step_kernel<8><<<1, 32, 0, st>>>(*pot, w0, t0, t1, t0p, t1p, c, scratch, ctrl.max_steps, status, nsteps);
+    CKL("dense_step_kernel");
+    if (M > 0) {
+        if (ctrl.solver == 5) dense_eval_kernel<5><<<nblk(M, 128), 128, 0, st>>>(scratch, ts, M, ys);
+        else dense_eval_kernel<8><<<nblk(M, 128), 128, 0, st>>>(scratch, ts, M, ys);
+        CKL("dense_eval_kernel");
+    }
+    return 0;
+}
+
+int ssb_orbit_dense_f64(const ssb_potential* pot, const double* w0, double t0, double t1, const double* ts, int64_t M, ssb_ctrl ctrl,
+                        double* ys, int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream) {
+    if (int e = ssb_validate_potential(pot)) return e;
+    if (int e = ssb_validate_ctrl(ctrl)) return e;
+    if (!w0 || M < 0 || (M > 0 && (!ts || !ys)) || !scratch) return ssb_set_error(SSB_ERR_ARG, "orbit_dense: NULL array");
+    if (scratch_bytes < ssb_scratch_bytes(ctrl.max_steps)) return ssb_set_error(SSB_ERR_SCRATCH, "orbit_dense: scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    return dense_launch(pot, w0, t0, t1, nullptr, nullptr, ts, M, ctrl, ys, status, nsteps, (double*)scratch, st);
+}
+
+int ssb_release_spray_f64(const ssb_potential* pot, double G, int64_t N, const double* prog, const double* Msat, const int64_t* idx,
+                          const double* t, int64_t seed, const double* kvals, const double* normals, double* pos_lead, double* pos_trail,
+                          double* vel_lead, double* vel_trail, void* stream) {
+    if (int e = ssb_validate_potential(pot)) return e;
+    if (N < 0) return ssb_set_error(SSB_ERR_ARG, "release_spray: negative N");
+    if (N == 0) return 0;
+    if (!prog || !Msat || !t || !kvals || !pos_lead || !pos_trail || !vel_lead || !vel_trail) return ssb_set_error(SSB_ERR_ARG, "release_spray: NULL array");
+    ReleaseArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = N; a.prog = prog; a.Msat = Msat; a.t = t; a.normals = normals; a.idx = idx; a.G = G;
+    int64_t r5[5]; host_randint5(seed, r5);
+    for (int q = 0; q < 4; ++q) a.r[q] = r5[q];
+    memcpy(a.kv, kvals, sizeof(a.kv));
+    a.pos_lead = pos_lead; a.pos_trail = pos_trail; a.vel_lead = vel_lead; a.vel_trail = vel_trail;
+    release_kernel<<<nblk(N, 128), 128, 0, (cudaStream_t)stream>>>(*pot, a);
+    CKL("release_kernel");
+    return 0;
+}
+
+// scratch layout of gen_stream: [dense scratch | prog Nts*6 | w0_packed 2*Nts*6 | w0 2n*6 | t0 2n | t1 2n | ys 2n*6]
+size_t ssb_stream_scratch_bytes(int64_t Nts, int32_t max_steps) {
+    return ssb_scratch_bytes(max_steps) + sizeof(double) * (size_t)Nts * (6 + 12 + 12 + 2 + 2 + 12) + 256;
+}
+
+int ssb_gen_stream_f64(const ssb_potential* pot, const ssb_potential* pot_release, double G, int64_t Nts, const double* ts, const double* prog_w0,
+                       const double* Msat, int64_t seed, const double* kvals, const double* normals, ssb_ctrl ctrl, int64_t i_begin, int64_t i_end,
+                       double* lead, double* trail, int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream) {
+    if (int e = ssb_validate_potential(pot)) return e;
+    if (int e = ssb_validate_potential(pot_release)) return e;
+    if (int e = ssb_validate_ctrl(ctrl)) return e;
+    if (Nts < 2 || !ts || !prog_w0 || !Msat || !kvals || !scratch) return ssb_set_error(SSB_ERR_ARG, "gen_stream: NULL array or Nts < 2");
+    if (i_begin < 0 || i_end > Nts - 1 || i_begin > i_end) return ssb_set_error(SSB_ERR_ARG, "gen_stream: particle range outside [0, Nts-1]");
+    if (scratch_bytes < ssb_stream_scratch_bytes(Nts, ctrl.max_steps)) return ssb_set_error(SSB_ERR_SCRATCH, "gen_stream: scratch too small");
+    const int64_t n = i_end - i_begin;
+    if (n > 0 && (!lead || !trail || !status || !nsteps)) return ssb_set_error(SSB_ERR_ARG, "gen_stream: NULL output");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* dense = (double*)scratch;
+    double* prog = dense + ssb_scratch_bytes(ctrl.max_steps) / sizeof(double);
+    double* w0p = prog + 6 * Nts;
+    double* w0 = w0p + 12 * Nts;
+    double* t0 = w0 + 12 * Nts;
+    double* t1 = t0 + 2 * Nts;
+    double* ys = t1 + 2 * Nts;
+    // (1) progenitor at every stripping time: integrate_orbit(prog_w0, ts) with t0 = ts.min, t1 = ts.max (main.py:289, 152-153)
+    if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts, ts + (Nts - 1), ts, Nts, ctrl, prog, nullptr, nullptr, dense, st)) return e;
+    // (2) release at every stripping time (main.py:293-303)
+    ReleaseArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = Nts; a.prog = prog; a.Msat = Msat; a.t = ts; a.normals = normals; a.idx = nullptr; a.G = G;
+    int64_t r5[5]; host_randint5(seed, r5);
+    for (int q = 0; q < 4; ++q) a.r[q] = r5[q];
+    memcpy(a.kv, kvals, sizeof(a.kv));
+    a.w0_packed = w0p;
+    release_kernel<<<nblk(Nts, 128), 128, 0, st>>>(*pot_release, a);
+    CKL("release_kernel");
+    if (n == 0) return 0;
+    // (3) 2n independent solves from ts[i] to ts[-1], keep the final state (main.py:349-368)
+    stream_pack_kernel<<<nblk(2 * n, 128), 128, 0, st>>>(Nts, i_begin, n, w0p, ts, w0, t0, t1);
+    CKL("stream_pack_kernel");
+    if (int e = ssb_orbit_integrate_f64(pot, 2 * n, w0, t0, t1, t1, 1, 1, ctrl, ys, status, nsteps, stream)) return e;
+    CK(cudaMemcpyAsync(lead, ys, sizeof(double) * 6 * n, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(trail, ys + 6 * n, sizeof(double) * 6 * n, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int ssb_fp64_peak_probe(int iters, double* flops_per_s, void* stream) {
+    if (!flops_per_s || iters <= 0) return ssb_set_error(SSB_ERR_ARG, "fp64_peak_probe: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* sink = nullptr;
+    CK(cudaMalloc(&sink, 8));
+    const int blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    dfma_probe_kernel<<<blocks, threads, 0, st>>>(iters / 4 + 1, sink);
+    CK(cudaEventRecord(e0, st));
+    dfma_probe_kernel<<<blocks, threads, 0, st>>>(iters, sink);
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *flops_per_s = 2.0 * 64.0 * (double)iters * blocks * threads / (ms * 1e-3);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,260 @@
+// Closed-form Phi, grad Phi, Hess Phi for the component set of the hot path (sm_100a device code).
+//
+// The reference obtains every derivative by autodiff of a scalar potential
+// (/root/reference/streamsculptor/main.py:37-65, fields.py:193); a fixed kernel needs them in closed form.
+// Formulas follow potential.py (line numbers at each case) and SURVEY.md Appendix C; tests compare them with
+// the oracle's AD of the same scalar formulas.
+#ifndef SSB_POTENTIAL_CUH
+#define SSB_POTENTIAL_CUH
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/ssb200.h"
+
+namespace ssb {
+
+enum { WANT_PHI = 1, WANT_GRAD = 2, WANT_HESS = 4 };
+
+// Hessian storage: symmetric 6 = {xx, yy, zz, xy, xz, yz}
+struct Sym3 { double xx, yy, zz, xy, xz, yz; };
+
+// ---------------------------------------------------------------------------------------------
+// tracks (potential.py:581-600 linear; interpax 'cubic' streamhelpers.py:520)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lower_bound_d(const double* __restrict__ a, int n, double v) {   // first i with a[i] >= v
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ int upper_bound_d(const double* __restrict__ a, int n, double v) {   // first i with a[i] > v
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(a + mid) <= v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+template <bool DERIV>
+__device__ __forceinline__ void track_eval(const ssb_track& T, double tq, double c[3], double dc[3]) {
+    const int n = T.n;
+    if (T.kind == SSB_TRACK_LINEAR) {
+        int i = lower_bound_d(T.t, n, tq) - 1;                     // jnp.searchsorted(side='left') - 1, clipped
+        i = min(max(i, 0), n - 2);
+        const double ta = __ldg(T.t + i), tb = __ldg(T.t + i + 1);
+        const double h = tb - ta, w = (tq - ta) / h;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double y0 = __ldg(T.y + 3 * i + k), y1 = __ldg(T.y + 3 * i + 3 + k);
+            c[k] = (1.0 - w) * y0 + w * y1;
+            if (DERIV) dc[k] = (y1 - y0) / h;
+        }
+    } else {
+        if (!(tq >= __ldg(T.t) && tq <= __ldg(T.t + n - 1))) {     // interpax extrap=False -> NaN
+            const double qn = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { c[k] = qn; if (DERIV) dc[k] = qn; }
+            return;
+        }
+        int i = upper_bound_d(T.t, n, tq);                          // searchsorted(side='right'), clipped to [1, n-1]
+        i = min(max(i, 1), n - 1);
+        const double ta = __ldg(T.t + i - 1), tb = __ldg(T.t + i);
+        const double dx = tb - ta, dxi = dx == 0.0 ? 0.0 : 1.0 / dx;
+        const double u = (tq - ta) * dxi;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double f0 = __ldg(T.y + 3 * (i - 1) + k), f1 = __ldg(T.y + 3 * i + k);
+            const double m0 = __ldg(T.s + 3 * (i - 1) + k) * dx, m1 = __ldg(T.s + 3 * i + k) * dx;
+            const double c2 = 3.0 * (f1 - f0) - 2.0 * m0 - m1;
+            const double c3 = 2.0 * (f0 - f1) + m0 + m1;
+            c[k] = f0 + u * (m0 + u * (c2 + u * c3));
+            if (DERIV) dc[k] = (m0 + u * (2.0 * c2 + 3.0 * u * c3)) * dxi;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// spherical building block: given x, the scalars q = Phi'/r and w = (Phi'' - Phi'/r)/r^2 give
+//   grad = q x,   H_ij = q delta_ij + w x_i x_j
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void add_spherical(const double x[3], double phi, double q, double w,
+                                              double& P, double g[3], Sym3& H) {
+    if (MODE & WANT_PHI) P += phi;
+    if (MODE & WANT_GRAD) { g[0] = fma(q, x[0], g[0]); g[1] = fma(q, x[1], g[1]); g[2] = fma(q, x[2], g[2]); }
+    if (MODE & WANT_HESS) {
+        H.xx += fma(w * x[0], x[0], q); H.yy += fma(w * x[1], x[1], q); H.zz += fma(w * x[2], x[2], q);
+        H.xy = fma(w * x[0], x[1], H.xy); H.xz = fma(w * x[0], x[2], H.xz); H.yz = fma(w * x[1], x[2], H.yz);
+    }
+}
+
+// NFW (potential.py:80-84): Phi = -(GM/rs) ln(1+m)/m, m = r/rs  =>  Phi = -GM u / r, u = log1p(r/rs)
+//   q  = Phi'/r = GM (u/r - 1/(r+rs)) / r^2
+//   q' = GM [3/(r^3 (r+rs)) - 3u/r^4 + 1/(r^2 (r+rs)^2)],   w = q'/r
+template <int MODE>
+__device__ __forceinline__ void nfw_terms(double GM, double rs, double r2, double& phi, double& q, double& w) {
+    const double ir = rsqrt(r2), r = r2 * ir;
+    const double u = log1p(r / rs);
+    const double irs = 1.0 / (r + rs);
+    const double ir2 = ir * ir;
+    if (MODE & WANT_PHI) phi = -GM * u * ir;
+    const double a = u * ir;                       // u/r
+    q = GM * (a - irs) * ir2;
+    if (MODE & WANT_HESS) w = GM * (3.0 * ir * (irs - a) + irs * irs) * ir2 * ir;     // q'/r
+}
+
+// Hernquist (potential.py:136-138): r = sqrt(|x|^2 + soft), Phi = -GM/(r+a)
+//   q = GM / ((r+a)^2 r),  dq/dr = -GM [2/((r+a)^3 r) + 1/((r+a)^2 r^2)],  w = (dq/dr)/r
+template <int MODE>
+__device__ __forceinline__ void hernquist_terms(double GM, double a, double r2soft, double& phi, double& q, double& w) {
+    const double ir = rsqrt(r2soft), r = r2soft * ir;
+    const double ira = 1.0 / (r + a);
+    if (MODE & WANT_PHI) phi = -GM * ira;
+    q = GM * ira * ira * ir;
+    if (MODE & WANT_HESS) w = -q * ir * (2.0 * ira + ir);
+}
+
+// Plummer (potential.py:128-130): Phi = -GM (r^2+a^2)^(-1/2);  q = GM s^3, w = -3 GM s^5, s = (r^2+a^2)^(-1/2)
+template <int MODE>
+__device__ __forceinline__ void plummer_terms(double GM, double a, double r2, double& phi, double& q, double& w) {
+    const double s = rsqrt(fma(a, a, r2));
+    const double s2 = s * s;
+    if (MODE & WANT_PHI) phi = -GM * s;
+    q = GM * s * s2;
+    if (MODE & WANT_HESS) w = -3.0 * q * s2;
+}
+
+// Isochrone (potential.py:120-122): Phi = -GM/(a + ww), ww = sqrt(r^2 + a^2): Hernquist form in ww
+template <int MODE>
+__device__ __forceinline__ void isochrone_terms(double GM, double a, double r2, double& phi, double& q, double& w) {
+    hernquist_terms<MODE>(GM, a, fma(a, a, r2), phi, q, w);
+}
+
+// d/d r_s of the subhalo profiles and the x-gradient of that (potential.py:862-864, 1226-1228):
+//   returns psi = dPhi/dr_s and qd with grad(psi) = qd * x
+__device__ __forceinline__ void profile_dradius(int profile, double GM, double a, double r2, double& psi, double& qd) {
+    if (profile == SSB_PROFILE_PLUMMER) {            // psi = GM a s^3, grad = -3 GM a s^5 x
+        const double s = rsqrt(fma(a, a, r2)), s2 = s * s;
+        psi = GM * a * s * s2; qd = -3.0 * psi * s2;
+    } else if (profile == SSB_PROFILE_HERNQUIST) {   // psi = GM/(r+a)^2, grad = -2 GM/((r+a)^3 r) x
+        const double ir = rsqrt(r2), r = r2 * ir, ira = 1.0 / (r + a);
+        psi = GM * ira * ira; qd = -2.0 * psi * ira * ir;
+    } else {                                         // NFW: psi = GM/(a (a+r)), grad = -GM/(a (a+r)^2 r) x
+        const double ir = rsqrt(r2), r = r2 * ir, ira = 1.0 / (r + a);
+        psi = GM * ira / a; qd = -psi * ira * ir;
+    }
+}
+template <int MODE>
+__device__ __forceinline__ void profile_terms(int profile, double GM, double a, double r2, double& phi, double& q, double& w) {
+    if (profile == SSB_PROFILE_PLUMMER) plummer_terms<MODE>(GM, a, r2, phi, q, w);
+    else if (profile == SSB_PROFILE_HERNQUIST) hernquist_terms<MODE>(GM, a, r2, phi, q, w);
+    else nfw_terms<MODE>(GM, a, r2, phi, q, w);
+}
+
+// Miyamoto-Nagai (potential.py:70-72): zeta = sqrt(z^2+b^2), D = R^2 + (a+zeta)^2, Phi = -GM D^(-1/2)
+template <int MODE>
+__device__ __forceinline__ void add_miyamoto(double GM, double a, double b, const double x[3], double& P, double g[3], Sym3& H) {
+    const double zb2 = fma(x[2], x[2], b * b);
+    const double iz = rsqrt(zb2), zeta = zb2 * iz;
+    const double az = a + zeta;
+    const double D = fma(x[0], x[0], fma(x[1], x[1], az * az));
+    const double id = rsqrt(D), id2 = id * id, id3 = id * id2;
+    const double s = az * iz;                                       // (a+zeta)/zeta
+    const double q = GM * id3;
+    if (MODE & WANT_PHI) P -= GM * id;
+    if (MODE & WANT_GRAD) { g[0] = fma(q, x[0], g[0]); g[1] = fma(q, x[1], g[1]); g[2] = fma(q * s, x[2], g[2]); }
+    if (MODE & WANT_HESS) {
+        const double q5 = 3.0 * q * id2;                            // 3 GM D^(-5/2)
+        const double zs = x[2] * s;
+        H.xx += q - q5 * x[0] * x[0]; H.yy += q - q5 * x[1] * x[1];
+        H.xy -= q5 * x[0] * x[1]; H.xz -= q5 * x[0] * zs; H.yz -= q5 * x[1] * zs;
+        H.zz += q * (s - a * x[2] * x[2] * iz * iz * iz) - q5 * zs * zs;
+    }
+}
+
+// one subhalo of a SubhaloLine* set at relative position (potential.py:813-830); window gate strict '<'
+template <int MODE>
+__device__ __forceinline__ void add_subhalos(const ssb_subhalos& S, const double x[3], double t, double& P, double g[3], Sym3& H) {
+    for (int j = 0; j < S.n; ++j) {
+        const double dt = t - __ldg(S.t0 + j);
+        if (!(fabs(dt) < __ldg(S.tw + j))) continue;
+        double rel[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) rel[k] = x[k] - fma(__ldg(S.v + 3 * j + k), dt, __ldg(S.x0 + 3 * j + k));
+        const double r2 = fma(rel[0], rel[0], fma(rel[1], rel[1], rel[2] * rel[2]));
+        double phi = 0, q = 0, w = 0;
+        profile_terms<MODE>(S.profile, S.G * __ldg(S.m + j), __ldg(S.rs + j), r2, phi, q, w);
+        add_spherical<MODE>(rel, phi, q, w, P, g, H);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// total field: sum over the program (Potential_Combine.gradient_func, potential.py:1291-1296)
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x[3], double t, double& P, double g[3], Sym3& H) {
+    if (MODE & WANT_PHI) P = 0.0;
+    if (MODE & WANT_GRAD) { g[0] = g[1] = g[2] = 0.0; }
+    if (MODE & WANT_HESS) { H.xx = H.yy = H.zz = H.xy = H.xz = H.yz = 0.0; }
+    const int nc = Pt.n_comp;
+    for (int ic = 0; ic < nc; ++ic) {
+        const ssb_component& c = Pt.comp[ic];
+        const int type = c.type;
+        if (type == SSB_UNIFORM_ACC) {                              // potential.py:497-499
+            if (MODE & WANT_GRAD) {
+                double cv[3], dv[3];
+                track_eval<true>(Pt.track[c.track], t, cv, dv);
+                g[0] += dv[0]; g[1] += dv[1]; g[2] += dv[2];
+            }
+            continue;
+        }
+        double xs[3] = {x[0], x[1], x[2]};
+        if (c.track >= 0) {                                         // potential.py:460-462
+            double ctr[3];
+            track_eval<false>(Pt.track[c.track], t, ctr, ctr);
+            xs[0] -= ctr[0]; xs[1] -= ctr[1]; xs[2] -= ctr[2];
+        }
+        double phi = 0, q = 0, w = 0;
+        switch (type) {
+            case SSB_NFW: {
+                const double r2 = fma(xs[0], xs[0], fma(xs[1], xs[1], xs[2] * xs[2]));
+                nfw_terms<MODE>(c.p[0], c.p[1], r2, phi, q, w);
+                add_spherical<MODE>(xs, phi, q, w, P, g, H);
+            } break;
+            case SSB_HERNQUIST: {
+                const double r2 = fma(xs[0], xs[0], fma(xs[1], xs[1], fma(xs[2], xs[2], c.p[2])));
+                hernquist_terms<MODE>(c.p[0], c.p[1], r2, phi, q, w);
+                add_spherical<MODE>(xs, phi, q, w, P, g, H);
+            } break;
+            case SSB_PLUMMER: {
+                const double r2 = fma(xs[0], xs[0], fma(xs[1], xs[1], xs[2] * xs[2]));
+                plummer_terms<MODE>(c.p[0], c.p[1], r2, phi, q, w);
+                add_spherical<MODE>(xs, phi, q, w, P, g, H);
+            } break;
+            case SSB_ISOCHRONE: {
+                const double r2 = fma(xs[0], xs[0], fma(xs[1], xs[1], xs[2] * xs[2]));
+                isochrone_terms<MODE>(c.p[0], c.p[1], r2, phi, q, w);
+                add_spherical<MODE>(xs, phi, q, w, P, g, H);
+            } break;
+            case SSB_MIYAMOTO:
+                add_miyamoto<MODE>(c.p[0], c.p[1], c.p[2], xs, P, g, H);
+                break;
+            case SSB_TRIAXNFW: {                                    // potential.py:94: x_i / q_i
+                const double i1 = 1.0 / c.p[2], i2 = 1.0 / c.p[3], i3 = 1.0 / c.p[4];
+                const double xq[3] = {xs[0] * i1, xs[1] * i2, xs[2] * i3};
+                const double r2 = fma(xq[0], xq[0], fma(xq[1], xq[1], xq[2] * xq[2]));
+                nfw_terms<MODE>(c.p[0], c.p[1], r2, phi, q, w);
+                if (MODE & WANT_PHI) P += phi;
+                if (MODE & WANT_GRAD) { g[0] = fma(q * i1, xq[0], g[0]); g[1] = fma(q * i2, xq[1], g[1]); g[2] = fma(q * i3, xq[2], g[2]); }
+                if (MODE & WANT_HESS) {
+                    H.xx += (q + w * xq[0] * xq[0]) * i1 * i1; H.yy += (q + w * xq[1] * xq[1]) * i2 * i2; H.zz += (q + w * xq[2] * xq[2]) * i3 * i3;
+                    H.xy += w * xq[0] * xq[1] * i1 * i2; H.xz += w * xq[0] * xq[2] * i1 * i3; H.yz += w * xq[1] * xq[2] * i2 * i3;
+                }
+            } break;
+            case SSB_SUBHALOS:
+                add_subhalos<MODE>(Pt.sh[c.sh], xs, t, P, g, H);
+                break;
+            default: break;
+        }
+    }
+}
+
+}  // namespace ssb
+#endif

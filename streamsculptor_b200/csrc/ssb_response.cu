@@ -1,0 +1,416 @@
+// K3: first-order (mass, mass x radius) response of every particle to N_sh subhalos.
+//
+// Reference: GenerateMassRadiusPerturbation*.compute_perturbation_OTF (perturbative.py:101-135, 425-454, 726-755)
+// integrating the field MassRadiusPerturbation_OTF.term (fields.py:175-206) with integrate_field (fields.py:35-99):
+// per particle ONE coupled ODE with state [w(6), D(N_sh,12)]; all N_sh responses share the particle's step-size
+// controller, whose RMS error norm runs over all 6 + 12 N_sh components.
+//
+// B200 mapping
+//   * one CTA per particle (persistent CTAs pull particles from an atomic queue - spans differ per particle);
+//   * the base orbit + tidal tensor are advanced ONCE per step attempt by one thread and broadcast through shared
+//     memory (13 stage positions, 13 symmetric 3x3 tensors, 13 times);
+//   * the 12 response components of a subhalo split into two independent second-order 3-vectors (mass block,
+//     radius block: fields.py:195-202) = 2 N_sh "items"; threads sweep the items with the Nystrom form of the
+//     same tableau (only force stages in registers), FSAL stage recomputed from the broadcast data;
+//   * item state lives in an L2-resident ping-pong scratch (SoA, coalesced), candidates become current by a
+//     pointer swap when the block-wide error reduction accepts the step;
+//   * outside its time window a subhalo exerts no force (strict '<', potential.py:826); its tidal term is still
+//     integrated, exactly as in the reference.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "ssb_common.cuh"
+
+using namespace ssb;
+
+#define SSB_RESP_THREADS 256
+#define CK(call) do { int _e = ssb_cuda_check((call), #call); if (_e) return _e; } while (0)
+#define CKL(what) do { int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
+
+struct RespArgs {
+    int64_t N;
+    const double *w0, *D0, *t0;
+    double t1;
+    CtrlDev c;
+    double *wout, *Dout;
+    int32_t *status, *nsteps;
+    double* scratch;          // [grid][2][6][n_items]
+    unsigned long long* counter;
+};
+
+template <int S>
+struct BaseShared {
+    double X[S][3];           // base stage positions
+    double T[S][6];           // tidal tensors d2H/dq2 = -Hess(Phi_base): xx, yy, zz, xy, xz, yz
+    double t[S];              // physical stage times
+};
+
+// base force + tidal tensor, recorded for the item sweep
+template <int S>
+__device__ __noinline__ double3 base_force_call(const ssb_potential* P, BaseShared<S>* sh, int stage, double x, double y, double z, double t) {
+    const double X[3] = {x, y, z};
+    double phi, g[3];
+    Sym3 H;
+    pot_eval<WANT_GRAD | WANT_HESS>(*P, X, t, phi, g, H);
+    sh->X[stage][0] = x; sh->X[stage][1] = y; sh->X[stage][2] = z;
+    sh->T[stage][0] = -H.xx; sh->T[stage][1] = -H.yy; sh->T[stage][2] = -H.zz;
+    sh->T[stage][3] = -H.xy; sh->T[stage][4] = -H.xz; sh->T[stage][5] = -H.yz;
+    sh->t[stage] = t;
+    return make_double3(-g[0], -g[1], -g[2]);
+}
+template <int S>
+struct BaseForce {
+    const ssb_potential* P; BaseShared<S>* sh; double dir; int stage;
+    __device__ __forceinline__ void operator()(const double X[3], double tau, double A[3]) {
+        const double3 a = base_force_call<S>(P, sh, stage, X[0], X[1], X[2], tau * dir);
+        stage++;
+        A[0] = a.x; A[1] = a.y; A[2] = a.z;
+    }
+};
+
+// one (subhalo, block) item: force = g_block(X_base(stage), t(stage)) + T(stage) . Q
+struct ItemParams { double GM, rs, x0[3], v[3], t0, tw; int profile, blk; };
+
+template <int S>
+struct ItemForce {
+    const BaseShared<S>* sh; const ItemParams* ip; int stage;
+    __device__ __forceinline__ void at(int i, const double Q[3], double A[3]) const {
+        const double* X = sh->X[i];
+        const double* T = sh->T[i];
+        const double dt = sh->t[i] - ip->t0;
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+        if (fabs(dt) < ip->tw) {                                   // potential.py:826 / 846
+            double rel[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rel[k] = X[k] - fma(ip->v[k], dt, ip->x0[k]);
+            const double r2 = fma(rel[0], rel[0], fma(rel[1], rel[1], rel[2] * rel[2]));
+            double ph, q, w = 0;
+            if (ip->blk) profile_dradius(ip->profile, ip->GM, ip->rs, r2, ph, q);          // fields.py:200
+            else profile_terms<WANT_GRAD>(ip->profile, ip->GM, ip->rs, r2, ph, q, w);      // fields.py:191
+            g0 = -q * rel[0]; g1 = -q * rel[1]; g2 = -q * rel[2];
+        }
+        A[0] = g0 + (T[0] * Q[0] + T[3] * Q[1] + T[4] * Q[2]);                              // fields.py:197 / 202
+        A[1] = g1 + (T[3] * Q[0] + T[1] * Q[1] + T[5] * Q[2]);
+        A[2] = g2 + (T[4] * Q[0] + T[5] * Q[1] + T[2] * Q[2]);
+    }
+    __device__ __forceinline__ void operator()(const double Q[3], double, double A[3]) { at(stage, Q, A); stage++; }
+};
+
+__device__ __forceinline__ double block_sum(double v, double* sred) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) sred[w] = v;
+    __syncthreads();
+    double tot = 0.0;
+    for (int i = 0; i < nw; ++i) tot += sred[i];
+    return tot;
+}
+
+__device__ __forceinline__ void load_item_params(const ssb_subhalos& Sh, int it, int n_sh, ItemParams& ip) {
+    const int j = it % n_sh;
+    ip.blk = it / n_sh;
+    ip.profile = Sh.profile;
+    ip.GM = Sh.G * __ldg(Sh.m + j); ip.rs = __ldg(Sh.rs + j); ip.t0 = __ldg(Sh.t0 + j); ip.tw = __ldg(Sh.tw + j);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ip.x0[k] = __ldg(Sh.x0 + 3 * j + k); ip.v[k] = __ldg(Sh.v + 3 * j + k); }
+}
+
+template <int SOLVER>
+__global__ void __launch_bounds__(SSB_RESP_THREADS) response_kernel(const __grid_constant__ ssb_potential Pin, const ssb_subhalos Sh,
+                                                                    const RespArgs a) {
+    typedef Tab<SOLVER> T;
+    constexpr int S = T::S;
+    __shared__ ssb_potential sP;
+    __shared__ BaseShared<S> sb;
+    __shared__ double sred[32];
+    __shared__ double sbc[4];          // broadcast: dt, keep, h_init ...
+    __shared__ long long s_part;
+    stage_potential(&sP, &Pin);
+    const int tid = threadIdx.x;
+    const int n_sh = Sh.n, n_items = 2 * n_sh, ncomp = 6 + 12 * n_sh;
+    double* buf0 = a.scratch + (size_t)blockIdx.x * 2 * 6 * n_items;
+    double* buf1 = buf0 + (size_t)6 * n_items;
+    const CtrlDev c = a.c;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_part = (long long)atomicAdd(a.counter, 1ULL);
+        __syncthreads();
+        const long long part = s_part;
+        if (part >= a.N) break;
+        const double t0_in = a.t0[part], t1_in = a.t1;
+        const double dir = (t0_in < t1_in) ? 1.0 : -1.0;
+        const double T0 = t0_in * dir, T1 = t1_in * dir;
+        double* cur = buf0;
+        double* nxt = buf1;
+        // ---- load item state (SoA [6][n_items]); momentum-like rows carry dir ----
+        for (int it = tid; it < n_items; it += blockDim.x) {
+            const int j = it % n_sh, blk = it / n_sh;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                double v = a.D0 ? a.D0[((size_t)part * n_sh + j) * 12 + blk * 6 + k] : 0.0;
+                if (k >= 3) v *= dir;
+                cur[(size_t)k * n_items + it] = v;
+            }
+        }
+        // base state lives in thread 0
+        double x[3] = {0, 0, 0}, p[3] = {0, 0, 0}, F[S][3];
+        BaseForce<S> bforce{&sP, &sb, dir, 0};
+        int status = 0, n_steps = 0, n_acc = 0, n_rej = 0;
+        bool at_dtmin = false;
+        double tprev = T0, tnext = T0;
+        // ================= initial step (HNW over the whole coupled state) =================
+        double d0s = 0.0, d1s = 0.0;
+        if (tid == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { x[k] = a.w0[6 * part + k]; p[k] = dir * a.w0[6 * part + 3 + k]; }
+            bforce.stage = 0;
+            bforce(x, T0, F[0]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double sx = fma(c.rtol, fabs(x[k]), c.atol), sp = fma(c.rtol, fabs(p[k]), c.atol);
+                double q;
+                q = x[k] / sx; d0s = fma(q, q, d0s); q = p[k] / sp; d0s = fma(q, q, d0s);
+                q = p[k] / sx; d1s = fma(q, q, d1s); q = F[0][k] / sp; d1s = fma(q, q, d1s);
+            }
+        }
+        __syncthreads();
+        for (int it = tid; it < n_items; it += blockDim.x) {
+            ItemParams ip; load_item_params(Sh, it, n_sh, ip);
+            ItemForce<S> f{&sb, &ip, 0};
+            double q[3], pp[3], G[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { q[k] = cur[(size_t)k * n_items + it]; pp[k] = cur[(size_t)(3 + k) * n_items + it]; }
+            f.at(0, q, G);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double sx = fma(c.rtol, fabs(q[k]), c.atol), sp = fma(c.rtol, fabs(pp[k]), c.atol);
+                double r;
+                r = q[k] / sx; d0s = fma(r, r, d0s); r = pp[k] / sp; d0s = fma(r, r, d0s);
+                r = pp[k] / sx; d1s = fma(r, r, d1s); r = G[k] / sp; d1s = fma(r, r, d1s);
+            }
+        }
+        const double d0 = sqrt(block_sum(d0s, sred) / ncomp);
+        const double d1 = sqrt(block_sum(d1s, sred) / ncomp);
+        const double h0 = hnw_h0(d0, d1);
+        double d2s = 0.0;
+        double F1[3];
+        if (tid == 0) {
+            double X1[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) X1[k] = fma(h0, p[k], x[k]);
+            bforce.stage = 1;
+            bforce(X1, T0 + h0, F1);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double sx = fma(c.rtol, fabs(x[k]), c.atol), sp = fma(c.rtol, fabs(p[k]), c.atol);
+                double q;
+                q = (fma(h0, F[0][k], p[k]) - p[k]) / sx; d2s = fma(q, q, d2s);
+                q = (F1[k] - F[0][k]) / sp; d2s = fma(q, q, d2s);
+            }
+        }
+        __syncthreads();
+        for (int it = tid; it < n_items; it += blockDim.x) {
+            ItemParams ip; load_item_params(Sh, it, n_sh, ip);
+            ItemForce<S> f{&sb, &ip, 0};
+            double q[3], pp[3], G0[3], G1[3], q1[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { q[k] = cur[(size_t)k * n_items + it]; pp[k] = cur[(size_t)(3 + k) * n_items + it]; }
+            f.at(0, q, G0);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) q1[k] = fma(h0, pp[k], q[k]);
+            f.at(1, q1, G1);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double sx = fma(c.rtol, fabs(q[k]), c.atol), sp = fma(c.rtol, fabs(pp[k]), c.atol);
+                double r;
+                r = (fma(h0, G0[k], pp[k]) - pp[k]) / sx; d2s = fma(r, r, d2s);
+                r = (G1[k] - G0[k]) / sp; d2s = fma(r, r, d2s);
+            }
+        }
+        const double d2 = sqrt(block_sum(d2s, sred) / ncomp) / h0;
+        {
+            double h = fmin(hnw_h1<T::ORDER>(h0, d1, d2), c.dtmax);
+            at_dtmin = h <= c.dtmin;                 // every thread keeps an identical copy of the controller state
+            h = fmax(h, c.dtmin);
+            tnext = fmin(T0 + h, T1);
+        }
+        // ================= main loop: all threads follow the same (uniform) control flow =================
+        while (tprev < T1 && status == 0) {
+            if (n_steps >= c.max_steps) { status = 1; break; }
+            const double dt = tnext - tprev;
+            double x1[3], p1[3];
+            double esq = 0.0;
+            int bad_local = 0;
+            __syncthreads();
+            if (tid == 0) {
+                double ex[3], ep[3];
+                bforce.stage = 1;
+                // stage 0 of sb (X, T, t at tprev) is already in place: FSAL copy below / initial evaluation above
+                rk_stages<SOLVER>(bforce, x, p, tprev, dt, F);
+                rk_candidate<SOLVER>(x, p, dt, F, x1, p1);
+                bforce.stage = S - 1;
+                bforce(x1, tprev + T::c(S - 1) * dt, F[S - 1]);
+                rk_error<SOLVER>(p, dt, F, ex, ep);
+                bool nan_cand = false;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    nan_cand |= isnan(x1[k]) | isnan(p1[k]);
+                    if (!isfinite(x1[k]) || !isfinite(p1[k])) bad_local = 1;
+                }
+                esq = err_sq6(x, p, x1, p1, ex, ep, c.rtol, c.atol, nan_cand);
+            }
+            __syncthreads();
+            // ---- item sweep ----
+            for (int it = tid; it < n_items; it += blockDim.x) {
+                ItemParams ip; load_item_params(Sh, it, n_sh, ip);
+                ItemForce<S> f{&sb, &ip, 1};
+                double q[3], pp[3], G[S][3], q1[3], pp1[3], ex[3], ep[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { q[k] = cur[(size_t)k * n_items + it]; pp[k] = cur[(size_t)(3 + k) * n_items + it]; }
+                f.at(0, q, G[0]);
+                rk_stages<SOLVER>(f, q, pp, 0.0, dt, G);
+                rk_candidate<SOLVER>(q, pp, dt, G, q1, pp1);
+                if (SOLVER == 5) f.at(S - 1, q1, G[S - 1]);          // Dopri8: e_14 = (e^T A)_14 = 0, stage unused
+                else { G[S - 1][0] = G[S - 1][1] = G[S - 1][2] = 0.0; }
+                rk_error<SOLVER>(pp, dt, G, ex, ep);
+                bool nan_cand = false;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    nan_cand |= isnan(q1[k]) | isnan(pp1[k]);
+                    if (!isfinite(q1[k]) || !isfinite(pp1[k])) bad_local = 1;
+                }
+                esq += err_sq6(q, pp, q1, pp1, ex, ep, c.rtol, c.atol, nan_cand);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { nxt[(size_t)k * n_items + it] = q1[k]; nxt[(size_t)(3 + k) * n_items + it] = pp1[k]; }
+            }
+            const double err = sqrt(block_sum(esq, sred) / ncomp);
+            const int any_bad = __syncthreads_or(bad_local);
+            double hn; bool bad;
+            const bool keep = pid_update<T::ORDER>(err, dt, c, at_dtmin, hn, bad);
+            n_steps++;
+            if (bad) { status = 2; n_rej++; break; }
+            if (keep) {
+                n_acc++;
+                if (any_bad) { status = 2; break; }
+                double* tmp = cur; cur = nxt; nxt = tmp;
+                if (tid == 0) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { x[k] = x1[k]; p[k] = p1[k]; F[0][k] = F[S - 1][k]; sb.X[0][k] = sb.X[S - 1][k]; }
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) sb.T[0][k] = sb.T[S - 1][k];
+                    sb.t[0] = sb.t[S - 1];
+                }
+                tprev = tnext;
+            } else {
+                n_rej++;
+            }
+            tprev = fmin(tprev, T1);
+            double tn = tprev + hn;
+            if (tn > T1 - 1e-10) tn = keep ? T1 : tprev + 0.5 * (T1 - tprev);
+            tnext = tn;
+        }
+        __syncthreads();
+        // ---- outputs: final state if the end was reached, +inf otherwise (diffrax SaveAt semantics) ----
+        const bool ok = (status == 0) && (T0 < T1);
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+        for (int it = tid; it < n_items; it += blockDim.x) {
+            const int j = it % n_sh, blk = it / n_sh;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                double v = cur[(size_t)k * n_items + it];
+                if (k >= 3) v *= dir;
+                a.Dout[((size_t)part * n_sh + j) * 12 + blk * 6 + k] = ok ? v : inf;
+            }
+        }
+        if (tid == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { a.wout[6 * part + k] = ok ? x[k] : inf; a.wout[6 * part + 3 + k] = ok ? dir * p[k] : inf; }
+            a.status[part] = status;
+            a.nsteps[3 * part] = n_steps; a.nsteps[3 * part + 1] = n_acc; a.nsteps[3 * part + 2] = n_rej;
+        }
+    }
+}
+
+// RHS of the coupled field at one state (fields.py:175-206): y = [w(6), D(n_sh,12)]
+__global__ void response_term_kernel(const __grid_constant__ ssb_potential Pin, const ssb_subhalos Sh, double t, const double* y, double* dy) {
+    __shared__ ssb_potential sP;
+    __shared__ BaseShared<1> sb;
+    stage_potential(&sP, &Pin);
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double3 acc = base_force_call<1>(&sP, &sb, 0, y[0], y[1], y[2], t);
+        dy[0] = y[3]; dy[1] = y[4]; dy[2] = y[5]; dy[3] = acc.x; dy[4] = acc.y; dy[5] = acc.z;
+    } else if (threadIdx.x == 0) {
+        base_force_call<1>(&sP, &sb, 0, y[0], y[1], y[2], t);
+    }
+    __syncthreads();
+    const int n_sh = Sh.n;
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < 2 * n_sh; it += gridDim.x * blockDim.x) {
+        ItemParams ip; load_item_params(Sh, it, n_sh, ip);
+        ItemForce<1> f{&sb, &ip, 0};
+        const int j = it % n_sh, blk = it / n_sh;
+        const double* d = y + 6 + 12 * j + 6 * blk;
+        double* o = dy + 6 + 12 * j + 6 * blk;
+        const double Q[3] = {d[0], d[1], d[2]};
+        double A[3];
+        f.at(0, Q, A);
+        o[0] = d[3]; o[1] = d[4]; o[2] = d[5]; o[3] = A[0]; o[4] = A[1]; o[5] = A[2];
+    }
+}
+
+static int resp_grid(int64_t N) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t g = (int64_t)sms * 2;
+    return (int)(N < g ? N : g);
+}
+
+extern "C" {
+
+size_t ssb_response_scratch_bytes(int32_t n_sh) {
+    const size_t per_cta = sizeof(double) * 2 * 6 * 2 * (size_t)(n_sh > 0 ? n_sh : 1);
+    return 256 + per_cta * (size_t)(148 * 2 + 64);      // counter header + one ping-pong state per persistent CTA (<= 2 x SMs)
+}
+
+int ssb_linear_response_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0, const double* D0,
+                            const double* t0, double t1, ssb_ctrl ctrl, double* wout, double* Dout, int32_t* status, int32_t* nsteps,
+                            void* scratch, size_t scratch_bytes, void* stream) {
+    if (int e = ssb_validate_potential(pot_base)) return e;
+    if (int e = ssb_validate_ctrl(ctrl)) return e;
+    if (!sh || sh->n < 0) return ssb_set_error(SSB_ERR_ARG, "linear_response: bad subhalo set");
+    if (sh->profile < SSB_PROFILE_PLUMMER || sh->profile > SSB_PROFILE_NFW) return ssb_set_error(SSB_ERR_UNSUPPORTED, "linear_response: unknown profile");
+    if (N < 0) return ssb_set_error(SSB_ERR_ARG, "linear_response: negative N");
+    if (N == 0) return 0;
+    if (!w0 || !t0 || !wout || !status || !nsteps || !scratch || (sh->n > 0 && !Dout)) return ssb_set_error(SSB_ERR_ARG, "linear_response: NULL array");
+    if (scratch_bytes < ssb_response_scratch_bytes(sh->n)) return ssb_set_error(SSB_ERR_SCRATCH, "linear_response: scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = resp_grid(N);
+    if (grid > 148 * 2 + 64) return ssb_set_error(SSB_ERR_SCRATCH, "linear_response: more SMs than the scratch layout assumes");
+    RespArgs a;
+    a.N = N; a.w0 = w0; a.D0 = D0; a.t0 = t0; a.t1 = t1; a.c.rtol = ctrl.rtol; a.c.atol = ctrl.atol; a.c.dtmin = ctrl.dtmin; a.c.dtmax = ctrl.dtmax;
+    a.c.max_steps = ctrl.max_steps; a.wout = wout; a.Dout = Dout; a.status = status; a.nsteps = nsteps;
+    a.counter = (unsigned long long*)scratch;
+    a.scratch = (double*)((char*)scratch + 256);
+    CK(cudaMemsetAsync(scratch, 0, 256, st));
+    if (ctrl.solver == 5) response_kernel<5><<<grid, SSB_RESP_THREADS, 0, st>>>(*pot_base, *sh, a);
+    else response_kernel<8><<<grid, SSB_RESP_THREADS, 0, st>>>(*pot_base, *sh, a);
+    CKL("response_kernel");
+    return 0;
+}
+
+int ssb_response_term_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, double t, const double* y, double* dy, void* stream) {
+    if (int e = ssb_validate_potential(pot_base)) return e;
+    if (!sh || !y || !dy) return ssb_set_error(SSB_ERR_ARG, "response_term: NULL argument");
+    const int items = 2 * sh->n;
+    int grid = (items + 127) / 128; if (grid < 1) grid = 1;
+    response_term_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*pot_base, *sh, t, y, dy);
+    CKL("response_term_kernel");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+// Adaptive Dormand-Prince stepping for second-order systems  x' = p, p' = F(x, t)  held in registers.
+//
+// Algorithm = diffrax.diffeqsolve(Dopri5|Dopri8, PIDController(rtol, atol, dtmin, dtmax, force_dtmin=True),
+// dt0=None, SaveAt(ts)) as configured at /root/reference/streamsculptor/main.py:139-162 and fields.py:85-98:
+// identical Butcher tableaus (ssb_tableau.h), I-controller (safety 0.9, factor in [0.2 | 1 after an accepted
+// step, 10], exponent 1/order), RMS error norm with scale atol + rtol*max(|y0|,|y1|), HNW initial step,
+// clip-to-end at 1e-10, steps at dt <= dtmin always accepted.
+//
+// B200 mapping: every orbit on the path is a second-order system whose force depends on (x, t) only, so the
+// tableau is applied in its algebraically identical Nystrom form (ssb_tableau.h: aa = A.A, ea = e^T A):
+// only the S force stages (3 doubles each) live in registers instead of S full 6-vectors, which halves the
+// register footprint of Dopri8 (42 instead of 84 doubles) and is what lets 16 warps/SM stay resident.
+#ifndef SSB_RK_CUH
+#define SSB_RK_CUH
+#include <cuda_runtime.h>
+#include <math.h>
+
+#define SSB_TABLEAU_QUAL static __device__ constexpr
+#include "ssb_tableau.h"
+
+namespace ssb {
+
+template <int SOLVER> struct Tab;
+template <> struct Tab<5> {
+    static constexpr int S = 7, ORDER = 5;
+    static __device__ __forceinline__ constexpr double a(int i, int j) { return ssb_tab::d5_a[i][j]; }
+    static __device__ __forceinline__ constexpr double aa(int i, int j) { return ssb_tab::d5_aa[i][j]; }
+    static __device__ __forceinline__ constexpr double c(int i) { return ssb_tab::d5_c[i]; }
+    static __device__ __forceinline__ constexpr double rs(int i) { return ssb_tab::d5_rs[i]; }
+    static __device__ __forceinline__ constexpr double e(int i) { return ssb_tab::d5_e[i]; }
+    static __device__ __forceinline__ constexpr double ea(int i) { return ssb_tab::d5_ea[i]; }
+    static __device__ __forceinline__ constexpr double esum() { return ssb_tab::d5_esum; }
+};
+template <> struct Tab<8> {
+    static constexpr int S = 14, ORDER = 8;
+    static __device__ __forceinline__ constexpr double a(int i, int j) { return ssb_tab::d8_a[i][j]; }
+    static __device__ __forceinline__ constexpr double aa(int i, int j) { return ssb_tab::d8_aa[i][j]; }
+    static __device__ __forceinline__ constexpr double c(int i) { return ssb_tab::d8_c[i]; }
+    static __device__ __forceinline__ constexpr double rs(int i) { return ssb_tab::d8_rs[i]; }
+    static __device__ __forceinline__ constexpr double e(int i) { return ssb_tab::d8_e[i]; }
+    static __device__ __forceinline__ constexpr double ea(int i) { return ssb_tab::d8_ea[i]; }
+    static __device__ __forceinline__ constexpr double esum() { return ssb_tab::d8_esum; }
+};
+
+struct CtrlDev { double rtol, atol, dtmin, dtmax; int max_steps; };
+
+// ---- stages 2..S-1 of one step attempt.  F[0] must hold the force at (x, t) (FSAL). ----
+template <int SOLVER, class Force>
+__device__ __forceinline__ void rk_stages(Force& force, const double x[3], const double p[3], double t, double h,
+                                          double (&F)[Tab<SOLVER>::S][3]) {
+    typedef Tab<SOLVER> T;
+#pragma unroll
+    for (int i = 1; i < T::S - 1; ++i) {
+        double X[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double acc = 0.0;
+#pragma unroll
+            for (int l = 0; l < i; ++l)
+                if (T::aa(i, l) != 0.0) acc = fma(T::aa(i, l), F[l][k], acc);
+            X[k] = fma(h, fma(h, acc, T::rs(i) * p[k]), x[k]);
+        }
+        force(X, t + T::c(i) * h, F[i]);
+    }
+}
+
+// candidate state = last stage value (the last tableau row equals b); caller then sets F[S-1] = force(x1, t + h)
+template <int SOLVER>
+__device__ __forceinline__ void rk_candidate(const double x[3], const double p[3], double h, const double (&F)[Tab<SOLVER>::S][3],
+                                             double x1[3], double p1[3]) {
+    typedef Tab<SOLVER> T;
+    constexpr int L = T::S - 1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double ax = 0.0, ap = 0.0;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            if (T::aa(L, l) != 0.0) ax = fma(T::aa(L, l), F[l][k], ax);
+            if (T::a(L, l) != 0.0) ap = fma(T::a(L, l), F[l][k], ap);
+        }
+        x1[k] = fma(h, fma(h, ax, T::rs(L) * p[k]), x[k]);
+        p1[k] = fma(h, ap, p[k]);
+    }
+}
+
+// embedded error estimate  y_err = h sum e_i f_i  (needs all S force stages)
+template <int SOLVER>
+__device__ __forceinline__ void rk_error(const double p[3], double h, const double (&F)[Tab<SOLVER>::S][3], double ex[3], double ep[3]) {
+    typedef Tab<SOLVER> T;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double bx = 0.0, bp = 0.0;
+#pragma unroll
+        for (int l = 0; l < T::S; ++l) {
+            if (T::ea(l) != 0.0) bx = fma(T::ea(l), F[l][k], bx);
+            if (T::e(l) != 0.0) bp = fma(T::e(l), F[l][k], bp);
+        }
+        ex[k] = h * fma(h, bx, T::esum() * p[k]);
+        ep[k] = h * bp;
+    }
+}
+
+// dense output at theta in (0,1): the same interpolants the oracle uses (orc_solver.h), in Nystrom form
+template <int SOLVER>
+__device__ __forceinline__ void rk_dense(const double x[3], const double p[3], const double x1[3], const double p1[3], double h,
+                                         const double (&F)[Tab<SOLVER>::S][3], double theta, double xo[3], double po[3]) {
+    if constexpr (SOLVER == 5) {
+        // diffrax Dopri5: quartic through y0, y1, k1 = h f0, k7 = h f1 and y_mid = y0 + h sum cmid_i f_i
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double mx = 0.0, mp = 0.0;
+#pragma unroll
+            for (int l = 0; l < 7; ++l) {
+                if (ssb_tab::d5_cmida[l] != 0.0) mx = fma(ssb_tab::d5_cmida[l], F[l][k], mx);
+                if (ssb_tab::d5_cmid[l] != 0.0) mp = fma(ssb_tab::d5_cmid[l], F[l][k], mp);
+            }
+            const double xm = fma(h, fma(h, mx, ssb_tab::d5_cmidsum * p[k]), x[k]);
+            const double pm = fma(h, mp, p[k]);
+            {   // position component: f0 = h p, f1 = h p1
+                const double f0 = h * p[k], f1 = h * p1[k], y0 = x[k], y1 = x1[k];
+                const double a = 2 * (f1 - f0) - 8 * (y1 + y0) + 16 * xm;
+                const double b = 5 * f0 - 3 * f1 + 18 * y0 + 14 * y1 - 32 * xm;
+                const double c = f1 - 4 * f0 - 11 * y0 - 5 * y1 + 16 * xm;
+                xo[k] = (((a * theta + b) * theta + c) * theta + f0) * theta + y0;
+            }
+            {   // momentum component: f0 = h F_1, f1 = h F_7
+                const double f0 = h * F[0][k], f1 = h * F[6][k], y0 = p[k], y1 = p1[k];
+                const double a = 2 * (f1 - f0) - 8 * (y1 + y0) + 16 * pm;
+                const double b = 5 * f0 - 3 * f1 + 18 * y0 + 14 * y1 - 32 * pm;
+                const double c = f1 - 4 * f0 - 11 * y0 - 5 * y1 + 16 * pm;
+                po[k] = (((a * theta + b) * theta + c) * theta + f0) * theta + y0;
+            }
+        }
+    } else {
+        // our C1 5th-order continuous extension of RK8(7)13M (tools/derive_dopri8_dense.py)
+        double wsum = 0.0;
+#pragma unroll
+        for (int q = 6; q >= 0; --q) wsum = fma(wsum, theta, ssb_tab::d8_dense_sum[q]);
+        wsum *= theta;
+        double accx[3] = {0, 0, 0}, accp[3] = {0, 0, 0};
+#pragma unroll
+        for (int l = 0; l < 14; ++l) {
+            double wa = 0.0, wb = 0.0;
+            bool anya = false, anyb = false;
+#pragma unroll
+            for (int q = 6; q >= 0; --q) {
+                wa = fma(wa, theta, ssb_tab::d8_dense_a[l][q]); anya |= ssb_tab::d8_dense_a[l][q] != 0.0;
+                wb = fma(wb, theta, ssb_tab::d8_dense[l][q]); anyb |= ssb_tab::d8_dense[l][q] != 0.0;
+            }
+            wa *= theta; wb *= theta;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (anya) accx[k] = fma(wa, F[l][k], accx[k]);
+                if (anyb) accp[k] = fma(wb, F[l][k], accp[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            xo[k] = fma(h, fma(h, accx[k], wsum * p[k]), x[k]);
+            po[k] = fma(h, accp[k], p[k]);
+        }
+    }
+}
+
+// sum of squared scaled errors of one 6-vector (x,p): sc = atol + rtol*max(|y0|,|y1|)  (NaN candidate -> y0)
+__device__ __forceinline__ double err_sq6(const double x[3], const double p[3], const double x1[3], const double p1[3],
+                                          const double ex[3], const double ep[3], double rtol, double atol, bool nan_cand) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double xc = nan_cand ? x[k] : x1[k], pc = nan_cand ? p[k] : p1[k];
+        const double sx = fma(rtol, fmax(fabs(x[k]), fabs(xc)), atol);
+        const double sp = fma(rtol, fmax(fabs(p[k]), fabs(pc)), atol);
+        const double qx = ex[k] / sx, qp = ep[k] / sp;
+        acc = fma(qx, qx, acc); acc = fma(qp, qp, acc);
+    }
+    return acc;
+}
+
+// PIDController.adapt_step_size with pcoeff = dcoeff = 0: returns keep, updates h_next / at_dtmin
+template <int ORDER>
+__device__ __forceinline__ bool pid_update(double err, double dt, const CtrlDev& c, bool& at_dtmin, double& h_next, bool& bad) {
+    const bool keep = (err < 1.0) || at_dtmin;
+    double factor = 0.9 * pow(1.0 / err, 1.0 / ORDER);
+    bad = isnan(factor);
+    factor = fmin(fmax(factor, keep ? 1.0 : 0.2), 10.0);
+    double hn = fmin(dt * factor, c.dtmax);
+    at_dtmin = hn <= c.dtmin;
+    h_next = fmax(hn, c.dtmin);
+    return keep;
+}
+
+// Hairer-Norsett-Wanner initial step from d0 = rms(y0/sc), d1 = rms(f0/sc); second RHS evaluation by caller
+__device__ __forceinline__ double hnw_h0(double d0, double d1) {
+    return (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+}
+template <int ORDER>
+__device__ __forceinline__ double hnw_h1(double h0, double d1, double d2) {
+    const double md = fmax(d1, d2);
+    const double h1 = (md <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / md, 1.0 / ORDER);
+    return fmin(100.0 * h0, h1);
+}
+
+}  // namespace ssb
+#endif

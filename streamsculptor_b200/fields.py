@@ -1,0 +1,87 @@
+"""fields.py of the reference (/root/reference/streamsculptor/fields.py): integration along non-Hamiltonian fields.
+
+On the B200 hot path a "field" is one of a closed set the CUDA kernels implement:
+  hamiltonian_field             -> K1 orbit kernel        (fields.py:101-113)
+  MassRadiusPerturbation_OTF    -> K3 response kernel     (fields.py:159-206)
+Arbitrary Python `term` functions (CustomField, Nbody_field, ...) raise NotImplementedError: no CPU fallback.
+"""
+import numpy as np
+
+from . import _runtime as rt
+from .main import Solution
+from .solvers import Dopri8
+
+
+class hamiltonian_field:
+    def __init__(self, pot):
+        self.pot = pot
+
+    def term(self, t, xv, args=None):
+        return self.pot.velocity_acceleration(t, xv, args)
+
+
+class MassRadiusPerturbation_OTF:
+    """coords = [w(6), D(nSH,12)] with D rows [dx/deps(3), dv/deps(3), d2x/dtheta deps(3), d2v/dtheta deps(3)]."""
+
+    def __init__(self, perturbation_generator):
+        self.pertgen = perturbation_generator
+
+    def term(self, t, coords, args=None):
+        w, D = np.asarray(coords[0], dtype=np.float64), np.asarray(coords[1], dtype=np.float64)
+        y = np.concatenate([w.reshape(6), D.reshape(-1)])
+        dy = rt.response_term(self.pertgen.potential_base_total, self.pertgen.subhalo_arrays, t, y).cpu().numpy()
+        return [dy[:6], dy[6:].reshape(D.shape)]
+
+
+def _interval(ts, t0, t1, backwards_int):
+    """fields.py:58-82: t0 == t1 (default 0.0) means 'derive the interval from ts'."""
+    if t0 != t1:
+        return float(t0), float(t1)
+    lo, hi = float(np.min(ts)), float(np.max(ts))
+    return (hi, lo) if backwards_int else (lo, hi)
+
+
+def integrate_field(w0=None, ts=None, dense=False, solver=Dopri8(scan_kind='bounded'), field=None, args=None, rtol=1e-7, atol=1e-7,
+                    dtmin=0.05, dtmax=None, max_steps=1_000, jump_ts=None, backwards_int=False, t0=0.0, t1=0.0, step_ts=None):
+    """Integrate a trajectory on a field (fields.py:35-99).  Raises on solver failure like the reference
+    (diffrax default throw=True)."""
+    if dense or jump_ts is not None or step_ts is not None:
+        raise NotImplementedError("dense / jump_ts / step_ts are not on the B200 hot path")
+    ts_h = np.asarray(ts.cpu() if hasattr(ts, "cpu") else ts, dtype=np.float64).reshape(-1)
+    a, b = _interval(ts_h, t0, t1, backwards_int)
+    if isinstance(field, hamiltonian_field):
+        sol = field.pot.integrate_orbit(w0=w0, ts=ts, solver=solver, rtol=rtol, atol=atol, dtmin=dtmin, dtmax=dtmax, max_steps=max_steps,
+                                        t0=a, t1=b, throw=True)
+        return sol
+    if isinstance(field, MassRadiusPerturbation_OTF):
+        pg = field.pertgen
+        if len(ts_h) != 2 and not (len(ts_h) == 1):
+            raise NotImplementedError("the response kernel keeps the final state only (ts = [t_start, t_end], perturbative.py:110,125)")
+        ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
+        w = rt.to_dev(w0[0]).reshape(1, 6)
+        D0 = rt.to_dev(w0[1]).reshape(1, pg.subhalo_arrays.n, 12)
+        wout, Dout, status, nsteps = rt.linear_response(pg.potential_base_total, pg.subhalo_arrays, w, D0, rt.to_dev([a]), b, ctrl)
+        if int(status[0]) != 0:
+            raise RuntimeError("integrate_field failed: " + ("max_steps reached" if int(status[0]) == 1 else "non-finite state"))
+        inf = np.full((1, 6), np.inf)
+        ys0 = np.vstack([np.asarray(w.cpu()) if ts_h[0] == a else inf, wout.cpu().numpy()]) if len(ts_h) == 2 else wout.cpu().numpy()
+        D0h, Dh = D0.cpu().numpy(), Dout.cpu().numpy()
+        ys1 = np.concatenate([D0h if ts_h[0] == a else np.full_like(D0h, np.inf), Dh]) if len(ts_h) == 2 else Dh
+        return Solution(ts_h, [ys0, ys1], status[0].cpu().numpy(), nsteps[0])
+    raise NotImplementedError(f"field {type(field).__name__} is not implemented on the device (closed set: hamiltonian_field, "
+                              "MassRadiusPerturbation_OTF)")
+
+
+def _unsupported(name):
+    class _X:
+        def __init__(self, *a, **k):
+            raise NotImplementedError(f"{name} is outside the B200 hot path (SURVEY.md section 8f)")
+    _X.__name__ = name
+    return _X
+
+
+Nbody_field = _unsupported("Nbody_field")
+MassRadiusPerturbation_Interp = _unsupported("MassRadiusPerturbation_Interp")
+MassRadiusPerturbation_OTF_SecondOrder = _unsupported("MassRadiusPerturbation_OTF_SecondOrder")
+MW_LMC_field = _unsupported("MW_LMC_field")
+CustomField = _unsupported("CustomField")

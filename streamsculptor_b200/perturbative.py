@@ -1,0 +1,133 @@
+"""perturbative.py of the reference: first-order stream response to subhalo impacts.
+
+Implemented on the device: the production path GenerateMassRadiusPerturbation_Chen25.compute_perturbation_OTF
+(perturbative.py:661-755) and the custom-base variant (perturbative.py:367-454), both of which integrate
+fields.MassRadiusPerturbation_OTF per particle from ts[i] to ts[-1] and keep the final state.
+"""
+import numpy as np
+
+from . import _runtime as rt
+from .main import Potential
+from .potential import Potential_Combine, SubhaloLinePotentialCustom_dRadius_fromFunc
+from .solvers import Dopri5, Dopri8
+from .units import usys
+
+
+class CustomBaseStreamModel(Potential):
+    """Stream model with user-supplied release offsets (perturbative.py:299-364)."""
+
+    def __init__(self, potential_base=None, prog_w0=None, ts=None, pos_rel=None, vel_rel=None, solver=Dopri5(), units=None, dense=False,
+                 cpu=True, **kwargs):
+        super().__init__(units, {'potential_base': potential_base, 'prog_w0': prog_w0, 'ts': ts, 'pos_rel': pos_rel, 'vel_rel': vel_rel,
+                                 'solver': solver, 'dense': dense, 'cpu': cpu})
+        if dense:
+            raise NotImplementedError("dense base streams (perturbative.py:331-333) are not on the B200 hot path")
+        self.ts = np.asarray(ts, dtype=np.float64)
+        self.solver = Dopri5(scan_kind='bounded') if solver is None else solver
+        self.prog_at_ts = np.asarray(potential_base.integrate_orbit(w0=prog_w0, ts=self.ts, t0=self.ts.min(), t1=self.ts.max(),
+                                                                    solver=self.solver, **kwargs).ys)          # perturbative.py:317
+        self.prog_loc_fwd = self.prog_at_ts
+        self.streamICs = np.hstack([self.prog_at_ts[:, :3] + np.asarray(pos_rel), self.prog_at_ts[:, 3:] + np.asarray(vel_rel)])
+        self.IDs = np.arange(len(self.ts))
+        # custom_release_model is additive, so its Jacobian w.r.t. the progenitor state is the identity (perturbative.py:349-364)
+        self.dRel_dIC = np.broadcast_to(np.eye(6), (len(self.ts), 6, 6)).copy()
+        self.stream_interp = None
+
+    def gen_stream(self):                             # perturbative.py:340-345
+        sol = self.potential_base.integrate_orbit_batch_vmapped(w0=self.streamICs[:-1], ts=np.full((len(self.ts) - 1, 1), self.ts[-1]),
+                                                                t0=self.ts[:-1], t1=self.ts[-1], solver=self.solver)
+        return sol
+
+
+class _ResponseGenerator(Potential):
+    """Shared implementation of compute_perturbation_OTF for the custom-base / Chen25 generators."""
+
+    def _init_common(self, potential_base_total, potential_perturbation):
+        self.gradient = None
+        self.potential_base_total = potential_base_total
+        self.num_pert = potential_perturbation._arrays.n
+        self.subhalo_arrays = potential_perturbation._arrays
+        self.jump_ts = None
+
+    def compute_perturbation_OTF(self, cpu=True, solver=Dopri8(scan_kind='bounded'), rtol=1e-6, atol=1e-6, dtmin=0.05, max_steps=10_000,
+                                 dtmax=None):
+        """Returns [w (N-1,6), D (N-1,N_sh,12)] like the reference (perturbative.py:425-454, 726-755).  `cpu` only chose
+        scan vs vmap in the reference; both schedules give the same result and there is one device schedule here."""
+        ts = np.asarray(self.base_stream.ts, dtype=np.float64)
+        n = len(ts) - 1
+        w0 = rt.to_dev(np.asarray(self.base_realspace_ICs)[:n])
+        pics = np.asarray(self.perturbation_ICs)[:n]
+        D0 = None if not np.any(pics) else rt.to_dev(pics)
+        ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
+        wout, Dout, status, nsteps = rt.linear_response(self.potential_base_total, self.subhalo_arrays, w0, D0, rt.to_dev(ts[:n]), float(ts[-1]), ctrl)
+        self.last_status, self.last_nsteps = status.cpu().numpy(), nsteps.cpu().numpy()
+        if (self.last_status != 0).any():     # integrate_field leaves diffrax's throw=True (fields.py:85-98)
+            raise RuntimeError("compute_perturbation_OTF: a particle failed (max_steps reached or non-finite state)")
+        return [wout.cpu().numpy(), Dout.cpu().numpy()]
+
+
+class GenerateMassRadiusPerturbation_CustomBase(_ResponseGenerator):      # perturbative.py:367-454
+    def __init__(self, potential_base, potential_perturbation, potential_structural=None, BaseStreamModel=None, units=None,
+                 perturbation_ICs=None, **kwargs):
+        super().__init__(units, {'potential_base': potential_base, 'potential_perturbation': potential_perturbation,
+                                 'potential_structural': potential_structural, 'BaseStreamModel': BaseStreamModel})
+        self._init_common(potential_base, potential_perturbation)
+        self.base_stream = BaseStreamModel
+        self.base_realspace_ICs = self.base_stream.streamICs
+        if perturbation_ICs is None:
+            raise NotImplementedError("the backward-integrated progenitor response (perturbative.py:391-399) needs saved responses at "
+                                      "every stripping time, which the device path does not provide yet; pass perturbation_ICs= explicitly")
+        self.perturbation_ICs = perturbation_ICs
+
+
+class BaseStreamModelChen25(Potential):               # perturbative.py:588-658
+    """Chen+25 base model.  The Chen25 release draws (jax multivariate_normal via SVD, streamhelpers.py:352-432) are not
+    reproduced on the device yet, so the release offsets are supplied: stream_ics = (pos_lead, pos_trail, vel_lead, vel_trail)
+    each [N,3], and prog_fwd [N,6] (the progenitor at ts)."""
+
+    def __init__(self, pot_base, ts, prog_w0, Msat=None, key=None, solver=Dopri5(scan_kind='bounded'), rtol=1e-7, atol=1e-7, dtmin=0.3,
+                 dtmax=None, max_steps=10_000, throw=False, prog_pot=None, units=usys, stream_ics=None, prog_fwd=None):
+        super().__init__(units, {'pot_base': pot_base, 'ts': ts, 'prog_w0': prog_w0, 'Msat': Msat, 'key': key, 'solver': solver, 'rtol': rtol,
+                                 'atol': atol, 'dtmin': dtmin, 'dtmax': dtmax, 'max_steps': max_steps, 'throw': throw, 'prog_pot': prog_pot})
+        if stream_ics is None:
+            raise NotImplementedError("Chen25 release sampling is not on the device path yet; pass stream_ics= and prog_fwd=")
+        from .potential import CubicTrack, TimeDepTranslatingPotential
+        ts = np.asarray(ts, dtype=np.float64)
+        if prog_fwd is None:
+            prog_fwd = np.asarray(pot_base.integrate_orbit(w0=prog_w0, ts=ts, solver=solver, rtol=rtol, atol=atol, dtmin=dtmin, dtmax=dtmax,
+                                                           max_steps=max_steps).ys)
+        pl, pt, vl, vt = [np.asarray(a, dtype=np.float64) for a in stream_ics]
+        pos_rel = np.vstack([pl - prog_fwd[:, :3], pt - prog_fwd[:, :3]])                  # perturbative.py:627-633
+        vel_rel = np.vstack([vl - prog_fwd[:, 3:], vt - prog_fwd[:, 3:]])
+        ts_stack = np.clip(np.hstack([ts, ts + 1e-12]), ts.min(), ts.max())                # perturbative.py:635-639
+        order = np.argsort(ts_stack, kind="stable")
+        pot_tot = pot_base
+        if prog_pot is not None and getattr(prog_pot, "m", 0.0) != 0.0:
+            pot_tot = Potential_Combine([pot_base, TimeDepTranslatingPotential(pot=prog_pot, center_spl=CubicTrack(ts, prog_fwd[:, :3]), units=usys)],
+                                        units=usys)                                        # perturbative.py:642-644
+        self.pot_tot = pot_tot
+        self.BaseModel = CustomBaseStreamModel(potential_base=pot_tot, prog_w0=prog_w0, ts=ts_stack[order], pos_rel=pos_rel[order],
+                                               vel_rel=vel_rel[order], solver=solver, units=usys, dense=False, cpu=False)
+
+
+class GenerateMassRadiusPerturbation_Chen25(_ResponseGenerator):          # perturbative.py:661-755
+    def __init__(self, potential_base, potential_perturbation, BaseStreamModel, units=None, **kwargs):
+        super().__init__(units, {'potential_base': potential_base, 'potential_perturbation': potential_perturbation,
+                                 'BaseStreamModel': BaseStreamModel})
+        self._init_common(BaseStreamModel.pot_tot, potential_perturbation)               # perturbative.py:677
+        self.potential_structural = SubhaloLinePotentialCustom_dRadius_fromFunc(
+            func=potential_perturbation.func, m=potential_perturbation.m, r_s=potential_perturbation.r_s,
+            subhalo_x0=potential_perturbation.subhalo_x0, subhalo_v=potential_perturbation.subhalo_v,
+            subhalo_t0=potential_perturbation.subhalo_t0, t_window=potential_perturbation.t_window, units=potential_perturbation.units)
+        self.base_stream = BaseStreamModel.BaseModel
+        self.perturbation_ICs = np.zeros((len(self.base_stream.ts), self.num_pert, 12))   # perturbative.py:712
+        self.base_realspace_ICs = self.base_stream.streamICs
+
+    def gradientPotentialPerturbation_per_SH(self, xyz, t):
+        return self.potential_perturbation.gradient_per_SH(xyz, t)
+
+    def gradientPotentialStructural_per_SH(self, xyz, t):
+        return self.potential_structural.gradient_per_SH(xyz, t)
+
+    def compute_base_stream(self, cpu=True):
+        return self.base_stream.gen_stream()

@@ -1,0 +1,92 @@
+"""Shared builders: the same physical setups expressed once for the oracle (oracle.Program) and once for the
+product (streamsculptor_b200 classes), independently, so parameter-order mistakes cannot cancel."""
+import numpy as np
+
+import oracle as O
+
+
+def mw3_oracle():
+    return O.Program().hernquist(5e9, 1.0).miyamoto(6.8e10, 3.0, 0.28).nfw(5.4e11, 15.62)
+
+
+def mw3_product():
+    import streamsculptor_b200 as ssc
+    P = ssc.potential
+    return P.Potential_Combine([P.HernquistPotential(m=5e9, r_s=1.0, units=ssc.usys), P.MiyamotoNagaiDisk(m=6.8e10, a=3.0, b=0.28, units=ssc.usys),
+                                P.NFWPotential(m=5.4e11, r_s=15.62, units=ssc.usys)], units=ssc.usys)
+
+
+def lmc_track(n=200, t_lo=-3000.0, t_hi=0.0):
+    """A smooth synthetic perturber track (SURVEY 8d C3 uses an orbit; any smooth table exercises the same code)."""
+    t = np.linspace(t_lo, t_hi, n)
+    y = np.stack([-1.0 + 0.02 * t + 30 * np.sin(t / 900.0), -41.0 - 0.01 * t + 10 * np.cos(t / 700.0), -28.0 + 0.015 * t], axis=1)
+    return t, y
+
+
+def random_orbits(n, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=(n, 3)) * np.array([12.0, 12.0, 6.0]) + np.array([10.0, 0.0, 5.0])
+    v = rng.normal(size=(n, 3)) * 0.08
+    return np.hstack([x, v])
+
+
+def halo_orbits(n, seed=0):
+    """Stream-progenitor-like orbits: r in [12, 30] kpc, mostly tangential velocities (pericentres of several kpc), so
+    that fixed-step runs are well resolved and rounding differences are not amplified by near-centre passages."""
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+    r = rng.uniform(12.0, 30.0, n)
+    x = d * r[:, None]
+    e = np.cross(d, rng.normal(size=(n, 3))); e /= np.linalg.norm(e, axis=1)[:, None]
+    v = e * rng.uniform(0.14, 0.22, n)[:, None] + d * rng.normal(size=(n, 1)) * 0.03
+    return np.hstack([x, v])
+
+
+def subhalo_set(n, seed=1, t_lo=-3000.0, t_hi=0.0, tw=150.0):
+    rng = np.random.default_rng(seed)
+    M = 10 ** rng.uniform(5, 9, n)
+    rs = 1.05 * np.sqrt(M / 1e8)
+    x0 = rng.normal(size=(n, 3)) * 10.0
+    v = rng.normal(size=(n, 3)) * 0.184
+    t0 = rng.uniform(t_lo, t_hi, n)
+    return dict(m=np.ones(n), M=M, rs=rs, x0=x0, v=v, t0=t0, tw=np.full(n, tw))
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = np.maximum(np.abs(b), 1e-300)
+    return np.max(np.abs(a - b) / np.maximum(scale, np.abs(b).max() * 1e-6 + 1e-300))
+
+
+def scaled_err(a, b, tol, ref=None):
+    """max over components of |a-b| / (tol * (1 + |ref|)), per leading row."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    ref = b if ref is None else np.asarray(ref, dtype=np.float64)
+    d = np.abs(a - b) / (tol * (1.0 + np.abs(ref)))
+    return d.reshape(d.shape[0], -1).max(axis=1)
+
+
+def assert_adaptive_close(gpu, orc, truth, tol, min_frac=0.85, what=""):
+    """Parity criterion for ADAPTIVE runs (DESIGN.md "Parity criteria").
+
+    Two correct implementations of the same adaptive solver follow the same step sequence only until a rounding-level
+    difference in the embedded error estimate changes a step-size factor (the estimate is a cancellation of O(h v) terms,
+    so for small steps / tight tolerances it is rounding noise); from there the two solutions differ by a fraction of the
+    solver's own global error, which for Gyr-long orbits is 10^2..10^4 x tol.  We therefore require
+      (1) most orbits (>= min_frac) agree within 10 x tol - they followed the same sequence;
+      (2) the CUDA path is as accurate as the oracle against a 1e-13 solution: its error distribution (median, 90th
+          percentile, maximum) is within 1.5x / 2x / 3x of the oracle's (+ a 10 x tol floor).
+    |gpu - oracle| <= |gpu - truth| + |oracle - truth| then bounds every individual difference by the solver's own error.
+    """
+    finite = np.isfinite(np.asarray(orc)).reshape(len(orc), -1).all(axis=1)
+    assert np.array_equal(finite, np.isfinite(np.asarray(gpu)).reshape(len(gpu), -1).all(axis=1)), what + ": inf pattern differs"
+    gpu, orc, truth = np.asarray(gpu)[finite], np.asarray(orc)[finite], np.asarray(truth)[finite]
+    d_ab = scaled_err(gpu, orc, tol, truth)
+    d_bt = scaled_err(orc, truth, tol, truth)
+    d_at = scaled_err(gpu, truth, tol, truth)
+    frac = np.mean(d_ab <= 10.0)
+    assert frac >= min_frac, f"{what}: only {frac:.2f} of the orbits agree within 10 x tol"
+    for q, fac in ((50, 1.5), (90, 2.0), (100, 3.0)):
+        a, b = np.percentile(d_at, q), np.percentile(d_bt, q)
+        assert a <= fac * b + 10.0, f"{what}: CUDA error percentile {q} = {a:.1f} x tol vs oracle {b:.1f} x tol"
+    return frac

@@ -1,0 +1,309 @@
+"""CUDA path vs the CPU oracle on the same seeded inputs (run with -m gpu on the B200 box).
+
+Tolerances (BASELINE.json north_star): fixed-step runs <= 1e-10 relative; adaptive runs <= 10 x rtol/atol;
+closed-form field evaluations <= 1e-11 relative against the oracle's autodiff of the reference's scalar formulas.
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+from common import assert_adaptive_close, halo_orbits, lmc_track, mw3_oracle, mw3_product, random_orbits, relerr, scaled_err, subhalo_set
+
+TRUTH = dict(solver=8, rtol=1e-13, atol=1e-13, dtmin=1e-3, max_steps=400_000, threads=8)
+
+pytestmark = pytest.mark.gpu
+
+
+def _full_pair(cuda):
+    """MW4 + translating Plummer on a linear track + uniform acceleration + Hernquist subhalos, built twice."""
+    import streamsculptor_b200 as ssc
+    P = ssc.potential
+    t, y = lmc_track()
+    tv = np.linspace(-3000, 0, 50)
+    vel = np.stack([1e-3 * np.sin(tv / 500.0), 2e-3 * np.cos(tv / 800.0), 1e-4 * tv / 3000.0], axis=1)
+    sh = subhalo_set(12, tw=400.0)
+    orc = O.Program().miyamoto(6.8e10, 3.0, 0.28).hernquist(5e9, 1.0).hernquist(1.71e9, 0.07, soft=1e-4).nfw(5.4e11, 15.62)
+    tr = orc.track(O.LINEAR, t, y)
+    orc.plummer(1.5e11, 10.8, track=tr).isochrone(3e10, 2.0).triaxnfw(1e11, 12.0, 1.0, 0.9, 0.8)
+    orc.uniform_acc(tv, vel)
+    orc.subhalos(O.PR_HERNQUIST, sh["M"], sh["rs"], sh["x0"], sh["v"], sh["t0"], sh["tw"])
+    prod = P.Potential_Combine([
+        P.MiyamotoNagaiDisk(m=6.8e10, a=3.0, b=0.28, units=ssc.usys), P.HernquistPotential(m=5e9, r_s=1.0, units=ssc.usys),
+        P.HernquistPotential(m=1.71e9, r_s=0.07, soft=1e-4, units=ssc.usys), P.NFWPotential(m=5.4e11, r_s=15.62, units=ssc.usys),
+        P.TimeDepTranslatingPotential(P.PlummerPotential(m=1.5e11, r_s=10.8, units=ssc.usys), ssc.LinearTrack(t, y), units=ssc.usys),
+        P.Isochrone(m=3e10, a=2.0, units=ssc.usys), P.TriaxialNFWPotential(m=1e11, r_s=12.0, q1=1.0, q2=0.9, q3=0.8, units=ssc.usys),
+        P.UniformAcceleration(ssc.LinearTrack(tv, vel), units=ssc.usys),
+        P.SubhaloLinePotentialCustom_fromFunc(func=P.HernquistPotential, m=sh["M"], r_s=sh["rs"], subhalo_x0=sh["x0"], subhalo_v=sh["v"],
+                                              subhalo_t0=sh["t0"], t_window=sh["tw"], units=ssc.usys)], units=ssc.usys)
+    return orc, prod
+
+
+def test_field_closed_forms_match_oracle_autodiff(cuda):
+    orc, prod = _full_pair(cuda)
+    rng = np.random.default_rng(3)
+    xyz = rng.normal(size=(257, 3)) * np.array([15, 15, 8.0])
+    t = rng.uniform(-3200, 100, 257)
+    g = prod.gradient(xyz, t)
+    h = prod.jacobian_force(xyz, t)
+    assert relerr(g, orc.gradient(xyz, t)) < 1e-11
+    assert relerr(h, orc.hessian(xyz, t)) < 1e-10
+    # potentials: everything except the force-only uniform acceleration
+    import streamsculptor_b200 as ssc
+    cons = ssc.potential.Potential_Combine([p for p in prod.potential_list if type(p).__name__ != "UniformAcceleration"], units=ssc.usys)
+    assert relerr(cons.potential(xyz, t), orc.potential(xyz, t)) < 1e-12
+
+
+def test_goldens_through_the_product_api(cuda):
+    import streamsculptor_b200 as ssc
+    nfw = ssc.potential.NFWPotential(m=1e12, r_s=20.0, units=ssc.usys)
+    rhs = nfw.velocity_acceleration(0.0, np.array([1., 2., 3., .2, .3, .4]))          # golden D1 (tests.ipynb cell 58)
+    assert np.allclose(rhs, [0.2, 0.3, 0.4, -0.0011937, -0.00238739, -0.00358109], rtol=0, atol=5e-9)
+    sol = nfw.integrate_orbit(w0=[20., 15., 20., .08, .1, -.05], ts=np.array([0.0, 30.0, 3000.0]))   # golden D2 (tests.ipynb cell 17)
+    assert np.allclose(sol.ys[1], [21.9793661, 17.67654451, 18.10530132, 0.051923, 0.07815599, -0.07552167], rtol=0, atol=6e-9)
+    mw = ssc.potential.GalaMilkyWayPotential(units=ssc.usys)                                # golden D5 (StreamSubhaloExample cell 1)
+    ic = mw.integrate_orbit(w0=[20.0, 0.0, 20, .0, .15, .0], ts=np.linspace(0, -3500, 1000), t0=0.0, t1=-3500).ys[-1]
+    assert np.allclose(ic, [-7.23164146, -7.96692572, -10.81840286, 0.19182623, -0.20351324, -0.01770436], rtol=0, atol=5e-6)
+
+
+@pytest.mark.parametrize("solver", [5, 8])
+def test_fixed_step_orbits_1e10(cuda, solver):
+    import streamsculptor_b200 as ssc
+    orc, prod = mw3_oracle(), mw3_product()
+    w0 = random_orbits(96, seed=5)
+    t0 = np.linspace(-3000, -100, 96)
+    for h in (0.5, 1.0):
+        ys_o, st_o, ns_o = orc.integrate_orbits(w0, t0, 0.0, solver=solver, dtmin=h, dtmax=h)
+        sol = prod.integrate_orbit_batch_vmapped(w0=w0, ts=np.zeros((96, 1)), t0=t0, t1=0.0, solver=ssc.Dopri8() if solver == 8 else ssc.Dopri5(),
+                                                 dtmin=h, dtmax=h, max_steps=10_000)
+        assert (np.asarray(sol.result) == 0).all()
+        assert np.array_equal(sol.stats["num_steps"], ns_o[:, 0])
+        assert relerr(sol.ys[:, 0], ys_o[:, 0]) < 1e-10
+
+
+@pytest.mark.parametrize("solver,tol,frac", [(5, 1e-7, 0.99), (8, 1e-7, 0.9), (8, 1e-10, 0.75)])
+def test_adaptive_orbits_within_10x_tol(cuda, solver, tol, frac):
+    import streamsculptor_b200 as ssc
+    orc, prod = mw3_oracle(), mw3_product()
+    w0 = random_orbits(200, seed=11)
+    t0 = np.linspace(-3000, -5, 200)
+    ys_o, st_o, ns_o = orc.integrate_orbits(w0, t0, 0.0, solver=solver, rtol=tol, atol=tol, threads=8)
+    ys_t, _, _ = orc.integrate_orbits(w0, t0, 0.0, **TRUTH)
+    sol = prod.integrate_orbit_batch_vmapped(w0=w0, ts=np.zeros((200, 1)), t0=t0, t1=0.0, solver=ssc.Dopri8() if solver == 8 else ssc.Dopri5(),
+                                             rtol=tol, atol=tol)
+    assert (np.asarray(sol.result) == 0).all()
+    assert_adaptive_close(sol.ys[:, 0], ys_o[:, 0], ys_t[:, 0], tol, min_frac=frac, what=f"Dopri{solver} tol={tol}")
+    # short integrations (a few steps) leave no room for the sequences to drift: strict 10 x tol for every orbit
+    ys_s, _, _ = orc.integrate_orbits(w0, -60.0, 0.0, solver=solver, rtol=tol, atol=tol)
+    sol_s = prod.integrate_orbit_batch_vmapped(w0=w0, ts=np.zeros((200, 1)), t0=-60.0, t1=0.0, solver=ssc.Dopri8() if solver == 8 else ssc.Dopri5(),
+                                               rtol=tol, atol=tol)
+    assert scaled_err(sol_s.ys[:, 0], ys_s[:, 0], tol).max() < 10.0
+
+
+def test_saved_snapshots_and_backward_integration(cuda):
+    """integrate_orbit_batch_vmapped with per-orbit save times ts[N,M] (main.py:186-202), forwards and backwards, in a
+    potential with every component type.  Fixed steps pin the in-kernel dense output at 1e-10; adaptive runs are compared
+    at the accuracy of the interpolant."""
+    import streamsculptor_b200 as ssc
+    orc, prod = _full_pair(cuda)
+    w0 = halo_orbits(40, seed=2)
+    ts = np.linspace(-2500, -100, 17)[None, :] + np.linspace(0, 50, 40)[:, None]
+    for solver in (5, 8):
+        sv = ssc.Dopri8() if solver == 8 else ssc.Dopri5()
+        for tsx in (ts, ts[:, ::-1].copy()):                      # forwards, then backwards (t1 < t0, ts decreasing)
+            ys_f, _, ns_f = orc.integrate_orbits(w0, tsx[:, 0], tsx[:, -1], ts=tsx, solver=solver, dtmin=1.0, dtmax=1.0, threads=8)
+            sol_f = prod.integrate_orbit_batch_vmapped(w0=w0, ts=tsx, t0=tsx[:, 0], t1=tsx[:, -1], solver=sv, dtmin=1.0, dtmax=1.0)
+            assert np.array_equal(sol_f.ys[:, 0], w0)              # ts[0] == t0 returns y0 exactly
+            assert np.array_equal(sol_f.stats["num_steps"], ns_f[:, 0])
+            assert scaled_err(sol_f.ys, ys_f, 1e-10).max() < 1.0
+            ys_o, _, _ = orc.integrate_orbits(w0, tsx[:, 0], tsx[:, -1], ts=tsx, solver=solver, dtmin=0.05, threads=8)
+            sol = prod.integrate_orbit_batch_vmapped(w0=w0, ts=tsx, t0=tsx[:, 0], t1=tsx[:, -1], solver=sv, dtmin=0.05)
+            assert np.mean(scaled_err(sol.ys, ys_o, 1e-7) < 10.0) > 0.5 and scaled_err(sol.ys, ys_o, 1e-4).max() < 10.0
+
+
+def test_dense_single_orbit_matches_oracle_saveat(cuda):
+    import streamsculptor_b200 as ssc
+    orc, prod = mw3_oracle(), mw3_product()
+    w0 = [20.0, 0.0, 20.0, 0.0, 0.15, 0.0]
+    ts = np.linspace(-3000.0, 0.0, 1001)
+    for solver in (5, 8):
+        sv = ssc.Dopri8() if solver == 8 else ssc.Dopri5()
+        ys_o, _, ns_o = orc.integrate_orbits(w0, -3000.0, 0.0, ts=ts, solver=solver)
+        sol = prod.integrate_orbit(w0=w0, ts=ts, solver=sv)
+        assert abs(int(sol.stats["num_steps"]) - ns_o[0, 0]) <= 2
+        assert scaled_err(sol.ys, ys_o[0], 1e-7).max() < 10.0
+        dense = prod.integrate_orbit(w0=w0, ts=ts, dense=True, solver=sv)
+        assert np.allclose(dense.evaluate(ts[37]), sol.ys[37], rtol=0, atol=1e-12)
+        # fixed steps: identical sequences, so the interpolants themselves are compared (1e-10)
+        ys_f, _, _ = orc.integrate_orbits(w0, -3000.0, 0.0, ts=ts, solver=solver, dtmin=2.0, dtmax=2.0)
+        sol_f = prod.integrate_orbit(w0=w0, ts=ts, solver=sv, dtmin=2.0, dtmax=2.0)
+        assert scaled_err(sol_f.ys, ys_f[0], 1e-10).max() < 1.0
+
+
+def test_failure_semantics(cuda):
+    import streamsculptor_b200 as ssc
+    prod = mw3_product()
+    w0 = random_orbits(4, seed=1)
+    sol = prod.integrate_orbit_batch_vmapped(w0=w0, ts=np.zeros((4, 1)), t0=np.array([-3000.0, -3000.0, 0.0, -10.0]), t1=0.0, max_steps=5)
+    res = np.asarray(sol.result)
+    assert res[0] == 1 and res[1] == 1 and np.isinf(sol.ys[0]).all()          # max_steps reached -> rows stay +inf (main.py:136)
+    assert res[2] == 0 and np.isinf(sol.ys[2]).all()                          # t0 == t1: the loop never runs, nothing is saved
+    assert res[3] == 0 and np.isfinite(sol.ys[3]).all()
+    with pytest.raises(NotImplementedError):
+        ssc.potential.CustomPotential(potential_func=lambda x, t: 0.0, units=ssc.usys)
+    with pytest.raises(NotImplementedError):
+        prod.integrate_orbit(w0=w0[0], ts=np.array([0.0, 1.0]), solver="Tsit5")
+
+
+def test_release_model_and_stream_c1(cuda):
+    """BASELINE config C1: 2000-particle spray stream, 3 Gyr, Dopri8, static MW3 - full path vs the oracle."""
+    import streamsculptor_b200 as ssc
+    orc, prod = mw3_oracle(), mw3_product()
+    prog_today = [20.0, 0.0, 20.0, 0.0, 0.15, 0.0]
+    back, _, _ = orc.integrate_orbits(prog_today, 0.0, -3000.0)
+    ts = np.linspace(-3000.0, 0.0, 1001)
+    for normals in (None, np.random.Generator(np.random.PCG64(0)).standard_normal((1001, 4))):
+        ics_o = orc.gen_stream_ics(ts, back[0, 0], 1e4, 583, solver=8, normals=normals)
+        ics_p = prod.gen_stream_ics(ts=ts, prog_w0=back[0, 0], Msat=1e4, seed_num=583, solver=ssc.Dopri8(), normals=normals)
+        for a, b in zip(ics_p, ics_o[:4]):
+            assert scaled_err(a, b, 1e-7).max() < 10.0
+        lead_o, trail_o, st_o, ns_o = orc.gen_stream(ts, back[0, 0], 1e4, 583, solver=8, normals=normals)
+        lead, trail, status, nsteps = prod.gen_stream_vmapped(ts=ts, prog_w0=back[0, 0], Msat=1e4, seed_num=583, solver=ssc.Dopri8(),
+                                                              normals=normals, _return_stats=True)
+        assert lead.shape == (1000, 6) and trail.shape == (1000, 6) and (status == 0).all()
+        prog_t, _, _ = orc.integrate_orbits(back[0, 0], -3000.0, 0.0, ts=ts, **TRUTH)
+        pl, pt_, vl, vt = orc.release(prog_t[0], 1e4, np.arange(1001), ts, 583, normals=normals)
+        tl, _, _ = orc.integrate_orbits(np.hstack([pl, vl])[:-1], ts[:-1], 0.0, **TRUTH)
+        tt_, _, _ = orc.integrate_orbits(np.hstack([pt_, vt])[:-1], ts[:-1], 0.0, **TRUTH)
+        assert_adaptive_close(lead, lead_o, tl[:, 0], 1e-7, min_frac=0.9, what="C1 lead")
+        assert_adaptive_close(trail, trail_o, tt_[:, 0], 1e-7, min_frac=0.9, what="C1 trail")
+    # fixed-step C1 (dtmin = dtmax = 1 Myr): whole pipeline to 1e-10 relative
+    nr = np.random.Generator(np.random.PCG64(0)).standard_normal((1001, 4))
+    lo, to, _, _ = orc.gen_stream(ts, back[0, 0], 1e4, 583, solver=8, normals=nr, dtmin=1.0, dtmax=1.0)
+    lf, tf = prod.gen_stream_vmapped(ts=ts, prog_w0=back[0, 0], Msat=1e4, seed_num=583, solver=ssc.Dopri8(), normals=nr, dtmin=1.0, dtmax=1.0)
+    assert scaled_err(lf, lo, 1e-10).max() < 1.0 and scaled_err(tf, to, 1e-10).max() < 1.0
+    # single release call, jax.random recipe, decaying mass array (StreamSubhaloExample cell 2)
+    pl, pt, vl, vt = prod.release_model(x=back[0, 0, :3], v=back[0, 0, 3:], Msat=1e4, i=7, t=-3000.0, seed_num=583)
+    ref = orc.release(back[0, 0][None], 1e4, [7], [-3000.0], 583)
+    assert relerr(np.hstack([pl, pt, vl, vt]), np.hstack([r[0] for r in ref])) < 1e-10
+
+
+def test_with_pert_streams(cuda):
+    import streamsculptor_b200 as ssc
+    P = ssc.potential
+    sh = subhalo_set(5, seed=4, tw=250.0)
+    orc_base, base = mw3_oracle(), mw3_product()
+    orc_tot = mw3_oracle().subhalos(O.PR_PLUMMER, sh["M"], sh["rs"], sh["x0"], sh["v"], sh["t0"], sh["tw"])
+    pert = P.SubhaloLinePotential(m=sh["M"], a=sh["rs"], subhalo_x0=sh["x0"], subhalo_v=sh["v"], subhalo_t0=sh["t0"], t_window=250.0, units=ssc.usys)
+    ts = np.linspace(-2000.0, 0.0, 301)
+    w0 = [-5.0, 12.0, 9.0, 0.12, 0.05, -0.06]
+    nr = np.random.Generator(np.random.PCG64(5)).standard_normal((301, 4))
+    # oracle version of gen_stream_vmapped_with_pert: progenitor + particles in total, release in base
+    prog, _, _ = orc_tot.integrate_orbits(w0, -2000.0, 0.0, ts=ts, solver=5, dtmin=0.1)
+    pl, pt, vl, vt = orc_base.release(prog[0], 1e4, np.arange(301), ts, 0, normals=nr)
+    w_l, w_t = np.hstack([pl, vl])[:-1], np.hstack([pt, vt])[:-1]
+    yl, _, _ = orc_tot.integrate_orbits(w_l, ts[:-1], 0.0, solver=5, dtmin=0.1)
+    yt, _, _ = orc_tot.integrate_orbits(w_t, ts[:-1], 0.0, solver=5, dtmin=0.1)
+    lead, trail = ssc.gen_stream_vmapped_with_pert(pot_base=base, pot_pert=pert, ts=ts, prog_w0=w0, Msat=1e4, seed_num=0, normals=nr)
+    assert np.mean(scaled_err(lead, yl[:, 0], 1e-7) < 10.0) > 0.9 and np.mean(scaled_err(trail, yt[:, 0], 1e-7) < 10.0) > 0.9
+    assert scaled_err(lead, yl[:, 0], 1e-5).max() < 10.0 and scaled_err(trail, yt[:, 0], 1e-5).max() < 10.0
+
+
+def test_linear_response_matches_oracle(cuda):
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import _runtime as rt
+    P = ssc.potential
+    nsh = 24
+    sh = subhalo_set(nsh, seed=9, t_lo=-1500.0)
+    orc_base, base = mw3_oracle(), mw3_product()
+    for prof_o, func in ((O.PR_HERNQUIST, P.HernquistPotential), (O.PR_PLUMMER, P.PlummerPotential)):
+        orc_sh = O.Program().subhalos(prof_o, sh["m"], sh["rs"], sh["x0"], sh["v"], sh["t0"], sh["tw"])
+        pert = P.SubhaloLinePotentialCustom_fromFunc(func=func, m=sh["m"], r_s=sh["rs"], subhalo_x0=sh["x0"], subhalo_v=sh["v"],
+                                                     subhalo_t0=sh["t0"], t_window=sh["tw"], units=ssc.usys)
+        # field term at a generic state (fields.py:175-206)
+        rng = np.random.default_rng(0)
+        y = np.concatenate([[8.0, -3.0, 4.0, 0.1, 0.12, -0.05], rng.normal(size=12 * nsh) * 1e-3])
+        dy_o = O.response_term(orc_base, orc_sh, sh["t0"][3] + 20.0, y)
+        dy = rt.response_term(base, pert._arrays, sh["t0"][3] + 20.0, y).cpu().numpy()
+        assert relerr(dy, dy_o) < 1e-11
+        # per-subhalo gradients incl. d/dr_s (perturbative.py:695-696)
+        phi_o, g_o = orc_sh.per_sh([3.0, 2.0, 1.0], sh["t0"][5] + 10.0)
+        assert relerr(pert.gradient_per_SH([3.0, 2.0, 1.0], sh["t0"][5] + 10.0), g_o) < 1e-11
+        # full solves: zero ICs (Chen25 convention) and non-zero ICs, Dopri8 and Dopri5
+        w0 = random_orbits(12, seed=21)
+        t0 = np.linspace(-1800.0, -50.0, 12)
+        D0 = rng.normal(size=(12, nsh, 12)) * 1e-4
+        for solver, tol, d0 in ((8, 1e-7, None), (8, 1e-9, D0), (5, 1e-7, D0)):
+            w_o, D_o, st_o, ns_o = O.linear_response(orc_base, orc_sh, w0, t0, 0.0, D0=d0, solver=solver, rtol=tol, atol=tol, dtmin=0.01)
+            ctrl = rt.make_ctrl(ssc.Dopri8() if solver == 8 else ssc.Dopri5(), tol, tol, 0.01, None, 10_000)
+            w, D, st, ns = rt.linear_response(base, pert._arrays, rt.to_dev(w0), None if d0 is None else rt.to_dev(d0), rt.to_dev(t0), 0.0, ctrl)
+            w, D, st, ns = w.cpu().numpy(), D.cpu().numpy(), st.cpu().numpy(), ns.cpu().numpy()
+            assert (st == 0).all() and (st_o == 0).all()
+            w_t, D_t, _, _ = O.linear_response(orc_base, orc_sh, w0, t0, 0.0, D0=d0, solver=8, rtol=1e-13, atol=1e-13, dtmin=1e-3,
+                                               max_steps=400_000, threads=8)
+            assert_adaptive_close(np.hstack([w, D.reshape(12, -1)]), np.hstack([w_o, D_o.reshape(12, -1)]),
+                                  np.hstack([w_t, D_t.reshape(12, -1)]), tol, min_frac=0.7, what=f"response Dopri{solver} tol={tol}")
+            # fixed steps: same sequence by construction -> 1e-10
+            w_f, D_f, _, _ = O.linear_response(orc_base, orc_sh, w0, t0, 0.0, D0=d0, solver=solver, dtmin=2.0, dtmax=2.0)
+            ctrl_f = rt.make_ctrl(ssc.Dopri8() if solver == 8 else ssc.Dopri5(), tol, tol, 2.0, 2.0, 10_000)
+            wf, Df, _, nsf = rt.linear_response(base, pert._arrays, rt.to_dev(w0), None if d0 is None else rt.to_dev(d0), rt.to_dev(t0), 0.0, ctrl_f)
+            assert scaled_err(wf.cpu().numpy(), w_f, 1e-10).max() < 1.0
+            assert scaled_err(Df.cpu().numpy().reshape(12, -1), D_f.reshape(12, -1), 1e-10).max() < 1.0
+
+
+def test_response_generator_api(cuda):
+    """GenerateMassRadiusPerturbation_Chen25.compute_perturbation_OTF shape contract (golden D7) + oracle parity."""
+    import streamsculptor_b200 as ssc
+    P, pt = ssc.potential, ssc.perturbative
+    nsh, nts = 10, 40
+    sh = subhalo_set(nsh, seed=13, t_lo=-900.0)
+    base, orc_base = mw3_product(), mw3_oracle()
+    ts = np.linspace(-1000.0, 0.0, nts)
+    prog_w0 = [12.0, 3.0, -6.0, -0.05, 0.15, 0.03]
+    rng = np.random.default_rng(2)
+    prog = np.asarray(base.integrate_orbit(w0=prog_w0, ts=ts, solver=ssc.Dopri8()).ys)
+    ics = [prog[:, :3] + rng.normal(size=(nts, 3)) * 0.05, prog[:, :3] - rng.normal(size=(nts, 3)) * 0.05,
+           prog[:, 3:] + rng.normal(size=(nts, 3)) * 1e-3, prog[:, 3:] - rng.normal(size=(nts, 3)) * 1e-3]
+    model = pt.BaseStreamModelChen25(pot_base=base, ts=ts, prog_w0=prog_w0, Msat=1e4, solver=ssc.Dopri8(), stream_ics=ics, prog_fwd=prog)
+    pert = P.SubhaloLinePotentialCustom_fromFunc(func=P.HernquistPotential, m=sh["m"], r_s=sh["rs"], subhalo_x0=sh["x0"], subhalo_v=sh["v"],
+                                                 subhalo_t0=sh["t0"], t_window=150.0, units=ssc.usys)
+    gen = pt.GenerateMassRadiusPerturbation_Chen25(potential_base=base, potential_perturbation=pert, BaseStreamModel=model, units=ssc.usys)
+    w, D = gen.compute_perturbation_OTF(cpu=False, solver=ssc.Dopri8(), rtol=1e-8, atol=1e-8, dtmin=0.01)
+    assert w.shape == (2 * nts - 1, 6) and D.shape == (2 * nts - 1, nsh, 12)
+    orc_sh = O.Program().subhalos(O.PR_HERNQUIST, sh["m"], sh["rs"], sh["x0"], sh["v"], sh["t0"], sh["tw"])
+    bs = gen.base_stream
+    w_o, D_o, st_o, _ = O.linear_response(orc_base, orc_sh, bs.streamICs[:-1], bs.ts[:-1], bs.ts[-1], solver=8, rtol=1e-8, atol=1e-8, dtmin=0.01)
+    ok = np.isfinite(w_o).all(axis=1)
+    assert np.array_equal(ok, np.isfinite(w).all(axis=1)) and ok.sum() == 2 * nts - 2     # the duplicated last release time has zero span
+    assert np.mean(scaled_err(w[ok], w_o[ok], 1e-8) < 10.0) > 0.8 and scaled_err(w[ok], w_o[ok], 1e-6).max() < 10.0
+    assert np.mean(scaled_err(D[ok].reshape(ok.sum(), -1), D_o[ok].reshape(ok.sum(), -1), 1e-8) < 10.0) > 0.8
+
+
+def test_cubic_track_and_host_entry_points(cuda):
+    import ctypes as C
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import _lib, _runtime as rt
+    P = ssc.potential
+    t, y = lmc_track(n=80)
+    orc = mw3_oracle()
+    tr = orc.track(O.CUBIC, t, y)
+    orc.plummer(2e10, 3.0, track=tr)
+    prod = P.Potential_Combine([mw3_product(), P.TimeDepTranslatingPotential(P.PlummerPotential(m=2e10, r_s=3.0, units=ssc.usys),
+                                                                             ssc.CubicTrack(t, y), units=ssc.usys)], units=ssc.usys)
+    tq = np.linspace(-2990.0, -10.0, 333)
+    c_o, d_o = orc.track_eval(tr, tq)
+    track = prod.potential_list[1]._track
+    assert relerr(track(tq), c_o) < 1e-12 and relerr(track(tq, derivative=True), d_o) < 1e-10
+    xyz = np.random.default_rng(1).normal(size=(50, 3)) * 10
+    assert relerr(prod.gradient(xyz, tq[:50]), orc.gradient(xyz, tq[:50])) < 1e-11
+    # host-pointer C-ABI entry (what a CPU-side plugin call binds): same numbers as the device-pointer path
+    w0 = random_orbits(33, seed=8)
+    t0 = np.full(33, -1500.0); t1 = np.zeros(33); ts = np.zeros((33, 1))
+    pot_static = mw3_product()
+    Pst, keep = rt.lower(pot_static)
+    host = _lib.Potential.from_buffer_copy(Pst)          # static program: no device pointers inside
+    ys = np.empty((33, 1, 6)); st = np.empty(33, np.int32); ns = np.empty((33, 3), np.int32)
+    ctrl = rt.make_ctrl(ssc.Dopri8(), 1e-7, 1e-7, 0.3, None, 10_000)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(_lib.lib().ssb_orbit_integrate_host(C.byref(host), 33, p(w0), p(t0), p(t1), p(ts), 1, 1, ctrl, p(ys), p(st), p(ns)))
+    sol = pot_static.integrate_orbit_batch_vmapped(w0=w0, ts=ts, t0=t0, t1=t1)
+    assert np.array_equal(ys, sol.ys) and (st == 0).all()
