@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: BASELINE.json metric "fp64 particle-steps/sec" on config C2
+(1e6-particle mock stream, static MW3 potential, adaptive Dopri8, sharded over the GPUs of one box).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                     (the CPU restatement of the reference on the host cores)
+
+A "step" = one full pass of gen_stream_vmapped (main.py:343-368) over one synthetic stream: serial progenitor orbit with
+dense output at every stripping time, particle-spray release (jax threefry recipe), then 2*(Nts-1) independent adaptive
+Dopri8 solves from ts[i] to ts[-1].  Per GPU the work is fixed (1e6 particle orbits): with N GPUs the stream has
+N * 1e6 particles, rank r integrates particles i = r (mod N), and the shares are all-gathered over NCCL ("weak").
+One particle-step = one RK step ATTEMPT (accepted or rejected) of one particle.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_STEP_DOPRI8 = 1920.0     # algorithmic flops per particle-step, unit-cost convention (SURVEY.md 8d / BASELINE.md section 3)
+FP64_NOMINAL_TFLOPS = 37.2        # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
+PROG_TODAY = [20.0, 0.0, 20.0, 0.0, 0.15, 0.0]
+T_AGE, MSAT, SEED = 3000.0, 1e4, 583
+CTRL = dict(rtol=1e-7, atol=1e-7, dtmin=0.3, dtmax=None, max_steps=10_000)
+
+
+def workload(n_release):
+    """Synthetic C2 inputs: ts = linspace(-3000, 0, Nts), progenitor integrated back 3 Gyr."""
+    ts = np.linspace(-T_AGE, 0.0, n_release + 1)
+    return ts, np.full(n_release + 1, MSAT)
+
+
+def prog_start():
+    """Progenitor state 3 Gyr ago, computed ONCE on the device (not part of the timed step)."""
+    import streamsculptor_b200 as ssc
+    pot = mw3()
+    return np.asarray(pot.integrate_orbit(w0=PROG_TODAY, ts=np.array([0.0, -T_AGE]), t0=0.0, t1=-T_AGE, solver=ssc.Dopri8()).ys[-1])
+
+
+def mw3():
+    import streamsculptor_b200 as ssc
+    P = ssc.potential
+    return P.Potential_Combine([P.HernquistPotential(m=5e9, r_s=1.0, units=ssc.usys), P.MiyamotoNagaiDisk(m=6.8e10, a=3.0, b=0.28, units=ssc.usys),
+                                P.NFWPotential(m=5.4e11, r_s=15.62, units=ssc.usys)], units=ssc.usys)
+
+
+def mw3_oracle():
+    import oracle as O
+    return O.Program().hernquist(5e9, 1.0).miyamoto(6.8e10, 3.0, 0.28).nfw(5.4e11, 15.62)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (C++ restatement of the reference algorithm) on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_stream_rate(n_release, threads):
+    """One pass of the same pipeline on the CPU: returns (particle_steps, seconds)."""
+    orc = mw3_oracle()
+    back, _, _ = orc.integrate_orbits(PROG_TODAY, 0.0, -T_AGE)
+    ts, ms = workload(n_release)
+    t = time.perf_counter()
+    _, _, _, ns = orc.gen_stream(ts, back[0, 0], ms, SEED, solver=8, threads=threads, **{k: v for k, v in CTRL.items()})
+    dt = time.perf_counter() - t
+    return int(ns[:, 0].sum()), dt
+
+
+def cpu_sample_size(threads, target_s):
+    steps, dt = cpu_stream_rate(500, threads)            # calibration pass (1000 particles)
+    rate = steps / dt
+    per_release = steps / 500.0
+    return int(np.clip(rate * target_s / per_release, 500, 500_000))
+
+
+def run_reference(args, rank, world):
+    import oracle as O
+    if rank != 0:
+        return
+    threads = O.num_threads()
+    n_rel = cpu_sample_size(threads, 6.0)
+    for _ in range(args.warmup):
+        cpu_stream_rate(max(500, n_rel // 8), threads)
+    tot_steps, tot_s = 0, 0.0
+    for _ in range(args.steps):
+        s, dt = cpu_stream_rate(n_rel, threads)
+        tot_steps += s; tot_s += dt
+    value = tot_steps / tot_s
+    sample = f"{2 * n_rel} particles of the C2 stream per step (ts=linspace(-3000,0,{n_rel + 1}), Dopri8 rtol=atol=1e-7)"
+    line = {"impl": "reference", "metric": "fp64 particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2: 1e6-particle mock stream per GPU, static MW3 (Hernquist+MiyamotoNagai+NFW), adaptive Dopri8 rtol=atol=1e-7, "
+                                   "final state kept; CPU arm runs a bounded sample of it", "particles_per_step": 2 * n_rel},
+            "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample,
+                             "note": "C++ restatement of the reference algorithm (oracle/), NOT jax[cpu]: jax/diffrax are not installable offline"},
+            "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world):
+    import torch
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import _lib, _runtime as rt, parallel as par
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    d = par.dist()
+    lib = _lib.lib()
+    pot = mw3()
+    n_rel_per_gpu = args.particles // 2
+    n_rel = n_rel_per_gpu * world
+    ts, ms = workload(n_rel)
+    w0 = prog_start()
+    ctrl = rt.make_ctrl(ssc.Dopri8(), **CTRL)
+    kv = ssc.main.DEFAULT_KVALS
+    ts_d, w0_d, ms_d = rt.to_dev(ts), rt.to_dev(w0), rt.to_dev(ms)
+    n_local = par.shard_count(n_rel, rank, world)
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)      # > 126 MB L2
+
+    def step_device():
+        lead, trail, status, nsteps = rt.gen_stream(pot, pot, pot._G, ts_d, w0_d, ms_d, SEED, kv, None, ctrl, i_begin=rank, i_stride=world,
+                                                    n_local=n_local)
+        if world > 1:
+            lead = par.gather_interleaved(lead, n_rel, rank, world)
+            trail = par.gather_interleaved(trail, n_rel, rank, world)
+        return lead, trail, status, nsteps
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            d.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step_device()
+    barrier()
+    psteps_local = int(out[3][..., 0].sum().item())
+    assert int((out[2] != 0).sum().item()) == 0, "an orbit failed in the benchmark stream"
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush.zero_()                      # L2 flush between timed iterations (untimed)
+        a.record()
+        step_device()
+        b.record()
+    barrier()
+    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop() if rank == 0 else None
+    tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    ps = torch.tensor([float(psteps_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        d.all_reduce(tt, op=d.ReduceOp.MAX)
+        d.all_reduce(ps, op=d.ReduceOp.SUM)
+    ms_total, psteps = float(tt.item()), float(ps.item())
+    value = psteps * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: the C-ABI host call (HOST buffers, H2D + D2H inside the timed region), same shard per rank ----
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_ts, h_ms, h_w0 = pin(ts), pin(ms), pin(w0)
+    h_lead, h_trail = torch.empty((n_local, 6), dtype=torch.float64).pin_memory(), torch.empty((n_local, 6), dtype=torch.float64).pin_memory()
+    h_stat, h_ns = torch.empty((2, n_local), dtype=torch.int32).pin_memory(), torch.empty((2, n_local, 3), dtype=torch.int32).pin_memory()
+    P, _keep = rt.lower(pot)
+    kvc = (C.c_double * 8)(*kv)
+    hp = lambda t: C.c_void_p(t.data_ptr())
+
+    def step_host():
+        _lib.check(lib.ssb_gen_stream_host(C.byref(P), C.byref(P), pot._G, n_rel + 1, hp(h_ts), hp(h_w0), hp(h_ms), SEED, kvc, None, ctrl, rank, world,
+                                           n_local, hp(h_lead), hp(h_trail), hp(h_stat), hp(h_ns)))
+    for _ in range(min(args.warmup, 3)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        d.all_reduce(te, op=d.ReduceOp.MAX)
+    e2e_value = psteps * args.steps / float(te.item())
+    assert np.allclose(h_lead.numpy(), out[0][rank::world].cpu().numpy() if world > 1 else out[0].cpu().numpy(), rtol=0, atol=0), "host and device paths disagree"
+    h2d = h_ts.numel() * 8 + h_ms.numel() * 8 + 48
+    d2h = h_lead.numel() * 8 * 2 + h_stat.numel() * 4 + h_ns.numel() * 4
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (orbit_kernel<8>): CUDA events around that launch alone ----
+    pl, pt, vl, vt = pot.gen_stream_ics(ts=ts_d, prog_w0=w0_d, Msat=ms_d, seed_num=SEED, solver=ssc.Dopri8(), **CTRL)
+    sel = torch.arange(rank, n_rel, world, device=dev)
+    w0_all = torch.cat([torch.cat([pl, vl], 1)[sel], torch.cat([pt, vt], 1)[sel]]).contiguous()
+    t0_all = torch.cat([ts_d[sel], ts_d[sel]]).contiguous()
+    t1_all = torch.zeros_like(t0_all)
+    kt = []
+    for i in range(args.steps + 2):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ys, st, ns = rt.orbit_integrate(pot, w0_all, t0_all, t1_all, t1_all.reshape(-1, 1), ctrl, ts_per_orbit=1)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            kt.append(a.elapsed_time(b))
+    k_ms = float(np.mean(kt))
+    k_steps = float(ns[:, 0].sum().item())
+    achieved = FLOP_PER_STEP_DOPRI8 * k_steps / (k_ms * 1e-3) / 1e12
+    peak = C.c_double(0.0)
+    _lib.check(lib.ssb_fp64_peak_probe(20000, C.byref(peak), rt.stream_ptr()))
+    peak_tf = peak.value / 1e12
+    roofline = {"bound": "fp64", "kernel": "orbit_kernel<8>", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "traffic": None, "kernel_ms": k_ms, "particle_steps_per_launch": k_steps, "flop_per_particle_step": FLOP_PER_STEP_DOPRI8,
+                "peak_source": "measured in this run by ssb_fp64_peak_probe (independent DFMA chains on every SM); MEASURED_PEAKS.json has no fp64 entry; "
+                               f"nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = {FP64_NOMINAL_TFLOPS} TFLOP/s",
+                "frac_of_nominal": achieved / FP64_NOMINAL_TFLOPS,
+                "hbm_gbs_of_kernel": (w0_all.numel() * 8 + ys.numel() * 8 + t0_all.numel() * 16 + ns.numel() * 4) / (k_ms * 1e-3) / 1e9}
+    # ---- CPU baseline on this box's host cores: bounded sample of the same workload ----
+    import oracle as O
+    threads = O.num_threads()
+    n_cpu = cpu_sample_size(threads, 12.0)
+    cs, cdt = cpu_stream_rate(n_cpu, threads)
+    cpu = {"value": cs / cdt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+           "sample": f"{2 * n_cpu} particles of the same stream (ts=linspace(-3000,0,{n_cpu + 1})), {cdt:.1f} s",
+           "note": "C++ restatement of the reference algorithm (oracle/), NOT jax[cpu]: jax/diffrax are not installable offline"}
+    line = {"metric": "fp64 particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C2: {args.particles}-particle mock stream per GPU ({args.particles * world} total), static MW3 "
+                                   "(Hernquist+MiyamotoNagai+NFW), 3 Gyr, adaptive Dopri8 rtol=atol=1e-7 dtmin=0.3, final state kept "
+                                   "(gen_stream_vmapped semantics), jax-threefry release draws",
+                       "particles_per_gpu": args.particles, "particle_steps_per_step": psteps, "parallelism": f"dp{world} (particles interleaved over ranks)",
+                       "l2": "512 MB buffer zeroed between timed iterations", "time_to_stream_ms": ms_total / args.steps},
+            "clocks": clocks, "gpu_launches": 5 * args.steps,
+            "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * float(te.item()) / args.steps, "call": "ssb_gen_stream_host (C ABI, pinned host buffers)"},
+            "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU (2 per stripping time)")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        from streamsculptor_b200 import parallel as par
+        par.init_from_env("nccl")
+    run_ours(args, rank, world)
+    if world > 1:
+        from streamsculptor_b200 import parallel as par
+        par.dist().destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

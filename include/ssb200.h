@@ -149,13 +149,15 @@ int ssb_release_spray_f64(const ssb_potential* pot, double G, int64_t N, const d
 /* A8  Potential.gen_stream_vmapped (main.py:343-368) as one enqueue: progenitor orbit at ts[Nts] (dense), release at
  * every ts[i], then 2 (Nts-1) independent solves from ts[i] to ts[Nts-1]; lead[Nts-1,6], trail[Nts-1,6].
  * pot_release: potential used by release_model (== pot for gen_stream_vmapped; the base potential for
- * gen_stream_vmapped_with_pert, streamhelpers.py:56-116).  Only particles [i_begin, i_end) are integrated (multi-GPU
- * sharding); outputs are indexed from i_begin.  scratch >= ssb_stream_scratch_bytes(). */
+ * gen_stream_vmapped_with_pert, streamhelpers.py:56-116).  Only the n_local particles i = i_begin + k*i_stride
+ * (k = 0..n_local-1, all < Nts-1) are integrated - interleaved multi-GPU sharding, every rank sees the same mix of
+ * integration spans; outputs are indexed by k.  scratch >= ssb_stream_scratch_bytes(). */
 int ssb_gen_stream_f64(const ssb_potential* pot, const ssb_potential* pot_release, double G, int64_t Nts,
                        const double* ts, const double* prog_w0 /*[6]*/, const double* Msat /*[Nts]*/, int64_t seed,
                        const double* kvals /*host[8]*/, const double* normals /*[Nts,4] or NULL*/, ssb_ctrl ctrl,
-                       int64_t i_begin, int64_t i_end, double* lead, double* trail, int32_t* status /*[2,(i_end-i_begin)]*/,
-                       int32_t* nsteps /*[2,(i_end-i_begin),3]*/, void* scratch, size_t scratch_bytes, void* stream);
+                       int64_t i_begin, int64_t i_stride, int64_t n_local, double* lead, double* trail,
+                       int32_t* status /*[2,n_local]*/, int32_t* nsteps /*[2,n_local,3]*/, void* scratch, size_t scratch_bytes,
+                       void* stream);
 size_t ssb_stream_scratch_bytes(int64_t Nts, int32_t max_steps);
 
 /* A12-A14  compute_perturbation_OTF (perturbative.py:101-135, 425-454, 726-755) with the field
@@ -177,8 +179,8 @@ int ssb_orbit_integrate_host(const ssb_potential* pot_hostptrs, int64_t N, const
                              double* ys, int32_t* status, int32_t* nsteps);
 int ssb_gen_stream_host(const ssb_potential* pot_hostptrs, const ssb_potential* pot_release_hostptrs, double G, int64_t Nts,
                         const double* ts, const double* prog_w0, const double* Msat, int64_t seed, const double* kvals,
-                        const double* normals, ssb_ctrl ctrl, int64_t i_begin, int64_t i_end, double* lead, double* trail,
-                        int32_t* status, int32_t* nsteps);
+                        const double* normals, ssb_ctrl ctrl, int64_t i_begin, int64_t i_stride, int64_t n_local, double* lead,
+                        double* trail, int32_t* status, int32_t* nsteps);
 int ssb_linear_response_host(const ssb_potential* pot_base_hostptrs, const ssb_subhalos* sh_hostptrs, int64_t N,
                              const double* w0, const double* D0, const double* t0, double t1, ssb_ctrl ctrl,
                              double* wout, double* Dout, int32_t* status, int32_t* nsteps);

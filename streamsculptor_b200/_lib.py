@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _OUT = os.path.join(_HERE, "_lib", "libssb200.so")
 _SOURCES = ["ssb_kernels.cu", "ssb_response.cu", "ssb_host.cu"]
-_HEADERS = ["ssb_common.cuh", "ssb_potential.cuh", "ssb_rk.cuh", "ssb_tableau.h", "../../include/ssb200.h"]
+_HEADERS = ["ssb_common.cuh", "ssb_potential.cuh", "ssb_rk.cuh", "ssb_fastmath.cuh", "ssb_tableau.h", "../../include/ssb200.h"]
 
 MAX_COMP, MAX_TRACK, MAX_SH = 12, 4, 2
 
@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.dirname(_OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr",
-           "-Xptxas", "-v" if verbose else "-O3", "-shared", "-Xcompiler", "-fPIC", "-o", _OUT] + srcs
+           "-Xptxas", "-v" if verbose else "-O3", "-shared", "-Xcompiler", "-fPIC", "-o", _OUT] + os.environ.get("SSB_NVCC_FLAGS", "").split() + srcs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise SSBError("nvcc failed:\n" + res.stdout + res.stderr)
@@ -82,14 +82,14 @@ _SIGNATURES = {
     "ssb_orbit_dense_f64": ([_PP, _dp, _dbl, _dbl, _dp, _i64, Ctrl, _dp, _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
     "ssb_scratch_bytes": ([_i32], C.c_size_t),
     "ssb_release_spray_f64": ([_PP, _dbl, _i64, _dp, _dp, _dp, _dp, _i64, C.POINTER(C.c_double), _dp, _dp, _dp, _dp, _dp, _dp], C.c_int),
-    "ssb_gen_stream_f64": ([_PP, _PP, _dbl, _i64, _dp, _dp, _dp, _i64, C.POINTER(C.c_double), _dp, Ctrl, _i64, _i64, _dp, _dp,
+    "ssb_gen_stream_f64": ([_PP, _PP, _dbl, _i64, _dp, _dp, _dp, _i64, C.POINTER(C.c_double), _dp, Ctrl, _i64, _i64, _i64, _dp, _dp,
                             _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
     "ssb_stream_scratch_bytes": ([_i64, _i32], C.c_size_t),
     "ssb_linear_response_f64": ([_PP, _SP, _i64, _dp, _dp, _dp, _dbl, Ctrl, _dp, _dp, _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
     "ssb_response_scratch_bytes": ([_i32], C.c_size_t),
     "ssb_response_term_f64": ([_PP, _SP, _dbl, _dp, _dp, _dp], C.c_int),
     "ssb_orbit_integrate_host": ([_PP, _i64, _dp, _dp, _dp, _dp, _i32, _i32, Ctrl, _dp, _dp, _dp], C.c_int),
-    "ssb_gen_stream_host": ([_PP, _PP, _dbl, _i64, _dp, _dp, _dp, _i64, C.POINTER(C.c_double), _dp, Ctrl, _i64, _i64, _dp, _dp,
+    "ssb_gen_stream_host": ([_PP, _PP, _dbl, _i64, _dp, _dp, _dp, _i64, C.POINTER(C.c_double), _dp, Ctrl, _i64, _i64, _i64, _dp, _dp,
                              _dp, _dp], C.c_int),
     "ssb_linear_response_host": ([_PP, _SP, _i64, _dp, _dp, _dp, _dbl, Ctrl, _dp, _dp, _dp, _dp], C.c_int),
     "ssb_fp64_peak_probe": ([C.c_int, C.POINTER(C.c_double), _dp], C.c_int),

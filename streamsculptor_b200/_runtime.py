@@ -245,21 +245,25 @@ def release_spray(pot, G, prog, Msat, idx, t, seed, kvals, normals):
     return outs
 
 
-def gen_stream(pot, pot_release, G, ts, prog_w0, Msat, seed, kvals, normals, ctrl, i_begin=None, i_end=None):
+def shard_count(n_particles, rank, world):
+    """Number of particles i = rank + k*world below n_particles (interleaved sharding)."""
+    return max(0, (n_particles - rank + world - 1) // world)
+
+
+def gen_stream(pot, pot_release, G, ts, prog_w0, Msat, seed, kvals, normals, ctrl, i_begin=0, i_stride=1, n_local=None):
     tt = torch()
     P, _k1 = lower(pot)
     PR, _k2 = lower(pot_release)
     Nts = ts.shape[0]
-    i_begin = 0 if i_begin is None else int(i_begin)
-    i_end = Nts - 1 if i_end is None else int(i_end)
-    n = i_end - i_begin
+    i_begin, i_stride = int(i_begin), int(i_stride)
+    n = shard_count(Nts - 1, i_begin, i_stride) if n_local is None else int(n_local)
     lead, trail = empty((n, 6)), empty((n, 6))
     status, nsteps = empty((2, n), tt.int32), empty((2, n, 3), tt.int32)
     nbytes = _lib.lib().ssb_stream_scratch_bytes(Nts, ctrl.max_steps)
     scratch = empty(((nbytes + 7) // 8,))
     kv = (C.c_double * 8)(*[float(k) for k in kvals])
     _lib.check(_lib.lib().ssb_gen_stream_f64(C.byref(P), C.byref(PR), float(G), Nts, ptr(ts), ptr(prog_w0), ptr(Msat), int(seed), kv, ptr(normals),
-                                             ctrl, i_begin, i_end, ptr(lead), ptr(trail), ptr(status), ptr(nsteps), ptr(scratch), nbytes,
+                                             ctrl, i_begin, i_stride, n, ptr(lead), ptr(trail), ptr(status), ptr(nsteps), ptr(scratch), nbytes,
                                              stream_ptr()))
     return lead, trail, status, nsteps
 

@@ -123,10 +123,10 @@ int ssb_orbit_integrate_host(const ssb_potential* pot_h, int64_t N, const double
 
 int ssb_gen_stream_host(const ssb_potential* pot_h, const ssb_potential* pot_release_h, double G, int64_t Nts, const double* ts,
                         const double* prog_w0, const double* Msat, int64_t seed, const double* kvals, const double* normals, ssb_ctrl ctrl,
-                        int64_t i_begin, int64_t i_end, double* lead, double* trail, int32_t* status, int32_t* nsteps) {
+                        int64_t i_begin, int64_t i_stride, int64_t n_local, double* lead, double* trail, int32_t* status, int32_t* nsteps) {
     if (Nts < 2 || !ts || !prog_w0 || !Msat || !kvals) return ssb_set_error(SSB_ERR_ARG, "gen_stream_host: NULL array or Nts < 2");
-    if (i_begin < 0 || i_end > Nts - 1 || i_begin > i_end) return ssb_set_error(SSB_ERR_ARG, "gen_stream_host: particle range outside [0, Nts-1]");
-    const size_t n = (size_t)(i_end - i_begin);
+    if (n_local < 0) return ssb_set_error(SSB_ERR_ARG, "gen_stream_host: negative n_local");
+    const size_t n = (size_t)n_local;
     if (n && (!lead || !trail || !status || !nsteps)) return ssb_set_error(SSB_ERR_ARG, "gen_stream_host: NULL output");
     cudaStream_t st = cudaStreamPerThread;
     Pool pool(st);
@@ -147,7 +147,7 @@ int ssb_gen_stream_host(const ssb_potential* pot_h, const ssb_potential* pot_rel
     const size_t sb = ssb_stream_scratch_bytes(Nts, ctrl.max_steps);
     if (int e = pool.alloc(&scr, sb)) return e;
     if (int e = ssb_gen_stream_f64(&pd, &prd, G, Nts, (const double*)dts, (const double*)dw0, (const double*)dms, seed, kvals,
-                                   (const double*)dnr, ctrl, i_begin, i_end, (double*)dl, (double*)dtr, (int32_t*)dstat, (int32_t*)dns, scr, sb, st)) return e;
+                                   (const double*)dnr, ctrl, i_begin, i_stride, n_local, (double*)dl, (double*)dtr, (int32_t*)dstat, (int32_t*)dns, scr, sb, st)) return e;
     if (int e = down(lead, dl, 48 * n, st)) return e;
     if (int e = down(trail, dtr, 48 * n, st)) return e;
     if (int e = down(status, dstat, 8 * n, st)) return e;

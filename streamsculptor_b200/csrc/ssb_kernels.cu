@@ -52,7 +52,9 @@ struct OrbitArgs {
 };
 
 // per-thread integration of one orbit; REC != nullptr records accepted steps (K0) instead of saving
-template <int SOLVER, bool RECORD>
+// MODE: 0 = SaveAt(ts) with dense output, 1 = RECORD accepted steps (K0), 2 = final state only (ts == t1; no dense-output
+// code in the instruction stream - the stream-generation hot path)
+template <int SOLVER, int MODE>
 __device__ __forceinline__ void integrate_one(const ssb_potential* P, const double* w0, double t0_in, double t1_in,
                                               const double* tsp, int M, double* ys, const CtrlDev& c, bool valid,
                                               int& status, int& n_steps, int& n_acc, int& n_rej, double* rec, int rec_cap) {
@@ -69,7 +71,7 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const doub
     if (valid) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) { x[k] = w0[k]; p[k] = dir * w0[3 + k]; }
-        if (!RECORD) {
+        if (MODE == 0) {
             const double inf = __longlong_as_double(0x7ff0000000000000LL);
             for (int m = 0; m < M; ++m)
 #pragma unroll
@@ -128,7 +130,7 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const doub
         if (keep) {
             n_acc++;
             if (!finite) { status = 2; continue; }
-            if (RECORD) {
+            if (MODE == 1) {
                 if (n_acc <= rec_cap) {
                     double* r = rec + (size_t)(n_acc - 1) * SSB_REC_STRIDE;
                     r[0] = tprev; r[1] = tnext;
@@ -139,7 +141,7 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const doub
 #pragma unroll
                         for (int k = 0; k < 3; ++k) r[14 + 3 * l + k] = F[l][k];
                 }
-            } else {
+            } else if (MODE == 0) {
                 // SaveAt(ts): every ts[save_idx] <= tnext is interpolated inside this accepted step
                 while (save_idx < M) {
                     const double tq = tsp[save_idx] * dir;
@@ -168,10 +170,16 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const doub
         if (tn > T1 - 1e-10) tn = keep ? T1 : tprev + 0.5 * (T1 - tprev);     // diffrax _clip_to_end (f64)
         tnext = tn;
     }
+    if (MODE == 2 && valid) {              // final state (or +inf if the end was not reached: diffrax leaves unsaved rows at inf)
+        const bool done = status == 0 && tprev >= T1 && T0 < T1;
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { ys[k] = done ? x[k] : inf; ys[3 + k] = done ? dir * p[k] : inf; }
+    }
 }
 
-template <int SOLVER>
-__global__ void __launch_bounds__(SSB_ORBIT_THREADS) orbit_kernel(const __grid_constant__ ssb_potential Pin, const OrbitArgs a) {
+template <int SOLVER, int MODE>
+__global__ void __launch_bounds__(SSB_ORBIT_THREADS, SSB_ORBIT_MIN_BLOCKS) orbit_kernel(const __grid_constant__ ssb_potential Pin, const OrbitArgs a) {
     __shared__ ssb_potential sP;
     stage_potential(&sP, &Pin);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,8 +187,8 @@ __global__ void __launch_bounds__(SSB_ORBIT_THREADS) orbit_kernel(const __grid_c
     const int64_t ii = valid ? i : 0;
     int status, n_steps, n_acc, n_rej;
     const double* tsp = a.ts + (a.ts_per_orbit ? ii * a.M : 0);
-    integrate_one<SOLVER, false>(&sP, a.w0 + ii * 6, a.t0[ii], a.t1[ii], tsp, a.M, a.ys + (size_t)ii * a.M * 6, a.c, valid,
-                                 status, n_steps, n_acc, n_rej, nullptr, 0);
+    integrate_one<SOLVER, MODE>(&sP, a.w0 + ii * 6, a.t0[ii], a.t1[ii], tsp, a.M, a.ys + (size_t)ii * a.M * 6, a.c, valid,
+                                status, n_steps, n_acc, n_rej, nullptr, 0);
     if (valid) {
         a.status[i] = status;
         a.nsteps[3 * i] = n_steps; a.nsteps[3 * i + 1] = n_acc; a.nsteps[3 * i + 2] = n_rej;
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(32) dense_step_kernel(const __grid_constant__ 
     if (t0p) { t0 = *t0p; t1 = *t1p; }              // interval ends read on the device (no host round trip in gen_stream)
     const bool valid = threadIdx.x == 0;
     int status, n_steps, n_acc, n_rej;
-    integrate_one<SOLVER, true>(&sP, w0, t0, t1, nullptr, 0, nullptr, c, valid, status, n_steps, n_acc, n_rej, scratch + 8, rec_cap);
+    integrate_one<SOLVER, 1>(&sP, w0, t0, t1, nullptr, 0, nullptr, c, valid, status, n_steps, n_acc, n_rej, scratch + 8, rec_cap);
     if (valid) {
         scratch[0] = (double)min(n_acc, rec_cap); scratch[1] = (double)status; scratch[4] = (t0 < t1) ? 1.0 : -1.0;
         if (status_out) *status_out = status;
@@ -406,12 +414,12 @@ __global__ void release_kernel(const __grid_constant__ ssb_potential Pin, const 
 }
 
 // gather the [i_begin, i_end) slice of the packed release output into the orbit-kernel input of the stream
-__global__ void stream_pack_kernel(int64_t Nts, int64_t i_begin, int64_t n, const double* w0_packed, const double* ts,
+__global__ void stream_pack_kernel(int64_t Nts, int64_t i_begin, int64_t i_stride, int64_t n, const double* w0_packed, const double* ts,
                                    double* w0, double* t0, double* t1) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= 2 * n) return;
     const int arm = j >= n;
-    const int64_t i = i_begin + (arm ? j - n : j);
+    const int64_t i = i_begin + (arm ? j - n : j) * i_stride;
     const double* src = w0_packed + 6 * ((int64_t)arm * Nts + i);
     for (int k = 0; k < 6; ++k) w0[6 * j + k] = src[k];
     t0[j] = ts[i];
@@ -558,8 +566,10 @@ int ssb_orbit_integrate_f64(const ssb_potential* pot, int64_t N, const double* w
     a.N = N; a.w0 = w0; a.t0 = t0; a.t1 = t1; a.ts = ts; a.M = M; a.ts_per_orbit = ts_per_orbit; a.ys = ys; a.status = status; a.nsteps = nsteps;
     a.c = to_dev(ctrl);
     const unsigned grid = nblk(N, SSB_ORBIT_THREADS);
-    if (ctrl.solver == 5) orbit_kernel<5><<<grid, SSB_ORBIT_THREADS, 0, (cudaStream_t)stream>>>(*pot, a);
-    else orbit_kernel<8><<<grid, SSB_ORBIT_THREADS, 0, (cudaStream_t)stream>>>(*pot, a);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool final_only = (M == 1 && ts_per_orbit && ts == t1);     // ts aliases t1: keep the final state, no dense output
+    if (ctrl.solver == 5) { if (final_only) orbit_kernel<5, 2><<<grid, SSB_ORBIT_THREADS, 0, st>>>(*pot, a); else orbit_kernel<5, 0><<<grid, SSB_ORBIT_THREADS, 0, st>>>(*pot, a); }
+    else { if (final_only) orbit_kernel<8, 2><<<grid, SSB_ORBIT_THREADS, 0, st>>>(*pot, a); else orbit_kernel<8, 0><<<grid, SSB_ORBIT_THREADS, 0, st>>>(*pot, a); }
     CKL("orbit_kernel");
     return 0;
 }
@@ -616,15 +626,16 @@ size_t ssb_stream_scratch_bytes(int64_t Nts, int32_t max_steps) {
 }
 
 int ssb_gen_stream_f64(const ssb_potential* pot, const ssb_potential* pot_release, double G, int64_t Nts, const double* ts, const double* prog_w0,
-                       const double* Msat, int64_t seed, const double* kvals, const double* normals, ssb_ctrl ctrl, int64_t i_begin, int64_t i_end,
-                       double* lead, double* trail, int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream) {
+                       const double* Msat, int64_t seed, const double* kvals, const double* normals, ssb_ctrl ctrl, int64_t i_begin, int64_t i_stride,
+                       int64_t n_local, double* lead, double* trail, int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream) {
     if (int e = ssb_validate_potential(pot)) return e;
     if (int e = ssb_validate_potential(pot_release)) return e;
     if (int e = ssb_validate_ctrl(ctrl)) return e;
     if (Nts < 2 || !ts || !prog_w0 || !Msat || !kvals || !scratch) return ssb_set_error(SSB_ERR_ARG, "gen_stream: NULL array or Nts < 2");
-    if (i_begin < 0 || i_end > Nts - 1 || i_begin > i_end) return ssb_set_error(SSB_ERR_ARG, "gen_stream: particle range outside [0, Nts-1]");
+    if (i_begin < 0 || i_stride < 1 || n_local < 0 || (n_local > 0 && i_begin + (n_local - 1) * i_stride > Nts - 2))
+        return ssb_set_error(SSB_ERR_ARG, "gen_stream: particle selection outside [0, Nts-1)");
     if (scratch_bytes < ssb_stream_scratch_bytes(Nts, ctrl.max_steps)) return ssb_set_error(SSB_ERR_SCRATCH, "gen_stream: scratch too small");
-    const int64_t n = i_end - i_begin;
+    const int64_t n = n_local;
     if (n > 0 && (!lead || !trail || !status || !nsteps)) return ssb_set_error(SSB_ERR_ARG, "gen_stream: NULL output");
     cudaStream_t st = (cudaStream_t)stream;
     double* dense = (double*)scratch;
@@ -648,7 +659,7 @@ int ssb_gen_stream_f64(const ssb_potential* pot, const ssb_potential* pot_releas
     CKL("release_kernel");
     if (n == 0) return 0;
     // (3) 2n independent solves from ts[i] to ts[-1], keep the final state (main.py:349-368)
-    stream_pack_kernel<<<nblk(2 * n, 128), 128, 0, st>>>(Nts, i_begin, n, w0p, ts, w0, t0, t1);
+    stream_pack_kernel<<<nblk(2 * n, 128), 128, 0, st>>>(Nts, i_begin, i_stride, n, w0p, ts, w0, t0, t1);
     CKL("stream_pack_kernel");
     if (int e = ssb_orbit_integrate_f64(pot, 2 * n, w0, t0, t1, t1, 1, 1, ctrl, ys, status, nsteps, stream)) return e;
     CK(cudaMemcpyAsync(lead, ys, sizeof(double) * 6 * n, cudaMemcpyDeviceToDevice, st));

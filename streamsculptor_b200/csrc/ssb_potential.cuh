@@ -10,6 +10,7 @@
 #include <math.h>
 
 #include "../../include/ssb200.h"
+#include "ssb_fastmath.cuh"
 
 namespace ssb {
 
@@ -90,9 +91,9 @@ __device__ __forceinline__ void add_spherical(const double x[3], double phi, dou
 //   q' = GM [3/(r^3 (r+rs)) - 3u/r^4 + 1/(r^2 (r+rs)^2)],   w = q'/r
 template <int MODE>
 __device__ __forceinline__ void nfw_terms(double GM, double rs, double r2, double& phi, double& q, double& w) {
-    const double ir = rsqrt(r2), r = r2 * ir;
-    const double u = log1p(r / rs);
-    const double irs = 1.0 / (r + rs);
+    const double ir = frsqrt(r2), r = r2 * ir;
+    const double u = flog1p_pos(r * frcp(rs));
+    const double irs = frcp(r + rs);
     const double ir2 = ir * ir;
     if (MODE & WANT_PHI) phi = -GM * u * ir;
     const double a = u * ir;                       // u/r
@@ -104,8 +105,8 @@ __device__ __forceinline__ void nfw_terms(double GM, double rs, double r2, doubl
 //   q = GM / ((r+a)^2 r),  dq/dr = -GM [2/((r+a)^3 r) + 1/((r+a)^2 r^2)],  w = (dq/dr)/r
 template <int MODE>
 __device__ __forceinline__ void hernquist_terms(double GM, double a, double r2soft, double& phi, double& q, double& w) {
-    const double ir = rsqrt(r2soft), r = r2soft * ir;
-    const double ira = 1.0 / (r + a);
+    const double ir = frsqrt(r2soft), r = r2soft * ir;
+    const double ira = frcp(r + a);
     if (MODE & WANT_PHI) phi = -GM * ira;
     q = GM * ira * ira * ir;
     if (MODE & WANT_HESS) w = -q * ir * (2.0 * ira + ir);
@@ -114,7 +115,7 @@ __device__ __forceinline__ void hernquist_terms(double GM, double a, double r2so
 // Plummer (potential.py:128-130): Phi = -GM (r^2+a^2)^(-1/2);  q = GM s^3, w = -3 GM s^5, s = (r^2+a^2)^(-1/2)
 template <int MODE>
 __device__ __forceinline__ void plummer_terms(double GM, double a, double r2, double& phi, double& q, double& w) {
-    const double s = rsqrt(fma(a, a, r2));
+    const double s = frsqrt(fma(a, a, r2));
     const double s2 = s * s;
     if (MODE & WANT_PHI) phi = -GM * s;
     q = GM * s * s2;
@@ -131,14 +132,14 @@ __device__ __forceinline__ void isochrone_terms(double GM, double a, double r2, 
 //   returns psi = dPhi/dr_s and qd with grad(psi) = qd * x
 __device__ __forceinline__ void profile_dradius(int profile, double GM, double a, double r2, double& psi, double& qd) {
     if (profile == SSB_PROFILE_PLUMMER) {            // psi = GM a s^3, grad = -3 GM a s^5 x
-        const double s = rsqrt(fma(a, a, r2)), s2 = s * s;
+        const double s = frsqrt(fma(a, a, r2)), s2 = s * s;
         psi = GM * a * s * s2; qd = -3.0 * psi * s2;
     } else if (profile == SSB_PROFILE_HERNQUIST) {   // psi = GM/(r+a)^2, grad = -2 GM/((r+a)^3 r) x
-        const double ir = rsqrt(r2), r = r2 * ir, ira = 1.0 / (r + a);
+        const double ir = frsqrt(r2), r = r2 * ir, ira = frcp(r + a);
         psi = GM * ira * ira; qd = -2.0 * psi * ira * ir;
     } else {                                         // NFW: psi = GM/(a (a+r)), grad = -GM/(a (a+r)^2 r) x
-        const double ir = rsqrt(r2), r = r2 * ir, ira = 1.0 / (r + a);
-        psi = GM * ira / a; qd = -psi * ira * ir;
+        const double ir = frsqrt(r2), r = r2 * ir, ira = frcp(r + a);
+        psi = GM * ira * frcp(a); qd = -psi * ira * ir;
     }
 }
 template <int MODE>
@@ -152,10 +153,10 @@ __device__ __forceinline__ void profile_terms(int profile, double GM, double a, 
 template <int MODE>
 __device__ __forceinline__ void add_miyamoto(double GM, double a, double b, const double x[3], double& P, double g[3], Sym3& H) {
     const double zb2 = fma(x[2], x[2], b * b);
-    const double iz = rsqrt(zb2), zeta = zb2 * iz;
+    const double iz = frsqrt(zb2), zeta = zb2 * iz;
     const double az = a + zeta;
     const double D = fma(x[0], x[0], fma(x[1], x[1], az * az));
-    const double id = rsqrt(D), id2 = id * id, id3 = id * id2;
+    const double id = frsqrt(D), id2 = id * id, id3 = id * id2;
     const double s = az * iz;                                       // (a+zeta)/zeta
     const double q = GM * id3;
     if (MODE & WANT_PHI) P -= GM * id;
@@ -237,7 +238,7 @@ __device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x
                 add_miyamoto<MODE>(c.p[0], c.p[1], c.p[2], xs, P, g, H);
                 break;
             case SSB_TRIAXNFW: {                                    // potential.py:94: x_i / q_i
-                const double i1 = 1.0 / c.p[2], i2 = 1.0 / c.p[3], i3 = 1.0 / c.p[4];
+                const double i1 = frcp(c.p[2]), i2 = frcp(c.p[3]), i3 = frcp(c.p[4]);
                 const double xq[3] = {xs[0] * i1, xs[1] * i2, xs[2] * i3};
                 const double r2 = fma(xq[0], xq[0], fma(xq[1], xq[1], xq[2] * xq[2]));
                 nfw_terms<MODE>(c.p[0], c.p[1], r2, phi, q, w);

@@ -17,6 +17,7 @@
 
 #define SSB_TABLEAU_QUAL static __device__ constexpr
 #include "ssb_tableau.h"
+#include "ssb_fastmath.cuh"
 
 namespace ssb {
 
@@ -171,7 +172,7 @@ __device__ __forceinline__ double err_sq6(const double x[3], const double p[3], 
         const double xc = nan_cand ? x[k] : x1[k], pc = nan_cand ? p[k] : p1[k];
         const double sx = fma(rtol, fmax(fabs(x[k]), fabs(xc)), atol);
         const double sp = fma(rtol, fmax(fabs(p[k]), fabs(pc)), atol);
-        const double qx = ex[k] / sx, qp = ep[k] / sp;
+        const double qx = ex[k] * frcp(sx), qp = ep[k] * frcp(sp);
         acc = fma(qx, qx, acc); acc = fma(qp, qp, acc);
     }
     return acc;
@@ -181,7 +182,7 @@ __device__ __forceinline__ double err_sq6(const double x[3], const double p[3], 
 template <int ORDER>
 __device__ __forceinline__ bool pid_update(double err, double dt, const CtrlDev& c, bool& at_dtmin, double& h_next, bool& bad) {
     const bool keep = (err < 1.0) || at_dtmin;
-    double factor = 0.9 * pow(1.0 / err, 1.0 / ORDER);
+    double factor = 0.9 * inv_root<ORDER>(err);
     bad = isnan(factor);
     factor = fmin(fmax(factor, keep ? 1.0 : 0.2), 10.0);
     double hn = fmin(dt * factor, c.dtmax);

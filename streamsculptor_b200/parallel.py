@@ -1,0 +1,86 @@
+"""Multi-GPU data parallelism for the hot path: one process per GPU, particles sharded, no data-path collective.
+
+The reference is single-device (no pmap / shard_map / NCCL call sites); particles are fully
+independent (main.py:343-368), so the stream shards trivially.  Particle i goes to rank i % world (interleaved: every
+rank sees the same mix of integration spans ts[-1] - ts[i], which a contiguous split would not give).  NCCL over NVLink is
+used only for the final gather of the (N, 6) stream (48 MB at 1e6 particles) and for summing response summaries.
+"""
+import os
+
+import numpy as np
+
+
+def dist():
+    import torch.distributed as d
+    return d
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from RANK / WORLD_SIZE / MASTER_* (torchrun).  Returns (rank, world)."""
+    import torch
+    d = dist()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1 and not d.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        d.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world
+
+
+def shard_indices(n, rank, world):
+    """Indices of the units owned by `rank` under interleaved sharding."""
+    return np.arange(rank, n, world)
+
+
+def shard_count(n, rank, world):
+    return max(0, (n - rank + world - 1) // world)
+
+
+def gather_interleaved(local, n_total, rank, world, group=None):
+    """All-gather per-rank shards (rows k <-> global index rank + k*world) into the global [n_total, ...] order.
+    `local` is a torch tensor on the device the process group works on."""
+    import torch
+    if world == 1:
+        return local
+    d = dist()
+    n_max = shard_count(n_total, 0, world)
+    pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    d.all_gather(bufs, pad, group=group)
+    out = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        out[r::world] = bufs[r][: shard_count(n_total, r, world)]
+    return out
+
+
+def gen_stream_sharded(pot, ts, prog_w0, Msat, seed_num, solver, rank, world, kval_arr=1.0, rtol=1e-7, atol=1e-7, dtmin=0.3, dtmax=None,
+                       max_steps=10_000, normals=None, gather=True, compute=None, group=None):
+    """gen_stream_vmapped (main.py:343-368) over `world` ranks.  Every rank recomputes the (cheap, serial) progenitor
+    orbit and release, integrates its interleaved share of the particles, and the shares are all-gathered.
+
+    compute(i_begin, i_stride, n_local) -> (lead[n_local,6], trail[n_local,6]) may be injected (CPU/gloo tests run the
+    host logic with the oracle standing in for the CUDA call)."""
+    n = len(ts) - 1
+    n_local = shard_count(n, rank, world)
+    if compute is None:
+        from . import _runtime as rt
+        ts_d, w0_d, Ms, kv, nr = pot._stream_inputs(ts, prog_w0, Msat, kval_arr, normals)
+        ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
+        lead, trail, status, nsteps = rt.gen_stream(pot, pot, pot._G, ts_d, w0_d, Ms, 0 if seed_num is None else int(seed_num), kv, nr, ctrl,
+                                                    i_begin=rank, i_stride=world, n_local=n_local)
+    else:
+        lead, trail = compute(rank, world, n_local)
+    if not gather:
+        return lead, trail
+    return gather_interleaved(lead, n, rank, world, group), gather_interleaved(trail, n, rank, world, group)
+
+
+def allreduce_sum(t, world, group=None):
+    """Sum of per-rank response summaries (e.g. sum_sh M_sh D[:, sh, :6] binned along the stream)."""
+    if world > 1:
+        dist().all_reduce(t, group=group)
+    return t
