@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
         return _OUT
     os.makedirs(os.path.dirname(_OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr",
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr", "--threads", "0", "-split-compile", "0",
            "-Xptxas", "-v" if verbose else "-O3", "-shared", "-Xcompiler", "-fPIC", "-o", _OUT] + os.environ.get("SSB_NVCC_FLAGS", "").split() + srcs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

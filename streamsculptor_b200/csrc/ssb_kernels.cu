@@ -23,19 +23,34 @@ using namespace ssb;
 // =============================================================================================
 // The force is a real function call (not inlined 13x into the unrolled stepper): the stepper body stays inside
 // the instruction cache and ptxas allocates the stage registers once.
-__device__ __noinline__ double3 accel_call(const ssb_potential* P, double x, double y, double z, double t) {
+__device__ __noinline__ double3 accel_call(const ssb_potential* P, int first, double x, double y, double z, double t) {
     const double X[3] = {x, y, z};
     double phi, g[3];
     Sym3 H;
-    pot_eval<WANT_GRAD>(*P, X, t, phi, g, H);
+    pot_eval<WANT_GRAD>(*P, X, t, phi, g, H, first);
     return make_double3(-g[0], -g[1], -g[2]);
 }
-struct OrbitForce {                      // Potential.velocity_acceleration (main.py:116-120) in mirrored time
-    const ssb_potential* P;
+// Potential.velocity_acceleration (main.py:116-120) in mirrored time.  SIG != 0: the leading NF components are a fused
+// static signature evaluated inline from the constant bank (Pc); any remaining components go through the interpreter (P).
+template <int SIG>
+struct OrbitForce {
+    const ssb_potential* P;      // shared-memory copy (dynamic indexing)
+    const ssb_potential* Pc;     // kernel parameter (constant bank)
     double dir;
+    bool extra;                  // components beyond the fused ones exist
     __device__ __forceinline__ void operator()(const double X[3], double tau, double A[3]) const {
-        const double3 a = accel_call(P, X[0], X[1], X[2], tau * dir);
-        A[0] = a.x; A[1] = a.y; A[2] = a.z;
+        if (SIG == SIG_GENERIC) {
+            const double3 a = accel_call(P, 0, X[0], X[1], X[2], tau * dir);
+            A[0] = a.x; A[1] = a.y; A[2] = a.z;
+        } else {
+            double g[3];
+            fused_grad<SIG>(*Pc, X, g);
+            A[0] = -g[0]; A[1] = -g[1]; A[2] = -g[2];
+            if (extra) {
+                const double3 a = accel_call(P, SigInfo<SIG>::NF, X[0], X[1], X[2], tau * dir);
+                A[0] += a.x; A[1] += a.y; A[2] += a.z;
+            }
+        }
     }
 };
 
@@ -54,15 +69,15 @@ struct OrbitArgs {
 // per-thread integration of one orbit; REC != nullptr records accepted steps (K0) instead of saving
 // MODE: 0 = SaveAt(ts) with dense output, 1 = RECORD accepted steps (K0), 2 = final state only (ts == t1; no dense-output
 // code in the instruction stream - the stream-generation hot path)
-template <int SOLVER, int MODE>
-__device__ __forceinline__ void integrate_one(const ssb_potential* P, const double* w0, double t0_in, double t1_in,
+template <int SOLVER, int MODE, int SIG>
+__device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_potential* Pc, const double* w0, double t0_in, double t1_in,
                                               const double* tsp, int M, double* ys, const CtrlDev& c, bool valid,
                                               int& status, int& n_steps, int& n_acc, int& n_rej, double* rec, int rec_cap) {
     typedef Tab<SOLVER> T;
     constexpr int S = T::S;
     const double dir = (t0_in < t1_in) ? 1.0 : -1.0;              // diffrax: direction = where(t0 < t1, 1, -1)
     const double T0 = t0_in * dir, T1 = t1_in * dir;
-    OrbitForce force{P, dir};
+    OrbitForce<SIG> force{P, Pc, dir, Pc->n_comp > SigInfo<SIG>::NF};
     double x[3], p[3], F[S][3];
     status = 0; n_steps = 0; n_acc = 0; n_rej = 0;
     double tprev = T0, tnext = T0, h = 0.0;
@@ -178,7 +193,7 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const doub
     }
 }
 
-template <int SOLVER, int MODE>
+template <int SOLVER, int MODE, int SIG>
 __global__ void __launch_bounds__(SSB_ORBIT_THREADS, SSB_ORBIT_MIN_BLOCKS) orbit_kernel(const __grid_constant__ ssb_potential Pin, const OrbitArgs a) {
     __shared__ ssb_potential sP;
     stage_potential(&sP, &Pin);
@@ -187,8 +202,8 @@ __global__ void __launch_bounds__(SSB_ORBIT_THREADS, SSB_ORBIT_MIN_BLOCKS) orbit
     const int64_t ii = valid ? i : 0;
     int status, n_steps, n_acc, n_rej;
     const double* tsp = a.ts + (a.ts_per_orbit ? ii * a.M : 0);
-    integrate_one<SOLVER, MODE>(&sP, a.w0 + ii * 6, a.t0[ii], a.t1[ii], tsp, a.M, a.ys + (size_t)ii * a.M * 6, a.c, valid,
-                                status, n_steps, n_acc, n_rej, nullptr, 0);
+    integrate_one<SOLVER, MODE, SIG>(&sP, &Pin, a.w0 + ii * 6, a.t0[ii], a.t1[ii], tsp, a.M, a.ys + (size_t)ii * a.M * 6, a.c, valid,
+                                     status, n_steps, n_acc, n_rej, nullptr, 0);
     if (valid) {
         a.status[i] = status;
         a.nsteps[3 * i] = n_steps; a.nsteps[3 * i + 1] = n_acc; a.nsteps[3 * i + 2] = n_rej;
@@ -199,7 +214,7 @@ __global__ void __launch_bounds__(SSB_ORBIT_THREADS, SSB_ORBIT_MIN_BLOCKS) orbit
 // K0: one orbit with dense output at M save times (progenitor at all stripping times, main.py:289)
 //   scratch layout: hdr[8] doubles {n_acc, status, n_steps, n_rej, dir}, then rec[max_steps][SSB_REC_STRIDE]
 // =============================================================================================
-template <int SOLVER>
+template <int SOLVER, int SIG>
 __global__ void __launch_bounds__(32) dense_step_kernel(const __grid_constant__ ssb_potential Pin, const double* w0, double t0, double t1,
                                                         const double* t0p, const double* t1p, CtrlDev c, double* scratch, int rec_cap,
                                                         int32_t* status_out, int32_t* nsteps_out) {
@@ -208,7 +223,7 @@ __global__ void __launch_bounds__(32) dense_step_kernel(const __grid_constant__ 
     if (t0p) { t0 = *t0p; t1 = *t1p; }              // interval ends read on the device (no host round trip in gen_stream)
     const bool valid = threadIdx.x == 0;
     int status, n_steps, n_acc, n_rej;
-    integrate_one<SOLVER, 1>(&sP, w0, t0, t1, nullptr, 0, nullptr, c, valid, status, n_steps, n_acc, n_rej, scratch + 8, rec_cap);
+    integrate_one<SOLVER, 1, SIG>(&sP, &Pin, w0, t0, t1, nullptr, 0, nullptr, c, valid, status, n_steps, n_acc, n_rej, scratch + 8, rec_cap);
     if (valid) {
         scratch[0] = (double)min(n_acc, rec_cap); scratch[1] = (double)status; scratch[4] = (t0 < t1) ? 1.0 : -1.0;
         if (status_out) *status_out = status;
@@ -484,6 +499,32 @@ int ssb_validate_ctrl(const ssb_ctrl& c) {
     if (!(c.rtol >= 0) || !(c.atol >= 0) || !(c.dtmin >= 0) || c.max_steps < 0) return ssb_set_error(SSB_ERR_ARG, "ctrl: negative tolerance / dtmin / max_steps");
     return 0;
 }
+// Move a fused static signature to the front of the program (summation order is free) and fill its derived constants.
+// Returns the signature id; `out` is the program the kernels receive.
+static int ssb_canonicalize(const ssb_potential* in, ssb_potential* out) {
+    *out = *in;
+    int idx_n = -1, idx_m = -1, idx_h[2] = {-1, -1}, nh = 0, nn = 0, nm = 0;
+    for (int i = 0; i < in->n_comp; ++i) {
+        const ssb_component& c = in->comp[i];
+        if (c.track >= 0) continue;
+        if (c.type == SSB_NFW) { if (nn++ == 0) idx_n = i; }
+        else if (c.type == SSB_HERNQUIST && c.p[2] == 0.0) { if (nh < 2) idx_h[nh] = i; nh++; }
+        else if (c.type == SSB_MIYAMOTO) { if (nm++ == 0) idx_m = i; }
+    }
+    int sig = SIG_GENERIC, order[4], nf = 0;
+    if (nn >= 1 && nh >= 2 && nm >= 1) { sig = SIG_NHHM; order[0] = idx_n; order[1] = idx_h[0]; order[2] = idx_h[1]; order[3] = idx_m; nf = 4; }
+    else if (nn >= 1 && nh >= 1 && nm >= 1) { sig = SIG_NHM; order[0] = idx_n; order[1] = idx_h[0]; order[2] = idx_m; nf = 3; }
+    else if (nn >= 1) { sig = SIG_N; order[0] = idx_n; nf = 1; }
+    if (sig == SIG_GENERIC) return sig;
+    bool used[SSB_MAX_COMP] = {false};
+    int k = 0;
+    for (int j = 0; j < nf; ++j) { out->comp[k++] = in->comp[order[j]]; used[order[j]] = true; }
+    for (int i = 0; i < in->n_comp; ++i) if (!used[i]) out->comp[k++] = in->comp[i];
+    out->comp[0].p[2] = 1.0 / out->comp[0].p[1];                               // NFW: 1 / r_s
+    if (nf >= 3) out->comp[nf - 1].p[3] = out->comp[nf - 1].p[2] * out->comp[nf - 1].p[2];   // Miyamoto-Nagai: b^2
+    return sig;
+}
+
 static CtrlDev to_dev(const ssb_ctrl& c) { CtrlDev d; d.rtol = c.rtol; d.atol = c.atol; d.dtmin = c.dtmin; d.dtmax = c.dtmax; d.max_steps = c.max_steps; return d; }
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
@@ -568,8 +609,13 @@ int ssb_orbit_integrate_f64(const ssb_potential* pot, int64_t N, const double* w
     const unsigned grid = nblk(N, SSB_ORBIT_THREADS);
     cudaStream_t st = (cudaStream_t)stream;
     const bool final_only = (M == 1 && ts_per_orbit && ts == t1);     // ts aliases t1: keep the final state, no dense output
-    if (ctrl.solver == 5) { if (final_only) orbit_kernel<5, 2><<<grid, SSB_ORBIT_THREADS, 0, st>>>(*pot, a); else orbit_kernel<5, 0><<<grid, SSB_ORBIT_THREADS, 0, st>>>(*pot, a); }
-    else { if (final_only) orbit_kernel<8, 2><<<grid, SSB_ORBIT_THREADS, 0, st>>>(*pot, a); else orbit_kernel<8, 0><<<grid, SSB_ORBIT_THREADS, 0, st>>>(*pot, a); }
+    ssb_potential pc;
+    const int sig = ssb_canonicalize(pot, &pc);
+#define SSB_LAUNCH_ORBIT(S, MD, SG) orbit_kernel<S, MD, SG><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a)
+#define SSB_LAUNCH_SIG(S, MD) do { switch (sig) { case SIG_N: SSB_LAUNCH_ORBIT(S, MD, SIG_N); break; case SIG_NHM: SSB_LAUNCH_ORBIT(S, MD, SIG_NHM); break; \
+        case SIG_NHHM: SSB_LAUNCH_ORBIT(S, MD, SIG_NHHM); break; default: SSB_LAUNCH_ORBIT(S, MD, SIG_GENERIC); } } while (0)
+    if (ctrl.solver == 5) { if (final_only) SSB_LAUNCH_SIG(5, 2); else SSB_LAUNCH_SIG(5, 0); }
+    else { if (final_only) SSB_LAUNCH_SIG(8, 2); else SSB_LAUNCH_SIG(8, 0); }
     CKL("orbit_kernel");
     return 0;
 }
@@ -580,8 +626,12 @@ static int dense_launch(const ssb_potential* pot, const double* w0, double t0, d
                         const double* ts, int64_t M, const ssb_ctrl& ctrl, double* ys, int32_t* status, int32_t* nsteps, double* scratch,
                         cudaStream_t st) {
     const CtrlDev c = to_dev(ctrl);
-    if (ctrl.solver == 5) dense_step_kernel<5><<<1, 32, 0, st>>>(*pot, w0, t0, t1, t0p, t1p, c, scratch, ctrl.max_steps, status, nsteps);
-    else dense_step_kernel<8><<<1, 32, 0, st>>>(*pot, w0, t0, t1, t0p, t1p, c, scratch, ctrl.max_steps, status, nsteps);
+    ssb_potential pc;
+    const int sig = ssb_canonicalize(pot, &pc);
+#define SSB_LAUNCH_DENSE(S, SG) dense_step_kernel<S, SG><<<1, 32, 0, st>>>(pc, w0, t0, t1, t0p, t1p, c, scratch, ctrl.max_steps, status, nsteps)
+#define SSB_LAUNCH_DENSE_SIG(S) do { switch (sig) { case SIG_N: SSB_LAUNCH_DENSE(S, SIG_N); break; case SIG_NHM: SSB_LAUNCH_DENSE(S, SIG_NHM); break; \
+        case SIG_NHHM: SSB_LAUNCH_DENSE(S, SIG_NHHM); break; default: SSB_LAUNCH_DENSE(S, SIG_GENERIC); } } while (0)
+    if (ctrl.solver == 5) SSB_LAUNCH_DENSE_SIG(5); else SSB_LAUNCH_DENSE_SIG(8);
     CKL("dense_step_kernel");
     if (M > 0) {
         if (ctrl.solver == 5) dense_eval_kernel<5><<<nblk(M, 128), 128, 0, st>>>(scratch, ts, M, ys);

@@ -190,12 +190,12 @@ __device__ __forceinline__ void add_subhalos(const ssb_subhalos& S, const double
 // total field: sum over the program (Potential_Combine.gradient_func, potential.py:1291-1296)
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
-__device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x[3], double t, double& P, double g[3], Sym3& H) {
+__device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x[3], double t, double& P, double g[3], Sym3& H, int first = 0) {
     if (MODE & WANT_PHI) P = 0.0;
     if (MODE & WANT_GRAD) { g[0] = g[1] = g[2] = 0.0; }
     if (MODE & WANT_HESS) { H.xx = H.yy = H.zz = H.xy = H.xz = H.yz = 0.0; }
     const int nc = Pt.n_comp;
-    for (int ic = 0; ic < nc; ++ic) {
+    for (int ic = first; ic < nc; ++ic) {
         const ssb_component& c = Pt.comp[ic];
         const int type = c.type;
         if (type == SSB_UNIFORM_ACC) {                              // potential.py:497-499
@@ -254,6 +254,46 @@ __device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x
                 break;
             default: break;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused static signatures: the reference's canonical galaxy models evaluated without the interpreter.
+// The host (ssb_canonicalize) moves the matching static components to the front of the program in the order below
+// and stores two derived constants (NFW p[2] = 1/r_s, Miyamoto p[3] = b^2); parameters are read straight from the
+// kernel-parameter constant bank (compile-time offsets), the radius is shared by the spherical terms.
+//   SIG_N    : [NFW]                                    (tests.ipynb's pot_NFW)
+//   SIG_NHM  : [NFW, Hernquist, Miyamoto]               (MW3: MW_LMC_Potential's Milky Way, BASELINE configs C1-C4)
+//   SIG_NHHM : [NFW, Hernquist, Hernquist, Miyamoto]    (GalaMilkyWayPotential, potential.py:390-418)
+// ---------------------------------------------------------------------------------------------
+enum { SIG_GENERIC = 0, SIG_N = 1, SIG_NHM = 2, SIG_NHHM = 3 };
+template <int SIG> struct SigInfo { static constexpr int NF = SIG == SIG_N ? 1 : SIG == SIG_NHM ? 3 : SIG == SIG_NHHM ? 4 : 0; };
+
+template <int SIG>
+__device__ __forceinline__ void fused_grad(const ssb_potential& P, const double x[3], double g[3]) {
+    const double r2 = fma(x[0], x[0], fma(x[1], x[1], x[2] * x[2]));
+    const double ir = frsqrt(r2), r = r2 * ir, ir2 = ir * ir;
+    // NFW (comp 0)
+    const double u = flog1p_pos(r * P.comp[0].p[2]);
+    double q = P.comp[0].p[0] * fma(u, ir, -frcp(r + P.comp[0].p[1])) * ir2;
+    if (SIG >= SIG_NHM) {                         // Hernquist (comp 1), soft == 0 guaranteed by the host
+        const double ira = frcp(r + P.comp[1].p[1]);
+        q = fma(P.comp[1].p[0] * ira, ira * ir, q);
+    }
+    if (SIG >= SIG_NHHM) {                        // second Hernquist (comp 2)
+        const double ira = frcp(r + P.comp[2].p[1]);
+        q = fma(P.comp[2].p[0] * ira, ira * ir, q);
+    }
+    g[0] = q * x[0]; g[1] = q * x[1]; g[2] = q * x[2];
+    if (SIG >= SIG_NHM) {                         // Miyamoto-Nagai (last fused comp)
+        constexpr int M = SigInfo<SIG>::NF - 1;
+        const double zb2 = fma(x[2], x[2], P.comp[M].p[3]);
+        const double iz = frsqrt(zb2);
+        const double az = fma(zb2, iz, P.comp[M].p[1]);
+        const double D = fma(x[0], x[0], fma(x[1], x[1], az * az));
+        const double id = frsqrt(D);
+        const double qm = P.comp[M].p[0] * id * id * id;
+        g[0] = fma(qm, x[0], g[0]); g[1] = fma(qm, x[1], g[1]); g[2] = fma(qm * az * iz, x[2], g[2]);
     }
 }
 
