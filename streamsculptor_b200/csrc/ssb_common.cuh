@@ -12,6 +12,9 @@
 #ifndef SSB_ORBIT_MIN_BLOCKS
 #define SSB_ORBIT_MIN_BLOCKS 3
 #endif
+#ifndef SSB_FUSED_INLINE
+#define SSB_FUSED_INLINE 1
+#endif
 #define SSB_REC_STRIDE 64   // doubles per recorded step: ta, tb, x, p, x1, p1 (14) + up to 14 force stages (42)
 
 namespace ssb {

@@ -30,6 +30,13 @@ __device__ __noinline__ double3 accel_call(const ssb_potential* P, int first, do
     pot_eval<WANT_GRAD>(*P, X, t, phi, g, H, first);
     return make_double3(-g[0], -g[1], -g[2]);
 }
+template <int SIG>
+__device__ __noinline__ double3 fused_call(const ssb_potential* P, double x, double y, double z) {
+    const double X[3] = {x, y, z};
+    double g[3];
+    fused_grad<SIG>(*P, X, g);
+    return make_double3(-g[0], -g[1], -g[2]);
+}
 // Potential.velocity_acceleration (main.py:116-120) in mirrored time.  SIG != 0: the leading NF components are a fused
 // static signature evaluated inline from the constant bank (Pc); any remaining components go through the interpreter (P).
 template <int SIG>
@@ -43,9 +50,14 @@ struct OrbitForce {
             const double3 a = accel_call(P, 0, X[0], X[1], X[2], tau * dir);
             A[0] = a.x; A[1] = a.y; A[2] = a.z;
         } else {
+#if SSB_FUSED_INLINE
             double g[3];
             fused_grad<SIG>(*Pc, X, g);
             A[0] = -g[0]; A[1] = -g[1]; A[2] = -g[2];
+#else
+            const double3 f = fused_call<SIG>(P, X[0], X[1], X[2]);
+            A[0] = f.x; A[1] = f.y; A[2] = f.z;
+#endif
             if (extra) {
                 const double3 a = accel_call(P, SigInfo<SIG>::NF, X[0], X[1], X[2], tau * dir);
                 A[0] += a.x; A[1] += a.y; A[2] += a.z;

@@ -1,0 +1,164 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every symbol of include/ssb200.h, struct layouts
+match the header, potential lowering, argument validation through the C ABI (error paths return before any CUDA call),
+and the multi-process sharding / gather logic on the gloo backend (world_size 2)."""
+import ctypes as C
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from streamsculptor_b200 import _lib
+    path = _lib.build()
+    L = C.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "ssb200.h")).read()
+    declared = set(re.findall(r"\b(ssb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/ssb200.h but not exported"
+    assert set(_lib.EXPORTED) == declared
+    assert L.ssb_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from streamsculptor_b200 import _lib
+    assert C.sizeof(_lib.Component) == 16 + 64
+    assert C.sizeof(_lib.Track) == 8 + 3 * 8
+    assert C.sizeof(_lib.Subhalos) == 16 + 6 * 8
+    assert C.sizeof(_lib.Potential) == 16 + 12 * 80 + 4 * 32 + 2 * 64
+    assert C.sizeof(_lib.Ctrl) == 8 + 4 * 8
+    # the CUDA side agrees (scratch sizes are computed from the same constants)
+    L = _lib.lib()
+    assert L.ssb_scratch_bytes(100) == 8 * (8 + 100 * 64)
+    assert L.ssb_response_scratch_bytes(1000) >= 2 * 148 * 2 * 6 * 2000 * 8
+
+
+def test_argument_validation_without_gpu():
+    from streamsculptor_b200 import _lib
+    L = _lib.lib()
+    P = _lib.Potential()
+    P.n_comp = 1
+    P.comp[0].type = 99
+    ctrl = _lib.Ctrl(solver=8, max_steps=10, rtol=1e-7, atol=1e-7, dtmin=0.3, dtmax=np.inf)
+    z = C.c_void_p(0)
+    assert L.ssb_orbit_integrate_f64(C.byref(P), 4, z, z, z, z, 1, 1, ctrl, z, z, z, z) == -2          # unsupported component
+    assert b"component type" in L.ssb_last_error()
+    P.comp[0].type = _lib.NFW
+    assert L.ssb_orbit_integrate_f64(C.byref(P), 4, z, z, z, z, 1, 1, ctrl, z, z, z, z) == -1 and b"missing track" in L.ssb_last_error()   # track 0 of 0
+    P.comp[0].track = -1
+    bad = _lib.Ctrl(solver=4, max_steps=10, rtol=1e-7, atol=1e-7, dtmin=0.3, dtmax=np.inf)
+    assert L.ssb_orbit_integrate_f64(C.byref(P), 4, z, z, z, z, 1, 1, bad, z, z, z, z) == -2           # Tsit5 & co are not on the path
+    assert L.ssb_orbit_integrate_f64(C.byref(P), 4, z, z, z, z, 1, 1, ctrl, z, z, z, z) == -1          # NULL arrays
+    assert L.ssb_orbit_integrate_f64(C.byref(P), 0, z, z, z, z, 1, 1, ctrl, z, z, z, z) == 0           # empty batch is a no-op
+    assert L.ssb_orbit_integrate_f64(C.byref(P), -1, z, z, z, z, 1, 1, ctrl, z, z, z, z) == -1
+    P.comp[0].type = _lib.UNIFORM_ACC
+    P.comp[0].track = -1
+    assert L.ssb_potential_eval_f64(C.byref(P), 1, z, z, z, z, z, z) == -1                               # uniform acceleration without a track
+    assert L.ssb_gen_stream_host(C.byref(P), C.byref(P), 1.0, 1, z, z, z, 0, None, z, ctrl, 0, 1, 0, z, z, z, z) == -1   # Nts < 2
+
+
+def test_lowering_flattens_the_object_tree():
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import _lib, _runtime as rt
+    P = ssc.potential
+    gala = P.GalaMilkyWayPotential(units=ssc.usys)
+    prog = rt.Program()
+    gala._lower(prog, -1)
+    assert [c[0] for c in prog.comps] == [_lib.MIYAMOTO, _lib.HERNQUIST, _lib.HERNQUIST, _lib.NFW]        # potential.py:413 order
+    assert prog.comps[0][1][:3] == [ssc.G_KPC_MYR_MSUN * 6.80e10, 3.0, 0.28]
+    assert prog.comps[3][1][:2] == [ssc.G_KPC_MYR_MSUN * 5.4e11, 15.62]
+    mn3 = P.MN3ExponentialDiskPotential(m=5e10, h_R=3.0, h_z=0.3, units=ssc.usys)
+    prog = rt.Program(); mn3._lower(prog, -1)
+    assert len(prog.comps) == 3 and all(c[0] == _lib.MIYAMOTO for c in prog.comps)
+    assert abs(sum(mn3._ms) / 5e10 - 1.0) < 0.5                                                         # the three disks share the mass
+    assert P.NFWPotential(m=1.0, r_s=1.0)._G == 1.0                                                     # units=None -> dimensionless (main.py:23-28)
+    with pytest.raises(NotImplementedError):
+        P.TimeDepTranslatingPotential(P.PlummerPotential(m=1.0, r_s=1.0, units=ssc.usys), center_spl=lambda t: np.zeros(3), units=ssc.usys)
+    with pytest.raises(NotImplementedError):
+        P.SubhaloLinePotentialCustom_fromFunc(func=P.Isochrone, m=[1.0], r_s=[1.0], subhalo_x0=np.zeros((1, 3)), subhalo_v=np.zeros((1, 3)),
+                                              subhalo_t0=[0.0], t_window=1.0, units=ssc.usys)
+    for name in ("CustomPotential", "ZhaoPotential", "GrowingPotential"):
+        with pytest.raises(NotImplementedError):
+            getattr(P, name)()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200._lib import SSBError
+    pot = ssc.potential.NFWPotential(m=1e12, r_s=20.0, units=ssc.usys)
+    with pytest.raises(SSBError):
+        pot.gradient(np.array([1.0, 2.0, 3.0]), 0.0)
+    with pytest.raises(SSBError):
+        pot.integrate_orbit(w0=np.ones(6), ts=np.array([0.0, 1.0]))
+    # the product package never imports the oracle
+    src = "".join(open(os.path.join(ROOT, "streamsculptor_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "streamsculptor_b200")) if f.endswith(".py"))
+    assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_shard_math():
+    from streamsculptor_b200 import parallel as par
+    for n in (0, 1, 7, 1000, 1001):
+        for world in (1, 2, 3, 8):
+            idx = [par.shard_indices(n, r, world) for r in range(world)]
+            assert [len(i) for i in idx] == [par.shard_count(n, r, world) for r in range(world)]
+            assert sorted(np.concatenate(idx).tolist()) == list(range(n))
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import numpy as np, torch
+import torch.distributed as dist
+import oracle as O
+from common import mw3_oracle
+from streamsculptor_b200 import parallel as par
+rank, world = par.init_from_env("gloo")
+ts = np.linspace(-600.0, 0.0, 38)
+w0 = [12.0, 3.0, -6.0, -0.05, 0.15, 0.03]
+nr = np.random.Generator(np.random.PCG64(3)).standard_normal((38, 4))
+orc = mw3_oracle()
+lead_all, trail_all, _, _ = orc.gen_stream(ts, w0, 1e4, 0, solver=5, normals=nr)
+def compute(rank, world, n_local):          # the oracle stands in for the CUDA call: host logic only
+    sel = par.shard_indices(len(ts) - 1, rank, world)
+    assert len(sel) == n_local
+    return torch.from_numpy(lead_all[sel].copy()), torch.from_numpy(trail_all[sel].copy())
+lead, trail = par.gen_stream_sharded(None, ts, w0, 1e4, 0, None, rank, world, compute=compute)
+assert lead.shape == (37, 6) and np.array_equal(lead.numpy(), lead_all) and np.array_equal(trail.numpy(), trail_all)
+s = par.allreduce_sum(torch.tensor([float(rank + 1)]), world)
+assert s.item() == world * (world + 1) / 2
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_gloo_world_size_2_shard_and_gather(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % {"root": ROOT})
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "rank 0 ok" in res.stdout and "rank 1 ok" in res.stdout
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    import json
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "particle-steps/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
