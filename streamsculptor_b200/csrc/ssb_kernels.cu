@@ -511,32 +511,6 @@ int ssb_validate_ctrl(const ssb_ctrl& c) {
     if (!(c.rtol >= 0) || !(c.atol >= 0) || !(c.dtmin >= 0) || c.max_steps < 0) return ssb_set_error(SSB_ERR_ARG, "ctrl: negative tolerance / dtmin / max_steps");
     return 0;
 }
-// Move a fused static signature to the front of the program (summation order is free) and fill its derived constants.
-// Returns the signature id; `out` is the program the kernels receive.
-static int ssb_canonicalize(const ssb_potential* in, ssb_potential* out) {
-    *out = *in;
-    int idx_n = -1, idx_m = -1, idx_h[2] = {-1, -1}, nh = 0, nn = 0, nm = 0;
-    for (int i = 0; i < in->n_comp; ++i) {
-        const ssb_component& c = in->comp[i];
-        if (c.track >= 0) continue;
-        if (c.type == SSB_NFW) { if (nn++ == 0) idx_n = i; }
-        else if (c.type == SSB_HERNQUIST && c.p[2] == 0.0) { if (nh < 2) idx_h[nh] = i; nh++; }
-        else if (c.type == SSB_MIYAMOTO) { if (nm++ == 0) idx_m = i; }
-    }
-    int sig = SIG_GENERIC, order[4], nf = 0;
-    if (nn >= 1 && nh >= 2 && nm >= 1) { sig = SIG_NHHM; order[0] = idx_n; order[1] = idx_h[0]; order[2] = idx_h[1]; order[3] = idx_m; nf = 4; }
-    else if (nn >= 1 && nh >= 1 && nm >= 1) { sig = SIG_NHM; order[0] = idx_n; order[1] = idx_h[0]; order[2] = idx_m; nf = 3; }
-    else if (nn >= 1) { sig = SIG_N; order[0] = idx_n; nf = 1; }
-    if (sig == SIG_GENERIC) return sig;
-    bool used[SSB_MAX_COMP] = {false};
-    int k = 0;
-    for (int j = 0; j < nf; ++j) { out->comp[k++] = in->comp[order[j]]; used[order[j]] = true; }
-    for (int i = 0; i < in->n_comp; ++i) if (!used[i]) out->comp[k++] = in->comp[i];
-    out->comp[0].p[2] = 1.0 / out->comp[0].p[1];                               // NFW: 1 / r_s
-    if (nf >= 3) out->comp[nf - 1].p[3] = out->comp[nf - 1].p[2] * out->comp[nf - 1].p[2];   // Miyamoto-Nagai: b^2
-    return sig;
-}
-
 static CtrlDev to_dev(const ssb_ctrl& c) { CtrlDev d; d.rtol = c.rtol; d.atol = c.atol; d.dtmin = c.dtmin; d.dtmax = c.dtmax; d.max_steps = c.max_steps; return d; }
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 

@@ -269,32 +269,82 @@ __device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x
 enum { SIG_GENERIC = 0, SIG_N = 1, SIG_NHM = 2, SIG_NHHM = 3 };
 template <int SIG> struct SigInfo { static constexpr int NF = SIG == SIG_N ? 1 : SIG == SIG_NHM ? 3 : SIG == SIG_NHHM ? 4 : 0; };
 
-template <int SIG>
-__device__ __forceinline__ void fused_grad(const ssb_potential& P, const double x[3], double g[3]) {
+template <int SIG, int MODE>
+__device__ __forceinline__ void fused_eval(const ssb_potential& P, const double x[3], double g[3], Sym3& H) {
     const double r2 = fma(x[0], x[0], fma(x[1], x[1], x[2] * x[2]));
     const double ir = frsqrt(r2), r = r2 * ir, ir2 = ir * ir;
+    // spherical components share x: accumulate q = sum Phi'/r and w = sum (Phi'' - Phi'/r)/r^2
     // NFW (comp 0)
     const double u = flog1p_pos(r * P.comp[0].p[2]);
-    double q = P.comp[0].p[0] * fma(u, ir, -frcp(r + P.comp[0].p[1])) * ir2;
+    const double irs = frcp(r + P.comp[0].p[1]);
+    const double a = u * ir;
+    double q = P.comp[0].p[0] * (a - irs) * ir2, w = 0.0;
+    if (MODE & WANT_HESS) w = P.comp[0].p[0] * (3.0 * ir * (irs - a) + irs * irs) * ir2 * ir;
     if (SIG >= SIG_NHM) {                         // Hernquist (comp 1), soft == 0 guaranteed by the host
         const double ira = frcp(r + P.comp[1].p[1]);
-        q = fma(P.comp[1].p[0] * ira, ira * ir, q);
+        const double qh = P.comp[1].p[0] * ira * ira * ir;
+        q += qh;
+        if (MODE & WANT_HESS) w -= qh * ir * (2.0 * ira + ir);
     }
     if (SIG >= SIG_NHHM) {                        // second Hernquist (comp 2)
         const double ira = frcp(r + P.comp[2].p[1]);
-        q = fma(P.comp[2].p[0] * ira, ira * ir, q);
+        const double qh = P.comp[2].p[0] * ira * ira * ir;
+        q += qh;
+        if (MODE & WANT_HESS) w -= qh * ir * (2.0 * ira + ir);
     }
-    g[0] = q * x[0]; g[1] = q * x[1]; g[2] = q * x[2];
+    if (MODE & WANT_GRAD) { g[0] = q * x[0]; g[1] = q * x[1]; g[2] = q * x[2]; }
+    if (MODE & WANT_HESS) {
+        H.xx = fma(w * x[0], x[0], q); H.yy = fma(w * x[1], x[1], q); H.zz = fma(w * x[2], x[2], q);
+        H.xy = w * x[0] * x[1]; H.xz = w * x[0] * x[2]; H.yz = w * x[1] * x[2];
+    }
     if (SIG >= SIG_NHM) {                         // Miyamoto-Nagai (last fused comp)
         constexpr int M = SigInfo<SIG>::NF - 1;
         const double zb2 = fma(x[2], x[2], P.comp[M].p[3]);
         const double iz = frsqrt(zb2);
         const double az = fma(zb2, iz, P.comp[M].p[1]);
         const double D = fma(x[0], x[0], fma(x[1], x[1], az * az));
-        const double id = frsqrt(D);
-        const double qm = P.comp[M].p[0] * id * id * id;
-        g[0] = fma(qm, x[0], g[0]); g[1] = fma(qm, x[1], g[1]); g[2] = fma(qm * az * iz, x[2], g[2]);
+        const double id = frsqrt(D), id2 = id * id;
+        const double qm = P.comp[M].p[0] * id * id2;
+        const double s = az * iz;
+        if (MODE & WANT_GRAD) { g[0] = fma(qm, x[0], g[0]); g[1] = fma(qm, x[1], g[1]); g[2] = fma(qm * s, x[2], g[2]); }
+        if (MODE & WANT_HESS) {
+            const double q5 = 3.0 * qm * id2, zs = x[2] * s;
+            H.xx += qm - q5 * x[0] * x[0]; H.yy += qm - q5 * x[1] * x[1];
+            H.xy -= q5 * x[0] * x[1]; H.xz -= q5 * x[0] * zs; H.yz -= q5 * x[1] * zs;
+            H.zz += qm * (s - P.comp[M].p[1] * x[2] * x[2] * iz * iz * iz) - q5 * zs * zs;
+        }
     }
+}
+template <int SIG>
+__device__ __forceinline__ void fused_grad(const ssb_potential& P, const double x[3], double g[3]) {
+    Sym3 H;
+    fused_eval<SIG, WANT_GRAD>(P, x, g, H);
+}
+
+// Move a fused static signature to the front of the program (summation order is free) and fill its derived constants
+// (host side).  Returns the signature id; `out` is the program the kernels receive.
+static inline int ssb_canonicalize(const ssb_potential* in, ssb_potential* out) {
+    *out = *in;
+    int idx_n = -1, idx_m = -1, idx_h[2] = {-1, -1}, nh = 0, nn = 0, nm = 0;
+    for (int i = 0; i < in->n_comp; ++i) {
+        const ssb_component& c = in->comp[i];
+        if (c.track >= 0) continue;
+        if (c.type == SSB_NFW) { if (nn++ == 0) idx_n = i; }
+        else if (c.type == SSB_HERNQUIST && c.p[2] == 0.0) { if (nh < 2) idx_h[nh] = i; nh++; }
+        else if (c.type == SSB_MIYAMOTO) { if (nm++ == 0) idx_m = i; }
+    }
+    int sig = SIG_GENERIC, order[4], nf = 0;
+    if (nn >= 1 && nh >= 2 && nm >= 1) { sig = SIG_NHHM; order[0] = idx_n; order[1] = idx_h[0]; order[2] = idx_h[1]; order[3] = idx_m; nf = 4; }
+    else if (nn >= 1 && nh >= 1 && nm >= 1) { sig = SIG_NHM; order[0] = idx_n; order[1] = idx_h[0]; order[2] = idx_m; nf = 3; }
+    else if (nn >= 1) { sig = SIG_N; order[0] = idx_n; nf = 1; }
+    if (sig == SIG_GENERIC) return sig;
+    bool used[SSB_MAX_COMP] = {false};
+    int k = 0;
+    for (int j = 0; j < nf; ++j) { out->comp[k++] = in->comp[order[j]]; used[order[j]] = true; }
+    for (int i = 0; i < in->n_comp; ++i) if (!used[i]) out->comp[k++] = in->comp[i];
+    out->comp[0].p[2] = 1.0 / out->comp[0].p[1];                                             // NFW: 1 / r_s
+    if (nf >= 3) out->comp[nf - 1].p[3] = out->comp[nf - 1].p[2] * out->comp[nf - 1].p[2];   // Miyamoto-Nagai: b^2
+    return sig;
 }
 
 }  // namespace ssb

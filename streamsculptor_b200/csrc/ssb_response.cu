@@ -15,7 +15,12 @@
 //   * item state lives in an L2-resident ping-pong scratch (SoA, coalesced), candidates become current by a
 //     pointer swap when the block-wide error reduction accepts the step;
 //   * outside its time window a subhalo exerts no force (strict '<', potential.py:826); its tidal term is still
-//     integrated, exactly as in the reference.
+//     integrated, exactly as in the reference;
+//   * subhalos are processed in the order of their window start t0 - t_window (sorted once per call on the device):
+//     warps see coherent window states, and - when the perturbation ICs are zero (perturbative.py:712) and time runs
+//     forwards - the subhalos whose window has not opened yet are still EXACTLY zero with zero error contribution, so
+//     the sweep stops at the last "born" subhalo.  The reference evaluates them (vmapped lax.cond = select); the result
+//     is bit-identical, the work is not.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -25,7 +30,9 @@
 
 using namespace ssb;
 
-#define SSB_RESP_THREADS 256
+#define SSB_RESP_THREADS 128
+#define SSB_RESP_CTAS_PER_SM 2
+#define SSB_RESP_MAX_SORT 4096
 #define CK(call) do { int _e = ssb_cuda_check((call), #call); if (_e) return _e; } while (0)
 #define CKL(what) do { int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
 
@@ -38,6 +45,10 @@ struct RespArgs {
     int32_t *status, *nsteps;
     double* scratch;          // [grid][2][6][n_items]
     unsigned long long* counter;
+    const double* sorted;     // [10][n_sh] subhalo parameters gathered in processing order: GM, rs, x0[3], v[3], t0, tw
+    const double* start;      // [n_sh] window start t0 - tw, ascending
+    const int* order;         // [n_sh] processing position -> user index
+    int skip_unborn;          // 1: D0 == NULL (zero ICs): subhalos whose window has not opened are exactly zero
 };
 
 template <int S>
@@ -47,24 +58,37 @@ struct BaseShared {
     double t[S];              // physical stage times
 };
 
-// base force + tidal tensor, recorded for the item sweep
-template <int S>
-__device__ __noinline__ double3 base_force_call(const ssb_potential* P, BaseShared<S>* sh, int stage, double x, double y, double z, double t) {
+// base force + tidal tensor, recorded for the item sweep.  SIG != 0: the leading components are a fused static
+// signature (parameters from the constant-bank copy Pc); the rest of the program goes through the interpreter.
+template <int S, int SIG>
+__device__ __noinline__ double3 base_force_call(const ssb_potential* P, const ssb_potential* Pc, BaseShared<S>* sh, int stage, double x, double y,
+                                                double z, double t) {
     const double X[3] = {x, y, z};
     double phi, g[3];
     Sym3 H;
-    pot_eval<WANT_GRAD | WANT_HESS>(*P, X, t, phi, g, H);
+    if (SIG == SIG_GENERIC) {
+        pot_eval<WANT_GRAD | WANT_HESS>(*P, X, t, phi, g, H);
+    } else {
+        fused_eval<SIG, WANT_GRAD | WANT_HESS>(*Pc, X, g, H);
+        if (Pc->n_comp > SigInfo<SIG>::NF) {
+            double g2[3];
+            Sym3 H2;
+            pot_eval<WANT_GRAD | WANT_HESS>(*P, X, t, phi, g2, H2, SigInfo<SIG>::NF);
+            g[0] += g2[0]; g[1] += g2[1]; g[2] += g2[2];
+            H.xx += H2.xx; H.yy += H2.yy; H.zz += H2.zz; H.xy += H2.xy; H.xz += H2.xz; H.yz += H2.yz;
+        }
+    }
     sh->X[stage][0] = x; sh->X[stage][1] = y; sh->X[stage][2] = z;
     sh->T[stage][0] = -H.xx; sh->T[stage][1] = -H.yy; sh->T[stage][2] = -H.zz;
     sh->T[stage][3] = -H.xy; sh->T[stage][4] = -H.xz; sh->T[stage][5] = -H.yz;
     sh->t[stage] = t;
     return make_double3(-g[0], -g[1], -g[2]);
 }
-template <int S>
+template <int S, int SIG>
 struct BaseForce {
-    const ssb_potential* P; BaseShared<S>* sh; double dir; int stage;
+    const ssb_potential* P; const ssb_potential* Pc; BaseShared<S>* sh; double dir; int stage;
     __device__ __forceinline__ void operator()(const double X[3], double tau, double A[3]) {
-        const double3 a = base_force_call<S>(P, sh, stage, X[0], X[1], X[2], tau * dir);
+        const double3 a = base_force_call<S, SIG>(P, Pc, sh, stage, X[0], X[1], X[2], tau * dir);
         stage++;
         A[0] = a.x; A[1] = a.y; A[2] = a.z;
     }
@@ -110,24 +134,61 @@ __device__ __forceinline__ double block_sum(double v, double* sred) {
     return tot;
 }
 
-__device__ __forceinline__ void load_item_params(const ssb_subhalos& Sh, int it, int n_sh, ItemParams& ip) {
-    const int j = it % n_sh;
-    ip.blk = it / n_sh;
-    ip.profile = Sh.profile;
-    ip.GM = Sh.G * __ldg(Sh.m + j); ip.rs = __ldg(Sh.rs + j); ip.t0 = __ldg(Sh.t0 + j); ip.tw = __ldg(Sh.tw + j);
+// item parameters from the gathered [10][n_sh] table (coalesced over j)
+__device__ __forceinline__ void load_item_params(const double* __restrict__ tab, int profile, int j, int blk, int n_sh, ItemParams& ip) {
+    ip.blk = blk;
+    ip.profile = profile;
+    ip.GM = __ldg(tab + j); ip.rs = __ldg(tab + n_sh + j);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { ip.x0[k] = __ldg(Sh.x0 + 3 * j + k); ip.v[k] = __ldg(Sh.v + 3 * j + k); }
+    for (int k = 0; k < 3; ++k) { ip.x0[k] = __ldg(tab + (size_t)(2 + k) * n_sh + j); ip.v[k] = __ldg(tab + (size_t)(5 + k) * n_sh + j); }
+    ip.t0 = __ldg(tab + (size_t)8 * n_sh + j); ip.tw = __ldg(tab + (size_t)9 * n_sh + j);
 }
 
-template <int SOLVER>
-__global__ void __launch_bounds__(SSB_RESP_THREADS) response_kernel(const __grid_constant__ ssb_potential Pin, const ssb_subhalos Sh,
-                                                                    const RespArgs a) {
+// ---- once per call: processing order (ascending window start) and the gathered parameter table ----
+__global__ void response_sort_kernel(const ssb_subhalos Sh, int npad, int* order, double* start) {
+    extern __shared__ unsigned char smem_raw[];
+    double* key = reinterpret_cast<double*>(smem_raw);
+    int* val = reinterpret_cast<int*>(key + npad);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) { key[i] = i < Sh.n ? Sh.t0[i] - Sh.tw[i] : inf; val[i] = i; }
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const double a = key[i], b = key[l];
+                    const bool sw = up ? (a > b || (a == b && val[i] > val[l])) : (a < b || (a == b && val[i] < val[l]));
+                    if (sw) { key[i] = b; key[l] = a; const int t = val[i]; val[i] = val[l]; val[l] = t; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < Sh.n; i += blockDim.x) { order[i] = val[i]; start[i] = key[i]; }
+}
+__global__ void response_identity_kernel(const ssb_subhalos Sh, int* order, double* start) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Sh.n) { order[i] = i; start[i] = -__longlong_as_double(0x7ff0000000000000LL); }
+}
+__global__ void response_gather_kernel(const ssb_subhalos Sh, const int* order, double* tab) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Sh.n) return;
+    const int o = order[j], n = Sh.n;
+    tab[j] = Sh.G * Sh.m[o]; tab[n + j] = Sh.rs[o];
+    for (int k = 0; k < 3; ++k) { tab[(size_t)(2 + k) * n + j] = Sh.x0[3 * o + k]; tab[(size_t)(5 + k) * n + j] = Sh.v[3 * o + k]; }
+    tab[(size_t)8 * n + j] = Sh.t0[o]; tab[(size_t)9 * n + j] = Sh.tw[o];
+}
+
+template <int SOLVER, int SIG>
+__global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) response_kernel(const __grid_constant__ ssb_potential Pin, const ssb_subhalos Sh,
+                                                                                          const RespArgs a) {
     typedef Tab<SOLVER> T;
     constexpr int S = T::S;
     __shared__ ssb_potential sP;
     __shared__ BaseShared<S> sb;
     __shared__ double sred[32];
-    __shared__ double sbc[4];          // broadcast: dt, keep, h_init ...
+    __shared__ int s_nact;
     __shared__ long long s_part;
     stage_potential(&sP, &Pin);
     const int tid = threadIdx.x;
@@ -147,19 +208,21 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS) response_kernel(const __grid
         const double T0 = t0_in * dir, T1 = t1_in * dir;
         double* cur = buf0;
         double* nxt = buf1;
-        // ---- load item state (SoA [6][n_items]); momentum-like rows carry dir ----
+        const bool skip = a.skip_unborn && dir > 0.0;
+        // ---- load item state (SoA [6][n_items], item = blk * n_sh + processing position); momentum-like rows carry dir ----
         for (int it = tid; it < n_items; it += blockDim.x) {
-            const int j = it % n_sh, blk = it / n_sh;
+            const int j = it % n_sh, blk = it / n_sh, o = a.order[j];
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
-                double v = a.D0 ? a.D0[((size_t)part * n_sh + j) * 12 + blk * 6 + k] : 0.0;
+                double v = a.D0 ? a.D0[((size_t)part * n_sh + o) * 12 + blk * 6 + k] : 0.0;
                 if (k >= 3) v *= dir;
                 cur[(size_t)k * n_items + it] = v;
+                nxt[(size_t)k * n_items + it] = v;         // unborn subhalos are never written again: both buffers hold their zeros
             }
         }
         // base state lives in thread 0
         double x[3] = {0, 0, 0}, p[3] = {0, 0, 0}, F[S][3];
-        BaseForce<S> bforce{&sP, &sb, dir, 0};
+        BaseForce<S, SIG> bforce{&sP, &Pin, &sb, dir, 0};
         int status = 0, n_steps = 0, n_acc = 0, n_rej = 0;
         bool at_dtmin = false;
         double tprev = T0, tnext = T0;
@@ -180,7 +243,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS) response_kernel(const __grid
         }
         __syncthreads();
         for (int it = tid; it < n_items; it += blockDim.x) {
-            ItemParams ip; load_item_params(Sh, it, n_sh, ip);
+            ItemParams ip; load_item_params(a.sorted, Sh.profile, it % n_sh, it / n_sh, n_sh, ip);
             ItemForce<S> f{&sb, &ip, 0};
             double q[3], pp[3], G[3];
 #pragma unroll
@@ -215,7 +278,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS) response_kernel(const __grid
         }
         __syncthreads();
         for (int it = tid; it < n_items; it += blockDim.x) {
-            ItemParams ip; load_item_params(Sh, it, n_sh, ip);
+            ItemParams ip; load_item_params(a.sorted, Sh.profile, it % n_sh, it / n_sh, n_sh, ip);
             ItemForce<S> f{&sb, &ip, 0};
             double q[3], pp[3], G0[3], G1[3], q1[3];
 #pragma unroll
@@ -239,6 +302,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS) response_kernel(const __grid
             h = fmax(h, c.dtmin);
             tnext = fmin(T0 + h, T1);
         }
+        int n_act_run = 0;
         // ================= main loop: all threads follow the same (uniform) control flow =================
         while (tprev < T1 && status == 0) {
             if (n_steps >= c.max_steps) { status = 1; break; }
@@ -263,11 +327,20 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS) response_kernel(const __grid
                     if (!isfinite(x1[k]) || !isfinite(p1[k])) bad_local = 1;
                 }
                 esq = err_sq6(x, p, x1, p1, ex, ep, c.rtol, c.atol, nan_cand);
+                // number of subhalos whose window start lies before the end of this attempt (sorted ascending)
+                int na = n_sh;
+                if (skip) { int lo = 0, hi = n_sh; while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.start[mid] < tnext) lo = mid + 1; else hi = mid; } na = lo; }
+                s_nact = na;
             }
             __syncthreads();
-            // ---- item sweep ----
-            for (int it = tid; it < n_items; it += blockDim.x) {
-                ItemParams ip; load_item_params(Sh, it, n_sh, ip);
+            // monotone within a particle: a subhalo touched by a (possibly rejected) attempt has a candidate in `nxt` that must be
+            // overwritten by every later attempt, even one that ends before its window opens
+            n_act_run = max(n_act_run, s_nact);
+            const int n_act = n_act_run;
+            // ---- item sweep over the born subhalos, both blocks ----
+            for (int idx = tid; idx < 2 * n_act; idx += blockDim.x) {
+                const int blk = idx >= n_act, j = idx - blk * n_act, it = blk * n_sh + j;
+                ItemParams ip; load_item_params(a.sorted, Sh.profile, j, blk, n_sh, ip);
                 ItemForce<S> f{&sb, &ip, 1};
                 double q[3], pp[3], G[S][3], q1[3], pp1[3], ex[3], ep[3];
 #pragma unroll
@@ -319,12 +392,12 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS) response_kernel(const __grid
         const bool ok = (status == 0) && (T0 < T1);
         const double inf = __longlong_as_double(0x7ff0000000000000LL);
         for (int it = tid; it < n_items; it += blockDim.x) {
-            const int j = it % n_sh, blk = it / n_sh;
+            const int j = it % n_sh, blk = it / n_sh, o = a.order[j];
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 double v = cur[(size_t)k * n_items + it];
                 if (k >= 3) v *= dir;
-                a.Dout[((size_t)part * n_sh + j) * 12 + blk * 6 + k] = ok ? v : inf;
+                a.Dout[((size_t)part * n_sh + o) * 12 + blk * 6 + k] = ok ? v : inf;
             }
         }
         if (tid == 0) {
@@ -342,17 +415,19 @@ __global__ void response_term_kernel(const __grid_constant__ ssb_potential Pin, 
     __shared__ BaseShared<1> sb;
     stage_potential(&sP, &Pin);
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const double3 acc = base_force_call<1>(&sP, &sb, 0, y[0], y[1], y[2], t);
+        const double3 acc = base_force_call<1, SIG_GENERIC>(&sP, &Pin, &sb, 0, y[0], y[1], y[2], t);
         dy[0] = y[3]; dy[1] = y[4]; dy[2] = y[5]; dy[3] = acc.x; dy[4] = acc.y; dy[5] = acc.z;
     } else if (threadIdx.x == 0) {
-        base_force_call<1>(&sP, &sb, 0, y[0], y[1], y[2], t);
+        base_force_call<1, SIG_GENERIC>(&sP, &Pin, &sb, 0, y[0], y[1], y[2], t);
     }
     __syncthreads();
     const int n_sh = Sh.n;
     for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < 2 * n_sh; it += gridDim.x * blockDim.x) {
-        ItemParams ip; load_item_params(Sh, it, n_sh, ip);
-        ItemForce<1> f{&sb, &ip, 0};
         const int j = it % n_sh, blk = it / n_sh;
+        ItemParams ip;
+        ip.blk = blk; ip.profile = Sh.profile; ip.GM = Sh.G * Sh.m[j]; ip.rs = Sh.rs[j]; ip.t0 = Sh.t0[j]; ip.tw = Sh.tw[j];
+        for (int k = 0; k < 3; ++k) { ip.x0[k] = Sh.x0[3 * j + k]; ip.v[k] = Sh.v[3 * j + k]; }
+        ItemForce<1> f{&sb, &ip, 0};
         const double* d = y + 6 + 12 * j + 6 * blk;
         double* o = dy + 6 + 12 * j + 6 * blk;
         const double Q[3] = {d[0], d[1], d[2]};
@@ -366,15 +441,18 @@ static int resp_grid(int64_t N) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t g = (int64_t)sms * 2;
+    const int64_t g = (int64_t)sms * SSB_RESP_CTAS_PER_SM;
     return (int)(N < g ? N : g);
 }
 
 extern "C" {
 
+// scratch layout: [256 B header: work counter] [sorted table 10*n] [start n] [order n (int)] [ping-pong state per persistent CTA]
+#define SSB_RESP_MAX_CTAS (160 * SSB_RESP_CTAS_PER_SM)
+static size_t resp_table_bytes(int32_t n_sh) { const size_t n = (size_t)(n_sh > 0 ? n_sh : 1); return ((sizeof(double) * 11 * n + sizeof(int) * n + 255) / 256) * 256; }
 size_t ssb_response_scratch_bytes(int32_t n_sh) {
     const size_t per_cta = sizeof(double) * 2 * 6 * 2 * (size_t)(n_sh > 0 ? n_sh : 1);
-    return 256 + per_cta * (size_t)(148 * 2 + 64);      // counter header + one ping-pong state per persistent CTA (<= 2 x SMs)
+    return 256 + resp_table_bytes(n_sh) + per_cta * (size_t)SSB_RESP_MAX_CTAS;
 }
 
 int ssb_linear_response_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0, const double* D0,
@@ -390,15 +468,36 @@ int ssb_linear_response_f64(const ssb_potential* pot_base, const ssb_subhalos* s
     if (scratch_bytes < ssb_response_scratch_bytes(sh->n)) return ssb_set_error(SSB_ERR_SCRATCH, "linear_response: scratch too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = resp_grid(N);
-    if (grid > 148 * 2 + 64) return ssb_set_error(SSB_ERR_SCRATCH, "linear_response: more SMs than the scratch layout assumes");
+    if (grid > SSB_RESP_MAX_CTAS) return ssb_set_error(SSB_ERR_SCRATCH, "linear_response: more SMs than the scratch layout assumes");
     RespArgs a;
     a.N = N; a.w0 = w0; a.D0 = D0; a.t0 = t0; a.t1 = t1; a.c.rtol = ctrl.rtol; a.c.atol = ctrl.atol; a.c.dtmin = ctrl.dtmin; a.c.dtmax = ctrl.dtmax;
     a.c.max_steps = ctrl.max_steps; a.wout = wout; a.Dout = Dout; a.status = status; a.nsteps = nsteps;
     a.counter = (unsigned long long*)scratch;
-    a.scratch = (double*)((char*)scratch + 256);
+    double* tab = (double*)((char*)scratch + 256);
+    double* start = tab + (size_t)10 * sh->n;
+    int* order = (int*)(start + sh->n);
+    a.sorted = tab; a.start = start; a.order = order;
+    a.scratch = (double*)((char*)scratch + 256 + resp_table_bytes(sh->n));
+    a.skip_unborn = (D0 == nullptr) ? 1 : 0;
     CK(cudaMemsetAsync(scratch, 0, 256, st));
-    if (ctrl.solver == 5) response_kernel<5><<<grid, SSB_RESP_THREADS, 0, st>>>(*pot_base, *sh, a);
-    else response_kernel<8><<<grid, SSB_RESP_THREADS, 0, st>>>(*pot_base, *sh, a);
+    if (sh->n > 0) {
+        if (sh->n <= SSB_RESP_MAX_SORT) {
+            int npad = 1; while (npad < sh->n) npad <<= 1;
+            response_sort_kernel<<<1, 1024, (size_t)npad * 12, st>>>(*sh, npad, order, start);
+            CKL("response_sort_kernel");
+        } else {                                   // identity order; every subhalo counts as born
+            response_identity_kernel<<<(sh->n + 127) / 128, 128, 0, st>>>(*sh, order, start);
+            CKL("response_identity_kernel");
+        }
+        response_gather_kernel<<<(sh->n + 127) / 128, 128, 0, st>>>(*sh, order, tab);
+        CKL("response_gather_kernel");
+    }
+    ssb_potential pc;
+    const int sig = ssb_canonicalize(pot_base, &pc);
+#define SSB_LAUNCH_RESP(S, SG) response_kernel<S, SG><<<grid, SSB_RESP_THREADS, 0, st>>>(pc, *sh, a)
+#define SSB_LAUNCH_RESP_SIG(S) do { switch (sig) { case SIG_N: SSB_LAUNCH_RESP(S, SIG_N); break; case SIG_NHM: SSB_LAUNCH_RESP(S, SIG_NHM); break; \
+        case SIG_NHHM: SSB_LAUNCH_RESP(S, SIG_NHHM); break; default: SSB_LAUNCH_RESP(S, SIG_GENERIC); } } while (0)
+    if (ctrl.solver == 5) SSB_LAUNCH_RESP_SIG(5); else SSB_LAUNCH_RESP_SIG(8);
     CKL("response_kernel");
     return 0;
 }
