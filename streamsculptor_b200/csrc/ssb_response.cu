@@ -30,8 +30,12 @@
 
 using namespace ssb;
 
+#ifndef SSB_RESP_THREADS
 #define SSB_RESP_THREADS 128
+#endif
+#ifndef SSB_RESP_CTAS_PER_SM
 #define SSB_RESP_CTAS_PER_SM 2
+#endif
 #define SSB_RESP_MAX_SORT 4096
 #define CK(call) do { int _e = ssb_cuda_check((call), #call); if (_e) return _e; } while (0)
 #define CKL(what) do { int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
