@@ -28,7 +28,15 @@ __device__ __forceinline__ double frsqrt(double x) {           // x^(-1/2)
 
 // ln(1 + m) for m >= 0 (NFW: m = r / r_s).  w = 1 + m carries the rounding error of the sum, which the classic
 // first-order correction (m - (w - 1)) / w removes; ln w = k ln2 + 2 atanh(s), s = (f - 1)/(f + 1), f in [sqrt(1/2), sqrt 2).
-__device__ __forceinline__ double flog1p_pos(double m) {
+#ifndef SSB_LOG1P_INLINE
+#define SSB_LOG1P_INLINE 1
+#endif
+#if SSB_LOG1P_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+double flog1p_pos(double m) {
     const double w = 1.0 + m;
     const double corr = m - (w - 1.0);                         // exact (Sterbenz-type) for m >= 0
     int hi = __double2hiint(w);

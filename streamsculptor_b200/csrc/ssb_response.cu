@@ -34,7 +34,7 @@ using namespace ssb;
 #define SSB_RESP_THREADS 128
 #endif
 #ifndef SSB_RESP_CTAS_PER_SM
-#define SSB_RESP_CTAS_PER_SM 2
+#define SSB_RESP_CTAS_PER_SM 3      // 168 registers/thread: three 128-thread CTAs (three particles) per SM overlap base and item phases
 #endif
 #define SSB_RESP_MAX_SORT 4096
 #define CK(call) do { int _e = ssb_cuda_check((call), #call); if (_e) return _e; } while (0)
@@ -101,10 +101,13 @@ struct BaseForce {
 // one (subhalo, block) item: force = g_block(X_base(stage), t(stage)) + T(stage) . Q
 struct ItemParams { double GM, rs, x0[3], v[3], t0, tw; int profile, blk; };
 
-template <int S>
+// PROFILE / BLK < 0: taken from the runtime fields (start-up code); >= 0: compile-time (the hot sweep)
+template <int S, int PROFILE = -1, int BLK = -1>
 struct ItemForce {
     const BaseShared<S>* sh; const ItemParams* ip; int stage;
     __device__ __forceinline__ void at(int i, const double Q[3], double A[3]) const {
+        const int profile = PROFILE >= 0 ? PROFILE : ip->profile;
+        const int blk = BLK >= 0 ? BLK : ip->blk;
         const double* X = sh->X[i];
         const double* T = sh->T[i];
         const double dt = sh->t[i] - ip->t0;
@@ -115,8 +118,8 @@ struct ItemForce {
             for (int k = 0; k < 3; ++k) rel[k] = X[k] - fma(ip->v[k], dt, ip->x0[k]);
             const double r2 = fma(rel[0], rel[0], fma(rel[1], rel[1], rel[2] * rel[2]));
             double ph, q, w = 0;
-            if (ip->blk) profile_dradius(ip->profile, ip->GM, ip->rs, r2, ph, q);          // fields.py:200
-            else profile_terms<WANT_GRAD>(ip->profile, ip->GM, ip->rs, r2, ph, q, w);      // fields.py:191
+            if (blk) profile_dradius(profile, ip->GM, ip->rs, r2, ph, q);                  // fields.py:200
+            else profile_terms<WANT_GRAD>(profile, ip->GM, ip->rs, r2, ph, q, w);          // fields.py:191
             g0 = -q * rel[0]; g1 = -q * rel[1]; g2 = -q * rel[2];
         }
         A[0] = g0 + (T[0] * Q[0] + T[3] * Q[1] + T[4] * Q[2]);                              // fields.py:197 / 202
@@ -184,7 +187,39 @@ __global__ void response_gather_kernel(const ssb_subhalos Sh, const int* order, 
     tab[(size_t)8 * n + j] = Sh.t0[o]; tab[(size_t)9 * n + j] = Sh.tw[o];
 }
 
-template <int SOLVER, int SIG>
+// the item sweep of one step attempt: candidates into `nxt`, squared scaled errors into esq.  PROFILE is a template
+// parameter so that the unrolled 13-stage body stays small (instruction cache).
+template <int SOLVER, int PROFILE>
+__device__ __forceinline__ void sweep_items(const BaseShared<Tab<SOLVER>::S>* sb, const double* __restrict__ tab, int n_sh, int n_items, int n_act,
+                                            const double* __restrict__ cur, double* __restrict__ nxt, double dt, const CtrlDev& c, double& esq,
+                                            int& bad_local) {
+    constexpr int S = Tab<SOLVER>::S;
+    for (int idx = threadIdx.x; idx < 2 * n_act; idx += blockDim.x) {
+        const int blk = idx >= n_act, j = idx - blk * n_act, it = blk * n_sh + j;
+        ItemParams ip; load_item_params(tab, PROFILE, j, blk, n_sh, ip);
+        ItemForce<S, PROFILE, -1> f{sb, &ip, 1};
+        double q[3], pp[3], G[S][3], q1[3], pp1[3], ex[3], ep[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { q[k] = cur[(size_t)k * n_items + it]; pp[k] = cur[(size_t)(3 + k) * n_items + it]; }
+        f.at(0, q, G[0]);
+        rk_stages<SOLVER>(f, q, pp, 0.0, dt, G);
+        rk_candidate<SOLVER>(q, pp, dt, G, q1, pp1);
+        if (SOLVER == 5) f.at(S - 1, q1, G[S - 1]);          // Dopri8: e_14 = (e^T A)_14 = 0, stage unused
+        else { G[S - 1][0] = G[S - 1][1] = G[S - 1][2] = 0.0; }
+        rk_error<SOLVER>(pp, dt, G, ex, ep);
+        bool nan_cand = false;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            nan_cand |= isnan(q1[k]) | isnan(pp1[k]);
+            if (!isfinite(q1[k]) || !isfinite(pp1[k])) bad_local = 1;
+        }
+        esq += err_sq6(q, pp, q1, pp1, ex, ep, c.rtol, c.atol, nan_cand);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { nxt[(size_t)k * n_items + it] = q1[k]; nxt[(size_t)(3 + k) * n_items + it] = pp1[k]; }
+    }
+}
+
+template <int SOLVER, int SIG, int PROFILE>
 __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) response_kernel(const __grid_constant__ ssb_potential Pin, const ssb_subhalos Sh,
                                                                                           const RespArgs a) {
     typedef Tab<SOLVER> T;
@@ -341,30 +376,8 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
             // overwritten by every later attempt, even one that ends before its window opens
             n_act_run = max(n_act_run, s_nact);
             const int n_act = n_act_run;
-            // ---- item sweep over the born subhalos, both blocks ----
-            for (int idx = tid; idx < 2 * n_act; idx += blockDim.x) {
-                const int blk = idx >= n_act, j = idx - blk * n_act, it = blk * n_sh + j;
-                ItemParams ip; load_item_params(a.sorted, Sh.profile, j, blk, n_sh, ip);
-                ItemForce<S> f{&sb, &ip, 1};
-                double q[3], pp[3], G[S][3], q1[3], pp1[3], ex[3], ep[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { q[k] = cur[(size_t)k * n_items + it]; pp[k] = cur[(size_t)(3 + k) * n_items + it]; }
-                f.at(0, q, G[0]);
-                rk_stages<SOLVER>(f, q, pp, 0.0, dt, G);
-                rk_candidate<SOLVER>(q, pp, dt, G, q1, pp1);
-                if (SOLVER == 5) f.at(S - 1, q1, G[S - 1]);          // Dopri8: e_14 = (e^T A)_14 = 0, stage unused
-                else { G[S - 1][0] = G[S - 1][1] = G[S - 1][2] = 0.0; }
-                rk_error<SOLVER>(pp, dt, G, ex, ep);
-                bool nan_cand = false;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    nan_cand |= isnan(q1[k]) | isnan(pp1[k]);
-                    if (!isfinite(q1[k]) || !isfinite(pp1[k])) bad_local = 1;
-                }
-                esq += err_sq6(q, pp, q1, pp1, ex, ep, c.rtol, c.atol, nan_cand);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { nxt[(size_t)k * n_items + it] = q1[k]; nxt[(size_t)(3 + k) * n_items + it] = pp1[k]; }
-            }
+            // ---- item sweep over the born subhalos: mass block, then radius block ----
+            sweep_items<SOLVER, PROFILE>(&sb, a.sorted, n_sh, n_items, n_act, cur, nxt, dt, c, esq, bad_local);
             const double err = sqrt(block_sum(esq, sred) / ncomp);
             const int any_bad = __syncthreads_or(bad_local);
             double hn; bool bad;
@@ -498,10 +511,13 @@ int ssb_linear_response_f64(const ssb_potential* pot_base, const ssb_subhalos* s
     }
     ssb_potential pc;
     const int sig = ssb_canonicalize(pot_base, &pc);
-#define SSB_LAUNCH_RESP(S, SG) response_kernel<S, SG><<<grid, SSB_RESP_THREADS, 0, st>>>(pc, *sh, a)
-#define SSB_LAUNCH_RESP_SIG(S) do { switch (sig) { case SIG_N: SSB_LAUNCH_RESP(S, SIG_N); break; case SIG_NHM: SSB_LAUNCH_RESP(S, SIG_NHM); break; \
-        case SIG_NHHM: SSB_LAUNCH_RESP(S, SIG_NHHM); break; default: SSB_LAUNCH_RESP(S, SIG_GENERIC); } } while (0)
-    if (ctrl.solver == 5) SSB_LAUNCH_RESP_SIG(5); else SSB_LAUNCH_RESP_SIG(8);
+    // base potentials of the response path: MW3 / Gala fused, everything else (incl. a lone NFW) through the interpreter
+#define SSB_LAUNCH_RESP(S, SG, PR) response_kernel<S, SG, PR><<<grid, SSB_RESP_THREADS, 0, st>>>(sig == SG ? pc : *pot_base, *sh, a)
+#define SSB_LAUNCH_RESP_SIG(S, PR) do { switch (sig) { case SIG_NHM: SSB_LAUNCH_RESP(S, SIG_NHM, PR); break; \
+        case SIG_NHHM: SSB_LAUNCH_RESP(S, SIG_NHHM, PR); break; default: SSB_LAUNCH_RESP(S, SIG_GENERIC, PR); } } while (0)
+#define SSB_LAUNCH_RESP_PR(S) do { switch (sh->profile) { case SSB_PROFILE_PLUMMER: SSB_LAUNCH_RESP_SIG(S, SSB_PROFILE_PLUMMER); break; \
+        case SSB_PROFILE_HERNQUIST: SSB_LAUNCH_RESP_SIG(S, SSB_PROFILE_HERNQUIST); break; default: SSB_LAUNCH_RESP_SIG(S, SSB_PROFILE_NFW); } } while (0)
+    if (ctrl.solver == 5) SSB_LAUNCH_RESP_PR(5); else SSB_LAUNCH_RESP_PR(8);
     CKL("response_kernel");
     return 0;
 }
