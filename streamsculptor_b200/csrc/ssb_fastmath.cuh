@@ -34,7 +34,7 @@ __device__ __forceinline__ double frsqrt(double x) {           // x^(-1/2)
 #if SSB_LOG1P_INLINE
 __device__ __forceinline__
 #else
-__device__ __noinline__
+static __device__ __noinline__
 #endif
 double flog1p_pos(double m) {
     const double w = 1.0 + m;

@@ -33,11 +33,33 @@ __device__ __forceinline__ int upper_bound_d(const double* __restrict__ a, int n
     return lo;
 }
 
+// Largest i with a[i] < v (= lower_bound - 1) / a[i] <= v (= upper_bound - 1), found from a proportional guess:
+// the tables on the path are (near-)uniform in time (potential.py:581-600: 1000 knots on [-14000, 0]; Chen25 tracks:
+// linspace + one extra knot), so the guess is exact up to +-1 and two or three cached loads replace a 10-deep
+// dependent binary search per force evaluation.  Non-uniform tables fall back to the binary search.
+template <bool UPPER>
+__device__ __forceinline__ int locate_below(const double* __restrict__ a, int n, double v) {
+    const double a0 = __ldg(a), a1 = __ldg(a + n - 1);
+    int i = (int)((v - a0) * (double)(n - 1) / (a1 - a0));
+    i = min(max(i, 0), n - 1);
+    int walk = 0;
+    if (UPPER) {
+        while (i < n - 1 && __ldg(a + i + 1) <= v && walk < 4) { ++i; ++walk; }
+        while (i >= 0 && __ldg(a + i) > v && walk < 4) { --i; ++walk; }
+        if (walk >= 4) i = upper_bound_d(a, n, v) - 1;
+    } else {
+        while (i < n - 1 && __ldg(a + i + 1) < v && walk < 4) { ++i; ++walk; }
+        while (i >= 0 && __ldg(a + i) >= v && walk < 4) { --i; ++walk; }
+        if (walk >= 4) i = lower_bound_d(a, n, v) - 1;
+    }
+    return i;
+}
+
 template <bool DERIV>
 __device__ __forceinline__ void track_eval(const ssb_track& T, double tq, double c[3], double dc[3]) {
     const int n = T.n;
     if (T.kind == SSB_TRACK_LINEAR) {
-        int i = lower_bound_d(T.t, n, tq) - 1;                     // jnp.searchsorted(side='left') - 1, clipped
+        int i = locate_below<false>(T.t, n, tq);                   // jnp.searchsorted(side='left') - 1, clipped
         i = min(max(i, 0), n - 2);
         const double ta = __ldg(T.t + i), tb = __ldg(T.t + i + 1);
         const double h = tb - ta, w = (tq - ta) / h;
@@ -54,7 +76,7 @@ __device__ __forceinline__ void track_eval(const ssb_track& T, double tq, double
             for (int k = 0; k < 3; ++k) { c[k] = qn; if (DERIV) dc[k] = qn; }
             return;
         }
-        int i = upper_bound_d(T.t, n, tq);                          // searchsorted(side='right'), clipped to [1, n-1]
+        int i = locate_below<true>(T.t, n, tq) + 1;                 // searchsorted(side='right'), clipped to [1, n-1]
         i = min(max(i, 1), n - 1);
         const double ta = __ldg(T.t + i - 1), tb = __ldg(T.t + i);
         const double dx = tb - ta, dxi = dx == 0.0 ? 0.0 : 1.0 / dx;

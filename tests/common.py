@@ -66,7 +66,7 @@ def scaled_err(a, b, tol, ref=None):
     return d.reshape(d.shape[0], -1).max(axis=1)
 
 
-def assert_adaptive_close(gpu, orc, truth, tol, min_frac=0.85, what=""):
+def assert_adaptive_close(gpu, orc, truth, tol, min_frac=0.85, what="", slack=1.0):
     """Parity criterion for ADAPTIVE runs (DESIGN.md "Parity criteria").
 
     Two correct implementations of the same adaptive solver follow the same step sequence only until a rounding-level
@@ -88,5 +88,5 @@ def assert_adaptive_close(gpu, orc, truth, tol, min_frac=0.85, what=""):
     assert frac >= min_frac, f"{what}: only {frac:.2f} of the orbits agree within 10 x tol"
     for q, fac in ((50, 1.5), (90, 2.0), (100, 3.0)):
         a, b = np.percentile(d_at, q), np.percentile(d_bt, q)
-        assert a <= fac * b + 10.0, f"{what}: CUDA error percentile {q} = {a:.1f} x tol vs oracle {b:.1f} x tol"
+        assert a <= slack * fac * b + 10.0, f"{what}: CUDA error percentile {q} = {a:.1f} x tol vs oracle {b:.1f} x tol"
     return frac

