@@ -253,6 +253,39 @@ def test_linear_response_matches_oracle(cuda):
             assert scaled_err(Df.cpu().numpy().reshape(12, -1), D_f.reshape(12, -1), 1e-10).max() < 1.0
 
 
+def test_response_c4_scale_fixed_step(cuda):
+    """BASELINE config C4 shape: 1000 Hernquist subhalos per particle (sorted / skipped / tiled inside the kernel).  Fixed steps
+    make the step sequence identical by construction, so the whole [N, 1000, 12] response is compared at 1e-10."""
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import _runtime as rt
+    P = ssc.potential
+    nsh = 1000
+    rng = np.random.Generator(np.random.PCG64(1234))
+    M = 10 ** rng.uniform(5, 9, nsh); rs = 1.05 * np.sqrt(M / 1e8)
+    sh = dict(x0=rng.normal(size=(nsh, 3)) * 12.0, v=rng.normal(size=(nsh, 3)) * 0.184, t0=rng.uniform(-1500.0, 100.0, nsh))
+    base, orc_base = mw3_product(), mw3_oracle()
+    pert = P.SubhaloLinePotentialCustom_fromFunc(func=P.HernquistPotential, m=np.ones(nsh), r_s=rs, subhalo_x0=sh["x0"], subhalo_v=sh["v"],
+                                                 subhalo_t0=sh["t0"], t_window=150.0, units=ssc.usys)
+    orc_sh = O.Program().subhalos(O.PR_HERNQUIST, np.ones(nsh), rs, sh["x0"], sh["v"], sh["t0"], 150.0)
+    w0 = halo_orbits(6, seed=4)
+    t0 = np.array([-1500.0, -1200.0, -900.0, -600.0, -300.0, -20.0])
+    w_f, D_f, st_f, ns_f = O.linear_response(orc_base, orc_sh, w0, t0, 0.0, solver=8, dtmin=2.0, dtmax=2.0, threads=8)
+    ctrl = rt.make_ctrl(ssc.Dopri8(), 1e-9, 1e-9, 2.0, 2.0, 10_000)
+    w, D, st, ns = rt.linear_response(base, pert._arrays, rt.to_dev(w0), None, rt.to_dev(t0), 0.0, ctrl)
+    assert (st.cpu().numpy() == 0).all() and np.array_equal(ns.cpu().numpy()[:, 0], ns_f[:, 0])
+    assert scaled_err(w.cpu().numpy(), w_f, 1e-10).max() < 1.0
+    D = D.cpu().numpy()
+    assert np.abs(D - D_f).max() <= 1e-10 * np.abs(D_f).max()
+    never = sh["t0"] + 150.0 < t0[-1]                        # windows that closed before the last particle was released
+    assert (D[-1, never] == 0.0).all() and (D_f[-1, never] == 0.0).all()
+    # non-zero ICs disable the unborn-subhalo shortcut: same answer as the oracle
+    D0 = rng.normal(size=(6, nsh, 12)) * 1e-9
+    w_g, D_g, _, _ = O.linear_response(orc_base, orc_sh, w0[:2], t0[:2], 0.0, D0=D0[:2], solver=5, dtmin=2.0, dtmax=2.0, threads=8)
+    ctrl5 = rt.make_ctrl(ssc.Dopri5(), 1e-9, 1e-9, 2.0, 2.0, 10_000)
+    w2, D2, _, _ = rt.linear_response(base, pert._arrays, rt.to_dev(w0[:2]), rt.to_dev(D0[:2]), rt.to_dev(t0[:2]), 0.0, ctrl5)
+    assert np.abs(D2.cpu().numpy() - D_g).max() <= 1e-10 * np.abs(D_g).max()
+
+
 def test_response_generator_api(cuda):
     """GenerateMassRadiusPerturbation_Chen25.compute_perturbation_OTF shape contract (golden D7) + oracle parity."""
     import streamsculptor_b200 as ssc
