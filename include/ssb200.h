@@ -146,6 +146,15 @@ int ssb_release_spray_f64(const ssb_potential* pot, double G, int64_t N, const d
                           const int64_t* idx, const double* t, int64_t seed, const double* kvals, const double* normals,
                           double* pos_lead, double* pos_trail, double* vel_lead, double* vel_trail, void* stream);
 
+/* A15  jacfwd(release_model) (BaseStreamModel.release_func_jacobian, perturbative.py:281-296): d(pos, vel of the lead / trail
+ * particle) / d(progenitor x, v) at every stripping time; needs the third derivatives of Phi (closed forms on the device).
+ * Arguments as ssb_release_spray_f64; jac[N,2,6,6]. */
+int ssb_release_jacobian_f64(const ssb_potential* pot, double G, int64_t N, const double* prog, const double* Msat,
+                             const int64_t* idx, const double* t, int64_t seed, const double* kvals, const double* normals,
+                             double* jac, void* stream);
+/* third derivatives d^3 Phi / dx_i dx_j dx_k at n points: third[n,3,3,3] (nested jacfwd of the gradient, fields.py:278-283) */
+int ssb_potential_third_f64(const ssb_potential* pot, int64_t n, const double* xyz, const double* t, double* third, void* stream);
+
 /* A8  Potential.gen_stream_vmapped (main.py:343-368) as one enqueue: progenitor orbit at ts[Nts] (dense), release at
  * every ts[i], then 2 (Nts-1) independent solves from ts[i] to ts[Nts-1]; lead[Nts-1,6], trail[Nts-1,6].
  * pot_release: potential used by release_model (== pot for gen_stream_vmapped; the base potential for
@@ -169,6 +178,13 @@ int ssb_linear_response_f64(const ssb_potential* pot_base, const ssb_subhalos* s
                             const double* D0, const double* t0, double t1, ssb_ctrl ctrl, double* wout, double* Dout,
                             int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream);
 size_t ssb_response_scratch_bytes(int32_t n_sh);
+/* Same field for ONE trajectory with SaveAt(ts): integrate_field(w0=[w, D], ts, backwards_int=...) as used for the backward
+ * progenitor response (perturbative.py:53-60, 394-398, 704-711).  w0[6], D0[n_sh,12] or NULL, t0[1] (device), ts[M] monotone
+ * from t0 towards t1; ws[M,6], Ds[M,n_sh,12]; scratch >= ssb_response_saveat_scratch_bytes(n_sh). */
+int ssb_linear_response_saveat_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, const double* w0, const double* D0,
+                                   const double* t0, double t1, const double* ts, int32_t M, ssb_ctrl ctrl, double* ws, double* Ds,
+                                   int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream);
+size_t ssb_response_saveat_scratch_bytes(int32_t n_sh);
 /* RHS of that field at one state (fields.py:175-206): y[6+12 n_sh] -> dy (device pointers), for unit tests */
 int ssb_response_term_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, double t, const double* y, double* dy,
                           void* stream);

@@ -250,6 +250,22 @@ def linear_response(base, shprog, w0, t0, t1, D0=None, sh=0, solver=8, rtol=1e-6
     return wout, Dout, status, nsteps
 
 
+def linear_response_saveat(base, shprog, w0, t0, t1, ts, D0=None, sh=0, solver=8, rtol=1e-7, atol=1e-7, dtmin=0.05, dtmax=None, max_steps=1_000):
+    """integrate_field(w0=[w, D], ts, field=MassRadiusPerturbation_OTF) for one trajectory (perturbative.py:53-60): ws[M,6], Ds[M,nsh,12]."""
+    w0, ts = _d(w0).reshape(6), _d(ts).reshape(-1)
+    nsh, M = shprog.n_sh[sh], len(_d(ts).reshape(-1))
+    D0p = None
+    if D0 is not None:
+        D0 = _d(D0).reshape(nsh, 12)
+        D0p = _p(D0)
+    ws, Ds = np.empty((M, 6)), np.empty((M, nsh, 12))
+    status, nsteps = np.zeros(1, dtype=np.int32), np.zeros(3, dtype=np.int32)
+    lib().orc_linear_response_saveat(base._h, shprog._h, sh, _p(w0), D0p, C.c_double(t0), C.c_double(t1), _p(ts), M, int(solver), C.c_double(rtol),
+                                     C.c_double(atol), C.c_double(dtmin), C.c_double(np.inf if dtmax is None else dtmax), int(max_steps), _p(ws), _p(Ds),
+                                     status.ctypes.data_as(_ip), nsteps.ctypes.data_as(_ip))
+    return ws, Ds, status, nsteps
+
+
 def response_term(base, shprog, t, y, sh=0):
     y = _d(y)
     dy = np.empty_like(y)

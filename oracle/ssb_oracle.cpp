@@ -358,6 +358,25 @@ void orc_linear_response(void* hbase, void* hsh, int sh, int N, const double* w0
     });
 }
 
+// the same coupled field for ONE trajectory with SaveAt(ts): the backward progenitor response (perturbative.py:53-60)
+void orc_linear_response_saveat(void* hbase, void* hsh, int sh, const double* w0, const double* D0, double t0, double t1, const double* ts, int M,
+                                int solver, double rtol, double atol, double dtmin, double dtmax, int max_steps, double* ws /*[M,6]*/,
+                                double* Ds /*[M,nsh,12]*/, int* status, int* nsteps) {
+    const Program& B = *(Program*)hbase; const SubhaloSet& S = ((Program*)hsh)->shs[sh];
+    Ctrl c; c.solver = solver; c.rtol = rtol; c.atol = atol; c.dtmin = dtmin; c.dtmax = dtmax; c.max_steps = max_steps;
+    const int nsh = S.n, n = 6 + 12 * nsh;
+    ResponseField f; f.base = &B; f.S = &S; f.Sdr = S; f.Sdr.dradius = 1; f.nsh = nsh;
+    std::vector<double> y0(n, 0.0), ys((size_t)M * n);
+    std::memcpy(y0.data(), w0, 48);
+    if (D0) std::memcpy(y0.data() + 6, D0, sizeof(double) * 12 * nsh);
+    Stats s = solve(f, n, t0, t1, y0.data(), ts, M, c, ys.data());
+    for (int m = 0; m < M; ++m) {
+        std::memcpy(ws + 6 * (size_t)m, ys.data() + (size_t)m * n, 48);
+        std::memcpy(Ds + (size_t)m * 12 * nsh, ys.data() + (size_t)m * n + 6, sizeof(double) * 12 * nsh);
+    }
+    *status = s.status; nsteps[0] = s.n_steps; nsteps[1] = s.n_acc; nsteps[2] = s.n_rej;
+}
+
 // RHS of the response field at one state (fields.py:175-206), for unit tests
 void orc_response_term(void* hbase, void* hsh, int sh, double t, const double* y, double* dy) {
     const Program& B = *(Program*)hbase; const SubhaloSet& S = ((Program*)hsh)->shs[sh];

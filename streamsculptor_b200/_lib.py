@@ -82,11 +82,15 @@ _SIGNATURES = {
     "ssb_orbit_dense_f64": ([_PP, _dp, _dbl, _dbl, _dp, _i64, Ctrl, _dp, _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
     "ssb_scratch_bytes": ([_i32], C.c_size_t),
     "ssb_release_spray_f64": ([_PP, _dbl, _i64, _dp, _dp, _dp, _dp, _i64, C.POINTER(C.c_double), _dp, _dp, _dp, _dp, _dp, _dp], C.c_int),
+    "ssb_release_jacobian_f64": ([_PP, _dbl, _i64, _dp, _dp, _dp, _dp, _i64, C.POINTER(C.c_double), _dp, _dp, _dp], C.c_int),
+    "ssb_potential_third_f64": ([_PP, _i64, _dp, _dp, _dp, _dp], C.c_int),
     "ssb_gen_stream_f64": ([_PP, _PP, _dbl, _i64, _dp, _dp, _dp, _i64, C.POINTER(C.c_double), _dp, Ctrl, _i64, _i64, _i64, _dp, _dp,
                             _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
     "ssb_stream_scratch_bytes": ([_i64, _i32], C.c_size_t),
     "ssb_linear_response_f64": ([_PP, _SP, _i64, _dp, _dp, _dp, _dbl, Ctrl, _dp, _dp, _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
     "ssb_response_scratch_bytes": ([_i32], C.c_size_t),
+    "ssb_linear_response_saveat_f64": ([_PP, _SP, _dp, _dp, _dp, _dbl, _dp, _i32, Ctrl, _dp, _dp, _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
+    "ssb_response_saveat_scratch_bytes": ([_i32], C.c_size_t),
     "ssb_response_term_f64": ([_PP, _SP, _dbl, _dp, _dp, _dp], C.c_int),
     "ssb_orbit_integrate_host": ([_PP, _i64, _dp, _dp, _dp, _dp, _i32, _i32, Ctrl, _dp, _dp, _dp], C.c_int),
     "ssb_gen_stream_host": ([_PP, _PP, _dbl, _i64, _dp, _dp, _dp, _i64, C.POINTER(C.c_double), _dp, Ctrl, _i64, _i64, _i64, _dp, _dp,

@@ -250,6 +250,26 @@ def shard_count(n_particles, rank, world):
     return max(0, (n_particles - rank + world - 1) // world)
 
 
+def release_jacobian(pot, G, prog, Msat, idx, t, seed, kvals, normals):
+    P, _keep = lower(pot)
+    N = prog.shape[0]
+    jac = empty((N, 2, 6, 6))
+    kv = (C.c_double * 8)(*[float(k) for k in kvals])
+    _lib.check(_lib.lib().ssb_release_jacobian_f64(C.byref(P), float(G), N, ptr(prog), ptr(Msat), ptr(idx), ptr(t), int(seed), kv, ptr(normals),
+                                                   ptr(jac), stream_ptr()))
+    return jac
+
+
+def potential_third(pot, xyz, t):
+    x = to_dev(xyz).reshape(-1, 3)
+    n = x.shape[0]
+    tt = to_dev(np.broadcast_to(np.asarray(t, dtype=np.float64), (n,)).copy())
+    P, _keep = lower(pot)
+    out3 = empty((n, 3, 3, 3))
+    _lib.check(_lib.lib().ssb_potential_third_f64(C.byref(P), n, ptr(x), ptr(tt), ptr(out3), stream_ptr()))
+    return out3
+
+
 def gen_stream(pot, pot_release, G, ts, prog_w0, Msat, seed, kvals, normals, ctrl, i_begin=0, i_stride=1, n_local=None):
     tt = torch()
     P, _k1 = lower(pot)
@@ -280,6 +300,21 @@ def linear_response(pot_base, sharrays, w0, D0, t0, t1, ctrl):
     _lib.check(_lib.lib().ssb_linear_response_f64(C.byref(P), C.byref(S), N, ptr(w0), ptr(D0), ptr(t0), float(t1), ctrl, ptr(wout), ptr(Dout),
                                                   ptr(status), ptr(nsteps), ptr(scratch), nbytes, stream_ptr()))
     return wout, Dout, status, nsteps
+
+
+def linear_response_saveat(pot_base, sharrays, w0, D0, t0, t1, ts, ctrl):
+    """One trajectory of the coupled field saved at ts[M]: returns ws[M,6], Ds[M,n_sh,12], status[1], nsteps[3]."""
+    tt = torch()
+    P, _keep = lower(pot_base)
+    S = sharrays.struct()
+    M = ts.shape[0]
+    ws, Ds = empty((M, 6)), empty((M, sharrays.n, 12))
+    status, nsteps = empty((1,), tt.int32), empty((1, 3), tt.int32)
+    nbytes = _lib.lib().ssb_response_saveat_scratch_bytes(sharrays.n)
+    scratch = empty(((nbytes + 7) // 8,))
+    _lib.check(_lib.lib().ssb_linear_response_saveat_f64(C.byref(P), C.byref(S), ptr(w0), ptr(D0), ptr(t0), float(t1), ptr(ts), M, ctrl, ptr(ws), ptr(Ds),
+                                                         ptr(status), ptr(nsteps), ptr(scratch), nbytes, stream_ptr()))
+    return ws, Ds, status, nsteps
 
 
 def response_term(pot_base, sharrays, t, y):

@@ -388,6 +388,67 @@ struct ReleaseArgs {
     double *w0_packed, *t0_packed;   // optional [2,N,6] / [2,N] in the orbit-kernel layout (lead block, trail block)
 };
 
+// ---- forward-mode dual numbers for jacfwd(release_model) (perturbative.py:281-296): value + 6 partials d/d(x, v) ----
+struct D6 {
+    double v, d[6];
+    __device__ D6() : v(0.0) { for (int i = 0; i < 6; ++i) d[i] = 0.0; }
+    __device__ D6(double c) : v(c) { for (int i = 0; i < 6; ++i) d[i] = 0.0; }
+};
+__device__ inline D6 operator+(const D6& a, const D6& b) { D6 r; r.v = a.v + b.v; for (int i = 0; i < 6; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
+__device__ inline D6 operator-(const D6& a, const D6& b) { D6 r; r.v = a.v - b.v; for (int i = 0; i < 6; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
+__device__ inline D6 operator-(const D6& a) { D6 r; r.v = -a.v; for (int i = 0; i < 6; ++i) r.d[i] = -a.d[i]; return r; }
+__device__ inline D6 operator*(const D6& a, const D6& b) { D6 r; r.v = a.v * b.v; for (int i = 0; i < 6; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
+__device__ inline D6 operator/(const D6& a, const D6& b) {
+    D6 r; const double inv = 1.0 / b.v; r.v = a.v * inv;
+    for (int i = 0; i < 6; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
+    return r;
+}
+__device__ inline D6 dsqrt(const D6& a) { D6 r; r.v = sqrt(a.v); const double f = 0.5 / r.v; for (int i = 0; i < 6; ++i) r.d[i] = a.d[i] * f; return r; }
+__device__ inline double dsqrt(double a) { return sqrt(a); }
+__device__ inline D6 dcbrt(const D6& a) { D6 r; r.v = pow(a.v, 1.0 / 3.0); const double f = r.v / (3.0 * a.v); for (int i = 0; i < 6; ++i) r.d[i] = a.d[i] * f; return r; }
+__device__ inline double dcbrt(double a) { return pow(a, 1.0 / 3.0); }
+
+// release_model (main.py:230-278) on scalar type T; Hrr = rhat^T Hess(Phi) rhat supplied by the caller.
+// out[12] = pos_lead(3), pos_trail(3), vel_lead(3), vel_trail(3)
+template <class T>
+__device__ inline void release_math(const T x[3], const T v[3], const T H[3][3], double GMsat, const double kv[8], const double nr[4], T out[12]) {
+    const T rad2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+    const T L[3] = {x[1] * v[2] - x[2] * v[1], x[2] * v[0] - x[0] * v[2], x[0] * v[1] - x[1] * v[0]};
+    const T Lmag = dsqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+    const T omega = Lmag / rad2;                                                 // main.py:88-96
+    const T r = dsqrt(rad2);
+    const T rhat[3] = {x[0] / r, x[1] / r, x[2] / r};
+    T d2 = T(0.0);                                                               // main.py:76-85 (rhat held fixed inside the derivative)
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) d2 = d2 + rhat[i] * H[i][j] * rhat[j];
+    const T rt = dcbrt(T(GMsat) / (omega * omega - d2));                         // main.py:104
+    const T vcirc = omega * rt;                                                  // main.py:238,242
+    const T zhat[3] = {L[0] / Lmag, L[1] / Lmag, L[2] / Lmag};
+    const T vr = v[0] * rhat[0] + v[1] * rhat[1] + v[2] * rhat[2];
+    const T pv[3] = {v[0] - vr * rhat[0], v[1] - vr * rhat[1], v[2] - vr * rhat[2]};
+    const T pn = dsqrt(pv[0] * pv[0] + pv[1] * pv[1] + pv[2] * pv[2]);
+    const T phat[3] = {pv[0] / pn, pv[1] / pn, pv[2] / pn};
+    const double kr = kv[0] + nr[0] * kv[4];                                     // main.py:263-266
+    const double kvphi = kr * (kv[1] + nr[1] * kv[5]);
+    const double kz = kv[2] + nr[2] * kv[6];
+    const double kvz = kv[3] + nr[3] * kv[7];
+    for (int k = 0; k < 3; ++k) {
+        T pt = x[k] + T(kr) * rhat[k] * rt;                                      // main.py:269-272 (trailing)
+        pt = pt + zhat[k] * T(kz) * rt;
+        T vt = v[k] + T(kvphi) * vcirc * phat[k];
+        vt = vt + T(kvz) * vcirc * zhat[k];
+        T pl = x[k] - T(kr) * rhat[k] * rt;                                      // main.py:275-278 (leading)
+        pl = pl - zhat[k] * T(kz) * rt;
+        T vl = v[k] - T(kvphi) * vcirc * phat[k];
+        vl = vl - T(kvz) * vcirc * zhat[k];
+        out[k] = pl; out[3 + k] = pt; out[6 + k] = vl; out[9 + k] = vt;
+    }
+}
+
+__device__ inline void release_draws(const ReleaseArgs& a, int64_t i, double nr[4]) {
+    if (a.normals) { for (int q = 0; q < 4; ++q) nr[q] = a.normals[4 * i + q]; }
+    else { const int64_t id = a.idx ? a.idx[i] : i; for (int q = 0; q < 4; ++q) nr[q] = jax_normal1(id * a.r[q]); }
+}
+
 __global__ void release_kernel(const __grid_constant__ ssb_potential Pin, const ReleaseArgs a) {
     __shared__ ssb_potential sP;
     stage_potential(&sP, &Pin);
@@ -397,47 +458,65 @@ __global__ void release_kernel(const __grid_constant__ ssb_potential Pin, const 
     const double x[3] = {w[0], w[1], w[2]}, v[3] = {w[3], w[4], w[5]};
     const double t = a.t[i];
     double nr[4];
-    if (a.normals) { for (int q = 0; q < 4; ++q) nr[q] = a.normals[4 * i + q]; }
-    else { const int64_t id = a.idx ? a.idx[i] : i; for (int q = 0; q < 4; ++q) nr[q] = jax_normal1(id * a.r[q]); }
-    // omega (main.py:88-96), d2phidr2 = rhat^T H rhat (main.py:76-85), tidal radius (main.py:104)
-    const double rad2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
-    const double L[3] = {x[1] * v[2] - x[2] * v[1], x[2] * v[0] - x[0] * v[2], x[0] * v[1] - x[1] * v[0]};
-    const double Lmag = sqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
-    const double omega = Lmag / rad2;
-    const double r = sqrt(rad2);
-    const double rhat[3] = {x[0] / r, x[1] / r, x[2] / r};
+    release_draws(a, i, nr);
     double P, g[3];
-    Sym3 H;
-    pot_eval<WANT_HESS>(sP, x, t, P, g, H);
-    const double d2 = rhat[0] * (H.xx * rhat[0] + H.xy * rhat[1] + H.xz * rhat[2]) + rhat[1] * (H.xy * rhat[0] + H.yy * rhat[1] + H.yz * rhat[2]) +
-                      rhat[2] * (H.xz * rhat[0] + H.yz * rhat[1] + H.zz * rhat[2]);
-    const double rt = pow((a.G * a.Msat[i]) / (omega * omega - d2), 1.0 / 3.0);
-    const double vcirc = omega * rt;                                   // main.py:238,242
-    const double zhat[3] = {L[0] / Lmag, L[1] / Lmag, L[2] / Lmag};
-    const double vr = v[0] * rhat[0] + v[1] * rhat[1] + v[2] * rhat[2];
-    const double pv[3] = {v[0] - vr * rhat[0], v[1] - vr * rhat[1], v[2] - vr * rhat[2]};
-    const double pn = sqrt(pv[0] * pv[0] + pv[1] * pv[1] + pv[2] * pv[2]);
-    const double phat[3] = {pv[0] / pn, pv[1] / pn, pv[2] / pn};
-    const double kr = a.kv[0] + nr[0] * a.kv[4];                       // main.py:263-266
-    const double kvphi = kr * (a.kv[1] + nr[1] * a.kv[5]);
-    const double kz = a.kv[2] + nr[2] * a.kv[6];
-    const double kvz = a.kv[3] + nr[3] * a.kv[7];
+    Sym3 Hs;
+    pot_eval<WANT_HESS>(sP, x, t, P, g, Hs);
+    const double H[3][3] = {{Hs.xx, Hs.xy, Hs.xz}, {Hs.xy, Hs.yy, Hs.yz}, {Hs.xz, Hs.yz, Hs.zz}};
+    double out[12];
+    release_math<double>(x, v, H, a.G * a.Msat[i], a.kv, nr, out);
     for (int k = 0; k < 3; ++k) {
-        double pt = x[k] + kr * rhat[k] * rt;                          // main.py:269-272 (trailing)
-        pt = pt + zhat[k] * kz * (rt / 1.0);
-        double vt = v[k] + (0.0 + kvphi * vcirc * 1.0) * phat[k];
-        vt = vt + (kvz * vcirc * 1.0) * zhat[k];
-        double pl = x[k] + kr * rhat[k] * (-rt);                       // main.py:275-278 (leading)
-        pl = pl + zhat[k] * kz * (-rt / 1.0);
-        double vl = v[k] + (0.0 + kvphi * vcirc * (-1.0)) * phat[k];
-        vl = vl + (kvz * vcirc * (-1.0)) * zhat[k];
-        if (a.pos_lead) { a.pos_lead[3 * i + k] = pl; a.pos_trail[3 * i + k] = pt; a.vel_lead[3 * i + k] = vl; a.vel_trail[3 * i + k] = vt; }
+        if (a.pos_lead) { a.pos_lead[3 * i + k] = out[k]; a.pos_trail[3 * i + k] = out[3 + k]; a.vel_lead[3 * i + k] = out[6 + k]; a.vel_trail[3 * i + k] = out[9 + k]; }
         if (a.w0_packed) {
-            a.w0_packed[6 * i + k] = pl; a.w0_packed[6 * i + 3 + k] = vl;
-            a.w0_packed[6 * (a.N + i) + k] = pt; a.w0_packed[6 * (a.N + i) + 3 + k] = vt;
+            a.w0_packed[6 * i + k] = out[k]; a.w0_packed[6 * i + 3 + k] = out[6 + k];
+            a.w0_packed[6 * (a.N + i) + k] = out[3 + k]; a.w0_packed[6 * (a.N + i) + 3 + k] = out[9 + k];
         }
     }
     if (a.t0_packed) { a.t0_packed[i] = t; a.t0_packed[a.N + i] = t; }
+}
+
+// jacfwd(release_func) (perturbative.py:281-296): jac[N,2,6,6], rows = (pos, vel) of lead / trail, columns = d/d(x, v)
+__global__ void release_jacobian_kernel(const __grid_constant__ ssb_potential Pin, const ReleaseArgs a, double* jac) {
+    __shared__ ssb_potential sP;
+    stage_potential(&sP, &Pin);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const double* w = a.prog + 6 * i;
+    const double xs[3] = {w[0], w[1], w[2]};
+    const double t = a.t[i];
+    double nr[4];
+    release_draws(a, i, nr);
+    double P, g[3];
+    Sym3 Hs;
+    Sym3x3 T3;
+    pot_eval<WANT_HESS>(sP, xs, t, P, g, Hs);
+    pot_third(sP, xs, t, T3);
+    const double Hv[3][3] = {{Hs.xx, Hs.xy, Hs.xz}, {Hs.xy, Hs.yy, Hs.yz}, {Hs.xz, Hs.yz, Hs.zz}};
+    D6 x[3], v[3], H[3][3], out[12];
+    for (int k = 0; k < 3; ++k) { x[k] = D6(w[k]); x[k].d[k] = 1.0; v[k] = D6(w[3 + k]); v[k].d[3 + k] = 1.0; }
+    for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) {
+        H[p][q] = D6(Hv[p][q]);
+        for (int k = 0; k < 3; ++k) H[p][q].d[k] = third_at(T3, p, q, k);
+    }
+    release_math<D6>(x, v, H, a.G * a.Msat[i], a.kv, nr, out);
+    double* J = jac + (size_t)i * 72;
+    for (int c = 0; c < 3; ++c) for (int q = 0; q < 6; ++q) {
+        J[0 * 36 + c * 6 + q] = out[c].d[q];             // lead position rows
+        J[0 * 36 + (3 + c) * 6 + q] = out[6 + c].d[q];   // lead velocity rows
+        J[1 * 36 + c * 6 + q] = out[3 + c].d[q];         // trail position rows
+        J[1 * 36 + (3 + c) * 6 + q] = out[9 + c].d[q];   // trail velocity rows
+    }
+}
+
+__global__ void potential_third_kernel(const __grid_constant__ ssb_potential Pin, int64_t n, const double* xyz, const double* t, double* third) {
+    __shared__ ssb_potential sP;
+    stage_potential(&sP, &Pin);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double X[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+    Sym3x3 T3;
+    pot_third(sP, X, t[i], T3);
+    for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) for (int k = 0; k < 3; ++k) third[27 * i + 9 * p + 3 * q + k] = third_at(T3, p, q, k);
 }
 
 // gather the [i_begin, i_end) slice of the packed release output into the orbit-kernel input of the stream
@@ -653,6 +732,32 @@ int ssb_release_spray_f64(const ssb_potential* pot, double G, int64_t N, const d
     a.pos_lead = pos_lead; a.pos_trail = pos_trail; a.vel_lead = vel_lead; a.vel_trail = vel_trail;
     release_kernel<<<nblk(N, 128), 128, 0, (cudaStream_t)stream>>>(*pot, a);
     CKL("release_kernel");
+    return 0;
+}
+
+int ssb_release_jacobian_f64(const ssb_potential* pot, double G, int64_t N, const double* prog, const double* Msat, const int64_t* idx,
+                             const double* t, int64_t seed, const double* kvals, const double* normals, double* jac, void* stream) {
+    if (int e = ssb_validate_potential(pot)) return e;
+    if (N < 0) return ssb_set_error(SSB_ERR_ARG, "release_jacobian: negative N");
+    if (N == 0) return 0;
+    if (!prog || !Msat || !t || !kvals || !jac) return ssb_set_error(SSB_ERR_ARG, "release_jacobian: NULL array");
+    ReleaseArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = N; a.prog = prog; a.Msat = Msat; a.t = t; a.normals = normals; a.idx = idx; a.G = G;
+    int64_t r5[5]; host_randint5(seed, r5);
+    for (int q = 0; q < 4; ++q) a.r[q] = r5[q];
+    memcpy(a.kv, kvals, sizeof(a.kv));
+    release_jacobian_kernel<<<nblk(N, 64), 64, 0, (cudaStream_t)stream>>>(*pot, a, jac);
+    CKL("release_jacobian_kernel");
+    return 0;
+}
+
+int ssb_potential_third_f64(const ssb_potential* pot, int64_t n, const double* xyz, const double* t, double* third, void* stream) {
+    if (int e = ssb_validate_potential(pot)) return e;
+    if (n < 0 || (n > 0 && (!xyz || !t || !third))) return ssb_set_error(SSB_ERR_ARG, "potential_third: bad n / NULL array");
+    if (n == 0) return 0;
+    potential_third_kernel<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(*pot, n, xyz, t, third);
+    CKL("potential_third_kernel");
     return 0;
 }
 

@@ -280,6 +280,121 @@ __device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x
 }
 
 // ---------------------------------------------------------------------------------------------
+// third derivatives of Phi (needed by jacfwd(release_model), perturbative.py:281-296, through main.py:76-104, and by the
+// second-order response).  Not on the per-step hot path: plain IEEE arithmetic, runtime loops.
+//   spherical:  Phi_ijk = u3 x_i x_j x_k + w (d_ij x_k + d_ik x_j + d_jk x_i),   w = q'/r,  u3 = w'/r,  q = Phi'/r
+//   storage: 10 unique components {xxx, yyy, zzz, xxy, xxz, xyy, yyz, xzz, yzz, xyz}
+// ---------------------------------------------------------------------------------------------
+struct Sym3x3 { double xxx, yyy, zzz, xxy, xxz, xyy, yyz, xzz, yzz, xyz; };
+
+__device__ inline void add_spherical_third(const double x[3], double w, double u3, double sc0, double sc1, double sc2, Sym3x3& T) {
+    // sc*: per-axis chain-rule factors (1 except for the triaxial NFW)
+    T.xxx += (u3 * x[0] * x[0] * x[0] + 3.0 * w * x[0]) * sc0 * sc0 * sc0;
+    T.yyy += (u3 * x[1] * x[1] * x[1] + 3.0 * w * x[1]) * sc1 * sc1 * sc1;
+    T.zzz += (u3 * x[2] * x[2] * x[2] + 3.0 * w * x[2]) * sc2 * sc2 * sc2;
+    T.xxy += (u3 * x[0] * x[0] * x[1] + w * x[1]) * sc0 * sc0 * sc1;
+    T.xxz += (u3 * x[0] * x[0] * x[2] + w * x[2]) * sc0 * sc0 * sc2;
+    T.xyy += (u3 * x[0] * x[1] * x[1] + w * x[0]) * sc0 * sc1 * sc1;
+    T.yyz += (u3 * x[1] * x[1] * x[2] + w * x[2]) * sc1 * sc1 * sc2;
+    T.xzz += (u3 * x[0] * x[2] * x[2] + w * x[0]) * sc0 * sc2 * sc2;
+    T.yzz += (u3 * x[1] * x[2] * x[2] + w * x[1]) * sc1 * sc2 * sc2;
+    T.xyz += (u3 * x[0] * x[1] * x[2]) * sc0 * sc1 * sc2;
+}
+// radial scalars w = q'/r and u3 = w'/r
+__device__ inline void nfw_wu(double GM, double rs, double r2, double& w, double& u3) {
+    const double r = sqrt(r2), s1 = r + rs, u = log1p(r / rs);
+    const double r3 = r2 * r, r4 = r2 * r2;
+    w = GM * (3.0 / (r4 * s1) - 3.0 * u / (r4 * r) + 1.0 / (r3 * s1 * s1));
+    u3 = GM * (-15.0 / (r4 * r * s1) - 6.0 / (r4 * s1 * s1) - 2.0 / (r3 * s1 * s1 * s1) + 15.0 * u / (r4 * r2)) / r;
+}
+__device__ inline void hernquist_wu(double GM, double a, double r2soft, double& w, double& u3) {
+    const double r = sqrt(r2soft), ir = 1.0 / r, ira = 1.0 / (r + a);
+    const double q = GM * ira * ira * ir;
+    w = -q * ir * (2.0 * ira + ir);
+    u3 = 3.0 * q * ir * ir * (2.0 * ira * ira + 2.0 * ira * ir + ir * ir);
+}
+__device__ inline void plummer_wu(double GM, double a, double r2, double& w, double& u3) {
+    const double s = 1.0 / sqrt(r2 + a * a), s2 = s * s, s5 = s2 * s2 * s;
+    w = -3.0 * GM * s5;
+    u3 = 15.0 * GM * s5 * s2;
+}
+__device__ inline void profile_wu(int profile, double GM, double a, double r2, double& w, double& u3) {
+    if (profile == SSB_PROFILE_PLUMMER) plummer_wu(GM, a, r2, w, u3);
+    else if (profile == SSB_PROFILE_HERNQUIST) hernquist_wu(GM, a, r2, w, u3);
+    else nfw_wu(GM, a, r2, w, u3);
+}
+
+__device__ inline void pot_third(const ssb_potential& Pt, const double x[3], double t, Sym3x3& T) {
+    T.xxx = T.yyy = T.zzz = T.xxy = T.xxz = T.xyy = T.yyz = T.xzz = T.yzz = T.xyz = 0.0;
+    for (int ic = 0; ic < Pt.n_comp; ++ic) {
+        const ssb_component& c = Pt.comp[ic];
+        if (c.type == SSB_UNIFORM_ACC) continue;
+        double xs[3] = {x[0], x[1], x[2]};
+        if (c.track >= 0) {
+            double ctr[3];
+            track_eval<false>(Pt.track[c.track], t, ctr, ctr);
+            xs[0] -= ctr[0]; xs[1] -= ctr[1]; xs[2] -= ctr[2];
+        }
+        const double r2 = xs[0] * xs[0] + xs[1] * xs[1] + xs[2] * xs[2];
+        double w, u3;
+        switch (c.type) {
+            case SSB_NFW: nfw_wu(c.p[0], c.p[1], r2, w, u3); add_spherical_third(xs, w, u3, 1, 1, 1, T); break;
+            case SSB_HERNQUIST: hernquist_wu(c.p[0], c.p[1], r2 + c.p[2], w, u3); add_spherical_third(xs, w, u3, 1, 1, 1, T); break;
+            case SSB_PLUMMER: plummer_wu(c.p[0], c.p[1], r2, w, u3); add_spherical_third(xs, w, u3, 1, 1, 1, T); break;
+            case SSB_ISOCHRONE: hernquist_wu(c.p[0], c.p[1], r2 + c.p[1] * c.p[1], w, u3); add_spherical_third(xs, w, u3, 1, 1, 1, T); break;
+            case SSB_TRIAXNFW: {
+                const double i1 = 1.0 / c.p[2], i2 = 1.0 / c.p[3], i3 = 1.0 / c.p[4];
+                const double xq[3] = {xs[0] * i1, xs[1] * i2, xs[2] * i3};
+                nfw_wu(c.p[0], c.p[1], xq[0] * xq[0] + xq[1] * xq[1] + xq[2] * xq[2], w, u3);
+                add_spherical_third(xq, w, u3, i1, i2, i3, T);
+            } break;
+            case SSB_MIYAMOTO: {
+                // Phi = f(D), f = -GM D^(-1/2), D = x^2 + y^2 + (a + zeta)^2, zeta = sqrt(z^2 + b^2):
+                // Phi_ijk = f''' D_i D_j D_k + f'' (D_ij D_k + D_ik D_j + D_jk D_i) + f' D_ijk
+                const double GM = c.p[0], a = c.p[1], b = c.p[2];
+                const double zeta = sqrt(xs[2] * xs[2] + b * b), az = a + zeta;
+                const double D = xs[0] * xs[0] + xs[1] * xs[1] + az * az;
+                const double sD = sqrt(D);
+                const double f1 = 0.5 * GM / (D * sD), f2 = -0.75 * GM / (D * D * sD), f3 = 1.875 * GM / (D * D * D * sD);
+                const double Dx = 2.0 * xs[0], Dy = 2.0 * xs[1], Dz = 2.0 * xs[2] * az / zeta;
+                const double Dzz = 2.0 + 2.0 * a * b * b / (zeta * zeta * zeta);
+                const double Dzzz = -6.0 * a * b * b * xs[2] / (zeta * zeta * zeta * zeta * zeta);
+                T.xxx += f3 * Dx * Dx * Dx + f2 * 3.0 * 2.0 * Dx;
+                T.yyy += f3 * Dy * Dy * Dy + f2 * 3.0 * 2.0 * Dy;
+                T.zzz += f3 * Dz * Dz * Dz + f2 * 3.0 * Dzz * Dz + f1 * Dzzz;
+                T.xxy += f3 * Dx * Dx * Dy + f2 * 2.0 * Dy;
+                T.xxz += f3 * Dx * Dx * Dz + f2 * 2.0 * Dz;
+                T.xyy += f3 * Dx * Dy * Dy + f2 * 2.0 * Dx;
+                T.yyz += f3 * Dy * Dy * Dz + f2 * 2.0 * Dz;
+                T.xzz += f3 * Dx * Dz * Dz + f2 * Dzz * Dx;
+                T.yzz += f3 * Dy * Dz * Dz + f2 * Dzz * Dy;
+                T.xyz += f3 * Dx * Dy * Dz;
+            } break;
+            case SSB_SUBHALOS: {
+                const ssb_subhalos& S = Pt.sh[c.sh];
+                for (int j = 0; j < S.n; ++j) {
+                    const double dt = t - S.t0[j];
+                    if (!(fabs(dt) < S.tw[j])) continue;
+                    double rel[3];
+                    for (int k = 0; k < 3; ++k) rel[k] = xs[k] - (S.x0[3 * j + k] + S.v[3 * j + k] * dt);
+                    profile_wu(S.profile, S.G * S.m[j], S.rs[j], rel[0] * rel[0] + rel[1] * rel[1] + rel[2] * rel[2], w, u3);
+                    add_spherical_third(rel, w, u3, 1, 1, 1, T);
+                }
+            } break;
+            default: break;
+        }
+    }
+}
+__device__ inline double third_at(const Sym3x3& T, int i, int j, int k) {
+    int c[3] = {0, 0, 0}; c[i]++; c[j]++; c[k]++;
+    const int key = c[0] * 16 + c[1] * 4 + c[2];
+    switch (key) {
+        case 48: return T.xxx; case 12: return T.yyy; case 3: return T.zzz; case 36: return T.xxy; case 33: return T.xxz;
+        case 24: return T.xyy; case 9: return T.yyz; case 18: return T.xzz; case 6: return T.yzz; default: return T.xyz;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // fused static signatures: the reference's canonical galaxy models evaluated without the interpreter.
 // The host (ssb_canonicalize) moves the matching static components to the front of the program in the order below
 // and stores two derived constants (NFW p[2] = 1/r_s, Miyamoto p[3] = b^2); parameters are read straight from the

@@ -53,6 +53,8 @@ struct RespArgs {
     const double* start;      // [n_sh] window start t0 - tw, ascending
     const int* order;         // [n_sh] processing position -> user index
     int skip_unborn;          // 1: D0 == NULL (zero ICs): subhalos whose window has not opened are exactly zero
+    // SaveAt(ts) for a single trajectory (backward progenitor response, perturbative.py:53-60): N == 1
+    const double* ts_save; int M; double* wsave; double* Dsave;
 };
 
 template <int S>
@@ -219,7 +221,36 @@ __device__ __forceinline__ void sweep_items(const BaseShared<Tab<SOLVER>::S>* sb
     }
 }
 
-template <int SOLVER, int SIG, int PROFILE>
+// dense output of every item at one save time inside an ACCEPTED step (stages recomputed from the pre-step state)
+template <int SOLVER>
+__device__ __noinline__ void save_items(const BaseShared<Tab<SOLVER>::S>* sb, const double* __restrict__ tab, int profile, int n_sh, int n_items,
+                                        const double* __restrict__ cur, const int* __restrict__ order, double dt, double theta, double dir,
+                                        double* __restrict__ Dsave_row) {
+    constexpr int S = Tab<SOLVER>::S;
+    for (int it = threadIdx.x; it < n_items; it += blockDim.x) {
+        const int j = it % n_sh, blk = it / n_sh;
+        ItemParams ip; load_item_params(tab, profile, j, blk, n_sh, ip);
+        ItemForce<S> f{sb, &ip, 1};
+        double q[3], pp[3], G[S][3], q1[3], pp1[3], qo[3], po[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { q[k] = cur[(size_t)k * n_items + it]; pp[k] = cur[(size_t)(3 + k) * n_items + it]; }
+        f.at(0, q, G[0]);
+        rk_stages<SOLVER>(f, q, pp, 0.0, dt, G);
+        rk_candidate<SOLVER>(q, pp, dt, G, q1, pp1);
+        f.at(S - 1, q1, G[S - 1]);
+        if (theta >= 1.0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { qo[k] = q1[k]; po[k] = pp1[k]; }
+        } else {
+            rk_dense<SOLVER>(q, pp, q1, pp1, dt, G, theta, qo, po);
+        }
+        double* o = Dsave_row + (size_t)order[j] * 12 + blk * 6;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { o[k] = qo[k]; o[3 + k] = dir * po[k]; }
+    }
+}
+
+template <int SOLVER, int SIG, int PROFILE, bool SAVE>
 __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) response_kernel(const __grid_constant__ ssb_potential Pin, const ssb_subhalos Sh,
                                                                                           const RespArgs a) {
     typedef Tab<SOLVER> T;
@@ -342,6 +373,13 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
             tnext = fmin(T0 + h, T1);
         }
         int n_act_run = 0;
+        int save_idx = 0;
+        if (SAVE) {                                   // rows never reached stay +inf (diffrax SaveAt semantics)
+            const double inf0 = __longlong_as_double(0x7ff0000000000000LL);
+            for (size_t q = tid; q < (size_t)a.M * n_sh * 12; q += blockDim.x) a.Dsave[q] = inf0;
+            for (int q = tid; q < a.M * 6; q += blockDim.x) a.wsave[q] = inf0;
+            __syncthreads();
+        }
         // ================= main loop: all threads follow the same (uniform) control flow =================
         while (tprev < T1 && status == 0) {
             if (n_steps >= c.max_steps) { status = 1; break; }
@@ -387,6 +425,22 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
             if (keep) {
                 n_acc++;
                 if (any_bad) { status = 2; break; }
+                if (SAVE) {
+                    // every ts[save_idx] <= tnext is interpolated inside this accepted step (base by thread 0, items by all)
+                    while (save_idx < a.M) {
+                        const double tq = a.ts_save[save_idx] * dir;
+                        if (!(tq <= tnext)) break;
+                        const double theta = (tq == tnext) ? 1.0 : (tq - tprev) / dt;
+                        if (tid == 0) {
+                            double xo[3], po[3];
+                            if (theta >= 1.0) { for (int k = 0; k < 3; ++k) { xo[k] = x1[k]; po[k] = p1[k]; } }
+                            else rk_dense<SOLVER>(x, p, x1, p1, dt, F, theta, xo, po);
+                            for (int k = 0; k < 3; ++k) { a.wsave[6 * save_idx + k] = xo[k]; a.wsave[6 * save_idx + 3 + k] = dir * po[k]; }
+                        }
+                        save_items<SOLVER>(&sb, a.sorted, Sh.profile, n_sh, n_items, cur, a.order, dt, theta, dir, a.Dsave + (size_t)save_idx * n_sh * 12);
+                        save_idx++;
+                    }
+                }
                 double* tmp = cur; cur = nxt; nxt = tmp;
                 if (tid == 0) {
 #pragma unroll
@@ -472,9 +526,9 @@ size_t ssb_response_scratch_bytes(int32_t n_sh) {
     return 256 + resp_table_bytes(n_sh) + per_cta * (size_t)SSB_RESP_MAX_CTAS;
 }
 
-int ssb_linear_response_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0, const double* D0,
-                            const double* t0, double t1, ssb_ctrl ctrl, double* wout, double* Dout, int32_t* status, int32_t* nsteps,
-                            void* scratch, size_t scratch_bytes, void* stream) {
+static int response_impl(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0, const double* D0,
+                         const double* t0, double t1, ssb_ctrl ctrl, double* wout, double* Dout, int32_t* status, int32_t* nsteps,
+                         void* scratch, size_t scratch_bytes, void* stream, const double* ts_save, int M, double* wsave, double* Dsave) {
     if (int e = ssb_validate_potential(pot_base)) return e;
     if (int e = ssb_validate_ctrl(ctrl)) return e;
     if (!sh || sh->n < 0) return ssb_set_error(SSB_ERR_ARG, "linear_response: bad subhalo set");
@@ -495,7 +549,8 @@ int ssb_linear_response_f64(const ssb_potential* pot_base, const ssb_subhalos* s
     int* order = (int*)(start + sh->n);
     a.sorted = tab; a.start = start; a.order = order;
     a.scratch = (double*)((char*)scratch + 256 + resp_table_bytes(sh->n));
-    a.skip_unborn = (D0 == nullptr) ? 1 : 0;
+    a.skip_unborn = (D0 == nullptr && M == 0) ? 1 : 0;
+    a.ts_save = ts_save; a.M = M; a.wsave = wsave; a.Dsave = Dsave;
     CK(cudaMemsetAsync(scratch, 0, 256, st));
     if (sh->n > 0) {
         if (sh->n <= SSB_RESP_MAX_SORT) {
@@ -512,14 +567,44 @@ int ssb_linear_response_f64(const ssb_potential* pot_base, const ssb_subhalos* s
     ssb_potential pc;
     const int sig = ssb_canonicalize(pot_base, &pc);
     // base potentials of the response path: MW3 / Gala fused, everything else (incl. a lone NFW) through the interpreter
-#define SSB_LAUNCH_RESP(S, SG, PR) response_kernel<S, SG, PR><<<grid, SSB_RESP_THREADS, 0, st>>>(sig == SG ? pc : *pot_base, *sh, a)
+#define SSB_LAUNCH_RESP(S, SG, PR) response_kernel<S, SG, PR, false><<<grid, SSB_RESP_THREADS, 0, st>>>(sig == SG ? pc : *pot_base, *sh, a)
 #define SSB_LAUNCH_RESP_SIG(S, PR) do { switch (sig) { case SIG_NHM: SSB_LAUNCH_RESP(S, SIG_NHM, PR); break; \
         case SIG_NHHM: SSB_LAUNCH_RESP(S, SIG_NHHM, PR); break; default: SSB_LAUNCH_RESP(S, SIG_GENERIC, PR); } } while (0)
 #define SSB_LAUNCH_RESP_PR(S) do { switch (sh->profile) { case SSB_PROFILE_PLUMMER: SSB_LAUNCH_RESP_SIG(S, SSB_PROFILE_PLUMMER); break; \
         case SSB_PROFILE_HERNQUIST: SSB_LAUNCH_RESP_SIG(S, SSB_PROFILE_HERNQUIST); break; default: SSB_LAUNCH_RESP_SIG(S, SSB_PROFILE_NFW); } } while (0)
-    if (ctrl.solver == 5) SSB_LAUNCH_RESP_PR(5); else SSB_LAUNCH_RESP_PR(8);
+    if (M > 0) {          // single saved trajectory: interpreter base force, runtime profile inside save_items; one CTA
+#define SSB_LAUNCH_SAVE(S, PR) response_kernel<S, SIG_GENERIC, PR, true><<<1, SSB_RESP_THREADS, 0, st>>>(*pot_base, *sh, a)
+#define SSB_LAUNCH_SAVE_PR(S) do { switch (sh->profile) { case SSB_PROFILE_PLUMMER: SSB_LAUNCH_SAVE(S, SSB_PROFILE_PLUMMER); break; \
+        case SSB_PROFILE_HERNQUIST: SSB_LAUNCH_SAVE(S, SSB_PROFILE_HERNQUIST); break; default: SSB_LAUNCH_SAVE(S, SSB_PROFILE_NFW); } } while (0)
+        if (ctrl.solver == 5) SSB_LAUNCH_SAVE_PR(5); else SSB_LAUNCH_SAVE_PR(8);
+    } else {
+        if (ctrl.solver == 5) SSB_LAUNCH_RESP_PR(5); else SSB_LAUNCH_RESP_PR(8);
+    }
     CKL("response_kernel");
     return 0;
+}
+
+int ssb_linear_response_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0, const double* D0,
+                            const double* t0, double t1, ssb_ctrl ctrl, double* wout, double* Dout, int32_t* status, int32_t* nsteps,
+                            void* scratch, size_t scratch_bytes, void* stream) {
+    return response_impl(pot_base, sh, N, w0, D0, t0, t1, ctrl, wout, Dout, status, nsteps, scratch, scratch_bytes, stream, nullptr, 0, nullptr, nullptr);
+}
+
+size_t ssb_response_saveat_scratch_bytes(int32_t n_sh) {
+    return ssb_response_scratch_bytes(n_sh) + sizeof(double) * (8 + 12 * (size_t)(n_sh > 0 ? n_sh : 1)) + 256;
+}
+
+int ssb_linear_response_saveat_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, const double* w0, const double* D0, const double* t0,
+                                   double t1, const double* ts, int32_t M, ssb_ctrl ctrl, double* ws, double* Ds, int32_t* status, int32_t* nsteps,
+                                   void* scratch, size_t scratch_bytes, void* stream) {
+    if (!sh) return ssb_set_error(SSB_ERR_ARG, "linear_response_saveat: bad subhalo set");
+    if (M <= 0 || !ts || !ws || (sh->n > 0 && !Ds)) return ssb_set_error(SSB_ERR_ARG, "linear_response_saveat: needs M > 0 save times and outputs");
+    if (scratch_bytes < ssb_response_saveat_scratch_bytes(sh->n)) return ssb_set_error(SSB_ERR_SCRATCH, "linear_response_saveat: scratch too small");
+    // the final state the common path always writes goes to the tail of the scratch buffer
+    const size_t head = ssb_response_scratch_bytes(sh->n);
+    double* wfin = (double*)((char*)scratch + head);
+    double* Dfin = wfin + 8;
+    return response_impl(pot_base, sh, 1, w0, D0, t0, t1, ctrl, wfin, Dfin, status, nsteps, scratch, head, stream, ts, M, ws, Ds);
 }
 
 int ssb_response_term_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, double t, const double* y, double* dy, void* stream) {

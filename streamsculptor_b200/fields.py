@@ -55,19 +55,14 @@ def integrate_field(w0=None, ts=None, dense=False, solver=Dopri8(scan_kind='boun
         return sol
     if isinstance(field, MassRadiusPerturbation_OTF):
         pg = field.pertgen
-        if len(ts_h) != 2 and not (len(ts_h) == 1):
-            raise NotImplementedError("the response kernel keeps the final state only (ts = [t_start, t_end], perturbative.py:110,125)")
         ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
-        w = rt.to_dev(w0[0]).reshape(1, 6)
-        D0 = rt.to_dev(w0[1]).reshape(1, pg.subhalo_arrays.n, 12)
-        wout, Dout, status, nsteps = rt.linear_response(pg.potential_base_total, pg.subhalo_arrays, w, D0, rt.to_dev([a]), b, ctrl)
-        if int(status[0]) != 0:
+        w = rt.to_dev(w0[0]).reshape(6)
+        D0h = np.asarray(w0[1].cpu() if hasattr(w0[1], "cpu") else w0[1], dtype=np.float64).reshape(pg.subhalo_arrays.n, 12)
+        D0 = rt.to_dev(D0h) if np.any(D0h) else None
+        ws, Ds, status, nsteps = rt.linear_response_saveat(pg.potential_base_total, pg.subhalo_arrays, w, D0, rt.to_dev([a]), b, rt.to_dev(ts_h), ctrl)
+        if int(status[0]) != 0:     # diffrax default throw=True (fields.py:85-98)
             raise RuntimeError("integrate_field failed: " + ("max_steps reached" if int(status[0]) == 1 else "non-finite state"))
-        inf = np.full((1, 6), np.inf)
-        ys0 = np.vstack([np.asarray(w.cpu()) if ts_h[0] == a else inf, wout.cpu().numpy()]) if len(ts_h) == 2 else wout.cpu().numpy()
-        D0h, Dh = D0.cpu().numpy(), Dout.cpu().numpy()
-        ys1 = np.concatenate([D0h if ts_h[0] == a else np.full_like(D0h, np.inf), Dh]) if len(ts_h) == 2 else Dh
-        return Solution(ts_h, [ys0, ys1], status[0].cpu().numpy(), nsteps[0])
+        return Solution(ts_h, [ws.cpu().numpy(), Ds.cpu().numpy()], status[0].cpu().numpy(), nsteps[0])
     raise NotImplementedError(f"field {type(field).__name__} is not implemented on the device (closed set: hamiltonian_field, "
                               "MassRadiusPerturbation_OTF)")
 

@@ -166,6 +166,22 @@ class Potential:
                                 0 if seed_num is None else int(seed_num), kv, None if normals is None else rt.to_dev(normals).reshape(1, 4))
         return tuple(o[0].cpu().numpy() for o in outs)           # pos_lead, pos_trail, v_lead, v_trail
 
+    def release_jacobian(self, prog, Msat, idx, ts, seed_num, kval_arr=1.0, normals=None):
+        """jacfwd(release_model) over a batch (perturbative.py:281-296): [N,2,6,6], rows (pos, vel) of lead/trail, columns d/d(x, v)."""
+        tt = rt.torch()
+        prog_d = rt.to_dev(prog).reshape(-1, 6)
+        n = prog_d.shape[0]
+        kv = DEFAULT_KVALS if np.isscalar(kval_arr) else tuple(np.asarray(kval_arr, dtype=np.float64).reshape(8))
+        Ms = rt.to_dev(np.broadcast_to(np.asarray(Msat, dtype=np.float64), (n,)).copy())
+        jac = rt.release_jacobian(self, self._G, prog_d, Ms, rt.to_dev(np.asarray(idx), tt.int64), rt.to_dev(ts).reshape(-1),
+                                  0 if seed_num is None else int(seed_num), kv, None if normals is None else rt.to_dev(normals).reshape(n, 4))
+        return jac.cpu().numpy()
+
+    def third_derivative(self, xyz, t):
+        """d^3 Phi / dx_i dx_j dx_k (the reference obtains it by nested jacfwd, fields.py:278-283)."""
+        out = rt.potential_third(self, xyz, t).cpu().numpy()
+        return out[0] if np.ndim(xyz) == 1 else out
+
     def _stream_inputs(self, ts, prog_w0, Msat, kval_arr, normals):
         ts_d = rt.to_dev(ts).reshape(-1)
         n = ts_d.shape[0]

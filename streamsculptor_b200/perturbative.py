@@ -13,6 +13,82 @@ from .solvers import Dopri5, Dopri8
 from .units import usys
 
 
+class BaseStreamModel(Potential):
+    """Stream model without linear perturbations (perturbative.py:243-296): release ICs, forward progenitor track and the
+    Jacobian of the release function w.r.t. the progenitor phase-space position."""
+
+    def __init__(self, potential_base, prog_w0, ts, Msat, seednum, solver, units=None, dense=False, cpu=True, normals=None, **kwargs):
+        super().__init__(units, {'potential_base': potential_base, 'prog_w0': prog_w0, 'ts': ts, 'Msat': Msat, 'seednum': seednum,
+                                 'solver': solver, 'dense': dense, 'cpu': cpu})
+        if dense:
+            raise NotImplementedError("dense base streams (perturbative.py:271-276) are not on the B200 hot path")
+        self.ts = np.asarray(ts, dtype=np.float64)
+        self.solver = Dopri5(scan_kind='bounded') if solver is None else solver
+        self._normals = normals
+        self.streamICs = potential_base.gen_stream_ics(ts=self.ts, prog_w0=prog_w0, Msat=Msat, seed_num=seednum, solver=self.solver, normals=normals,
+                                                       **kwargs)                                                    # perturbative.py:265
+        self.IDs = np.arange(len(self.ts))
+        self.prog_loc_fwd = np.asarray(potential_base.integrate_orbit(w0=prog_w0, ts=self.ts, t0=self.ts.min(), t1=self.ts.max(), solver=self.solver,
+                                                                      **kwargs).ys)                                 # perturbative.py:268
+        self.dRel_dIC = self.release_func_jacobian()
+        self.stream_interp = None
+
+    def release_func_jacobian(self):
+        """[len(ts), 2, 6, 6] (perturbative.py:281-296)."""
+        return self.potential_base.release_jacobian(self.prog_loc_fwd, self.Msat, self.IDs, self.ts, self.seednum, normals=self._normals)
+
+
+class GenerateMassRadiusPerturbation(Potential):
+    """Classic lead/trail perturbation generator (perturbative.py:24-221): the progenitor's own response is integrated backwards
+    and mapped through the release Jacobian into the particles' perturbation ICs."""
+
+    def __init__(self, potential_base, potential_perturbation, potential_structural=None, BaseStreamModel=None, units=None, **kwargs):
+        super().__init__(units, {'potential_base': potential_base, 'potential_perturbation': potential_perturbation,
+                                 'potential_structural': potential_structural, 'BaseStreamModel': BaseStreamModel})
+        from . import fields
+        self.gradient = None
+        self.potential_base_total = potential_base
+        self.subhalo_arrays = potential_perturbation._arrays
+        self.jump_ts = None
+        if BaseStreamModel is not None:
+            self.base_stream = BaseStreamModel
+            self.num_pert = potential_perturbation._arrays.n
+            self.field_wobs = [BaseStreamModel.prog_loc_fwd[-1], np.zeros((self.num_pert, 12))]                       # perturbative.py:53
+            flipped_times = np.flip(BaseStreamModel.ts)
+            prog_fieldICs = fields.integrate_field(w0=self.field_wobs, ts=flipped_times, field=fields.MassRadiusPerturbation_OTF(self),
+                                                   backwards_int=True, **kwargs)                                     # perturbative.py:57
+            self.prog_base = prog_fieldICs
+            self.prog_fieldICs = np.flipud(prog_fieldICs.ys[1])
+            self.perturbation_ICs_lead, self.perturbation_ICs_trail = self.compute_perturbation_ICs()
+            s = self.base_stream.streamICs
+            self.base_realspace_ICs_lead = np.hstack([s[0], s[2]])
+            self.base_realspace_ICs_trail = np.hstack([s[1], s[3]])
+
+    def compute_base_stream(self, cpu=True):          # perturbative.py:68-81
+        b = self.base_stream
+        return self.potential_base.gen_stream_vmapped(ts=b.ts, prog_w0=b.prog_w0, Msat=b.Msat, seed_num=b.seednum, solver=b.solver, normals=b._normals)
+
+    def compute_perturbation_ICs(self):               # perturbative.py:84-98
+        J, F = self.base_stream.dRel_dIC, self.prog_fieldICs
+        lead = np.dstack([np.einsum('ijk,ilk->ilj', J[:, 0], F[:, :, :6]), np.einsum('ijk,ilk->ilj', J[:, 0], F[:, :, 6:])])
+        trail = np.dstack([np.einsum('ijk,ilk->ilj', J[:, 1], F[:, :, :6]), np.einsum('ijk,ilk->ilj', J[:, 1], F[:, :, 6:])])
+        return lead, trail
+
+    def compute_perturbation_OTF(self, cpu=True, solver=Dopri8(scan_kind='bounded'), rtol=1e-6, atol=1e-6, dtmin=0.05, dtmax=None, max_steps=10_000):
+        """(lead_and_derivs, trail_and_derivs), each [w (N-1,6), D (N-1,N_sh,12)] (perturbative.py:101-135)."""
+        ts = self.base_stream.ts
+        n = len(ts) - 1
+        ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
+        outs = []
+        for w0, D0 in ((self.base_realspace_ICs_lead, self.perturbation_ICs_lead), (self.base_realspace_ICs_trail, self.perturbation_ICs_trail)):
+            wout, Dout, status, nsteps = rt.linear_response(self.potential_base_total, self.subhalo_arrays, rt.to_dev(w0[:n]), rt.to_dev(D0[:n]),
+                                                            rt.to_dev(ts[:n]), float(ts[-1]), ctrl)
+            if bool((status != 0).any()):
+                raise RuntimeError("compute_perturbation_OTF: a particle failed (max_steps reached or non-finite state)")
+            outs.append([wout.cpu().numpy(), Dout.cpu().numpy()])
+        return outs[0], outs[1]
+
+
 class CustomBaseStreamModel(Potential):
     """Stream model with user-supplied release offsets (perturbative.py:299-364)."""
 

@@ -343,3 +343,68 @@ def test_cubic_track_and_host_entry_points(cuda):
     _lib.check(_lib.lib().ssb_orbit_integrate_host(C.byref(host), 33, p(w0), p(t0), p(t1), p(ts), 1, 1, ctrl, p(ys), p(st), p(ns)))
     sol = pot_static.integrate_orbit_batch_vmapped(w0=w0, ts=ts, t0=t0, t1=t1)
     assert np.array_equal(ys, sol.ys) and (st == 0).all()
+
+
+def test_third_derivatives_and_release_jacobian(cuda):
+    """A15: closed-form third derivatives and jacfwd(release_model) (perturbative.py:281-296) vs the oracle's nested autodiff."""
+    import streamsculptor_b200 as ssc
+    orc, prod = _full_pair(cuda)
+    rng = np.random.default_rng(5)
+    xyz = rng.normal(size=(64, 3)) * np.array([14, 14, 7.0])
+    t = rng.uniform(-2900, -100, 64)
+    assert relerr(prod.third_derivative(xyz, t), orc.third(xyz, t)) < 1e-9
+    orc3, mw3 = mw3_oracle(), mw3_product()
+    prog = halo_orbits(50, seed=8)
+    ts = np.linspace(-2000.0, 0.0, 50)
+    nr = np.random.Generator(np.random.PCG64(2)).standard_normal((50, 4))
+    for normals in (nr, None):
+        J = mw3.release_jacobian(prog, 1e4, np.arange(50), ts, 493, normals=normals)
+        Jo = orc3.release(prog, 1e4, np.arange(50), ts, 493, normals=normals, jacobian=True)
+        assert J.shape == (50, 2, 6, 6) and np.abs(J - Jo).max() < 1e-9 * np.abs(Jo).max()
+    assert np.allclose(J[:, 0] + J[:, 1], 2 * np.eye(6), atol=1e-12)          # lead/trail are mirror images: J_lead + J_trail = 2 I (golden D8's structure)
+
+
+def test_saved_response_trajectory_and_classic_generator(cuda):
+    """A12-A15 classic path: BaseStreamModel + GenerateMassRadiusPerturbation (perturbative.py:24-296): backward progenitor
+    response saved at every stripping time, release Jacobian, perturbation ICs, lead / trail responses."""
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import _runtime as rt
+    P, pt = ssc.potential, ssc.perturbative
+    nsh, nts = 8, 31
+    sh = subhalo_set(nsh, seed=17, t_lo=-900.0)
+    sh["x0"] = sh["x0"] * 0.3 + np.array([12.0, 3.0, -6.0])
+    base, orc_base = mw3_product(), mw3_oracle()
+    ts = np.linspace(-1000.0, 0.0, nts)
+    prog_w0 = [12.0, 3.0, -6.0, -0.05, 0.15, 0.03]
+    nr = np.random.Generator(np.random.PCG64(4)).standard_normal((nts, 4))
+    pert = P.SubhaloLinePotential(m=sh["m"], a=sh["rs"], subhalo_x0=sh["x0"], subhalo_v=sh["v"], subhalo_t0=sh["t0"], t_window=150.0, units=ssc.usys)
+    struct = P.SubhaloLinePotential_dRadius(m=sh["m"], a=sh["rs"], subhalo_x0=sh["x0"], subhalo_v=sh["v"], subhalo_t0=sh["t0"], t_window=150.0, units=ssc.usys)
+    orc_sh = O.Program().subhalos(O.PR_PLUMMER, sh["m"], sh["rs"], sh["x0"], sh["v"], sh["t0"], 150.0)
+    fixed = dict(rtol=1e-8, atol=1e-8, dtmin=2.0, dtmax=2.0)                  # identical step sequences -> 1e-10 comparisons
+    model = pt.BaseStreamModel(potential_base=base, prog_w0=prog_w0, ts=ts, Msat=1e4, seednum=7, solver=ssc.Dopri8(), normals=nr, **fixed)
+    # oracle pieces of the same constructor
+    prog_o, _, _ = orc_base.integrate_orbits(prog_w0, ts[0], ts[-1], ts=ts, solver=8, **fixed)
+    assert scaled_err(model.prog_loc_fwd, prog_o[0], 1e-10).max() < 1.0
+    Jo = orc_base.release(prog_o[0], 1e4, np.arange(nts), ts, 7, normals=nr, jacobian=True)
+    assert np.abs(model.dRel_dIC - Jo).max() < 1e-8
+    gen = pt.GenerateMassRadiusPerturbation(potential_base=base, potential_perturbation=pert, potential_structural=struct, BaseStreamModel=model,
+                                            units=ssc.usys, solver=ssc.Dopri8(), max_steps=5000, **fixed)
+    ws_o, Ds_o, st_o, _ = O.linear_response_saveat(orc_base, orc_sh, prog_o[0, -1], ts[-1], ts[0], ts[::-1].copy(), solver=8, max_steps=5000, **fixed)
+    assert st_o[0] == 0
+    F_o = Ds_o[::-1]
+    assert np.abs(gen.prog_fieldICs - F_o).max() <= 1e-10 * np.abs(F_o).max()
+    assert scaled_err(gen.prog_base.ys[0], ws_o, 1e-10).max() < 1.0              # the base orbit integrated backwards alongside
+    lead_ic = np.dstack([np.einsum('ijk,ilk->ilj', Jo[:, 0], F_o[:, :, :6]), np.einsum('ijk,ilk->ilj', Jo[:, 0], F_o[:, :, 6:])])
+    assert np.abs(gen.perturbation_ICs_lead - lead_ic).max() <= 1e-8 * np.abs(lead_ic).max()
+    (wl, Dl), (wt, Dt) = gen.compute_perturbation_OTF(cpu=False, solver=ssc.Dopri8(), **fixed)
+    assert wl.shape == (nts - 1, 6) and Dl.shape == (nts - 1, nsh, 12) and Dt.shape == Dl.shape
+    pl, pt_, vl, vt = orc_base.release(prog_o[0], 1e4, np.arange(nts), ts, 7, normals=nr)
+    w_o, D_o, _, _ = O.linear_response(orc_base, orc_sh, np.hstack([pl, vl])[:-1], ts[:-1], 0.0, D0=gen.perturbation_ICs_lead[:-1], solver=8, **fixed)
+    assert scaled_err(wl, w_o, 1e-10).max() < 1.0 and np.abs(Dl - D_o).max() <= 1e-9 * np.abs(D_o).max()
+    # adaptive saved trajectory through the public integrate_field (fields.py:35-99), forwards
+    fld = ssc.fields.MassRadiusPerturbation_OTF(gen)
+    D0 = np.random.default_rng(1).normal(size=(nsh, 12)) * 1e-6
+    sol = ssc.integrate_field(w0=[np.asarray(prog_w0), D0], ts=ts, field=fld, solver=ssc.Dopri5(), rtol=1e-8, atol=1e-8, dtmin=0.05, max_steps=5000)
+    ws2, Ds2, _, _ = O.linear_response_saveat(orc_base, orc_sh, prog_w0, ts[0], ts[-1], ts, D0=D0, solver=5, rtol=1e-8, atol=1e-8, dtmin=0.05, max_steps=5000)
+    assert np.array_equal(sol.ys[0][0], prog_w0) and np.array_equal(sol.ys[1][0], D0)
+    assert scaled_err(sol.ys[0], ws2, 1e-8).max() < 10.0 and scaled_err(sol.ys[1].reshape(nts, -1), Ds2.reshape(nts, -1), 1e-8).max() < 10.0
