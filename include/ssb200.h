@@ -146,6 +146,14 @@ int ssb_release_spray_f64(const ssb_potential* pot, double G, int64_t N, const d
                           const int64_t* idx, const double* t, int64_t seed, const double* kvals, const double* normals,
                           double* pos_lead, double* pos_trail, double* vel_lead, double* vel_trail, void* stream);
 
+/* A9  release_model_Chen25 vmapped over stripping times (streamhelpers.py:352-459): per release 6 correlated normals
+ * (jax.random.multivariate_normal(key_i, mean, cov, method='svd'), key_i = jax.random.split(key, N)[i]) turned into offsets
+ * in units of the tidal radius / escape velocity.  key[2] (host) = the jax PRNG key words; mean[6], factor[36] (host, row
+ * major) with sample = mean + factor @ z; normals[N,6] optional externally supplied standard normals (then key may be NULL). */
+int ssb_release_chen25_f64(const ssb_potential* pot, double G, int64_t N, const double* prog, const double* Msat, const double* t,
+                           const uint32_t* key, const double* mean, const double* factor, const double* normals,
+                           double* pos_lead, double* pos_trail, double* vel_lead, double* vel_trail, void* stream);
+
 /* A15  jacfwd(release_model) (BaseStreamModel.release_func_jacobian, perturbative.py:281-296): d(pos, vel of the lead / trail
  * particle) / d(progenitor x, v) at every stripping time; needs the third derivatives of Phi (closed forms on the device).
  * Arguments as ssb_release_spray_f64; jac[N,2,6,6]. */

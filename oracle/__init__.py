@@ -213,6 +213,19 @@ class Program:
                           C.c_int64(int(seed)), _p(kv), nrp, _p(out))
         return out[:, 0:3].copy(), out[:, 3:6].copy(), out[:, 6:9].copy(), out[:, 9:12].copy()
 
+    def release_chen25(self, xv, Msat, t, key, mean, factor, normals=None):
+        """release_model_Chen25 for a batch (streamhelpers.py:352-459): pos_lead, pos_trail, v_lead, v_trail [n,3]."""
+        xv = _d(xv).reshape(-1, 6)
+        n = len(xv)
+        Msat, t = _d(np.broadcast_to(_d(Msat), (n,))), _d(np.broadcast_to(_d(t), (n,)))
+        mean, factor = _d(mean).reshape(6), _d(factor).reshape(36)
+        nr = None if normals is None else _d(normals).reshape(n, 6)
+        out = np.empty((n, 12))
+        k0, k1 = (0, 0) if key is None else key
+        lib().orc_release_chen25(self._h, C.c_double(self.G), n, _p(xv), _p(Msat), _p(t), C.c_uint32(k0), C.c_uint32(k1), _p(mean), _p(factor),
+                                 _p(nr) if nr is not None else None, _p(out))
+        return out[:, 0:3].copy(), out[:, 3:6].copy(), out[:, 6:9].copy(), out[:, 9:12].copy()
+
     # ---- stream generation (main.py:287-368) ---------------------------------------------------
     def gen_stream_ics(self, ts, prog_w0, Msat, seed, solver=5, kvals=None, normals=None, **ctl):
         ts = _d(ts)

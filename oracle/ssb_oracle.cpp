@@ -316,6 +316,53 @@ void orc_release(void* h, double G, int n, const double* xv /*[n,6]*/, const dou
         release_T<double>(P, G, xv + 6 * i, xv + 6 * i + 3, Msat[i], t[i], kvals, nr, out + 12 * i);
     }
 }
+// release_model_Chen25 over a batch (streamhelpers.py:352-459); key words of the jax PRNG key; normals==NULL -> threefry recipe
+void orc_release_chen25(void* h, double G, int n, const double* xv, const double* Msat, const double* t, uint32_t k0, uint32_t k1,
+                        const double* mean, const double* factor, const double* normals /*[n,6] or NULL*/, double* out /*[n,12]*/) {
+    const Program& P = *(Program*)h;
+    for (int i = 0; i < n; ++i) {
+        double z[6];
+        if (normals) std::memcpy(z, normals + 6 * i, 48);
+        else {
+            uint32_t ki[2];
+            for (int hh = 0; hh < 2; ++hh) {                   // jax.random.split(key, n)[i]
+                const int f = 2 * i + hh, j = f < n ? f : f - n;
+                uint32_t o0, o1; threefry2x32(k0, k1, (uint32_t)j, (uint32_t)(n + j), &o0, &o1);
+                ki[hh] = f < n ? o0 : o1;
+            }
+            uint64_t bits[6]; random_bits64(Key{ki[0], ki[1]}, 6, bits);
+            for (int q = 0; q < 6; ++q) {
+                uint64_t fb = (bits[q] >> 12) | 0x3FF0000000000000ull; double f; std::memcpy(&f, &fb, 8); f -= 1.0;
+                const double lo = std::nextafter(-1.0, 0.0);
+                z[q] = std::sqrt(2.0) * erfinv_f64(std::fmax(lo, f * (1.0 - lo) + lo));
+            }
+        }
+        double pv[6];
+        for (int r = 0; r < 6; ++r) { pv[r] = mean[r]; for (int c = 0; c < 6; ++c) pv[r] += factor[6 * r + c] * z[c]; }
+        const double* x = xv + 6 * i; const double* v = x + 3;
+        double L[3]; cross3(x, v, L);
+        const double rad2 = dot3(x, x), r = std::sqrt(rad2), Lm = std::sqrt(dot3(L, L)), omega = Lm / rad2;
+        double xh[3] = {x[0] / r, x[1] / r, x[2] / r}, zh[3] = {L[0] / Lm, L[1] / Lm, L[2] / Lm};
+        double H[3][3]; hessian<double>(P, x, t[i], H);
+        double d2 = 0; for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) d2 += xh[a] * H[a][b] * xh[b];
+        const double GM = G * Msat[i], rt = std::pow(GM / (omega * omega - d2), 1.0 / 3.0);          // main.py:104
+        const double vr = dot3(v, xh);
+        double ph[3] = {v[0] - vr * xh[0], v[1] - vr * xh[1], v[2] - vr * xh[2]};
+        const double pn = std::sqrt(dot3(ph, ph));
+        double yh[3] = {ph[0] / pn, ph[1] / pn, ph[2] / pn};
+        const double Dr = pv[0] * rt, Dv = pv[3] * std::sqrt(2 * GM / Dr), d2r = 0.017453292519943295;           // streamhelpers.py:389-398
+        const double phi = pv[1] * d2r, th = pv[2] * d2r, al = pv[4] * d2r, be = pv[5] * d2r;
+        for (int k = 0; k < 3; ++k) {
+            const double dx = (Dr * std::cos(th) * std::cos(phi)) * xh[k] + (Dr * std::cos(th) * std::sin(phi)) * yh[k];
+            const double dvv = (Dv * std::cos(be) * std::cos(al)) * xh[k] + (Dv * std::cos(be) * std::sin(al)) * yh[k];
+            out[12 * i + k] = x[k] - dx + (Dr * std::sin(th)) * zh[k];            // lead  (streamhelpers.py:419-430)
+            out[12 * i + 3 + k] = x[k] + dx + (Dr * std::sin(th)) * zh[k];        // trail (streamhelpers.py:405-416)
+            out[12 * i + 6 + k] = v[k] - dvv + (Dv * std::sin(be)) * zh[k];
+            out[12 * i + 9 + k] = v[k] + dvv + (Dv * std::sin(be)) * zh[k];
+        }
+    }
+}
+
 // jacfwd(release_func) (perturbative.py:281-296): out[n,2,6,6], rows = (pos,vel) of lead / trail, cols = d/d(x,v)
 void orc_release_jacobian(void* h, double G, int n, const double* xv, const double* Msat, const int64_t* idx, const double* t,
                           int64_t seed, const double* kvals, const double* normals, double* out) {

@@ -250,6 +250,18 @@ def shard_count(n_particles, rank, world):
     return max(0, (n_particles - rank + world - 1) // world)
 
 
+def release_chen25(pot, G, prog, Msat, t, key, mean, factor, normals):
+    P, _keep = lower(pot)
+    N = prog.shape[0]
+    outs = [empty((N, 3)) for _ in range(4)]
+    kc = None if key is None else (C.c_uint32 * 2)(int(key[0]), int(key[1]))
+    mc = (C.c_double * 6)(*[float(v) for v in mean])
+    fc = (C.c_double * 36)(*[float(v) for v in np.asarray(factor, dtype=np.float64).reshape(36)])
+    _lib.check(_lib.lib().ssb_release_chen25_f64(C.byref(P), float(G), N, ptr(prog), ptr(Msat), ptr(t), kc, mc, fc, ptr(normals), ptr(outs[0]),
+                                                 ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), stream_ptr()))
+    return outs
+
+
 def release_jacobian(pot, G, prog, Msat, idx, t, seed, kvals, normals):
     P, _keep = lower(pot)
     N = prog.shape[0]

@@ -475,6 +475,76 @@ __global__ void release_kernel(const __grid_constant__ ssb_potential Pin, const 
     if (a.t0_packed) { a.t0_packed[i] = t; a.t0_packed[a.N + i] = t; }
 }
 
+// ---- Chen+25 release (streamhelpers.py:352-432): 6 correlated normals per stripping time -> (Dr, phi, theta, Dv, alpha, beta) ----
+struct Chen25Args {
+    int64_t N;
+    const double *prog, *Msat, *t, *normals;     // normals: optional [N,6] standard normals
+    uint32_t key[2];                             // jax PRNG key; per-release keys = jax.random.split(key, N) (streamhelpers.py:455)
+    double mean[6], factor[36];                  // multivariate_normal(mean, cov, method='svd'): sample = mean + factor @ z
+    double G;
+    double *pos_lead, *pos_trail, *vel_lead, *vel_trail;
+};
+__global__ void release_chen25_kernel(const __grid_constant__ ssb_potential Pin, const Chen25Args a) {
+    __shared__ ssb_potential sP;
+    stage_potential(&sP, &Pin);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const double* w = a.prog + 6 * i;
+    const double x[3] = {w[0], w[1], w[2]}, v[3] = {w[3], w[4], w[5]};
+    double z[6];
+    if (a.normals) { for (int q = 0; q < 6; ++q) z[q] = a.normals[6 * i + q]; }
+    else {
+        // key_i = split(key, N)[i]: threefry(key, iota(2N)) reshaped (N, 2)
+        uint32_t ki[2];
+        for (int h = 0; h < 2; ++h) {
+            const int64_t f = 2 * i + h;                       // flat index into concat(o0[0..N-1], o1[0..N-1])
+            const int64_t j = f < a.N ? f : f - a.N;
+            uint32_t o0, o1;
+            threefry2x32(a.key[0], a.key[1], (uint32_t)j, (uint32_t)(a.N + j), o0, o1);
+            ki[h] = f < a.N ? o0 : o1;
+        }
+        for (int q = 0; q < 6; ++q) {                          // jax.random.normal(key_i, (6,)) float64
+            uint32_t o0, o1;
+            threefry2x32(ki[0], ki[1], (uint32_t)q, (uint32_t)(6 + q), o0, o1);
+            const uint64_t bits = ((uint64_t)o0 << 32) | (uint64_t)o1;
+            const double f = __longlong_as_double((long long)((bits >> 12) | 0x3FF0000000000000ull)) - 1.0;
+            const double lo = -0.99999999999999989;
+            z[q] = 1.4142135623730951 * erfinv(fmax(lo, fma(f, 1.0 - lo, lo)));
+        }
+    }
+    double pv6[6];
+    for (int r = 0; r < 6; ++r) { double acc = a.mean[r]; for (int c = 0; c < 6; ++c) acc += a.factor[6 * r + c] * z[c]; pv6[r] = acc; }
+    // tidal radius (main.py:98-104)
+    const double rad2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+    const double L[3] = {x[1] * v[2] - x[2] * v[1], x[2] * v[0] - x[0] * v[2], x[0] * v[1] - x[1] * v[0]};
+    const double Lmag = sqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+    const double omega = Lmag / rad2, r = sqrt(rad2);
+    const double xh[3] = {x[0] / r, x[1] / r, x[2] / r};
+    double P, g[3];
+    Sym3 H;
+    pot_eval<WANT_HESS>(sP, x, a.t[i], P, g, H);
+    const double d2 = xh[0] * (H.xx * xh[0] + H.xy * xh[1] + H.xz * xh[2]) + xh[1] * (H.xy * xh[0] + H.yy * xh[1] + H.yz * xh[2]) +
+                      xh[2] * (H.xz * xh[0] + H.yz * xh[1] + H.zz * xh[2]);
+    const double GM = a.G * a.Msat[i];
+    const double rt = pow(GM / (omega * omega - d2), 1.0 / 3.0);
+    const double zh[3] = {L[0] / Lmag, L[1] / Lmag, L[2] / Lmag};
+    const double vr = v[0] * xh[0] + v[1] * xh[1] + v[2] * xh[2];
+    const double pvv[3] = {v[0] - vr * xh[0], v[1] - vr * xh[1], v[2] - vr * xh[2]};
+    const double pn = sqrt(pvv[0] * pvv[0] + pvv[1] * pvv[1] + pvv[2] * pvv[2]);
+    const double yh[3] = {pvv[0] / pn, pvv[1] / pn, pvv[2] / pn};
+    const double Dr = pv6[0] * rt;                                   // streamhelpers.py:389-398
+    const double Dv = pv6[3] * sqrt(2.0 * GM / Dr);
+    const double d2r = 0.017453292519943295;
+    double sphi, cphi, sth, cth, sal, cal, sbe, cbe;
+    sincos(pv6[1] * d2r, &sphi, &cphi); sincos(pv6[2] * d2r, &sth, &cth); sincos(pv6[4] * d2r, &sal, &cal); sincos(pv6[5] * d2r, &sbe, &cbe);
+    for (int k = 0; k < 3; ++k) {
+        a.pos_trail[3 * i + k] = x[k] + (Dr * cth * cphi) * xh[k] + (Dr * cth * sphi) * yh[k] + (Dr * sth) * zh[k];     // streamhelpers.py:405-416
+        a.vel_trail[3 * i + k] = v[k] + (Dv * cbe * cal) * xh[k] + (Dv * cbe * sal) * yh[k] + (Dv * sbe) * zh[k];
+        a.pos_lead[3 * i + k] = x[k] - (Dr * cth * cphi) * xh[k] - (Dr * cth * sphi) * yh[k] + (Dr * sth) * zh[k];      // streamhelpers.py:419-430
+        a.vel_lead[3 * i + k] = v[k] - (Dv * cbe * cal) * xh[k] - (Dv * cbe * sal) * yh[k] + (Dv * sbe) * zh[k];
+    }
+}
+
 // jacfwd(release_func) (perturbative.py:281-296): jac[N,2,6,6], rows = (pos, vel) of lead / trail, columns = d/d(x, v)
 __global__ void release_jacobian_kernel(const __grid_constant__ ssb_potential Pin, const ReleaseArgs a, double* jac) {
     __shared__ ssb_potential sP;
@@ -732,6 +802,25 @@ int ssb_release_spray_f64(const ssb_potential* pot, double G, int64_t N, const d
     a.pos_lead = pos_lead; a.pos_trail = pos_trail; a.vel_lead = vel_lead; a.vel_trail = vel_trail;
     release_kernel<<<nblk(N, 128), 128, 0, (cudaStream_t)stream>>>(*pot, a);
     CKL("release_kernel");
+    return 0;
+}
+
+int ssb_release_chen25_f64(const ssb_potential* pot, double G, int64_t N, const double* prog, const double* Msat, const double* t,
+                           const uint32_t* key, const double* mean, const double* factor, const double* normals, double* pos_lead,
+                           double* pos_trail, double* vel_lead, double* vel_trail, void* stream) {
+    if (int e = ssb_validate_potential(pot)) return e;
+    if (N < 0) return ssb_set_error(SSB_ERR_ARG, "release_chen25: negative N");
+    if (N == 0) return 0;
+    if (!prog || !Msat || !t || !mean || !factor || (!key && !normals) || !pos_lead || !pos_trail || !vel_lead || !vel_trail)
+        return ssb_set_error(SSB_ERR_ARG, "release_chen25: NULL array");
+    Chen25Args a;
+    memset(&a, 0, sizeof(a));
+    a.N = N; a.prog = prog; a.Msat = Msat; a.t = t; a.normals = normals; a.G = G;
+    if (key) { a.key[0] = key[0]; a.key[1] = key[1]; }
+    memcpy(a.mean, mean, sizeof(a.mean)); memcpy(a.factor, factor, sizeof(a.factor));
+    a.pos_lead = pos_lead; a.pos_trail = pos_trail; a.vel_lead = vel_lead; a.vel_trail = vel_trail;
+    release_chen25_kernel<<<nblk(N, 128), 128, 0, (cudaStream_t)stream>>>(*pot, a);
+    CKL("release_chen25_kernel");
     return 0;
 }
 

@@ -157,18 +157,21 @@ class GenerateMassRadiusPerturbation_CustomBase(_ResponseGenerator):      # pert
 
 
 class BaseStreamModelChen25(Potential):               # perturbative.py:588-658
-    """Chen+25 base model.  The Chen25 release draws (jax multivariate_normal via SVD, streamhelpers.py:352-432) are not
-    reproduced on the device yet, so the release offsets are supplied: stream_ics = (pos_lead, pos_trail, vel_lead, vel_trail)
-    each [N,3], and prog_fwd [N,6] (the progenitor at ts)."""
+    """Chen+25 base model (perturbative.py:588-658).  `key`: int seed (= jax.random.PRNGKey(seed)) or the two key words.
+    Optionally the release can be supplied instead of drawn: stream_ics = (pos_lead, pos_trail, vel_lead, vel_trail) each [N,3]
+    and prog_fwd [N,6] (the progenitor at ts)."""
 
     def __init__(self, pot_base, ts, prog_w0, Msat=None, key=None, solver=Dopri5(scan_kind='bounded'), rtol=1e-7, atol=1e-7, dtmin=0.3,
                  dtmax=None, max_steps=10_000, throw=False, prog_pot=None, units=usys, stream_ics=None, prog_fwd=None):
         super().__init__(units, {'pot_base': pot_base, 'ts': ts, 'prog_w0': prog_w0, 'Msat': Msat, 'key': key, 'solver': solver, 'rtol': rtol,
                                  'atol': atol, 'dtmin': dtmin, 'dtmax': dtmax, 'max_steps': max_steps, 'throw': throw, 'prog_pot': prog_pot})
-        if stream_ics is None:
-            raise NotImplementedError("Chen25 release sampling is not on the device path yet; pass stream_ics= and prog_fwd=")
         from .potential import CubicTrack, TimeDepTranslatingPotential
+        from .streamhelpers import gen_stream_ics_Chen25
         ts = np.asarray(ts, dtype=np.float64)
+        if stream_ics is None:                                                             # perturbative.py:615-625
+            stream_ics, orb_fwd = gen_stream_ics_Chen25(pot_base=pot_base, ts=ts, prog_w0=prog_w0, Msat=Msat, key=key, solver=solver, rtol=rtol,
+                                                        atol=atol, dtmin=dtmin, dtmax=dtmax, max_steps=max_steps)
+            prog_fwd = np.asarray(orb_fwd.ys)
         if prog_fwd is None:
             prog_fwd = np.asarray(pot_base.integrate_orbit(w0=prog_w0, ts=ts, solver=solver, rtol=rtol, atol=atol, dtmin=dtmin, dtmax=dtmax,
                                                            max_steps=max_steps).ys)

@@ -408,3 +408,37 @@ def test_saved_response_trajectory_and_classic_generator(cuda):
     ws2, Ds2, _, _ = O.linear_response_saveat(orc_base, orc_sh, prog_w0, ts[0], ts[-1], ts, D0=D0, solver=5, rtol=1e-8, atol=1e-8, dtmin=0.05, max_steps=5000)
     assert np.array_equal(sol.ys[0][0], prog_w0) and np.array_equal(sol.ys[1][0], D0)
     assert scaled_err(sol.ys[0], ws2, 1e-8).max() < 10.0 and scaled_err(sol.ys[1].reshape(nts, -1), Ds2.reshape(nts, -1), 1e-8).max() < 10.0
+
+
+def test_chen25_release_and_streams(cuda):
+    """A9: release_model_Chen25 / gen_stream_ics_Chen25 / gen_stream_vmapped_Chen25 (streamhelpers.py:352-545) incl. the progenitor's
+    own Plummer potential on an interpax-'cubic' track, vs the oracle.  Fixed steps -> 1e-10."""
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import streamhelpers as sh_
+    P = ssc.potential
+    base, orc = mw3_product(), mw3_oracle()
+    ts = np.linspace(-1500.0, 0.0, 61)
+    prog_w0 = [12.0, 3.0, -6.0, -0.05, 0.15, 0.03]
+    fixed = dict(rtol=1e-8, atol=1e-8, dtmin=1.0, dtmax=1.0)
+    mean, fac = sh_.CHEN25_MEAN, sh_.chen25_factor()
+    assert np.allclose(fac @ fac.T, sh_.CHEN25_COV, atol=1e-10)
+    prog_o, _, _ = orc.integrate_orbits(prog_w0, ts[0], ts[-1], ts=ts, solver=8, **fixed)
+    for key, normals in ((1234, None), ((7, 99), None), (None, np.random.Generator(np.random.PCG64(9)).standard_normal((61, 6)))):
+        ics, orb = ssc.gen_stream_ics_Chen25(pot_base=base, ts=ts, prog_w0=prog_w0, Msat=2e4, key=key, solver=ssc.Dopri8(), normals=normals, **fixed)
+        ref = orc.release_chen25(prog_o[0], 2e4, ts, sh_.key_words(key), mean, fac, normals=normals)
+        assert scaled_err(np.asarray(orb.ys), prog_o[0], 1e-10).max() < 1.0
+        for a, b in zip(ics, ref):
+            assert scaled_err(a, b, 1e-9).max() < 1.0
+    # full stream with a live progenitor potential on the cubic track
+    prog_pot = P.PlummerPotential(m=2e4, r_s=0.01, units=ssc.usys)
+    lead, trail = ssc.gen_stream_vmapped_Chen25(base, ts, prog_w0, 2e4, 1234, solver=ssc.Dopri8(), prog_pot=prog_pot, **fixed)
+    pl, pt, vl, vt = orc.release_chen25(prog_o[0], 2e4, ts, sh_.key_words(1234), mean, fac)
+    tot = mw3_oracle()
+    tr = tot.track(O.CUBIC, ts, prog_o[0][:, :3])
+    tot.plummer(2e4, 0.01, track=tr)
+    yl, _, _ = tot.integrate_orbits(np.hstack([pl, vl])[:-1], ts[:-1], 0.0, solver=8, **fixed)
+    yt, _, _ = tot.integrate_orbits(np.hstack([pt, vt])[:-1], ts[:-1], 0.0, solver=8, **fixed)
+    assert scaled_err(lead, yl[:, 0], 1e-9).max() < 1.0 and scaled_err(trail, yt[:, 0], 1e-9).max() < 1.0
+    # BaseStreamModelChen25 draws its own release when none is supplied (perturbative.py:615-625)
+    model = ssc.perturbative.BaseStreamModelChen25(pot_base=base, ts=ts, prog_w0=prog_w0, Msat=2e4, key=1234, solver=ssc.Dopri8(), **fixed)
+    assert model.BaseModel.streamICs.shape == (2 * 61, 6) and np.all(np.diff(model.BaseModel.ts) >= 0)
