@@ -136,6 +136,9 @@ int ssb_orbit_dense_f64(const ssb_potential* pot, const double* w0 /*[6] device*
                         const double* ts, int64_t M, ssb_ctrl ctrl, double* ys /*[M,6]*/, int32_t* status /*[1]*/,
                         int32_t* nsteps /*[3]*/, void* scratch, size_t scratch_bytes, void* stream);
 size_t ssb_scratch_bytes(int32_t max_steps);
+/* Solution.evaluate(t) of a dense=True solve (main.py:131, 141): interpolate M more times inside the steps recorded in `scratch` by a
+ * previous ssb_orbit_dense_f64 call with the same solver; ys[M,6] (+inf outside the integrated interval). */
+int ssb_orbit_dense_eval_f64(int32_t solver, const void* scratch, const double* ts, int64_t M, double* ys, void* stream);
 
 /* A6  Potential.release_model vmapped over stripping times (main.py:209-306).
  *   prog[N,6] progenitor phase-space at t[N]; Msat[N]; idx[N] the stripping index i that seeds jax.random

@@ -32,8 +32,15 @@ _lp = C.POINTER(C.c_int64)
 
 def build(force=False):
     """Compile oracle/_build/libssb_oracle.so with the committed Makefile."""
+    import fcntl
     args = ["make", "-C", _HERE] + (["-B"] if force else [])
-    subprocess.run(args, check=True, stdout=subprocess.DEVNULL)
+    os.makedirs(os.path.join(_HERE, "_build"), exist_ok=True)
+    with open(os.path.join(_HERE, "_build", ".lock"), "w") as lock:      # several test ranks may import at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            subprocess.run(args, check=True, stdout=subprocess.DEVNULL)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return os.path.join(_HERE, "_build", "libssb_oracle.so")
 
 

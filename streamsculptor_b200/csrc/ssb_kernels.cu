@@ -786,6 +786,17 @@ int ssb_orbit_dense_f64(const ssb_potential* pot, const double* w0, double t0, d
     return dense_launch(pot, w0, t0, t1, nullptr, nullptr, ts, M, ctrl, ys, status, nsteps, (double*)scratch, st);
 }
 
+int ssb_orbit_dense_eval_f64(int32_t solver, const void* scratch, const double* ts, int64_t M, double* ys, void* stream) {
+    if (solver != 5 && solver != 8) return ssb_set_error(SSB_ERR_UNSUPPORTED, "solver must be 5 (Dopri5) or 8 (Dopri8)");
+    if (!scratch || M < 0 || (M > 0 && (!ts || !ys))) return ssb_set_error(SSB_ERR_ARG, "orbit_dense_eval: NULL array");
+    if (M == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (solver == 5) dense_eval_kernel<5><<<nblk(M, 128), 128, 0, st>>>((const double*)scratch, ts, M, ys);
+    else dense_eval_kernel<8><<<nblk(M, 128), 128, 0, st>>>((const double*)scratch, ts, M, ys);
+    CKL("dense_eval_kernel");
+    return 0;
+}
+
 int ssb_release_spray_f64(const ssb_potential* pot, double G, int64_t N, const double* prog, const double* Msat, const int64_t* idx,
                           const double* t, int64_t seed, const double* kvals, const double* normals, double* pos_lead, double* pos_trail,
                           double* vel_lead, double* vel_trail, void* stream) {

@@ -233,14 +233,8 @@ class _DenseEval:
         self.pot, self.scratch, self.ctrl, self.w0, self.t0, self.t1 = pot, scratch, ctrl, w0, t0, t1
 
     def __call__(self, t):
-        import ctypes as C
         tq = rt.to_dev(np.atleast_1d(np.asarray(t, dtype=np.float64)))
-        # re-run the (cheap, serial) step recorder only if the scratch was not kept; here it is kept
         ys = rt.empty((tq.shape[0], 6))
-        lib = _lib.lib()
-        P, _keep = rt.lower(self.pot)
-        # evaluation only: M save times against the recorded steps (the step kernel is not relaunched)
-        _lib.check(lib.ssb_orbit_dense_f64(C.byref(P), rt.ptr(self.w0), self.t0, self.t1, rt.ptr(tq), tq.shape[0], self.ctrl, rt.ptr(ys), None,
-                                           None, rt.ptr(self.scratch), self.scratch.numel() * 8, rt.stream_ptr()))
+        _lib.check(_lib.lib().ssb_orbit_dense_eval_f64(self.ctrl.solver, rt.ptr(self.scratch), rt.ptr(tq), tq.shape[0], rt.ptr(ys), rt.stream_ptr()))
         res = ys.cpu().numpy()
         return res[0] if np.ndim(t) == 0 else res

@@ -200,27 +200,33 @@ class MW_LMC_Potential(Potential):                    # potential.py:555-662
 
 
 def _load_mw_lmc_tables(data_dir):
-    """Recover the float64 payloads of the reference's pickled tables without importing jax (stub unpickler)."""
+    """Read the reference's pickled tables (data/LMC_MW_potential/*.npy hold dicts of jax Arrays) without importing jax:
+    a jax Array pickles as _reconstruct_array(numpy_reconstruct, args, ndarray_state, aval_state), which a stub rebuilds."""
     import pickle
     if data_dir is None:
-        raise FileNotFoundError("MW_LMC_Potential needs its motion tables: pass t_lmc/xyz_lmc/t_mw/vel_mw or data_dir=")
+        raise FileNotFoundError("MW_LMC_Potential needs its motion tables: pass t_lmc/xyz_lmc/t_mw/vel_mw, or data_dir= pointing at "
+                                "streamsculptor/data/LMC_MW_potential of a reference checkout")
+
+    def _rebuild(fun, args, arr_state, *rest):
+        arr = fun(*args)
+        arr.__setstate__(arr_state)
+        return arr
 
     class _Stub(pickle.Unpickler):
         def find_class(self, module, name):
-            if module.startswith("jax") or module.startswith("jaxlib"):
-                return lambda *a, **k: a
+            if module.split(".")[0] in ("jax", "jaxlib"):
+                return _rebuild
             return super().find_class(module, name)
 
     def load(fn):
         with open(os.path.join(data_dir, fn), "rb") as f:
-            arr = np.load(f, allow_pickle=True)
-        return arr.item()
-    try:
-        lmc, mw = load("LMC_motion_dict.npy"), load("MW_motion_dict.npy")
-        return (np.asarray(lmc['flip_tsave']), np.asarray(lmc['flip_trajLMC'])[:, :3], np.asarray(mw['flip_tsave']),
-                np.asarray(mw['flip_traj'])[:, 3:6])
-    except Exception as exc:
-        raise RuntimeError("could not read the reference's pickled tables (they need jax to unpickle); pass the arrays explicitly") from exc
+            major, minor = np.lib.format.read_magic(f)
+            (np.lib.format.read_array_header_1_0 if (major, minor) == (1, 0) else np.lib.format.read_array_header_2_0)(f)
+            obj = _Stub(f).load()
+            return obj.item() if isinstance(obj, np.ndarray) else obj     # np.save(dict) stores a 0-d object array
+    lmc, mw = load("LMC_motion_dict.npy"), load("MW_motion_dict.npy")
+    return (np.asarray(lmc['flip_tsave'], dtype=np.float64), np.asarray(lmc['flip_trajLMC'], dtype=np.float64)[:, :3],
+            np.asarray(mw['flip_tsave'], dtype=np.float64), np.asarray(mw['flip_traj'], dtype=np.float64)[:, 3:6])
 
 
 # ---- subhalo ensembles (potential.py:802-956, 1110-1268) ------------------------------------------------------------

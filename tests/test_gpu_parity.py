@@ -442,3 +442,29 @@ def test_chen25_release_and_streams(cuda):
     # BaseStreamModelChen25 draws its own release when none is supplied (perturbative.py:615-625)
     model = ssc.perturbative.BaseStreamModelChen25(pot_base=base, ts=ts, prog_w0=prog_w0, Msat=2e4, key=1234, solver=ssc.Dopri8(), **fixed)
     assert model.BaseModel.streamICs.shape == (2 * 61, 6) and np.all(np.diff(model.BaseModel.ts) >= 0)
+
+
+def test_mw_lmc_potential_api(cuda):
+    """A10: MW_LMC_Potential (potential.py:555-662) = MW3' + translating NFW LMC + uniform frame acceleration on 1000-knot
+    LINEAR tables with linear extrapolation; force-only (no .potential).  Synthetic tables of the reference's shape."""
+    import streamsculptor_b200 as ssc
+    P = ssc.potential
+    tk = np.linspace(-14000.0, 0.0, 1000)
+    xyz = np.stack([-1.0 + 0.004 * tk + 60 * np.sin(tk / 4000.0), -41.0 - 0.006 * tk, -27.0 + 0.003 * tk + 20 * np.cos(tk / 3000.0)], axis=1)
+    vel = np.stack([2e-3 * np.sin(tk / 2500.0), 1e-3 * np.cos(tk / 1800.0), 5e-8 * tk], axis=1)
+    pot = P.MW_LMC_Potential(units=ssc.usys, t_lmc=tk, xyz_lmc=xyz, t_mw=tk, vel_mw=vel)
+    orc = O.Program().hernquist(5e9, 1.0).miyamoto(5.0e10, 3.0, 0.3).nfw(5.4e11, 15.62)
+    tr = orc.track(O.LINEAR, tk, xyz)
+    orc.nfw(.85e11, (.85e11 / 1e11) ** 0.6 * 8.5, track=tr).uniform_acc(tk, vel)
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(100, 3)) * 20
+    t = rng.uniform(-14500.0, 300.0, 100)                         # incl. extrapolation on both sides
+    assert relerr(pot.gradient(x, t), orc.gradient(x, t)) < 1e-11
+    assert relerr(pot.acceleration(x[0], t[0]), -orc.gradient(x[0], t[0])[0]) < 1e-11
+    with pytest.raises(NotImplementedError):
+        pot.potential(x[0], 0.0)
+    w0 = halo_orbits(20, seed=3)
+    ys_o, _, _ = orc.integrate_orbits(w0, -3000.0, 0.0, solver=8, dtmin=1.0, dtmax=1.0)
+    sol = pot.integrate_orbit_batch_vmapped(w0=w0, ts=np.zeros((20, 1)), t0=-3000.0, t1=0.0, dtmin=1.0, dtmax=1.0)
+    assert scaled_err(sol.ys[:, 0], ys_o[:, 0], 1e-10).max() < 1.0
+    assert np.allclose(pot.LMC_center_spline(-7000.0), orc.track_eval(tr, [-7000.0])[0][0], rtol=1e-14)
