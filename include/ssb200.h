@@ -196,6 +196,16 @@ int ssb_linear_response_saveat_f64(const ssb_potential* pot_base, const ssb_subh
                                    const double* t0, double t1, const double* ts, int32_t M, ssb_ctrl ctrl, double* ws, double* Ds,
                                    int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream);
 size_t ssb_response_saveat_scratch_bytes(int32_t n_sh);
+/* A16  second-order mass response: fields.MassRadiusPerturbation_OTF_SecondOrder (fields.py:260-320) integrated per particle as in
+ * GenerateMassRadiusPerturbation_Chen25.compute_perturbation_second_order_OTF (perturbative.py:757-772): state
+ * [w(6), D(n_sh,12), E(n_sh,6)], one controller over all 6 + 18 n_sh components, final state kept.
+ * D0 / E0 may be NULL (= zeros, perturbative.py:715).  scratch >= ssb_second_order_scratch_bytes(n_sh). */
+int ssb_second_order_response_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0, const double* D0,
+                                  const double* E0, const double* t0, double t1, ssb_ctrl ctrl, double* wout, double* Dout, double* Eout,
+                                  int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream);
+size_t ssb_second_order_scratch_bytes(int32_t n_sh);
+/* RHS of the second-order field at one state y = [w(6), D(n_sh,12), E(n_sh,6)] (fields.py:289-320), for unit tests */
+int ssb_second_order_term_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, double t, const double* y, double* dy, void* stream);
 /* RHS of that field at one state (fields.py:175-206): y[6+12 n_sh] -> dy (device pointers), for unit tests */
 int ssb_response_term_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, double t, const double* y, double* dy,
                           void* stream);

@@ -286,6 +286,30 @@ def linear_response_saveat(base, shprog, w0, t0, t1, ts, D0=None, sh=0, solver=8
     return ws, Ds, status, nsteps
 
 
+def second_order_response(base, shprog, w0, t0, t1, D0=None, E0=None, sh=0, solver=8, rtol=1e-6, atol=1e-6, dtmin=0.05, dtmax=None,
+                          max_steps=10_000, threads=1):
+    """compute_perturbation_second_order_OTF (perturbative.py:757-772): w[N,6], D[N,nsh,12], E[N,nsh,6], status, nsteps."""
+    w0 = _d(w0).reshape(-1, 6)
+    N, nsh = len(w0), shprog.n_sh[sh]
+    t0 = _d(np.broadcast_to(_d(t0), (N,)))
+    D0 = None if D0 is None else _d(D0).reshape(N, nsh, 12)
+    E0 = None if E0 is None else _d(E0).reshape(N, nsh, 6)
+    wout, Dout, Eout = np.empty((N, 6)), np.empty((N, nsh, 12)), np.empty((N, nsh, 6))
+    status, nsteps = np.empty(N, dtype=np.int32), np.empty((N, 3), dtype=np.int32)
+    lib().orc_second_order_response(base._h, shprog._h, sh, N, _p(w0), None if D0 is None else _p(D0), None if E0 is None else _p(E0), _p(t0),
+                                    C.c_double(t1), int(solver), C.c_double(rtol), C.c_double(atol), C.c_double(dtmin),
+                                    C.c_double(np.inf if dtmax is None else dtmax), int(max_steps), _p(wout), _p(Dout), _p(Eout),
+                                    status.ctypes.data_as(_ip), nsteps.ctypes.data_as(_ip), int(threads))
+    return wout, Dout, Eout, status, nsteps
+
+
+def second_order_term(base, shprog, t, y, sh=0):
+    y = _d(y)
+    dy = np.empty_like(y)
+    lib().orc_second_order_term(base._h, shprog._h, sh, C.c_double(t), _p(y), _p(dy))
+    return dy
+
+
 def response_term(base, shprog, t, y, sh=0):
     y = _d(y)
     dy = np.empty_like(y)

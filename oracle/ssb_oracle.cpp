@@ -208,6 +208,42 @@ struct ResponseField {                 // MassRadiusPerturbation_OTF.term (field
     }
 };
 
+struct ResponseField2 {                // MassRadiusPerturbation_OTF_SecondOrder.term (fields.py:289-320): y = [w(6), D(nsh,12), E(nsh,6)]
+    const Program* base; const SubhaloSet* S; SubhaloSet Sdr; int nsh;
+    void operator()(double t, const double* y, double* dy) const {
+        const double* x0 = y;
+        double g[3]; gradient<double>(*base, x0, t, g);
+        typedef Dual<double, 3> D;
+        D xd[3]; for (int i = 0; i < 3; ++i) xd[i] = D::var(x0[i], i);
+        D Hd[3][3]; hessian<D>(*base, xd, t, Hd);                              // value = Hess, .d = third derivatives (fields.py:279-280)
+        dy[0] = y[3]; dy[1] = y[4]; dy[2] = y[5]; dy[3] = -g[0]; dy[4] = -g[1]; dy[5] = -g[2];
+        typedef Dual<D, 3> DD;
+        const double* Dm = y + 6; const double* E = y + 6 + 12 * (size_t)nsh;
+        double* dD = dy + 6; double* dE = dy + 6 + 12 * (size_t)nsh;
+        for (int j = 0; j < nsh; ++j) {
+            const double* d = Dm + 12 * j; const double* e = E + 6 * j;
+            // per-subhalo gradient and Hessian of the perturbing potential (fields.py:282-283)
+            DD xdd[3]; for (int i = 0; i < 3; ++i) xdd[i] = DD::var(xd[i], i);
+            DD ph = phi_subhalo<DD>(*S, j, xdd, t);
+            D p2 = phi_subhalo<D>(Sdr, j, xd, t);
+            for (int i = 0; i < 3; ++i) {
+                double tx1 = 0, tx2 = 0, tdx = 0, quad = 0, hp = 0;
+                for (int q = 0; q < 3; ++q) {
+                    tx1 += -Hd[i][q].v * d[q]; tx2 += -Hd[i][q].v * e[q]; tdx += -Hd[i][q].v * d[6 + q];
+                    hp += -ph.d[i].d[q] * d[q];                                                       // dapert_dx . x1 (fields.py:312)
+                    for (int r = 0; r < 3; ++r) quad += -Hd[i][q].d[r] * d[q] * d[r];                   // d2a_dx2[i,k,j] x1_k x1_j (fields.py:310-311)
+                }
+                dD[12 * j + i] = d[3 + i];
+                dD[12 * j + 3 + i] = -ph.d[i].v + tx1;                                                // da (fields.py:307)
+                dD[12 * j + 6 + i] = d[9 + i];
+                dD[12 * j + 9 + i] = -p2.d[i] + tdx;                                                  // fields.py:314-315
+                dE[6 * j + i] = e[3 + i];
+                dE[6 * j + 3 + i] = tx2 + quad + hp;                                                  // d2a (fields.py:309-312)
+            }
+        }
+    }
+};
+
 // =============================================================================================
 // C ABI for the ctypes binding (oracle/__init__.py)
 // =============================================================================================
@@ -422,6 +458,33 @@ void orc_linear_response_saveat(void* hbase, void* hsh, int sh, const double* w0
         std::memcpy(Ds + (size_t)m * 12 * nsh, ys.data() + (size_t)m * n + 6, sizeof(double) * 12 * nsh);
     }
     *status = s.status; nsteps[0] = s.n_steps; nsteps[1] = s.n_acc; nsteps[2] = s.n_rej;
+}
+
+// compute_perturbation_second_order_OTF (perturbative.py:757-772): per particle [w, D(nsh,12), E(nsh,6)] -> final state
+void orc_second_order_response(void* hbase, void* hsh, int sh, int N, const double* w0, const double* D0, const double* E0, const double* t0,
+                               double t1, int solver, double rtol, double atol, double dtmin, double dtmax, int max_steps, double* wout,
+                               double* Dout, double* Eout, int* status, int* nsteps, int parallel) {
+    const Program& B = *(Program*)hbase; const SubhaloSet& S = ((Program*)hsh)->shs[sh];
+    Ctrl c; c.solver = solver; c.rtol = rtol; c.atol = atol; c.dtmin = dtmin; c.dtmax = dtmax; c.max_steps = max_steps;
+    const int nsh = S.n, n = 6 + 18 * nsh;
+    parallel_for(N, parallel, 1, [&](int i) {
+        ResponseField2 f; f.base = &B; f.S = &S; f.Sdr = S; f.Sdr.dradius = 1; f.nsh = nsh;
+        std::vector<double> y0(n, 0.0), yf(n);
+        std::memcpy(y0.data(), w0 + 6 * (size_t)i, 48);
+        if (D0) std::memcpy(y0.data() + 6, D0 + (size_t)i * 12 * nsh, sizeof(double) * 12 * nsh);
+        if (E0) std::memcpy(y0.data() + 6 + 12 * nsh, E0 + (size_t)i * 6 * nsh, sizeof(double) * 6 * nsh);
+        double tsv = t1;
+        Stats s = solve(f, n, t0[i], t1, y0.data(), &tsv, 1, c, yf.data());
+        std::memcpy(wout + 6 * (size_t)i, yf.data(), 48);
+        std::memcpy(Dout + (size_t)i * 12 * nsh, yf.data() + 6, sizeof(double) * 12 * nsh);
+        std::memcpy(Eout + (size_t)i * 6 * nsh, yf.data() + 6 + 12 * nsh, sizeof(double) * 6 * nsh);
+        status[i] = s.status; nsteps[3 * i] = s.n_steps; nsteps[3 * i + 1] = s.n_acc; nsteps[3 * i + 2] = s.n_rej;
+    });
+}
+void orc_second_order_term(void* hbase, void* hsh, int sh, double t, const double* y, double* dy) {
+    const Program& B = *(Program*)hbase; const SubhaloSet& S = ((Program*)hsh)->shs[sh];
+    ResponseField2 f; f.base = &B; f.S = &S; f.Sdr = S; f.Sdr.dradius = 1; f.nsh = S.n;
+    f(t, y, dy);
 }
 
 // RHS of the response field at one state (fields.py:175-206), for unit tests

@@ -329,6 +329,29 @@ def linear_response_saveat(pot_base, sharrays, w0, D0, t0, t1, ts, ctrl):
     return ws, Ds, status, nsteps
 
 
+def second_order_response(pot_base, sharrays, w0, D0, E0, t0, t1, ctrl):
+    tt = torch()
+    P, _keep = lower(pot_base)
+    S = sharrays.struct()
+    N = w0.shape[0]
+    wout, Dout, Eout = empty((N, 6)), empty((N, sharrays.n, 12)), empty((N, sharrays.n, 6))
+    status, nsteps = empty((N,), tt.int32), empty((N, 3), tt.int32)
+    nbytes = _lib.lib().ssb_second_order_scratch_bytes(sharrays.n)
+    scratch = empty(((nbytes + 7) // 8,))
+    _lib.check(_lib.lib().ssb_second_order_response_f64(C.byref(P), C.byref(S), N, ptr(w0), ptr(D0), ptr(E0), ptr(t0), float(t1), ctrl, ptr(wout),
+                                                        ptr(Dout), ptr(Eout), ptr(status), ptr(nsteps), ptr(scratch), nbytes, stream_ptr()))
+    return wout, Dout, Eout, status, nsteps
+
+
+def second_order_term(pot_base, sharrays, t, y):
+    P, _keep = lower(pot_base)
+    S = sharrays.struct()
+    yd = to_dev(y).reshape(-1)
+    dy = empty(yd.shape)
+    _lib.check(_lib.lib().ssb_second_order_term_f64(C.byref(P), C.byref(S), float(t), ptr(yd), ptr(dy), stream_ptr()))
+    return dy
+
+
 def response_term(pot_base, sharrays, t, y):
     P, _keep = lower(pot_base)
     S = sharrays.struct()

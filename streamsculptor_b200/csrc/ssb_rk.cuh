@@ -45,16 +45,19 @@ template <> struct Tab<8> {
 
 struct CtrlDev { double rtol, atol, dtmin, dtmax; int max_steps; };
 
+// The helpers are written for systems of D second-order components (D = 3 for an orbit or a response block, D = 6 for the
+// coupled first+second-order mass block); D is deduced from the array arguments.
+
 // ---- stages 2..S-1 of one step attempt.  F[0] must hold the force at (x, t) (FSAL). ----
-template <int SOLVER, class Force>
-__device__ __forceinline__ void rk_stages(Force& force, const double x[3], const double p[3], double t, double h,
-                                          double (&F)[Tab<SOLVER>::S][3]) {
+template <int SOLVER, class Force, int D>
+__device__ __forceinline__ void rk_stages(Force& force, const double (&x)[D], const double (&p)[D], double t, double h,
+                                          double (&F)[Tab<SOLVER>::S][D]) {
     typedef Tab<SOLVER> T;
 #pragma unroll
     for (int i = 1; i < T::S - 1; ++i) {
-        double X[3];
+        double X[D];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < D; ++k) {
             double acc = 0.0;
 #pragma unroll
             for (int l = 0; l < i; ++l)
@@ -66,13 +69,13 @@ __device__ __forceinline__ void rk_stages(Force& force, const double x[3], const
 }
 
 // candidate state = last stage value (the last tableau row equals b); caller then sets F[S-1] = force(x1, t + h)
-template <int SOLVER>
-__device__ __forceinline__ void rk_candidate(const double x[3], const double p[3], double h, const double (&F)[Tab<SOLVER>::S][3],
-                                             double x1[3], double p1[3]) {
+template <int SOLVER, int D>
+__device__ __forceinline__ void rk_candidate(const double (&x)[D], const double (&p)[D], double h, const double (&F)[Tab<SOLVER>::S][D],
+                                             double (&x1)[D], double (&p1)[D]) {
     typedef Tab<SOLVER> T;
     constexpr int L = T::S - 1;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < D; ++k) {
         double ax = 0.0, ap = 0.0;
 #pragma unroll
         for (int l = 0; l < L; ++l) {
@@ -85,11 +88,11 @@ __device__ __forceinline__ void rk_candidate(const double x[3], const double p[3
 }
 
 // embedded error estimate  y_err = h sum e_i f_i  (needs all S force stages)
-template <int SOLVER>
-__device__ __forceinline__ void rk_error(const double p[3], double h, const double (&F)[Tab<SOLVER>::S][3], double ex[3], double ep[3]) {
+template <int SOLVER, int D>
+__device__ __forceinline__ void rk_error(const double (&p)[D], double h, const double (&F)[Tab<SOLVER>::S][D], double (&ex)[D], double (&ep)[D]) {
     typedef Tab<SOLVER> T;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < D; ++k) {
         double bx = 0.0, bp = 0.0;
 #pragma unroll
         for (int l = 0; l < T::S; ++l) {
@@ -164,11 +167,12 @@ __device__ __forceinline__ void rk_dense(const double x[3], const double p[3], c
 }
 
 // sum of squared scaled errors of one 6-vector (x,p): sc = atol + rtol*max(|y0|,|y1|)  (NaN candidate -> y0)
-__device__ __forceinline__ double err_sq6(const double x[3], const double p[3], const double x1[3], const double p1[3],
-                                          const double ex[3], const double ep[3], double rtol, double atol, bool nan_cand) {
+template <int D>
+__device__ __forceinline__ double err_sq(const double (&x)[D], const double (&p)[D], const double (&x1)[D], const double (&p1)[D],
+                                         const double (&ex)[D], const double (&ep)[D], double rtol, double atol, bool nan_cand) {
     double acc = 0.0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < D; ++k) {
         const double xc = nan_cand ? x[k] : x1[k], pc = nan_cand ? p[k] : p1[k];
         const double sx = fma(rtol, fmax(fabs(x[k]), fabs(xc)), atol);
         const double sp = fma(rtol, fmax(fabs(p[k]), fabs(pc)), atol);
@@ -176,6 +180,10 @@ __device__ __forceinline__ double err_sq6(const double x[3], const double p[3], 
         acc = fma(qx, qx, acc); acc = fma(qp, qp, acc);
     }
     return acc;
+}
+__device__ __forceinline__ double err_sq6(const double (&x)[3], const double (&p)[3], const double (&x1)[3], const double (&p1)[3],
+                                          const double (&ex)[3], const double (&ep)[3], double rtol, double atol, bool nan_cand) {
+    return err_sq<3>(x, p, x1, p1, ex, ep, rtol, atol, nan_cand);
 }
 
 // PIDController.adapt_step_size with pcoeff = dcoeff = 0: returns keep, updates h_next / at_dtmin

@@ -33,6 +33,20 @@ class MassRadiusPerturbation_OTF:
         return [dy[:6], dy[6:].reshape(D.shape)]
 
 
+class MassRadiusPerturbation_OTF_SecondOrder:
+    """coords = [w(6), D(nSH,12), E(nSH,6)], E = second-order mass derivative (x2, v2) (fields.py:260-320)."""
+
+    def __init__(self, perturbation_generator):
+        self.pertgen = perturbation_generator
+
+    def term(self, t, coords, args=None):
+        w, D, E = [np.asarray(c, dtype=np.float64) for c in coords]
+        y = np.concatenate([w.reshape(6), D.reshape(-1), E.reshape(-1)])
+        dy = rt.second_order_term(self.pertgen.potential_base_total, self.pertgen.subhalo_arrays, t, y).cpu().numpy()
+        n = D.shape[0]
+        return [dy[:6], dy[6:6 + 12 * n].reshape(n, 12), dy[6 + 12 * n:].reshape(n, 6)]
+
+
 def _interval(ts, t0, t1, backwards_int):
     """fields.py:58-82: t0 == t1 (default 0.0) means 'derive the interval from ts'."""
     if t0 != t1:
@@ -63,8 +77,22 @@ def integrate_field(w0=None, ts=None, dense=False, solver=Dopri8(scan_kind='boun
         if int(status[0]) != 0:     # diffrax default throw=True (fields.py:85-98)
             raise RuntimeError("integrate_field failed: " + ("max_steps reached" if int(status[0]) == 1 else "non-finite state"))
         return Solution(ts_h, [ws.cpu().numpy(), Ds.cpu().numpy()], status[0].cpu().numpy(), nsteps[0])
+    if isinstance(field, MassRadiusPerturbation_OTF_SecondOrder):
+        pg = field.pertgen
+        if len(ts_h) > 2 or (len(ts_h) == 2 and ts_h[0] != a):
+            raise NotImplementedError("the second-order kernel keeps the final state only (ts = [t_start, t_end], perturbative.py:764)")
+        ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
+        n = pg.subhalo_arrays.n
+        w = rt.to_dev(w0[0]).reshape(1, 6)
+        D0, E0 = rt.to_dev(w0[1]).reshape(1, n, 12), rt.to_dev(w0[2]).reshape(1, n, 6)
+        wout, Dout, Eout, status, nsteps = rt.second_order_response(pg.potential_base_total, pg.subhalo_arrays, w, D0, E0, rt.to_dev([a]), b, ctrl)
+        if int(status[0]) != 0:
+            raise RuntimeError("integrate_field failed: " + ("max_steps reached" if int(status[0]) == 1 else "non-finite state"))
+        first = len(ts_h) == 2
+        stack = lambda y0, y1: np.concatenate([y0.cpu().numpy(), y1.cpu().numpy()]) if first else y1.cpu().numpy()
+        return Solution(ts_h, [stack(w, wout), stack(D0, Dout), stack(E0, Eout)], status[0].cpu().numpy(), nsteps[0])
     raise NotImplementedError(f"field {type(field).__name__} is not implemented on the device (closed set: hamiltonian_field, "
-                              "MassRadiusPerturbation_OTF)")
+                              "MassRadiusPerturbation_OTF, MassRadiusPerturbation_OTF_SecondOrder)")
 
 
 def _unsupported(name):
@@ -77,6 +105,5 @@ def _unsupported(name):
 
 Nbody_field = _unsupported("Nbody_field")
 MassRadiusPerturbation_Interp = _unsupported("MassRadiusPerturbation_Interp")
-MassRadiusPerturbation_OTF_SecondOrder = _unsupported("MassRadiusPerturbation_OTF_SecondOrder")
 MW_LMC_field = _unsupported("MW_LMC_field")
 CustomField = _unsupported("CustomField")

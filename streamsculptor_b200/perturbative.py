@@ -210,3 +210,17 @@ class GenerateMassRadiusPerturbation_Chen25(_ResponseGenerator):          # pert
 
     def compute_base_stream(self, cpu=True):
         return self.base_stream.gen_stream()
+
+    def compute_perturbation_second_order_OTF(self, cpu=True, solver=Dopri8(scan_kind='bounded'), rtol=1e-6, atol=1e-6, dtmin=0.05, max_steps=10_000,
+                                              dtmax=None):
+        """[w (N-1,6), D (N-1,N_sh,12), E (N-1,N_sh,6)] (perturbative.py:757-772); zero perturbation ICs (perturbative.py:715)."""
+        ts = np.asarray(self.base_stream.ts, dtype=np.float64)
+        n = len(ts) - 1
+        ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
+        wout, Dout, Eout, status, nsteps = rt.second_order_response(self.potential_base_total, self.subhalo_arrays,
+                                                                    rt.to_dev(np.asarray(self.base_realspace_ICs)[:n]), None, None, rt.to_dev(ts[:n]),
+                                                                    float(ts[-1]), ctrl)
+        self.last_status, self.last_nsteps = status.cpu().numpy(), nsteps.cpu().numpy()
+        if (self.last_status != 0).any():
+            raise RuntimeError("compute_perturbation_second_order_OTF: a particle failed (max_steps reached or non-finite state)")
+        return [wout.cpu().numpy(), Dout.cpu().numpy(), Eout.cpu().numpy()]

@@ -468,3 +468,41 @@ def test_mw_lmc_potential_api(cuda):
     sol = pot.integrate_orbit_batch_vmapped(w0=w0, ts=np.zeros((20, 1)), t0=-3000.0, t1=0.0, dtmin=1.0, dtmax=1.0)
     assert scaled_err(sol.ys[:, 0], ys_o[:, 0], 1e-10).max() < 1.0
     assert np.allclose(pot.LMC_center_spline(-7000.0), orc.track_eval(tr, [-7000.0])[0][0], rtol=1e-14)
+
+
+def test_second_order_response(cuda):
+    """A16: MassRadiusPerturbation_OTF_SecondOrder (fields.py:260-320) and compute_perturbation_second_order_OTF
+    (perturbative.py:757-772) vs the oracle (third derivatives and per-subhalo Hessians by nested autodiff there)."""
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import _runtime as rt
+    P = ssc.potential
+    nsh = 7
+    sh = subhalo_set(nsh, seed=23, t_lo=-900.0)
+    sh["x0"] = sh["x0"] * 0.2 + np.array([12.0, 3.0, -6.0]); sh["rs"] = sh["rs"] + 0.3
+    base, orc_base = mw3_product(), mw3_oracle()
+    for prof_o, func in ((O.PR_HERNQUIST, P.HernquistPotential), (O.PR_PLUMMER, P.PlummerPotential)):
+        orc_sh = O.Program().subhalos(prof_o, sh["M"], sh["rs"], sh["x0"], sh["v"], sh["t0"], sh["tw"])
+        pert = P.SubhaloLinePotentialCustom_fromFunc(func=func, m=sh["M"], r_s=sh["rs"], subhalo_x0=sh["x0"], subhalo_v=sh["v"], subhalo_t0=sh["t0"],
+                                                     t_window=sh["tw"], units=ssc.usys)
+        rng = np.random.default_rng(3)
+        y = np.concatenate([[11.0, 2.5, -5.0, 0.1, 0.12, -0.05], rng.normal(size=12 * nsh) * 1e-2, rng.normal(size=6 * nsh) * 1e-2])
+        tq = sh["t0"][2] + 15.0
+        assert relerr(rt.second_order_term(base, pert._arrays, tq, y).cpu().numpy(), O.second_order_term(orc_base, orc_sh, tq, y)) < 1e-9
+        w0 = halo_orbits(5, seed=31); w0[:, :3] = np.array([12.0, 3.0, -6.0]) + np.random.default_rng(5).normal(size=(5, 3))
+        t0 = np.linspace(-1000.0, -100.0, 5)
+        for solver in (8, 5):
+            w_o, D_o, E_o, st_o, ns_o = O.second_order_response(orc_base, orc_sh, w0, t0, 0.0, solver=solver, dtmin=1.0, dtmax=1.0)
+            ctrl = rt.make_ctrl(ssc.Dopri8() if solver == 8 else ssc.Dopri5(), 1e-8, 1e-8, 1.0, 1.0, 10_000)
+            w, D, E, st, ns = rt.second_order_response(base, pert._arrays, rt.to_dev(w0), None, None, rt.to_dev(t0), 0.0, ctrl)
+            assert (st.cpu().numpy() == 0).all() and np.array_equal(ns.cpu().numpy()[:, 0], ns_o[:, 0])
+            assert scaled_err(w.cpu().numpy(), w_o, 1e-10).max() < 1.0
+            assert np.abs(D.cpu().numpy() - D_o).max() <= 1e-9 * np.abs(D_o).max() and np.abs(E.cpu().numpy() - E_o).max() <= 1e-9 * np.abs(E_o).max()
+            assert np.abs(E_o).max() > 0
+    # adaptive, through the public field API with non-zero ICs
+    gen = type("G", (), {"potential_base_total": base, "subhalo_arrays": pert._arrays})()
+    fld = ssc.fields.MassRadiusPerturbation_OTF_SecondOrder(gen)
+    D0, E0 = rng.normal(size=(nsh, 12)) * 1e-8, rng.normal(size=(nsh, 6)) * 1e-8
+    sol = ssc.integrate_field(w0=[w0[0], D0, E0], ts=np.array([-300.0, 0.0]), field=fld, solver=ssc.Dopri8(), rtol=1e-9, atol=1e-12, dtmin=0.01, max_steps=5000)
+    w_o, D_o, E_o, _, _ = O.second_order_response(orc_base, orc_sh, w0[:1], -300.0, 0.0, D0=D0[None], E0=E0[None], solver=8, rtol=1e-9, atol=1e-12, dtmin=0.01)
+    assert np.array_equal(sol.ys[2][0], E0) and np.abs(sol.ys[2][1] - E_o[0]).max() < 1e-4 * np.abs(E_o).max()
+    assert np.abs(sol.ys[1][1] - D_o[0]).max() < 1e-4 * np.abs(D_o).max()
