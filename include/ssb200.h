@@ -210,6 +210,25 @@ int ssb_second_order_term_f64(const ssb_potential* pot_base, const ssb_subhalos*
 int ssb_response_term_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, double t, const double* y, double* dy,
                           void* stream);
 
+/* A17  N tracers integrated as ONE ODE state with a shared step-size controller: RestrictedNbody_generator.term
+ * (RestrictedNbody.py:93-106) integrated by fields.integrate_field (RestrictedNbody.py:131, fields.py:85-98).  `pot` = external
+ * potential + progenitor monopole on its track (a translating component).  The RMS error norm runs over all 6N components;
+ * w0/wout [N,6]; status[1]; nsteps[3] = steps, accepted, rejected.  scratch >= ssb_shared_scratch_bytes(N).  The call polls a
+ * device flag between batches of step attempts, so it synchronises the stream. */
+int ssb_shared_step_orbits_f64(const ssb_potential* pot, int64_t N, const double* w0, double t0, double t1, ssb_ctrl ctrl, double* wout,
+                               int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream);
+size_t ssb_shared_scratch_bytes(int64_t N);
+/* A17  fields.Nbody_field (fields.py:115-155) through integrate_field: N <= 1024 live bodies, softened all-pairs gravity
+ * (softening eps) + optional external potential (ext NULL or n_comp == 0 -> none), ONE ODE state (N,6), SaveAt(ts[M]) ->
+ * ys[M,N,6].  scratch >= ssb_nbody_scratch_bytes(N). */
+int ssb_nbody_integrate_f64(const ssb_potential* ext, int32_t N, const double* masses, double G, double eps, const double* w0, double t0, double t1,
+                            const double* ts, int32_t M, ssb_ctrl ctrl, double* ys, int32_t* status, int32_t* nsteps, void* scratch,
+                            size_t scratch_bytes, void* stream);
+size_t ssb_nbody_scratch_bytes(int32_t N);
+/* Nbody_field.term at one state (fields.py:134-155): y[N,6] -> dy[N,6]; scratch >= 3 N doubles */
+int ssb_nbody_term_f64(const ssb_potential* ext, int32_t N, const double* masses, double G, double eps, double t, const double* y, double* dy,
+                       void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---- host-pointer conveniences (H2D, launch, D2H, synchronise) - what a CPU-side plugin call looks like ---------- */
 int ssb_orbit_integrate_host(const ssb_potential* pot_hostptrs, int64_t N, const double* w0, const double* t0,
                              const double* t1, const double* ts, int32_t M, int32_t ts_per_orbit, ssb_ctrl ctrl,

@@ -317,6 +317,40 @@ def response_term(base, shprog, t, y, sh=0):
     return dy
 
 
+
+def shared_step_orbits(prog, w0, t0, t1, ts=None, solver=8, rtol=1e-7, atol=1e-7, dtmin=0.05, dtmax=None, max_steps=1_000):
+    """integrate_field(w0[N,6], field=RestrictedNbody_generator) (RestrictedNbody.py:93-106,131): all N tracers are ONE ODE
+    state with a shared controller.  Returns ys[M,N,6] (ts None -> [t1]), status, nsteps[3]."""
+    w0 = _d(w0).reshape(-1, 6)
+    N = len(w0)
+    ts = _d([t1] if ts is None else ts).reshape(-1)
+    ys = np.empty((len(ts), N, 6))
+    status, nsteps = np.zeros(1, dtype=np.int32), np.zeros(3, dtype=np.int32)
+    lib().orc_shared_step_orbits(prog._h, N, _p(w0), C.c_double(t0), C.c_double(t1), _p(ts), len(ts), int(solver), C.c_double(rtol), C.c_double(atol),
+                                 C.c_double(dtmin), C.c_double(np.inf if dtmax is None else dtmax), int(max_steps), _p(ys),
+                                 status.ctypes.data_as(_ip), nsteps.ctypes.data_as(_ip))
+    return ys, int(status[0]), nsteps
+
+
+def nbody(ext, masses, w0, t0, t1, ts=None, eps=1e-3, G=G_KPC_MYR_MSUN, solver=8, rtol=1e-7, atol=1e-7, dtmin=0.05, dtmax=None, max_steps=1_000):
+    """integrate_field(w0[N,6], field=Nbody_field(ext_pot, masses, eps)) (fields.py:115-155).  ext: Program or None."""
+    w0, masses = _d(w0).reshape(-1, 6), _d(masses).reshape(-1)
+    N = len(w0)
+    ts = _d([t1] if ts is None else ts).reshape(-1)
+    ys = np.empty((len(ts), N, 6))
+    status, nsteps = np.zeros(1, dtype=np.int32), np.zeros(3, dtype=np.int32)
+    lib().orc_nbody(None if ext is None else ext._h, N, _p(masses), C.c_double(G), C.c_double(eps), _p(w0), C.c_double(t0), C.c_double(t1), _p(ts),
+                    len(ts), int(solver), C.c_double(rtol), C.c_double(atol), C.c_double(dtmin), C.c_double(np.inf if dtmax is None else dtmax),
+                    int(max_steps), _p(ys), status.ctypes.data_as(_ip), nsteps.ctypes.data_as(_ip))
+    return ys, int(status[0]), nsteps
+
+
+def nbody_term(ext, masses, t, y, eps=1e-3, G=G_KPC_MYR_MSUN):
+    y, masses = _d(y).reshape(-1, 6), _d(masses).reshape(-1)
+    dy = np.empty_like(y)
+    lib().orc_nbody_term(None if ext is None else ext._h, len(y), _p(masses), C.c_double(G), C.c_double(eps), C.c_double(t), _p(y), _p(dy))
+    return dy
+
 def threefry2x32(k0, k1, c0, c1):
     out = (C.c_uint32 * 2)()
     lib().orc_threefry(C.c_uint32(k0), C.c_uint32(k1), C.c_uint32(c0), C.c_uint32(c1), out)

@@ -494,4 +494,64 @@ void orc_response_term(void* hbase, void* hsh, int sh, double t, const double* y
     f(t, y, dy);
 }
 
+// RestrictedNbody_generator.term integrated by integrate_field (RestrictedNbody.py:93-106, 131): the WHOLE (N,6) tracer
+// array is ONE diffrax state -> one step sequence, RMS error norm over all 6N components.  The field is the external
+// potential + progenitor monopole on its track = one potential program with a translating component.
+struct SharedOrbitField {
+    const Program* P; int N;
+    void operator()(double t, const double* y, double* dy) const {
+        for (int i = 0; i < N; ++i) {
+            const double* w = y + 6 * (size_t)i; double* d = dy + 6 * (size_t)i;
+            double g[3]; gradient<double>(*P, w, t, g);
+            d[0] = w[3]; d[1] = w[4]; d[2] = w[5]; d[3] = -g[0]; d[4] = -g[1]; d[5] = -g[2];
+        }
+    }
+};
+void orc_shared_step_orbits(void* h, int N, const double* w0, double t0, double t1, const double* ts, int M, int solver, double rtol, double atol,
+                            double dtmin, double dtmax, int max_steps, double* ys /*[M,N,6]*/, int* status, int* nsteps) {
+    const Program& P = *(Program*)h;
+    Ctrl c; c.solver = solver; c.rtol = rtol; c.atol = atol; c.dtmin = dtmin; c.dtmax = dtmax; c.max_steps = max_steps;
+    SharedOrbitField f{&P, N};
+    Stats s = solve(f, 6 * N, t0, t1, w0, ts, M, c, ys);
+    *status = s.status; nsteps[0] = s.n_steps; nsteps[1] = s.n_acc; nsteps[2] = s.n_rej;
+}
+
+// Nbody_field.term (fields.py:134-155): softened all-pairs self gravity + external potential, state (N,6) as ONE ODE.
+// force_ij on i from j = G m_i m_j (x_i - x_j) / d^3 with d^2 = |x_i-x_j|^2 + eps^2; the reference sums forces[j, i] over j
+// (axis 0) = sum_j G m_j m_i (x_j - x_i)/d^3, then divides by m_i.
+struct NbodyField {
+    const Program* P; int N; const double* m; double G, eps;
+    void operator()(double t, const double* y, double* dy) const {
+        for (int i = 0; i < N; ++i) {
+            const double* w = y + 6 * (size_t)i; double* d = dy + 6 * (size_t)i;
+            double acc[3] = {0, 0, 0};
+            for (int j = 0; j < N; ++j) {
+                if (j == i) continue;
+                const double* wj = y + 6 * (size_t)j;
+                double dx[3] = {wj[0] - w[0], wj[1] - w[1], wj[2] - w[2]};
+                double d2 = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2] + eps * eps;
+                double dd = std::sqrt(d2);
+                double fmag = G * m[j] * m[i] / d2;
+                for (int k = 0; k < 3; ++k) acc[k] += fmag * dx[k] / dd;
+            }
+            double g[3] = {0, 0, 0};
+            if (P) gradient<double>(*P, w, t, g);
+            d[0] = w[3]; d[1] = w[4]; d[2] = w[5];
+            for (int k = 0; k < 3; ++k) d[3 + k] = acc[k] / m[i] - g[k];
+        }
+    }
+};
+void orc_nbody(void* h /*ext potential or NULL*/, int N, const double* masses, double G, double eps, const double* w0, double t0, double t1,
+               const double* ts, int M, int solver, double rtol, double atol, double dtmin, double dtmax, int max_steps, double* ys /*[M,N,6]*/,
+               int* status, int* nsteps) {
+    Ctrl c; c.solver = solver; c.rtol = rtol; c.atol = atol; c.dtmin = dtmin; c.dtmax = dtmax; c.max_steps = max_steps;
+    NbodyField f{(const Program*)h, N, masses, G, eps};
+    Stats s = solve(f, 6 * N, t0, t1, w0, ts, M, c, ys);
+    *status = s.status; nsteps[0] = s.n_steps; nsteps[1] = s.n_acc; nsteps[2] = s.n_rej;
+}
+void orc_nbody_term(void* h, int N, const double* masses, double G, double eps, double t, const double* y, double* dy) {
+    NbodyField f{(const Program*)h, N, masses, G, eps};
+    f(t, y, dy);
+}
+
 }  // extern "C"

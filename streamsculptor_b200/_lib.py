@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _OUT = os.path.join(_HERE, "_lib", "libssb200.so")
-_SOURCES = ["ssb_kernels.cu", "ssb_response.cu", "ssb_response2.cu", "ssb_host.cu"]
+_SOURCES = ["ssb_kernels.cu", "ssb_response.cu", "ssb_response2.cu", "ssb_shared.cu", "ssb_host.cu"]
 _HEADERS = ["ssb_common.cuh", "ssb_potential.cuh", "ssb_rk.cuh", "ssb_fastmath.cuh", "ssb_tableau.h", "../../include/ssb200.h"]
 
 MAX_COMP, MAX_TRACK, MAX_SH = 12, 4, 2
@@ -98,6 +98,11 @@ _SIGNATURES = {
     "ssb_second_order_scratch_bytes": ([_i32], C.c_size_t),
     "ssb_second_order_term_f64": ([_PP, _SP, _dbl, _dp, _dp, _dp], C.c_int),
     "ssb_response_term_f64": ([_PP, _SP, _dbl, _dp, _dp, _dp], C.c_int),
+    "ssb_shared_step_orbits_f64": ([_PP, _i64, _dp, _dbl, _dbl, Ctrl, _dp, _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
+    "ssb_shared_scratch_bytes": ([_i64], C.c_size_t),
+    "ssb_nbody_integrate_f64": ([_PP, _i32, _dp, _dbl, _dbl, _dp, _dbl, _dbl, _dp, _i32, Ctrl, _dp, _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
+    "ssb_nbody_scratch_bytes": ([_i32], C.c_size_t),
+    "ssb_nbody_term_f64": ([_PP, _i32, _dp, _dbl, _dbl, _dbl, _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
     "ssb_orbit_integrate_host": ([_PP, _i64, _dp, _dp, _dp, _dp, _i32, _i32, Ctrl, _dp, _dp, _dp], C.c_int),
     "ssb_gen_stream_host": ([_PP, _PP, _dbl, _i64, _dp, _dp, _dp, _i64, C.POINTER(C.c_double), _dp, Ctrl, _i64, _i64, _i64, _dp, _dp,
                              _dp, _dp], C.c_int),

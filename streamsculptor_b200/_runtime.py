@@ -367,3 +367,47 @@ def subhalo_eval(sharrays, dradius, xyz, t):
     phi, grad = empty((sharrays.n,)), empty((sharrays.n, 3))
     _lib.check(_lib.lib().ssb_subhalo_eval_f64(C.byref(S), int(bool(dradius)), x, float(t), ptr(phi), ptr(grad), stream_ptr()))
     return phi, grad
+
+
+def shared_step_orbits(pot, w0, t0, t1, ctrl):
+    """N tracers as ONE ODE state with a shared controller (RestrictedNbody.py:93-106,131): wout[N,6], status[1], nsteps[3]."""
+    tt = torch()
+    P, _keep = lower(pot)
+    N = w0.shape[0]
+    wout = empty((N, 6))
+    status, nsteps = empty((1,), tt.int32), empty((3,), tt.int32)
+    nbytes = _lib.lib().ssb_shared_scratch_bytes(N)
+    scratch = empty(((nbytes + 7) // 8,))
+    _lib.check(_lib.lib().ssb_shared_step_orbits_f64(C.byref(P), N, ptr(w0), float(t0), float(t1), ctrl, ptr(wout), ptr(status), ptr(nsteps),
+                                                     ptr(scratch), nbytes, stream_ptr()))
+    return wout, status, nsteps
+
+
+def _ext_struct(ext_pot):
+    if ext_pot is None:
+        return _lib.Potential(), None
+    return lower(ext_pot)
+
+
+def nbody_integrate(ext_pot, masses, G, eps, w0, t0, t1, ts, ctrl):
+    """Nbody_field through integrate_field (fields.py:115-155): ys[M,N,6], status[1], nsteps[3]."""
+    tt = torch()
+    P, _keep = _ext_struct(ext_pot)
+    N, M = w0.shape[0], ts.shape[0]
+    ys = empty((M, N, 6))
+    status, nsteps = empty((1,), tt.int32), empty((3,), tt.int32)
+    nbytes = _lib.lib().ssb_nbody_scratch_bytes(N)
+    scratch = empty(((nbytes + 7) // 8,))
+    _lib.check(_lib.lib().ssb_nbody_integrate_f64(C.byref(P), N, ptr(masses), float(G), float(eps), ptr(w0), float(t0), float(t1), ptr(ts), M, ctrl,
+                                                  ptr(ys), ptr(status), ptr(nsteps), ptr(scratch), nbytes, stream_ptr()))
+    return ys, status, nsteps
+
+
+def nbody_term(ext_pot, masses, G, eps, t, y):
+    P, _keep = _ext_struct(ext_pot)
+    yd = to_dev(y).reshape(-1, 6)
+    N = yd.shape[0]
+    dy, scratch = empty((N, 6)), empty((3 * N,))
+    _lib.check(_lib.lib().ssb_nbody_term_f64(C.byref(P), N, ptr(masses), float(G), float(eps), float(t), ptr(yd), ptr(dy), ptr(scratch), 24 * N,
+                                             stream_ptr()))
+    return dy

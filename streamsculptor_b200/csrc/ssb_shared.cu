@@ -1,0 +1,464 @@
+// K5: N tracers integrated as ONE ODE with a shared step-size controller.
+//
+// Reference: RestrictedNbody_generator.term (RestrictedNbody.py:93-106) integrated by fields.integrate_field
+// (RestrictedNbody.py:131, fields.py:85-98): the whole (N,6) particle array is a single diffrax state, so there is one
+// step sequence and the RMS error norm runs over all 6N components.  The field is the external potential plus the
+// progenitor's monopole centred on its interpolated orbit = a potential program with a translating component.
+//
+// B200 mapping: one step ATTEMPT = one grid-wide kernel (thread per tracer, Nystrom stages in registers, block-reduced
+// squared errors atomically added to a device accumulator) followed by a 1-thread controller kernel that decides
+// accept/reject, flips the double buffer and writes the next (t, dt) into a device control block.  No host round trip per
+// step: the host enqueues batches of attempts and polls a done flag between batches (an attempt at N >= 1e5 is >= tens of
+// microseconds, a 1e7-tracer attempt ~13 ms).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "ssb_common.cuh"
+
+using namespace ssb;
+
+#define CK(call) do { int _e = ssb_cuda_check((call), #call); if (_e) return _e; } while (0)
+#define CKL(what) do { int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
+
+struct SharedCtl {            // device control block
+    double tprev, tnext, T1, dir, acc, acc2, h0, d1;
+    int which, at_dtmin, status, done, n_steps, n_acc, n_rej, bad;
+};
+
+__device__ __noinline__ double3 shared_accel(const ssb_potential* P, double x, double y, double z, double t) {
+    const double X[3] = {x, y, z};
+    double phi, g[3];
+    Sym3 H;
+    pot_eval<WANT_GRAD>(*P, X, t, phi, g, H);
+    return make_double3(-g[0], -g[1], -g[2]);
+}
+struct SharedForce {
+    const ssb_potential* P; double dir;
+    __device__ __forceinline__ void operator()(const double X[3], double tau, double A[3]) const {
+        const double3 a = shared_accel(P, X[0], X[1], X[2], tau * dir);
+        A[0] = a.x; A[1] = a.y; A[2] = a.z;
+    }
+};
+
+__device__ __forceinline__ void block_atomic_add(double v, double* target) {
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { double tot = 0.0; for (int i = 0; i < nw; ++i) tot += red[i]; atomicAdd(target, tot); }
+}
+
+// state buffers: buf[which] = {x[3N] (AoS rows of 3), p[3N], F[3N]}
+// init pass 1: p = dir*v, F0 = force(x, T0); sums d0^2 -> acc, d1^2 -> acc2
+__global__ void shared_init1(const __grid_constant__ ssb_potential Pin, int64_t N, const double* w0, double* buf, SharedCtl* ctl, CtrlDev c) {
+    __shared__ ssb_potential sP;
+    stage_potential(&sP, &Pin);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double d0 = 0.0, d1 = 0.0;
+    if (i < N) {
+        const double dir = ctl->dir, T0 = ctl->tprev;
+        SharedForce f{&sP, dir};
+        double x[3], p[3], F[3];
+        for (int k = 0; k < 3; ++k) { x[k] = w0[6 * i + k]; p[k] = dir * w0[6 * i + 3 + k]; }
+        f(x, T0, F);
+        double* X = buf; double* Pm = buf + 3 * N; double* Fm = buf + 6 * N;
+        for (int k = 0; k < 3; ++k) {
+            X[3 * i + k] = x[k]; Pm[3 * i + k] = p[k]; Fm[3 * i + k] = F[k];
+            const double sx = fma(c.rtol, fabs(x[k]), c.atol), sp = fma(c.rtol, fabs(p[k]), c.atol);
+            double q;
+            q = x[k] / sx; d0 = fma(q, q, d0); q = p[k] / sp; d0 = fma(q, q, d0);
+            q = p[k] / sx; d1 = fma(q, q, d1); q = F[k] / sp; d1 = fma(q, q, d1);
+        }
+    }
+    block_atomic_add(d0, &ctl->acc);
+    block_atomic_add(d1, &ctl->acc2);
+}
+__global__ void shared_init_ctl1(int64_t N, SharedCtl* ctl) {
+    const double d0 = sqrt(ctl->acc / (6.0 * N)), d1 = sqrt(ctl->acc2 / (6.0 * N));
+    ctl->h0 = hnw_h0(d0, d1); ctl->d1 = d1; ctl->acc = 0.0; ctl->acc2 = 0.0;
+}
+// init pass 2: f1 = f(T0 + h0, y0 + h0 f0); sum ((f1 - f0)/sc)^2 -> acc
+__global__ void shared_init2(const __grid_constant__ ssb_potential Pin, int64_t N, const double* buf, SharedCtl* ctl, CtrlDev c) {
+    __shared__ ssb_potential sP;
+    stage_potential(&sP, &Pin);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double d2 = 0.0;
+    if (i < N) {
+        const double dir = ctl->dir, T0 = ctl->tprev, h0 = ctl->h0;
+        SharedForce f{&sP, dir};
+        const double* X = buf; const double* Pm = buf + 3 * N; const double* Fm = buf + 6 * N;
+        double x[3], p[3], F0[3], X1[3], F1[3];
+        for (int k = 0; k < 3; ++k) { x[k] = X[3 * i + k]; p[k] = Pm[3 * i + k]; F0[k] = Fm[3 * i + k]; X1[k] = fma(h0, p[k], x[k]); }
+        f(X1, T0 + h0, F1);
+        for (int k = 0; k < 3; ++k) {
+            const double sx = fma(c.rtol, fabs(x[k]), c.atol), sp = fma(c.rtol, fabs(p[k]), c.atol);
+            double q;
+            q = (fma(h0, F0[k], p[k]) - p[k]) / sx; d2 = fma(q, q, d2);
+            q = (F1[k] - F0[k]) / sp; d2 = fma(q, q, d2);
+        }
+    }
+    block_atomic_add(d2, &ctl->acc);
+}
+template <int ORDER>
+__global__ void shared_init_ctl2(int64_t N, SharedCtl* ctl, CtrlDev c) {
+    const double d2 = sqrt(ctl->acc / (6.0 * N)) / ctl->h0;
+    double h = fmin(hnw_h1<ORDER>(ctl->h0, ctl->d1, d2), c.dtmax);
+    ctl->at_dtmin = h <= c.dtmin;
+    h = fmax(h, c.dtmin);
+    ctl->tnext = fmin(ctl->tprev + h, ctl->T1);
+    ctl->acc = 0.0;
+    ctl->done = !(ctl->tprev < ctl->T1);
+}
+
+// one step attempt for every tracer
+template <int SOLVER>
+__global__ void __launch_bounds__(128) shared_attempt(const __grid_constant__ ssb_potential Pin, int64_t N, double* buf0, double* buf1, SharedCtl* ctl, CtrlDev c) {
+    typedef Tab<SOLVER> T;
+    constexpr int S = T::S;
+    __shared__ ssb_potential sP;
+    stage_potential(&sP, &Pin);
+    if (ctl->done) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const double tprev = ctl->tprev, dt = ctl->tnext - ctl->tprev, dir = ctl->dir;
+    const double* cur = ctl->which ? buf1 : buf0;
+    double* nxt = ctl->which ? buf0 : buf1;
+    double esq = 0.0;
+    int bad = 0;
+    if (i < N) {
+        SharedForce f{&sP, dir};
+        double x[3], p[3], F[S][3], x1[3], p1[3], ex[3], ep[3];
+        for (int k = 0; k < 3; ++k) { x[k] = cur[3 * i + k]; p[k] = cur[3 * N + 3 * i + k]; F[0][k] = cur[6 * N + 3 * i + k]; }
+        rk_stages<SOLVER>(f, x, p, tprev, dt, F);
+        rk_candidate<SOLVER>(x, p, dt, F, x1, p1);
+        f(x1, tprev + T::c(S - 1) * dt, F[S - 1]);
+        rk_error<SOLVER>(p, dt, F, ex, ep);
+        bool nanc = false;
+        for (int k = 0; k < 3; ++k) { nanc |= isnan(x1[k]) | isnan(p1[k]); if (!isfinite(x1[k]) || !isfinite(p1[k])) bad = 1; }
+        esq = err_sq6(x, p, x1, p1, ex, ep, c.rtol, c.atol, nanc);
+        for (int k = 0; k < 3; ++k) { nxt[3 * i + k] = x1[k]; nxt[3 * N + 3 * i + k] = p1[k]; nxt[6 * N + 3 * i + k] = F[S - 1][k]; }
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(&ctl->bad, 1);
+    block_atomic_add(esq, &ctl->acc);
+}
+template <int ORDER>
+__global__ void shared_control(int64_t N, SharedCtl* ctl, CtrlDev c) {
+    if (ctl->done) return;
+    if (ctl->n_steps >= c.max_steps) { ctl->status = 1; ctl->done = 1; return; }
+    const double dt = ctl->tnext - ctl->tprev;
+    const double err = sqrt(ctl->acc / (6.0 * N));
+    bool at_dtmin = ctl->at_dtmin != 0, bad;
+    double hn;
+    const bool keep = pid_update<ORDER>(err, dt, c, at_dtmin, hn, bad);
+    ctl->at_dtmin = at_dtmin;
+    ctl->n_steps++;
+    ctl->acc = 0.0;
+    if (bad) { ctl->status = 2; ctl->n_rej++; ctl->done = 1; return; }
+    if (keep) {
+        ctl->n_acc++;
+        if (ctl->bad) { ctl->status = 2; ctl->done = 1; return; }
+        ctl->which ^= 1;
+        ctl->tprev = ctl->tnext;
+    } else {
+        ctl->n_rej++;
+        ctl->bad = 0;
+    }
+    ctl->tprev = fmin(ctl->tprev, ctl->T1);
+    double tn = ctl->tprev + hn;
+    if (tn > ctl->T1 - 1e-10) tn = keep ? ctl->T1 : ctl->tprev + 0.5 * (ctl->T1 - ctl->tprev);
+    ctl->tnext = tn;
+    if (!(ctl->tprev < ctl->T1)) ctl->done = 1;
+}
+__global__ void shared_finish(int64_t N, const double* buf0, const double* buf1, const SharedCtl* ctl, double* wout, int32_t* status, int32_t* nsteps) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const double* cur = ctl->which ? buf1 : buf0;
+    const bool ok = ctl->status == 0 && !(ctl->tprev < ctl->T1) && ctl->n_acc > 0;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    if (i < N) for (int k = 0; k < 3; ++k) { wout[6 * i + k] = ok ? cur[3 * i + k] : inf; wout[6 * i + 3 + k] = ok ? ctl->dir * cur[3 * N + 3 * i + k] : inf; }
+    if (i == 0) { status[0] = ctl->status; nsteps[0] = ctl->n_steps; nsteps[1] = ctl->n_acc; nsteps[2] = ctl->n_rej; }
+}
+
+// =====================================================================================================================
+// K6: Nbody_field (fields.py:115-155): N live bodies with softened all-pairs gravity (+ external potential) as ONE ODE.
+// Few-body problems (3-body tests, MW-LMC, ~100 live perturbers): pure latency, so ONE persistent CTA steps the system;
+// thread b owns body b (strided for N > blockDim), stage positions are exchanged through shared memory, the Nystrom force
+// stages live in an L1/L2-resident scratch, the shared controller is evaluated redundantly by every thread from a
+// block-wide error sum.  SaveAt(ts) rows are interpolated inside the accepted step that covers them.
+// =====================================================================================================================
+#define SSB_NBODY_MAX 1024
+#define SSB_NBODY_THREADS 256
+
+__device__ __forceinline__ double block_sum_all(double v, double* red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double tot = 0.0;
+    for (int i = 0; i < (SSB_NBODY_THREADS >> 5); ++i) tot += red[i];
+    return tot;
+}
+
+struct NbodyArgs {
+    int N, M, has_ext;
+    double G, eps2, t0, t1;
+    const double* w0; const double* masses; const double* ts;
+    double* scratch; double* ys; int32_t* status; int32_t* nsteps;
+};
+
+// accelerations of all bodies at stage positions sX (shared) -> Fout[3N] (global)
+__device__ __noinline__ void nbody_force_all(const ssb_potential* sP, const NbodyArgs& a, const double* sX, const double* sM, double treal, double* Fout) {
+    for (int b = threadIdx.x; b < a.N; b += blockDim.x) {
+        const double X[3] = {sX[3 * b], sX[3 * b + 1], sX[3 * b + 2]};
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        for (int j = 0; j < a.N; ++j) {
+            if (j == b) continue;
+            const double dx = sX[3 * j] - X[0], dy = sX[3 * j + 1] - X[1], dz = sX[3 * j + 2] - X[2];
+            const double d2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, a.eps2)));
+            const double inv = 1.0 / sqrt(d2);
+            const double w = a.G * sM[j] * inv * inv * inv;          // (G m_b m_j / d^2)(1/d) / m_b
+            ax = fma(w, dx, ax); ay = fma(w, dy, ay); az = fma(w, dz, az);
+        }
+        if (a.has_ext) {
+            double phi, g[3]; Sym3 H;
+            pot_eval<WANT_GRAD>(*sP, X, treal, phi, g, H);
+            ax -= g[0]; ay -= g[1]; az -= g[2];
+        }
+        Fout[3 * b] = ax; Fout[3 * b + 1] = ay; Fout[3 * b + 2] = az;
+    }
+}
+
+template <int SOLVER>
+__global__ void __launch_bounds__(SSB_NBODY_THREADS) nbody_kernel(const __grid_constant__ ssb_potential Pin, NbodyArgs a, CtrlDev c) {
+    typedef Tab<SOLVER> T;
+    constexpr int S = T::S;
+    __shared__ ssb_potential sP;
+    __shared__ double sX[3 * SSB_NBODY_MAX];
+    __shared__ double sM[SSB_NBODY_MAX];
+    __shared__ double red[SSB_NBODY_THREADS >> 5];
+    stage_potential(&sP, &Pin);
+    const int N = a.N, n3 = 3 * a.N;
+    const double dir = (a.t0 < a.t1) ? 1.0 : -1.0, T0 = a.t0 * dir, T1 = a.t1 * dir;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double* x = a.scratch; double* p = x + n3; double* x1 = p + n3; double* p1 = x1 + n3; double* F = p1 + n3;   // F[l] = F + l*n3
+    for (int64_t i = threadIdx.x; i < (int64_t)a.M * N * 6; i += blockDim.x) a.ys[i] = inf;
+    for (int b = threadIdx.x; b < N; b += blockDim.x) {
+        sM[b] = a.masses[b];
+        for (int k = 0; k < 3; ++k) { x[3 * b + k] = a.w0[6 * b + k]; p[3 * b + k] = dir * a.w0[6 * b + 3 + k]; sX[3 * b + k] = x[3 * b + k]; }
+    }
+    __syncthreads();
+    nbody_force_all(&sP, a, sX, sM, T0 * dir, F);
+    // ---- Hairer-Norsett-Wanner initial step over the whole 6N state ----
+    double h;
+    {
+        double s0 = 0.0, s1 = 0.0;
+        for (int b = threadIdx.x; b < N; b += blockDim.x)
+            for (int k = 0; k < 3; ++k) {
+                const double xv = x[3 * b + k], pv = p[3 * b + k], fv = F[3 * b + k];
+                const double sx = fma(c.rtol, fabs(xv), c.atol), sp = fma(c.rtol, fabs(pv), c.atol);
+                double q;
+                q = xv / sx; s0 = fma(q, q, s0); q = pv / sp; s0 = fma(q, q, s0);
+                q = pv / sx; s1 = fma(q, q, s1); q = fv / sp; s1 = fma(q, q, s1);
+            }
+        const double d0 = sqrt(block_sum_all(s0, red) / (6.0 * N)), d1 = sqrt(block_sum_all(s1, red) / (6.0 * N));
+        const double h0 = hnw_h0(d0, d1);
+        for (int b = threadIdx.x; b < N; b += blockDim.x)
+            for (int k = 0; k < 3; ++k) sX[3 * b + k] = fma(h0, p[3 * b + k], x[3 * b + k]);
+        __syncthreads();
+        nbody_force_all(&sP, a, sX, sM, (T0 + h0) * dir, F + n3);
+        double s2 = 0.0;
+        for (int b = threadIdx.x; b < N; b += blockDim.x)
+            for (int k = 0; k < 3; ++k) {
+                const double xv = x[3 * b + k], pv = p[3 * b + k];
+                const double sx = fma(c.rtol, fabs(xv), c.atol), sp = fma(c.rtol, fabs(pv), c.atol);
+                double q;
+                q = (fma(h0, F[3 * b + k], pv) - pv) / sx; s2 = fma(q, q, s2);
+                q = (F[n3 + 3 * b + k] - F[3 * b + k]) / sp; s2 = fma(q, q, s2);
+            }
+        const double d2 = sqrt(block_sum_all(s2, red) / (6.0 * N)) / h0;
+        h = fmin(hnw_h1<T::ORDER>(h0, d1, d2), c.dtmax);
+    }
+    bool at_dtmin = h <= c.dtmin;
+    h = fmax(h, c.dtmin);
+    double tprev = T0, tnext = fmin(T0 + h, T1);
+    int n_steps = 0, n_acc = 0, n_rej = 0, status = 0, save_idx = 0;
+
+    while (tprev < T1) {
+        if (n_steps >= c.max_steps) { status = 1; break; }
+        const double dt = tnext - tprev;
+        for (int i = 1; i < S; ++i) {
+            __syncthreads();                                             // everyone is done reading the previous sX
+            for (int b = threadIdx.x; b < N; b += blockDim.x)
+                for (int k = 0; k < 3; ++k) {
+                    double ax = 0.0;
+                    for (int l = 0; l < i; ++l) ax = fma(T::aa(i, l), F[l * n3 + 3 * b + k], ax);
+                    const double X = fma(dt, fma(dt, ax, T::rs(i) * p[3 * b + k]), x[3 * b + k]);
+                    sX[3 * b + k] = X;
+                    if (i == S - 1) {                                    // last row == b: candidate state
+                        double ap = 0.0;
+                        for (int l = 0; l < i; ++l) ap = fma(T::a(i, l), F[l * n3 + 3 * b + k], ap);
+                        x1[3 * b + k] = X; p1[3 * b + k] = fma(dt, ap, p[3 * b + k]);
+                    }
+                }
+            __syncthreads();
+            nbody_force_all(&sP, a, sX, sM, (tprev + T::c(i) * dt) * dir, F + i * n3);
+        }
+        // ---- error norm over all 6N components (scale uses y0 if ANY candidate component is NaN) ----
+        int fl = 0;
+        for (int b = threadIdx.x; b < N; b += blockDim.x)
+            for (int k = 0; k < 3; ++k) {
+                const double a1 = x1[3 * b + k], b1 = p1[3 * b + k];
+                if (isnan(a1) || isnan(b1)) fl |= 1;
+                if (!isfinite(a1) || !isfinite(b1)) fl |= 2;
+            }
+        const int anynan = __syncthreads_or(fl & 1), anybad = __syncthreads_or(fl & 2);
+        double es = 0.0;
+        for (int b = threadIdx.x; b < N; b += blockDim.x)
+            for (int k = 0; k < 3; ++k) {
+                double bx = 0.0, bp = 0.0;
+                for (int l = 0; l < S; ++l) { const double f = F[l * n3 + 3 * b + k]; bx = fma(T::ea(l), f, bx); bp = fma(T::e(l), f, bp); }
+                const double xv = x[3 * b + k], pv = p[3 * b + k];
+                const double ex = dt * fma(dt, bx, T::esum() * pv), ep = dt * bp;
+                const double xc = anynan ? xv : x1[3 * b + k], pc = anynan ? pv : p1[3 * b + k];
+                const double sx = fma(c.rtol, fmax(fabs(xv), fabs(xc)), c.atol), sp = fma(c.rtol, fmax(fabs(pv), fabs(pc)), c.atol);
+                const double qx = ex / sx, qp = ep / sp;
+                es = fma(qx, qx, es); es = fma(qp, qp, es);
+            }
+        const double err = sqrt(block_sum_all(es, red) / (6.0 * N));
+        double hn; bool bad;
+        const bool keep = pid_update<T::ORDER>(err, dt, c, at_dtmin, hn, bad);
+        n_steps++;
+        if (bad) { status = 2; n_rej++; break; }
+        if (keep) {
+            n_acc++;
+            if (anybad) { status = 2; break; }
+            while (save_idx < a.M && a.ts[save_idx] * dir <= tnext) {
+                const double tq = a.ts[save_idx] * dir, theta = (tq - tprev) / dt;
+                for (int b = threadIdx.x; b < N; b += blockDim.x) {
+                    double* o = a.ys + ((int64_t)save_idx * N + b) * 6;
+                    if (tq == tnext) { for (int k = 0; k < 3; ++k) { o[k] = x1[3 * b + k]; o[3 + k] = dir * p1[3 * b + k]; } }
+                    else {
+                        double Fl[S][3], xb[3], pb[3], x1b[3], p1b[3], xo[3], po[3];
+                        for (int k = 0; k < 3; ++k) { xb[k] = x[3 * b + k]; pb[k] = p[3 * b + k]; x1b[k] = x1[3 * b + k]; p1b[k] = p1[3 * b + k]; }
+                        for (int l = 0; l < S; ++l) for (int k = 0; k < 3; ++k) Fl[l][k] = F[l * n3 + 3 * b + k];
+                        rk_dense<SOLVER>(xb, pb, x1b, p1b, dt, Fl, theta, xo, po);
+                        for (int k = 0; k < 3; ++k) { o[k] = xo[k]; o[3 + k] = dir * po[k]; }
+                    }
+                }
+                save_idx++;
+            }
+            for (int b = threadIdx.x; b < N; b += blockDim.x)
+                for (int k = 0; k < 3; ++k) { x[3 * b + k] = x1[3 * b + k]; p[3 * b + k] = p1[3 * b + k]; F[3 * b + k] = F[(S - 1) * n3 + 3 * b + k]; }
+            tprev = tnext;
+        } else {
+            n_rej++;
+        }
+        tprev = fmin(tprev, T1);
+        double tn = tprev + hn;
+        if (tn > T1 - 1e-10) tn = keep ? T1 : tprev + 0.5 * (T1 - tprev);
+        tnext = tn;
+    }
+    if (threadIdx.x == 0) { a.status[0] = status; a.nsteps[0] = n_steps; a.nsteps[1] = n_acc; a.nsteps[2] = n_rej; }
+}
+
+// Nbody_field.term at one state (unit tests / facade .term): dy[N,6]
+__global__ void __launch_bounds__(SSB_NBODY_THREADS) nbody_term_kernel(const __grid_constant__ ssb_potential Pin, NbodyArgs a, double t, const double* y, double* dy) {
+    __shared__ ssb_potential sP;
+    __shared__ double sX[3 * SSB_NBODY_MAX];
+    __shared__ double sM[SSB_NBODY_MAX];
+    stage_potential(&sP, &Pin);
+    for (int b = threadIdx.x; b < a.N; b += blockDim.x) { sM[b] = a.masses[b]; for (int k = 0; k < 3; ++k) sX[3 * b + k] = y[6 * b + k]; }
+    __syncthreads();
+    nbody_force_all(&sP, a, sX, sM, t, a.scratch);
+    __syncthreads();
+    for (int b = threadIdx.x; b < a.N; b += blockDim.x)
+        for (int k = 0; k < 3; ++k) { dy[6 * b + k] = y[6 * b + 3 + k]; dy[6 * b + 3 + k] = a.scratch[3 * b + k]; }
+}
+
+extern "C" {
+
+size_t ssb_shared_scratch_bytes(int64_t N) { return 512 + sizeof(double) * 18 * (size_t)(N > 0 ? N : 1); }
+
+int ssb_shared_step_orbits_f64(const ssb_potential* pot, int64_t N, const double* w0, double t0, double t1, ssb_ctrl ctrl, double* wout,
+                               int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream) {
+    if (int e = ssb_validate_potential(pot)) return e;
+    if (int e = ssb_validate_ctrl(ctrl)) return e;
+    if (N <= 0 || !w0 || !wout || !status || !nsteps || !scratch) return ssb_set_error(SSB_ERR_ARG, "shared_step_orbits: NULL array or N <= 0");
+    if (scratch_bytes < ssb_shared_scratch_bytes(N)) return ssb_set_error(SSB_ERR_SCRATCH, "shared_step_orbits: scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    SharedCtl* ctl = (SharedCtl*)scratch;
+    double* buf0 = (double*)((char*)scratch + 512);
+    double* buf1 = buf0 + 9 * N;
+    CtrlDev c; c.rtol = ctrl.rtol; c.atol = ctrl.atol; c.dtmin = ctrl.dtmin; c.dtmax = ctrl.dtmax; c.max_steps = ctrl.max_steps;
+    SharedCtl h;
+    memset(&h, 0, sizeof(h));
+    h.dir = (t0 < t1) ? 1.0 : -1.0; h.tprev = t0 * h.dir; h.tnext = h.tprev; h.T1 = t1 * h.dir;
+    CK(cudaMemcpyAsync(ctl, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                 // h lives on the host stack
+    const unsigned grid = (unsigned)((N + 127) / 128);
+    shared_init1<<<grid, 128, 0, st>>>(*pot, N, w0, buf0, ctl, c);
+    shared_init_ctl1<<<1, 1, 0, st>>>(N, ctl);
+    shared_init2<<<grid, 128, 0, st>>>(*pot, N, buf0, ctl, c);
+    if (ctrl.solver == 5) shared_init_ctl2<5><<<1, 1, 0, st>>>(N, ctl, c); else shared_init_ctl2<8><<<1, 1, 0, st>>>(N, ctl, c);
+    CKL("shared_init");
+    // batches of attempts; poll the done flag between batches
+    const int batch = N >= 1000000 ? 4 : 32;
+    for (int64_t launched = 0; launched <= (int64_t)ctrl.max_steps + batch;) {
+        for (int b = 0; b < batch; ++b) {
+            if (ctrl.solver == 5) { shared_attempt<5><<<grid, 128, 0, st>>>(*pot, N, buf0, buf1, ctl, c); shared_control<5><<<1, 1, 0, st>>>(N, ctl, c); }
+            else { shared_attempt<8><<<grid, 128, 0, st>>>(*pot, N, buf0, buf1, ctl, c); shared_control<8><<<1, 1, 0, st>>>(N, ctl, c); }
+        }
+        launched += batch;
+        CKL("shared_attempt");
+        int done = 0;
+        CK(cudaMemcpyAsync(&done, &ctl->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (done) break;
+    }
+    shared_finish<<<grid, 128, 0, st>>>(N, buf0, buf1, ctl, wout, status, nsteps);
+    CKL("shared_finish");
+    return 0;
+}
+
+size_t ssb_nbody_scratch_bytes(int32_t N) { return sizeof(double) * 3 * (size_t)(N > 0 ? N : 1) * (4 + 14); }
+
+static int nbody_fill(NbodyArgs& a, ssb_potential& P, const ssb_potential* ext, int32_t N, const double* masses, double G, double eps) {
+    memset(&P, 0, sizeof(P));
+    a.has_ext = 0;
+    if (ext && ext->n_comp > 0) { if (int e = ssb_validate_potential(ext)) return e; P = *ext; a.has_ext = 1; }
+    if (N <= 0 || N > SSB_NBODY_MAX) return ssb_set_error(SSB_ERR_ARG, "nbody: need 1 <= N <= 1024 live bodies");
+    if (!masses) return ssb_set_error(SSB_ERR_ARG, "nbody: NULL masses");
+    a.N = N; a.masses = masses; a.G = G; a.eps2 = eps * eps;
+    return 0;
+}
+
+int ssb_nbody_integrate_f64(const ssb_potential* ext, int32_t N, const double* masses, double G, double eps, const double* w0, double t0, double t1,
+                            const double* ts, int32_t M, ssb_ctrl ctrl, double* ys, int32_t* status, int32_t* nsteps, void* scratch,
+                            size_t scratch_bytes, void* stream) {
+    if (int e = ssb_validate_ctrl(ctrl)) return e;
+    NbodyArgs a; ssb_potential P;
+    if (int e = nbody_fill(a, P, ext, N, masses, G, eps)) return e;
+    if (!w0 || !ts || M <= 0 || !ys || !status || !nsteps || !scratch) return ssb_set_error(SSB_ERR_ARG, "nbody: NULL array or M <= 0");
+    if (scratch_bytes < ssb_nbody_scratch_bytes(N)) return ssb_set_error(SSB_ERR_SCRATCH, "nbody: scratch too small");
+    a.M = M; a.t0 = t0; a.t1 = t1; a.w0 = w0; a.ts = ts; a.scratch = (double*)scratch; a.ys = ys; a.status = status; a.nsteps = nsteps;
+    CtrlDev c; c.rtol = ctrl.rtol; c.atol = ctrl.atol; c.dtmin = ctrl.dtmin; c.dtmax = ctrl.dtmax; c.max_steps = ctrl.max_steps;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctrl.solver == 5) nbody_kernel<5><<<1, SSB_NBODY_THREADS, 0, st>>>(P, a, c); else nbody_kernel<8><<<1, SSB_NBODY_THREADS, 0, st>>>(P, a, c);
+    CKL("nbody_kernel");
+    return 0;
+}
+
+int ssb_nbody_term_f64(const ssb_potential* ext, int32_t N, const double* masses, double G, double eps, double t, const double* y, double* dy,
+                       void* scratch, size_t scratch_bytes, void* stream) {
+    NbodyArgs a; ssb_potential P;
+    if (int e = nbody_fill(a, P, ext, N, masses, G, eps)) return e;
+    if (!y || !dy || !scratch || scratch_bytes < sizeof(double) * 3 * (size_t)N) return ssb_set_error(SSB_ERR_ARG, "nbody_term: NULL array / scratch");
+    a.scratch = (double*)scratch;
+    nbody_term_kernel<<<1, SSB_NBODY_THREADS, 0, (cudaStream_t)stream>>>(P, a, t, y, dy);
+    CKL("nbody_term_kernel");
+    return 0;
+}
+
+}  // extern "C"

@@ -3,7 +3,10 @@
 On the B200 hot path a "field" is one of a closed set the CUDA kernels implement:
   hamiltonian_field             -> K1 orbit kernel        (fields.py:101-113)
   MassRadiusPerturbation_OTF    -> K3 response kernel     (fields.py:159-206)
-Arbitrary Python `term` functions (CustomField, Nbody_field, ...) raise NotImplementedError: no CPU fallback.
+  MassRadiusPerturbation_OTF_SecondOrder -> K4           (fields.py:260-320)
+  Nbody_field                   -> K6 one-CTA N-body kernel (fields.py:115-155)
+  RestrictedNbody_generator     -> K5 shared-step tracer kernels (RestrictedNbody.py:93-106)
+Arbitrary Python `term` functions (CustomField, ...) raise NotImplementedError: no CPU fallback.
 """
 import numpy as np
 
@@ -18,6 +21,27 @@ class hamiltonian_field:
 
     def term(self, t, xv, args=None):
         return self.pot.velocity_acceleration(t, xv, args)
+
+
+class Nbody_field:
+    """Softened all-pairs self gravity + external potential; state (N,6) is ONE ODE (fields.py:115-155)."""
+
+    def __init__(self, ext_pot=None, masses=None, units=None, eps=1e-3):
+        from .units import resolve_G, usys
+        self.ext_pot = ext_pot                       # None == the reference's zero-mass Plummer placeholder (fields.py:127-128)
+        self.masses = np.ascontiguousarray(np.asarray(masses, dtype=np.float64).reshape(-1))
+        self._G = resolve_G(usys if units is None else units)
+        self.eps = float(eps)
+        self._masses_dev = None
+
+    def masses_dev(self):
+        if self._masses_dev is None:
+            self._masses_dev = rt.to_dev(self.masses)
+        return self._masses_dev
+
+    def term(self, t, xv, args=None):
+        dev_in = rt.is_dev(xv)
+        return rt.out(rt.nbody_term(self.ext_pot, self.masses_dev(), self._G, self.eps, t, xv), dev_in)
 
 
 class MassRadiusPerturbation_OTF:
@@ -91,8 +115,31 @@ def integrate_field(w0=None, ts=None, dense=False, solver=Dopri8(scan_kind='boun
         first = len(ts_h) == 2
         stack = lambda y0, y1: np.concatenate([y0.cpu().numpy(), y1.cpu().numpy()]) if first else y1.cpu().numpy()
         return Solution(ts_h, [stack(w, wout), stack(D0, Dout), stack(E0, Eout)], status[0].cpu().numpy(), nsteps[0])
-    raise NotImplementedError(f"field {type(field).__name__} is not implemented on the device (closed set: hamiltonian_field, "
-                              "MassRadiusPerturbation_OTF, MassRadiusPerturbation_OTF_SecondOrder)")
+    if isinstance(field, Nbody_field):
+        dev_in = rt.is_dev(w0)
+        ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
+        w = rt.to_dev(w0).reshape(-1, 6)
+        if w.shape[0] != len(field.masses):
+            raise ValueError("Nbody_field: w0 must be (N,6) with N = len(masses)")
+        ys, status, nsteps = rt.nbody_integrate(field.ext_pot, field.masses_dev(), field._G, field.eps, w, a, b, rt.to_dev(ts_h), ctrl)
+        if int(status[0]) != 0:
+            raise RuntimeError("integrate_field failed: " + ("max_steps reached" if int(status[0]) == 1 else "non-finite state"))
+        return Solution(ts_h, rt.out(ys, dev_in), status[0].cpu().numpy(), nsteps)
+    from .RestrictedNbody import RestrictedNbody_generator
+    if isinstance(field, RestrictedNbody_generator):
+        dev_in = rt.is_dev(w0)
+        if len(ts_h) > 2 or (len(ts_h) == 2 and ts_h[0] != a) or ts_h[-1] != b:
+            raise NotImplementedError("the shared-step tracer kernel keeps the final state only (ts = [t_start, t_end], RestrictedNbody.py:131)")
+        ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
+        w = rt.to_dev(w0).reshape(-1, 6)
+        wout, status, nsteps = rt.shared_step_orbits(field.potential_total, w, a, b, ctrl)
+        if int(status[0]) != 0:
+            raise RuntimeError("integrate_field failed: " + ("max_steps reached" if int(status[0]) == 1 else "non-finite state"))
+        t = rt.torch()
+        ys = t.stack([w, wout]) if len(ts_h) == 2 else wout[None]
+        return Solution(ts_h, rt.out(ys, dev_in), status[0].cpu().numpy(), nsteps)
+    raise NotImplementedError(f"field {type(field).__name__} is not implemented on the device (closed set: hamiltonian_field, Nbody_field, "
+                              "RestrictedNbody_generator, MassRadiusPerturbation_OTF, MassRadiusPerturbation_OTF_SecondOrder)")
 
 
 def _unsupported(name):
@@ -103,7 +150,6 @@ def _unsupported(name):
     return _X
 
 
-Nbody_field = _unsupported("Nbody_field")
 MassRadiusPerturbation_Interp = _unsupported("MassRadiusPerturbation_Interp")
 MW_LMC_field = _unsupported("MW_LMC_field")
 CustomField = _unsupported("CustomField")
