@@ -144,6 +144,24 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one orbit_kernel<8> launch of this workload, from the committed
+    `ncu --set full` summary (profiles/*orbit_kernel_ncu.txt; a number taken under the profiler is never timed here)."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*orbit_kernel_ncu.txt")))
+    if not files:
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        m = re.search(re.escape(name) + r" \[(\w+)\] = ([0-9.eE+-]+)", open(files[-1]).read())
+        if not m:
+            return None, None
+        tot += float(m.group(2)) * unit.get(m.group(1), 1.0)
+    return tot, os.path.relpath(files[-1], ROOT)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
@@ -267,14 +285,17 @@ def run_ours(args, rank, world):
                                f"nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = {FP64_NOMINAL_TFLOPS} TFLOP/s",
                 "frac_of_nominal": achieved / FP64_NOMINAL_TFLOPS,
                 "hbm_gbs_of_kernel": (w0_all.numel() * 8 + ys.numel() * 8 + t0_all.numel() * 16 + ns.numel() * 4) / (k_ms * 1e-3) / 1e9}
-    # ---- CPU baseline on this box's host cores: bounded sample of the same workload ----
-    import oracle as O
-    threads = O.num_threads()
-    n_cpu = cpu_sample_size(threads, 12.0)
-    cs, cdt = cpu_stream_rate(n_cpu, threads)
-    cpu = {"value": cs / cdt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
-           "sample": f"{2 * n_cpu} particles of the same stream (ts=linspace(-3000,0,{n_cpu + 1})), {cdt:.1f} s",
-           "note": "C++ restatement of the reference algorithm (oracle/), NOT jax[cpu]: jax/diffrax are not installable offline"}
+    roofline["traffic"], roofline["traffic_source"] = ncu_traffic()
+    # ---- CPU baseline on this box's host cores: bounded sample of the same workload (rank 0, N = 1 only) ----
+    cpu = None
+    if world == 1:
+        import oracle as O
+        threads = O.num_threads()
+        n_cpu = cpu_sample_size(threads, 12.0)
+        cs, cdt = cpu_stream_rate(n_cpu, threads)
+        cpu = {"value": cs / cdt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+               "sample": f"{2 * n_cpu} particles of the same stream (ts=linspace(-3000,0,{n_cpu + 1})), {cdt:.1f} s",
+               "note": "C++ restatement of the reference algorithm (oracle/), NOT jax[cpu]: jax/diffrax are not installable offline"}
     line = {"metric": "fp64 particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C2: {args.particles}-particle mock stream per GPU ({args.particles * world} total), static MW3 "

@@ -229,6 +229,17 @@ size_t ssb_nbody_scratch_bytes(int32_t N);
 int ssb_nbody_term_f64(const ssb_potential* ext, int32_t N, const double* masses, double G, double eps, double t, const double* y, double* dy,
                        void* scratch, size_t scratch_bytes, void* stream);
 
+/* A16 / N3  variational (tangent) equations along unperturbed orbits: examples/higher_order_variationalEqn.ipynb cell 3
+ * (second_order_field.term through fields.CustomField, fields.py:362-377; integrate_field, fields.py:35-99).  Per particle ONE
+ * solve of [w(6), M(6,6) = dw/dw_init, M2(6,6,6) = d2w/dw_init^2] (order 1: w and M only) from t0[i] to t1 with one controller over
+ * all 42 (258) components; final state kept.  M0 NULL = identity, M20 NULL = zeros.  M is the state-transition matrix, i.e. the
+ * forward-mode Jacobian of integrate_orbit (main.py:149-162 with adjoint=ForwardMode()) with respect to w0.
+ * Layouts: M[N,6,6] row-major M[a][k] = dw_a/dw0_k; M2[N,6,6,6] M2[a][k][l].  status[N], nsteps[N,3]. */
+int ssb_variational_f64(const ssb_potential* pot, int32_t order, int64_t N, const double* w0, const double* M0, const double* M20, const double* t0,
+                        double t1, ssb_ctrl ctrl, double* wout, double* Mout, double* M2out, int32_t* status, int32_t* nsteps, void* stream);
+/* the variational field at one state y[42 | 258] -> dy (device pointers), for unit tests */
+int ssb_variational_term_f64(const ssb_potential* pot, int32_t order, double t, const double* y, double* dy, void* stream);
+
 /* ---- host-pointer conveniences (H2D, launch, D2H, synchronise) - what a CPU-side plugin call looks like ---------- */
 int ssb_orbit_integrate_host(const ssb_potential* pot_hostptrs, int64_t N, const double* w0, const double* t0,
                              const double* t1, const double* ts, int32_t M, int32_t ts_per_orbit, ssb_ctrl ctrl,

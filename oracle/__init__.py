@@ -351,6 +351,29 @@ def nbody_term(ext, masses, t, y, eps=1e-3, G=G_KPC_MYR_MSUN):
     lib().orc_nbody_term(None if ext is None else ext._h, len(y), _p(masses), C.c_double(G), C.c_double(eps), C.c_double(t), _p(y), _p(dy))
     return dy
 
+
+def variational(prog, w0, t0, t1, order=1, M0=None, M20=None, solver=8, rtol=1e-7, atol=1e-7, dtmin=0.05, dtmax=None, max_steps=10_000, threads=1):
+    """Variational equations along each orbit (higher_order_variationalEqn.ipynb cell 3): returns w[N,6], M[N,6,6], M2[N,6,6,6] | None."""
+    w0 = _d(w0).reshape(-1, 6)
+    N = len(w0)
+    t0 = _d(np.broadcast_to(_d(t0), (N,)))
+    M0p = None if M0 is None else _p(_d(M0).reshape(N, 6, 6))
+    M20p = None if M20 is None else _p(_d(M20).reshape(N, 6, 6, 6))
+    wout, Mout = np.empty((N, 6)), np.empty((N, 6, 6))
+    M2out = np.empty((N, 6, 6, 6)) if order == 2 else np.empty(1)
+    status, nsteps = np.empty(N, dtype=np.int32), np.empty((N, 3), dtype=np.int32)
+    lib().orc_variational(prog._h, int(order), N, _p(w0), M0p, M20p, _p(t0), C.c_double(t1), int(solver), C.c_double(rtol), C.c_double(atol),
+                          C.c_double(dtmin), C.c_double(np.inf if dtmax is None else dtmax), int(max_steps), _p(wout), _p(Mout), _p(M2out),
+                          status.ctypes.data_as(_ip), nsteps.ctypes.data_as(_ip), int(threads))
+    return wout, Mout, (M2out if order == 2 else None), status, nsteps
+
+
+def variational_term(prog, t, y, order=1):
+    y = _d(y).reshape(-1)
+    dy = np.empty_like(y)
+    lib().orc_variational_term(prog._h, int(order), C.c_double(t), _p(y), _p(dy))
+    return dy
+
 def threefry2x32(k0, k1, c0, c1):
     out = (C.c_uint32 * 2)()
     lib().orc_threefry(C.c_uint32(k0), C.c_uint32(k1), C.c_uint32(c0), C.c_uint32(c1), out)

@@ -554,4 +554,61 @@ void orc_nbody_term(void* h, int N, const double* masses, double G, double eps, 
     f(t, y, dy);
 }
 
+// Variational (tangent) equations along an unperturbed orbit: examples/higher_order_variationalEqn.ipynb cell 3
+// (second_order_field.term wrapped in fields.CustomField, fields.py:362-377).  State [w(6), M(6,6) = dw/dw_init,
+// M2(6,6,6) = d2w/dw_init^2] flattened row-major; da/dw = [-Hess Phi, 0], d2a/dw2 = -Phi_ijk on the position block.
+struct VariationalFieldOrc {
+    const Program* P; int order;
+    int dim() const { return order == 2 ? 258 : 42; }
+    void operator()(double t, const double* y, double* dy) const {
+        typedef Dual<double, 3> D;
+        D xd[3]; for (int c = 0; c < 3; ++c) xd[c] = D::var(y[c], c);
+        D H[3][3]; hessian<D>(*P, xd, t, H);                       // H[a][b].v = Phi_ab, .d[c] = Phi_abc
+        double g[3]; gradient<double>(*P, y, t, g);
+        for (int a = 0; a < 3; ++a) { dy[a] = y[3 + a]; dy[3 + a] = -g[a]; }
+        const double* M = y + 6; double* dM = dy + 6;
+        for (int k = 0; k < 6; ++k)
+            for (int a = 0; a < 3; ++a) {
+                dM[6 * a + k] = M[6 * (a + 3) + k];
+                double acc = 0; for (int j = 0; j < 3; ++j) acc += -H[a][j].v * M[6 * j + k];
+                dM[6 * (a + 3) + k] = acc;
+            }
+        if (order < 2) return;
+        const double* M2 = y + 42; double* dM2 = dy + 42;
+        for (int k = 0; k < 6; ++k)
+            for (int l = 0; l < 6; ++l)
+                for (int a = 0; a < 3; ++a) {
+                    dM2[36 * a + 6 * k + l] = M2[36 * (a + 3) + 6 * k + l];
+                    double acc = 0;
+                    for (int j = 0; j < 3; ++j) acc += -H[a][j].v * M2[36 * j + 6 * k + l];            // term1: da/dw . d2w
+                    for (int j = 0; j < 3; ++j) for (int q = 0; q < 3; ++q) acc += -H[a][j].d[q] * M[6 * q + l] * M[6 * j + k];   // term2
+                    dM2[36 * (a + 3) + 6 * k + l] = acc;
+                }
+    }
+};
+void orc_variational(void* h, int order, int N, const double* w0, const double* M0 /*[N,6,6] or NULL = I*/, const double* M20 /*or NULL = 0*/,
+                     const double* t0, double t1, int solver, double rtol, double atol, double dtmin, double dtmax, int max_steps, double* wout,
+                     double* Mout, double* M2out, int* status, int* nsteps, int parallel) {
+    const Program& P = *(Program*)h;
+    Ctrl c; c.solver = solver; c.rtol = rtol; c.atol = atol; c.dtmin = dtmin; c.dtmax = dtmax; c.max_steps = max_steps;
+    VariationalFieldOrc f{&P, order};
+    const int n = f.dim();
+    parallel_for(N, parallel, 1, [&](int i) {
+        std::vector<double> y0(n, 0.0), yf(n);
+        std::memcpy(y0.data(), w0 + 6 * (size_t)i, 48);
+        if (M0) std::memcpy(y0.data() + 6, M0 + 36 * (size_t)i, 36 * 8); else for (int a = 0; a < 6; ++a) y0[6 + 7 * a] = 1.0;
+        if (order == 2 && M20) std::memcpy(y0.data() + 42, M20 + 216 * (size_t)i, 216 * 8);
+        double tsv = t1;
+        Stats s = solve(f, n, t0[i], t1, y0.data(), &tsv, 1, c, yf.data());
+        std::memcpy(wout + 6 * (size_t)i, yf.data(), 48);
+        std::memcpy(Mout + 36 * (size_t)i, yf.data() + 6, 36 * 8);
+        if (order == 2) std::memcpy(M2out + 216 * (size_t)i, yf.data() + 42, 216 * 8);
+        status[i] = s.status; nsteps[3 * i] = s.n_steps; nsteps[3 * i + 1] = s.n_acc; nsteps[3 * i + 2] = s.n_rej;
+    });
+}
+void orc_variational_term(void* h, int order, double t, const double* y, double* dy) {
+    VariationalFieldOrc f{(const Program*)h, order};
+    f(t, y, dy);
+}
+
 }  // extern "C"

@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _OUT = os.path.join(_HERE, "_lib", "libssb200.so")
-_SOURCES = ["ssb_kernels.cu", "ssb_response.cu", "ssb_response2.cu", "ssb_shared.cu", "ssb_host.cu"]
+_SOURCES = ["ssb_kernels.cu", "ssb_response.cu", "ssb_response2.cu", "ssb_shared.cu", "ssb_variational.cu", "ssb_host.cu"]
 _HEADERS = ["ssb_common.cuh", "ssb_potential.cuh", "ssb_rk.cuh", "ssb_fastmath.cuh", "ssb_tableau.h", "../../include/ssb200.h"]
 
 MAX_COMP, MAX_TRACK, MAX_SH = 12, 4, 2
@@ -49,8 +49,11 @@ class SSBError(RuntimeError):
     pass
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None):
     """nvcc -gencode arch=compute_100a,code=sm_100a -> streamsculptor_b200/_lib/libssb200.so"""
+    global _OUT
+    if out is not None:
+        _OUT, force = out, True
     srcs = [os.path.join(_CSRC, s) for s in _SOURCES]
     deps = srcs + [os.path.join(_CSRC, h) for h in _HEADERS]
     if not force and os.path.exists(_OUT) and all(os.path.getmtime(_OUT) >= os.path.getmtime(d) for d in deps):
@@ -103,6 +106,8 @@ _SIGNATURES = {
     "ssb_nbody_integrate_f64": ([_PP, _i32, _dp, _dbl, _dbl, _dp, _dbl, _dbl, _dp, _i32, Ctrl, _dp, _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
     "ssb_nbody_scratch_bytes": ([_i32], C.c_size_t),
     "ssb_nbody_term_f64": ([_PP, _i32, _dp, _dbl, _dbl, _dbl, _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
+    "ssb_variational_f64": ([_PP, _i32, _i64, _dp, _dp, _dp, _dp, _dbl, Ctrl, _dp, _dp, _dp, _dp, _dp, _dp], C.c_int),
+    "ssb_variational_term_f64": ([_PP, _i32, _dbl, _dp, _dp, _dp], C.c_int),
     "ssb_orbit_integrate_host": ([_PP, _i64, _dp, _dp, _dp, _dp, _i32, _i32, Ctrl, _dp, _dp, _dp], C.c_int),
     "ssb_gen_stream_host": ([_PP, _PP, _dbl, _i64, _dp, _dp, _dp, _i64, C.POINTER(C.c_double), _dp, Ctrl, _i64, _i64, _i64, _dp, _dp,
                              _dp, _dp], C.c_int),
@@ -116,7 +121,7 @@ def lib():
     """Load the shared object (building it first if the sources are newer).  Raises SSBError if impossible."""
     global _LIB
     if _LIB is None:
-        path = _OUT
+        path = os.environ.get("SSB_LIB_PATH", _OUT)      # A/B builds of the same sources (tools/bench_k1.py)
         if not os.path.exists(path) or os.environ.get("SSB_REBUILD"):
             path = build()
         L = C.CDLL(path)

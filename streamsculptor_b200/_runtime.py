@@ -411,3 +411,24 @@ def nbody_term(ext_pot, masses, G, eps, t, y):
     _lib.check(_lib.lib().ssb_nbody_term_f64(C.byref(P), N, ptr(masses), float(G), float(eps), float(t), ptr(yd), ptr(dy), ptr(scratch), 24 * N,
                                              stream_ptr()))
     return dy
+
+
+def variational(pot, order, w0, M0, M20, t0, t1, ctrl):
+    """Variational equations along N orbits: wout[N,6], Mout[N,6,6], M2out[N,6,6,6] | None, status[N], nsteps[N,3]."""
+    tt = torch()
+    P, _keep = lower(pot)
+    N = w0.shape[0]
+    wout, Mout = empty((N, 6)), empty((N, 6, 6))
+    M2out = empty((N, 6, 6, 6)) if order == 2 else None
+    status, nsteps = empty((N,), tt.int32), empty((N, 3), tt.int32)
+    _lib.check(_lib.lib().ssb_variational_f64(C.byref(P), int(order), N, ptr(w0), ptr(M0), ptr(M20), ptr(t0), float(t1), ctrl, ptr(wout), ptr(Mout),
+                                              ptr(M2out), ptr(status), ptr(nsteps), stream_ptr()))
+    return wout, Mout, M2out, status, nsteps
+
+
+def variational_term(pot, order, t, y):
+    P, _keep = lower(pot)
+    yd = to_dev(y).reshape(-1)
+    dy = empty(yd.shape)
+    _lib.check(_lib.lib().ssb_variational_term_f64(C.byref(P), int(order), float(t), ptr(yd), ptr(dy), stream_ptr()))
+    return dy

@@ -44,6 +44,46 @@ class Nbody_field:
         return rt.out(rt.nbody_term(self.ext_pot, self.masses_dev(), self._G, self.eps, t, xv), dev_in)
 
 
+class variational_field:
+    """Variational (tangent) equations along an unperturbed orbit - the built-in equivalent of the `second_order_field` the reference's
+    tutorial wraps in CustomField (examples/higher_order_variationalEqn.ipynb cell 3): coords = [w(6), dw/dw_init (6,6)] (order 1) or
+    [w, dw/dw_init, d2w/dw_init^2 (6,6,6)] (order 2).  The tidal tensor and third derivatives are closed forms on the device."""
+
+    def __init__(self, pot, order=2):
+        if order not in (1, 2):
+            raise ValueError("order must be 1 or 2")
+        self.pot, self.order = pot, int(order)
+
+    def _flat(self, coords):
+        parts = [np.asarray(c.cpu() if hasattr(c, "cpu") else c, dtype=np.float64).reshape(-1) for c in coords[:1 + self.order]]
+        if [len(p) for p in parts] != [6, 36, 216][:1 + self.order]:
+            raise ValueError("variational_field: coords must be [w(6), M(6,6)" + (", M2(6,6,6)]" if self.order == 2 else "]"))
+        return np.concatenate(parts)
+
+    def term(self, t, coords, args=None):
+        dy = rt.variational_term(self.pot, self.order, t, self._flat(coords)).cpu().numpy()
+        out = [dy[:6], dy[6:42].reshape(6, 6)]
+        if self.order == 2:
+            out.append(dy[42:].reshape(6, 6, 6))
+        return out
+
+
+def integrate_variational_batch(pot, w0, t0, t1, order=1, M0=None, M20=None, solver=Dopri8(scan_kind='bounded'), rtol=1e-7, atol=1e-7, dtmin=0.05,
+                                dtmax=None, max_steps=10_000):
+    """vmap of integrate_field(w0=[w_i, I, 0], t0=t0_i, t1=t1, ts=[t1], field=variational_field(pot, order)) over particles - what the
+    tutorial's scan does per arm (higher_order_variationalEqn.ipynb cells 10-11).  Returns (w[N,6], M[N,6,6], M2[N,6,6,6] | None, status[N]).
+    M is also the forward-mode Jacobian d integrate_orbit / d w0 (main.py:160)."""
+    dev_in = rt.is_dev(w0)
+    w = rt.to_dev(w0).reshape(-1, 6)
+    N = w.shape[0]
+    t0d = rt.to_dev(np.broadcast_to(np.asarray(t0.cpu() if hasattr(t0, "cpu") else t0, dtype=np.float64), (N,)).copy())
+    M0d = None if M0 is None else rt.to_dev(M0).reshape(N, 6, 6)
+    M20d = None if M20 is None else rt.to_dev(M20).reshape(N, 6, 6, 6)
+    ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
+    wout, Mout, M2out, status, nsteps = rt.variational(pot, order, w, M0d, M20d, t0d, float(t1), ctrl)
+    return rt.out(wout, dev_in), rt.out(Mout, dev_in), (None if M2out is None else rt.out(M2out, dev_in)), rt.out(status, dev_in)
+
+
 class MassRadiusPerturbation_OTF:
     """coords = [w(6), D(nSH,12)] with D rows [dx/deps(3), dv/deps(3), d2x/dtheta deps(3), d2v/dtheta deps(3)]."""
 
@@ -125,6 +165,22 @@ def integrate_field(w0=None, ts=None, dense=False, solver=Dopri8(scan_kind='boun
         if int(status[0]) != 0:
             raise RuntimeError("integrate_field failed: " + ("max_steps reached" if int(status[0]) == 1 else "non-finite state"))
         return Solution(ts_h, rt.out(ys, dev_in), status[0].cpu().numpy(), nsteps)
+    if isinstance(field, variational_field):
+        if len(ts_h) > 2 or (len(ts_h) == 2 and ts_h[0] != a) or ts_h[-1] != b:
+            raise NotImplementedError("the variational kernel keeps the final state only (ts = [t_end] or [t_start, t_end])")
+        y0 = field._flat(w0)
+        ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
+        M20 = rt.to_dev(y0[42:]).reshape(1, 6, 6, 6) if field.order == 2 else None
+        wout, Mout, M2out, status, nsteps = rt.variational(field.pot, field.order, rt.to_dev(y0[:6]).reshape(1, 6), rt.to_dev(y0[6:42]).reshape(1, 6, 6),
+                                                           M20, rt.to_dev([a]), b, ctrl)
+        if int(status[0]) != 0:
+            raise RuntimeError("integrate_field failed: " + ("max_steps reached" if int(status[0]) == 1 else "non-finite state"))
+        first = len(ts_h) == 2
+        stack = lambda y_start, y_end: np.concatenate([y_start[None], y_end.cpu().numpy()]) if first else y_end.cpu().numpy()
+        ys = [stack(y0[:6], wout), stack(y0[6:42].reshape(6, 6), Mout)]
+        if field.order == 2:
+            ys.append(stack(y0[42:].reshape(6, 6, 6), M2out))
+        return Solution(ts_h, ys, status[0].cpu().numpy(), nsteps[0])
     from .RestrictedNbody import RestrictedNbody_generator
     if isinstance(field, RestrictedNbody_generator):
         dev_in = rt.is_dev(w0)

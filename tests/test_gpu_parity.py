@@ -623,3 +623,73 @@ def test_nbody_field(cuda):
     sol = ssc.integrate_field(w0=wb, ts=tsb, t0=0.0, t1=-100.0, solver=ssc.Dopri8(), field=fb, dtmin=0.25, dtmax=0.25, max_steps=1000)
     yo, st, _ = O.nbody(mw3_oracle(), mb, wb, 0.0, -100.0, ts=tsb, eps=0.1, solver=8, dtmin=0.25, dtmax=0.25, max_steps=1000)
     assert st == 0 and relerr(sol.ys, yo) < 1e-10
+
+
+def _blockerr(A, B):
+    """max over the (position | velocity)^rank unit blocks of max|A - B| / max|B| (entries of one block share units and scale)."""
+    A, B = np.asarray(A), np.asarray(B)
+    err = 0.0
+    sl = (slice(0, 3), slice(3, 6))
+    import itertools
+    for idx in itertools.product(sl, repeat=A.ndim - 1):
+        a, b = A[(slice(None),) + idx], B[(slice(None),) + idx]
+        err = max(err, np.abs(a - b).max() / np.abs(b).max())
+    return err
+
+
+def test_variational_equations(cuda):
+    """A16/N3: state-transition matrix and second-order tensor along unperturbed orbits (higher_order_variationalEqn.ipynb cell 3)
+    vs the oracle (nested AD of the reference's scalar potentials), plus the physics check M == d w_f / d w_0 by finite differences."""
+    import streamsculptor_b200 as ssc
+    F = ssc.fields
+    orc, prod = _full_pair(cuda)                 # every component type incl. tracks and subhalos (generic interpreter)
+    mwo, mwp = mw3_oracle(), mw3_product()       # fused signature
+    gala = ssc.potential.GalaMilkyWayPotential(units=ssc.usys)
+    galo = O.Program().miyamoto(6.8e10, 3.0, 0.28).hernquist(5e9, 1.0).hernquist(1.71e9, 0.07).nfw(5.4e11, 15.62)
+    rng = np.random.default_rng(11)
+    # the field itself
+    for order, n in ((1, 42), (2, 258)):
+        y = np.concatenate([[8.0, -3.0, 5.0, 0.1, 0.15, -0.05], rng.normal(size=n - 6)])
+        for po, pp in ((orc, prod), (mwo, mwp)):
+            fld = F.variational_field(pp, order=order)
+            coords = [y[:6], y[6:42].reshape(6, 6)] + ([y[42:].reshape(6, 6, 6)] if order == 2 else [])
+            dy = np.concatenate([np.ravel(c) for c in fld.term(-700.0, coords)])
+            assert relerr(dy, O.variational_term(po, -700.0, y, order=order)) < 1e-10
+    w0 = halo_orbits(37, seed=4)
+    t0 = rng.uniform(-1500.0, -300.0, 37)
+    # fixed step, both solvers, both orders, fused and generic programs: 1e-10 relative
+    for po, pp in ((mwo, mwp), (galo, gala), (orc, prod)):
+        for solver, sid in ((ssc.Dopri8(), 8), (ssc.Dopri5(), 5)):
+            for order in (1, 2):
+                w, M, M2, st = F.integrate_variational_batch(pp, w0, t0, 0.0, order=order, solver=solver, dtmin=2.0, dtmax=2.0, max_steps=5000)
+                wo, Mo, M2o, sto, nso = O.variational(po, w0, t0, 0.0, order=order, solver=sid, dtmin=2.0, dtmax=2.0, max_steps=5000, threads=8)
+                assert not st.any() and not sto.any()
+                assert relerr(w, wo) < 1e-10 and _blockerr(M, Mo) < 1e-10
+                if order == 2:
+                    assert _blockerr(M2, M2o) < 1e-10 and np.abs(M2 - M2.transpose(0, 1, 3, 2)).max() == 0.0
+    # adaptive: shared controller over 42 / 258 components -> same accept/reject sequence on short spans, 10 x tol
+    for order in (1, 2):
+        w, M, M2, st = F.integrate_variational_batch(mwp, w0, -400.0, 0.0, order=order, rtol=1e-9, atol=1e-9, dtmin=0.05)
+        wo, Mo, M2o, sto, nso = O.variational(mwo, w0, -400.0, 0.0, order=order, rtol=1e-9, atol=1e-9, dtmin=0.05, threads=8)
+        assert not st.any()
+        assert np.mean(scaled_err(M, Mo, 1e-9) < 10.0) >= 0.9 and np.mean(scaled_err(w, wo, 1e-9) < 10.0) >= 0.9
+    # backward in time with non-trivial initial tensors, through integrate_field (single trajectory, tutorial usage)
+    M0 = np.eye(6) + 0.01 * rng.normal(size=(6, 6))
+    M20 = 0.01 * rng.normal(size=(6, 6, 6)); M20 = M20 + M20.transpose(0, 2, 1)
+    sol = ssc.integrate_field(w0=[w0[0], M0, M20], ts=np.array([0.0, -600.0]), t0=0.0, t1=-600.0, field=F.variational_field(mwp, order=2),
+                              solver=ssc.Dopri8(), dtmin=1.5, dtmax=1.5, max_steps=5000)
+    wo, Mo, M2o, _, _ = O.variational(mwo, w0[:1], 0.0, -600.0, order=2, M0=M0[None], M20=M20[None], dtmin=1.5, dtmax=1.5, max_steps=5000)
+    assert sol.ys[0].shape == (2, 6) and sol.ys[1].shape == (2, 6, 6) and sol.ys[2].shape == (2, 6, 6, 6)
+    assert relerr(sol.ys[0][-1], wo[0]) < 1e-10 and _blockerr(sol.ys[1][-1:], Mo) < 1e-10 and _blockerr(sol.ys[2][-1:], M2o) < 1e-10
+    # physics: M is the Jacobian of the flow map (forward-mode derivative of integrate_orbit w.r.t. w0)
+    w, M, _, _ = F.integrate_variational_batch(mwp, w0[:4], -500.0, 0.0, order=1, rtol=1e-11, atol=1e-11, dtmin=0.01)
+    eps = 1e-5
+    for k in range(6):
+        d = np.zeros(6); d[k] = eps
+        yp = mwp.integrate_orbit_batch_vmapped(w0=w0[:4] + d, ts=np.array([-500.0, 0.0]), rtol=1e-12, atol=1e-12, dtmin=0.01, max_steps=100_000)
+        ym = mwp.integrate_orbit_batch_vmapped(w0=w0[:4] - d, ts=np.array([-500.0, 0.0]), rtol=1e-12, atol=1e-12, dtmin=0.01, max_steps=100_000)
+        fd = (np.asarray(yp.ys)[:, -1] - np.asarray(ym.ys)[:, -1]) / (2 * eps)
+        assert np.abs(fd - M[:, :, k]).max() < 2e-5 * max(1.0, np.abs(M[:, :, k]).max())
+    # failure semantics: max_steps -> +inf rows, status 1
+    w, M, _, st = F.integrate_variational_batch(mwp, w0[:3], -500.0, 0.0, order=1, rtol=1e-10, atol=1e-10, dtmin=0.01, max_steps=4)
+    assert (st == 1).all() and np.isinf(w).all() and np.isinf(M).all()
