@@ -209,6 +209,7 @@ template <int SOLVER, int MODE, int SIG>
 __global__ void __launch_bounds__(SSB_ORBIT_THREADS, SSB_ORBIT_MIN_BLOCKS) orbit_kernel(const __grid_constant__ ssb_potential Pin, const OrbitArgs a) {
     __shared__ ssb_potential sP;
     stage_potential(&sP, &Pin);
+    logtab_init();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < a.N;
     const int64_t ii = valid ? i : 0;
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(32) dense_step_kernel(const __grid_constant__ 
                                                         int32_t* status_out, int32_t* nsteps_out) {
     __shared__ ssb_potential sP;
     stage_potential(&sP, &Pin);
+    logtab_init();
     if (t0p) { t0 = *t0p; t1 = *t1p; }              // interval ends read on the device (no host round trip in gen_stream)
     const bool valid = threadIdx.x == 0;
     int status, n_steps, n_acc, n_rej;

@@ -408,12 +408,13 @@ template <int SIG> struct SigInfo { static constexpr int NF = SIG == SIG_N ? 1 :
 
 template <int SIG, int MODE>
 __device__ __forceinline__ void fused_eval(const ssb_potential& P, const double x[3], double g[3], Sym3& H) {
-    const double r2 = fma(x[0], x[0], fma(x[1], x[1], x[2] * x[2]));
+    const double R2 = fma(x[0], x[0], x[1] * x[1]);           // shared by the spherical radius and the Miyamoto-Nagai denominator
+    const double r2 = fma(x[2], x[2], R2);
     const double ir = frsqrt(r2), r = r2 * ir, ir2 = ir * ir;
     // spherical components share x: accumulate q = sum Phi'/r and w = sum (Phi'' - Phi'/r)/r^2
-    // NFW (comp 0)
-    const double u = flog1p_pos(r * P.comp[0].p[2]);
+    // NFW (comp 0): 1/(1 + r/r_s) = r_s/(r + r_s) feeds the log1p rounding correction
     const double irs = frcp(r + P.comp[0].p[1]);
+    const double u = flog1p_tab(r * P.comp[0].p[2], P.comp[0].p[1] * irs);
     const double a = u * ir;
     double q = P.comp[0].p[0] * (a - irs) * ir2, w = 0.0;
     if (MODE & WANT_HESS) w = P.comp[0].p[0] * (3.0 * ir * (irs - a) + irs * irs) * ir2 * ir;
@@ -429,7 +430,6 @@ __device__ __forceinline__ void fused_eval(const ssb_potential& P, const double 
         q += qh;
         if (MODE & WANT_HESS) w -= qh * ir * (2.0 * ira + ir);
     }
-    if (MODE & WANT_GRAD) { g[0] = q * x[0]; g[1] = q * x[1]; g[2] = q * x[2]; }
     if (MODE & WANT_HESS) {
         H.xx = fma(w * x[0], x[0], q); H.yy = fma(w * x[1], x[1], q); H.zz = fma(w * x[2], x[2], q);
         H.xy = w * x[0] * x[1]; H.xz = w * x[0] * x[2]; H.yz = w * x[1] * x[2];
@@ -439,18 +439,18 @@ __device__ __forceinline__ void fused_eval(const ssb_potential& P, const double 
         const double zb2 = fma(x[2], x[2], P.comp[M].p[3]);
         const double iz = frsqrt(zb2);
         const double az = fma(zb2, iz, P.comp[M].p[1]);
-        const double D = fma(x[0], x[0], fma(x[1], x[1], az * az));
+        const double D = fma(az, az, R2);
         const double id = frsqrt(D), id2 = id * id;
         const double qm = P.comp[M].p[0] * id * id2;
         const double s = az * iz;
-        if (MODE & WANT_GRAD) { g[0] = fma(qm, x[0], g[0]); g[1] = fma(qm, x[1], g[1]); g[2] = fma(qm * s, x[2], g[2]); }
+        if (MODE & WANT_GRAD) { const double qx = q + qm; g[0] = qx * x[0]; g[1] = qx * x[1]; g[2] = fma(qm, s, q) * x[2]; }
         if (MODE & WANT_HESS) {
             const double q5 = 3.0 * qm * id2, zs = x[2] * s;
             H.xx += qm - q5 * x[0] * x[0]; H.yy += qm - q5 * x[1] * x[1];
             H.xy -= q5 * x[0] * x[1]; H.xz -= q5 * x[0] * zs; H.yz -= q5 * x[1] * zs;
             H.zz += qm * (s - P.comp[M].p[1] * x[2] * x[2] * iz * iz * iz) - q5 * zs * zs;
         }
-    }
+    } else if (MODE & WANT_GRAD) { g[0] = q * x[0]; g[1] = q * x[1]; g[2] = q * x[2]; }
 }
 template <int SIG>
 __device__ __forceinline__ void fused_grad(const ssb_potential& P, const double x[3], double g[3]) {

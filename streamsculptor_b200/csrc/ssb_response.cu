@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
     __shared__ int s_nact;
     __shared__ long long s_part;
     stage_potential(&sP, &Pin);
+    logtab_init();
     const int tid = threadIdx.x;
     const int n_sh = Sh.n, n_items = 2 * n_sh, ncomp = 6 + 12 * n_sh;
     double* buf0 = a.scratch + (size_t)blockIdx.x * 2 * 6 * n_items;

@@ -53,6 +53,10 @@ template <int SOLVER, class Force, int D>
 __device__ __forceinline__ void rk_stages(Force& force, const double (&x)[D], const double (&p)[D], double t, double h,
                                           double (&F)[Tab<SOLVER>::S][D]) {
     typedef Tab<SOLVER> T;
+    const double h2 = h * h;
+    double hp[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) hp[k] = h * p[k];
 #pragma unroll
     for (int i = 1; i < T::S - 1; ++i) {
         double X[D];
@@ -62,7 +66,7 @@ __device__ __forceinline__ void rk_stages(Force& force, const double (&x)[D], co
 #pragma unroll
             for (int l = 0; l < i; ++l)
                 if (T::aa(i, l) != 0.0) acc = fma(T::aa(i, l), F[l][k], acc);
-            X[k] = fma(h, fma(h, acc, T::rs(i) * p[k]), x[k]);
+            X[k] = fma(h2, acc, fma(T::rs(i), hp[k], x[k]));            // x + c_i h p + h^2 sum_l (A.A)_il F_l
         }
         force(X, t + T::c(i) * h, F[i]);
     }
@@ -74,6 +78,7 @@ __device__ __forceinline__ void rk_candidate(const double (&x)[D], const double 
                                              double (&x1)[D], double (&p1)[D]) {
     typedef Tab<SOLVER> T;
     constexpr int L = T::S - 1;
+    const double h2 = h * h;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         double ax = 0.0, ap = 0.0;
@@ -82,7 +87,7 @@ __device__ __forceinline__ void rk_candidate(const double (&x)[D], const double 
             if (T::aa(L, l) != 0.0) ax = fma(T::aa(L, l), F[l][k], ax);
             if (T::a(L, l) != 0.0) ap = fma(T::a(L, l), F[l][k], ap);
         }
-        x1[k] = fma(h, fma(h, ax, T::rs(L) * p[k]), x[k]);
+        x1[k] = fma(h2, ax, fma(T::rs(L) * h, p[k], x[k]));
         p1[k] = fma(h, ap, p[k]);
     }
 }

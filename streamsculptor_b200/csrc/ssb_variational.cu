@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(SSB_VAR_THREADS, 3) variational_kernel(const _
     constexpr double NCOMP = ORDER == 2 ? 258.0 : 42.0;
     __shared__ ssb_potential sP;
     stage_potential(&sP, &Pin);
+    logtab_init();
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t part = gtid / G;
     const int gl = (int)(gtid % G);
