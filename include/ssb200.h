@@ -71,6 +71,8 @@ typedef struct {
     const double* t;  /* [n] increasing (device) */
     const double* y;  /* [n,3] (device) */
     const double* s;  /* [n,3] knot slopes for SSB_TRACK_CUBIC (device; fill with ssb_track_slopes_f64), NULL for linear */
+    double t_first;   /* reserved, set to 0: the kernels fill t[0] ... */
+    double inv_dt;    /* ... and (n-1)/(t[n-1]-t[0]) in their shared-memory copy (segment guess without a division per force) */
 } ssb_track;
 
 typedef enum { SSB_PROFILE_PLUMMER = 0, SSB_PROFILE_HERNQUIST = 1, SSB_PROFILE_NFW = 2 } ssb_profile;

@@ -27,7 +27,7 @@ class Component(C.Structure):
 
 
 class Track(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("t", _dp), ("y", _dp), ("s", _dp)]
+    _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("t", _dp), ("y", _dp), ("s", _dp), ("t_first", C.c_double), ("inv_dt", C.c_double)]
 
 
 class Subhalos(C.Structure):

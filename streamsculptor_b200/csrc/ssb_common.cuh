@@ -25,6 +25,13 @@ __device__ __forceinline__ void stage_potential(ssb_potential* dst, const ssb_po
     int* d = reinterpret_cast<int*>(dst);
     for (int i = threadIdx.x; i < (int)(sizeof(ssb_potential) / sizeof(int)); i += blockDim.x) d[i] = s[i];
     __syncthreads();
+    if ((int)threadIdx.x < dst->n_track) {             // segment-guess constants of every track, once per CTA (track_eval)
+        ssb_track& T = dst->track[threadIdx.x];
+        const double a0 = T.t[0], a1 = T.t[T.n - 1];
+        T.t_first = a0;
+        T.inv_dt = (a1 > a0) ? (double)(T.n - 1) / (a1 - a0) : 0.0;
+    }
+    if (dst->n_track > 0) __syncthreads();
 }
 
 }  // namespace ssb

@@ -39,12 +39,13 @@ __device__ __noinline__ double3 fused_call(const ssb_potential* P, double x, dou
 }
 // Potential.velocity_acceleration (main.py:116-120) in mirrored time.  SIG != 0: the leading NF components are a fused
 // static signature evaluated inline from the constant bank (Pc); any remaining components go through the interpreter (P).
-template <int SIG>
+template <int SIG, int XS = 0>
 struct OrbitForce {
     const ssb_potential* P;      // shared-memory copy (dynamic indexing)
     const ssb_potential* Pc;     // kernel parameter (constant bank)
     double dir;
     bool extra;                  // components beyond the fused ones exist
+    const FastX* fx;             // XS > 0: the XS extras are "fast extras" (ssb_potential.cuh), evaluated inline
     __device__ __forceinline__ void operator()(const double X[3], double tau, double A[3]) const {
         if (SIG == SIG_GENERIC) {
             const double3 a = accel_call(P, 0, X[0], X[1], X[2], tau * dir);
@@ -59,8 +60,15 @@ struct OrbitForce {
             A[0] = f.x; A[1] = f.y; A[2] = f.z;
 #endif
             if (extra) {
-                const double3 a = accel_call(P, SigInfo<SIG>::NF, X[0], X[1], X[2], tau * dir);
-                A[0] += a.x; A[1] += a.y; A[2] += a.z;
+                if (XS > 0) {
+                    double g2[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                    for (int e = 0; e < XS; ++e) fastx_grad(fx[e], X, tau * dir, g2);
+                    A[0] -= g2[0]; A[1] -= g2[1]; A[2] -= g2[2];
+                } else {
+                    const double3 a = accel_call(P, SigInfo<SIG>::NF, X[0], X[1], X[2], tau * dir);
+                    A[0] += a.x; A[1] += a.y; A[2] += a.z;
+                }
             }
         }
     }
@@ -81,15 +89,16 @@ struct OrbitArgs {
 // per-thread integration of one orbit; REC != nullptr records accepted steps (K0) instead of saving
 // MODE: 0 = SaveAt(ts) with dense output, 1 = RECORD accepted steps (K0), 2 = final state only (ts == t1; no dense-output
 // code in the instruction stream - the stream-generation hot path)
-template <int SOLVER, int MODE, int SIG>
+template <int SOLVER, int MODE, int SIG, int XS = 0>
 __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_potential* Pc, const double* w0, double t0_in, double t1_in,
                                               const double* tsp, int M, double* ys, const CtrlDev& c, bool valid,
-                                              int& status, int& n_steps, int& n_acc, int& n_rej, double* rec, int rec_cap) {
+                                              int& status, int& n_steps, int& n_acc, int& n_rej, double* rec, int rec_cap,
+                                              const FastX* fxp = nullptr) {
     typedef Tab<SOLVER> T;
     constexpr int S = T::S;
     const double dir = (t0_in < t1_in) ? 1.0 : -1.0;              // diffrax: direction = where(t0 < t1, 1, -1)
     const double T0 = t0_in * dir, T1 = t1_in * dir;
-    OrbitForce<SIG> force{P, Pc, dir, Pc->n_comp > SigInfo<SIG>::NF};
+    OrbitForce<SIG, XS> force{P, Pc, dir, Pc->n_comp > SigInfo<SIG>::NF, fxp};
     double x[3], p[3], F[S][3];
     status = 0; n_steps = 0; n_acc = 0; n_rej = 0;
     double tprev = T0, tnext = T0, h = 0.0;
@@ -205,18 +214,23 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
     }
 }
 
-template <int SOLVER, int MODE, int SIG>
+template <int SOLVER, int MODE, int SIG, int XS>
 __global__ void __launch_bounds__(SSB_ORBIT_THREADS, SSB_ORBIT_MIN_BLOCKS) orbit_kernel(const __grid_constant__ ssb_potential Pin, const OrbitArgs a) {
     __shared__ ssb_potential sP;
     stage_potential(&sP, &Pin);
     logtab_init();
+    __shared__ FastX sfx[XS > 0 ? XS : 1];
+    if (XS > 0) {
+        if ((int)threadIdx.x < XS) fastx_fill(&sfx[threadIdx.x], sP, SigInfo<SIG>::NF + threadIdx.x);
+        __syncthreads();
+    }
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < a.N;
     const int64_t ii = valid ? i : 0;
     int status, n_steps, n_acc, n_rej;
     const double* tsp = a.ts + (a.ts_per_orbit ? ii * a.M : 0);
-    integrate_one<SOLVER, MODE, SIG>(&sP, &Pin, a.w0 + ii * 6, a.t0[ii], a.t1[ii], tsp, a.M, a.ys + (size_t)ii * a.M * 6, a.c, valid,
-                                     status, n_steps, n_acc, n_rej, nullptr, 0);
+    integrate_one<SOLVER, MODE, SIG, XS>(&sP, &Pin, a.w0 + ii * 6, a.t0[ii], a.t1[ii], tsp, a.M, a.ys + (size_t)ii * a.M * 6, a.c, valid,
+                                     status, n_steps, n_acc, n_rej, nullptr, 0, sfx);
     if (valid) {
         a.status[i] = status;
         a.nsteps[3 * i] = n_steps; a.nsteps[3 * i + 1] = n_acc; a.nsteps[3 * i + 2] = n_rej;
@@ -748,11 +762,17 @@ int ssb_orbit_integrate_f64(const ssb_potential* pot, int64_t N, const double* w
     const bool final_only = (M == 1 && ts_per_orbit && ts == t1);     // ts aliases t1: keep the final state, no dense output
     ssb_potential pc;
     const int sig = ssb_canonicalize(pot, &pc);
-#define SSB_LAUNCH_ORBIT(S, MD, SG) orbit_kernel<S, MD, SG><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a)
+    // XS = number of "fast extras" (linear-track moving perturbers / frame acceleration) next to a fused MW signature, final-state mode
+    const int xs = (final_only && (sig == SIG_NHM || sig == SIG_NHHM)) ? ssb_fast_extras(&pc, sig == SIG_NHM ? 3 : 4) : 0;
+#define SSB_LAUNCH_ORBIT(S, MD, SG) orbit_kernel<S, MD, SG, 0><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a)
 #define SSB_LAUNCH_SIG(S, MD) do { switch (sig) { case SIG_N: SSB_LAUNCH_ORBIT(S, MD, SIG_N); break; case SIG_NHM: SSB_LAUNCH_ORBIT(S, MD, SIG_NHM); break; \
         case SIG_NHHM: SSB_LAUNCH_ORBIT(S, MD, SIG_NHHM); break; default: SSB_LAUNCH_ORBIT(S, MD, SIG_GENERIC); } } while (0)
-    if (ctrl.solver == 5) { if (final_only) SSB_LAUNCH_SIG(5, 2); else SSB_LAUNCH_SIG(5, 0); }
-    else { if (final_only) SSB_LAUNCH_SIG(8, 2); else SSB_LAUNCH_SIG(8, 0); }
+#define SSB_LAUNCH_XS(S) do { if (sig == SIG_NHM) { if (xs == 1) orbit_kernel<S, 2, SIG_NHM, 1><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
+                                                      else orbit_kernel<S, 2, SIG_NHM, 2><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); } \
+        else { if (xs == 1) orbit_kernel<S, 2, SIG_NHHM, 1><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
+               else orbit_kernel<S, 2, SIG_NHHM, 2><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); } } while (0)
+    if (ctrl.solver == 5) { if (xs) SSB_LAUNCH_XS(5); else if (final_only) SSB_LAUNCH_SIG(5, 2); else SSB_LAUNCH_SIG(5, 0); }
+    else { if (xs) SSB_LAUNCH_XS(8); else if (final_only) SSB_LAUNCH_SIG(8, 2); else SSB_LAUNCH_SIG(8, 0); }
     CKL("orbit_kernel");
     return 0;
 }

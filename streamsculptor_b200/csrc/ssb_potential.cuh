@@ -37,20 +37,33 @@ __device__ __forceinline__ int upper_bound_d(const double* __restrict__ a, int n
 // the tables on the path are (near-)uniform in time (potential.py:581-600: 1000 knots on [-14000, 0]; Chen25 tracks:
 // linspace + one extra knot), so the guess is exact up to +-1 and two or three cached loads replace a 10-deep
 // dependent binary search per force evaluation.  Non-uniform tables fall back to the binary search.
-template <bool UPPER>
-__device__ __forceinline__ int locate_below(const double* __restrict__ a, int n, double v) {
-    const double a0 = __ldg(a), a1 = __ldg(a + n - 1);
-    int i = (int)((v - a0) * (double)(n - 1) / (a1 - a0));
-    i = min(max(i, 0), n - 1);
+// Segment lookup.  The tables on the path are (near-)uniform in time (potential.py:581-600: 1000 knots on [-14000, 0]; Chen25
+// tracks: linspace + one extra knot), so a proportional guess is exact up to +-1; the two knot times that bracket the guess are
+// the ones the interpolation needs anyway, so the common case costs ONE round of loads instead of a 10-deep dependent binary
+// search per force evaluation.  T.t_first / T.inv_dt are prepared once per CTA by stage_potential (0 = not prepared).
+//   LINEAR: i = clip(searchsorted(t, v, 'left') - 1, 0, n-2):  t[i] <  v <= t[i+1] inside the table
+//   CUBIC : i = clip(searchsorted(t, v, 'right'), 1, n-1) - 1: t[i] <= v <  t[i+1] inside the table
+template <bool CUBIC>
+__device__ __forceinline__ int segment_guess(const ssb_track& T, double v) {
+    double a0 = T.t_first, sc = T.inv_dt;
+    if (sc == 0.0) { a0 = __ldg(T.t); sc = (double)(T.n - 1) / (__ldg(T.t + T.n - 1) - a0); }
+    const int i = (int)((v - a0) * sc);
+    return min(max(i, 0), T.n - 2);
+}
+// correct a guessed segment given its end times (ta, tb); returns the true segment, reloading ta/tb only if it moved
+template <bool CUBIC>
+__device__ __forceinline__ int segment_fix(const ssb_track& T, double v, int i, double& ta, double& tb) {
+    const double* __restrict__ a = T.t;
+    const int n = T.n;
     int walk = 0;
-    if (UPPER) {
-        while (i < n - 1 && __ldg(a + i + 1) <= v && walk < 4) { ++i; ++walk; }
-        while (i >= 0 && __ldg(a + i) > v && walk < 4) { --i; ++walk; }
-        if (walk >= 4) i = upper_bound_d(a, n, v) - 1;
+    if (CUBIC) {
+        while (i > 0 && ta > v && walk < 4) { --i; tb = ta; ta = __ldg(a + i); ++walk; }
+        while (i < n - 2 && tb <= v && walk < 4) { ++i; ta = tb; tb = __ldg(a + i + 1); ++walk; }
+        if (walk >= 4) { i = min(max(upper_bound_d(a, n, v), 1), n - 1) - 1; ta = __ldg(a + i); tb = __ldg(a + i + 1); }
     } else {
-        while (i < n - 1 && __ldg(a + i + 1) < v && walk < 4) { ++i; ++walk; }
-        while (i >= 0 && __ldg(a + i) >= v && walk < 4) { --i; ++walk; }
-        if (walk >= 4) i = lower_bound_d(a, n, v) - 1;
+        while (i > 0 && ta >= v && walk < 4) { --i; tb = ta; ta = __ldg(a + i); ++walk; }
+        while (i < n - 2 && tb < v && walk < 4) { ++i; ta = tb; tb = __ldg(a + i + 1); ++walk; }
+        if (walk >= 4) { i = min(max(lower_bound_d(a, n, v) - 1, 0), n - 2); ta = __ldg(a + i); tb = __ldg(a + i + 1); }
     }
     return i;
 }
@@ -59,15 +72,22 @@ template <bool DERIV>
 __device__ __forceinline__ void track_eval(const ssb_track& T, double tq, double c[3], double dc[3]) {
     const int n = T.n;
     if (T.kind == SSB_TRACK_LINEAR) {
-        int i = locate_below<false>(T.t, n, tq);                   // jnp.searchsorted(side='left') - 1, clipped
-        i = min(max(i, 0), n - 2);
-        const double ta = __ldg(T.t + i), tb = __ldg(T.t + i + 1);
-        const double h = tb - ta, w = (tq - ta) / h;
+        // knot times AND knot values of the guessed segment are fetched in one round of loads; a wrong guess (rare) reloads
+        const int ig = segment_guess<false>(T, tq);
+        double ta = __ldg(T.t + ig), tb = __ldg(T.t + ig + 1);
+        double y0[3], y1[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { y0[k] = __ldg(T.y + 3 * ig + k); y1[k] = __ldg(T.y + 3 * ig + 3 + k); }
+        const int i = segment_fix<false>(T, tq, ig, ta, tb);
+        if (i != ig) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { y0[k] = __ldg(T.y + 3 * i + k); y1[k] = __ldg(T.y + 3 * i + 3 + k); }
+        }
+        const double ih = frcp(tb - ta), w = (tq - ta) * ih;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const double y0 = __ldg(T.y + 3 * i + k), y1 = __ldg(T.y + 3 * i + 3 + k);
-            c[k] = (1.0 - w) * y0 + w * y1;
-            if (DERIV) dc[k] = (y1 - y0) / h;
+            c[k] = (1.0 - w) * y0[k] + w * y1[k];
+            if (DERIV) dc[k] = (y1[k] - y0[k]) * ih;
         }
     } else {
         if (!(tq >= __ldg(T.t) && tq <= __ldg(T.t + n - 1))) {     // interpax extrap=False -> NaN
@@ -76,10 +96,10 @@ __device__ __forceinline__ void track_eval(const ssb_track& T, double tq, double
             for (int k = 0; k < 3; ++k) { c[k] = qn; if (DERIV) dc[k] = qn; }
             return;
         }
-        int i = locate_below<true>(T.t, n, tq) + 1;                 // searchsorted(side='right'), clipped to [1, n-1]
-        i = min(max(i, 1), n - 1);
-        const double ta = __ldg(T.t + i - 1), tb = __ldg(T.t + i);
-        const double dx = tb - ta, dxi = dx == 0.0 ? 0.0 : 1.0 / dx;
+        const int ig = segment_guess<true>(T, tq);
+        double ta = __ldg(T.t + ig), tb = __ldg(T.t + ig + 1);
+        const int i = segment_fix<true>(T, tq, ig, ta, tb) + 1;     // searchsorted(side='right'), clipped to [1, n-1]
+        const double dx = tb - ta, dxi = dx == 0.0 ? 0.0 : frcp(dx);
         const double u = (tq - ta) * dxi;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -277,6 +297,75 @@ __device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x
             default: break;
         }
     }
+}
+
+// "Fast extras": the moving-perturber terms of the reference next to a fused galaxy signature - a spherical component translating
+// on a LINEAR table (MW_LMC_Potential's LMC, potential.py:581-650; BASELINE config C3) or a uniform frame acceleration
+// (potential.py:480-502, 646-650).  Their constants are gathered once per CTA into a compact shared-memory record; the evaluation
+// is one straight-line block (segment guess -> ONE round of table loads -> interpolation -> force) that the scheduler overlaps with
+// the galaxy arithmetic; a wrong segment guess (non-uniform table, or t within rounding of a knot) takes a rare out-of-line path.
+struct FastX {
+    double t_first, inv_dt, GM, a, soft;
+    const double* t; const double* y;
+    int n, type;
+};
+static __device__ __noinline__ void fastx_slow(const double* __restrict__ t, const double* __restrict__ y, int n, double v, double* out /*ta, tb, y0[3], y1[3]*/) {
+    const int i = min(max(lower_bound_d(t, n, v) - 1, 0), n - 2);
+    out[0] = __ldg(t + i); out[1] = __ldg(t + i + 1);
+    for (int k = 0; k < 3; ++k) { out[2 + k] = __ldg(y + 3 * i + k); out[5 + k] = __ldg(y + 3 * i + 3 + k); }
+}
+__device__ __forceinline__ void fastx_fill(FastX* fx, const ssb_potential& Pt, int ic) {
+    const ssb_component& c = Pt.comp[ic];
+    const ssb_track& T = Pt.track[c.track];
+    fx->t_first = T.t_first; fx->inv_dt = T.inv_dt; fx->t = T.t; fx->y = T.y; fx->n = T.n; fx->type = c.type;
+    fx->GM = c.p[0]; fx->a = c.p[1]; fx->soft = c.type == SSB_HERNQUIST ? c.p[2] : 0.0;
+}
+__device__ __forceinline__ void fastx_grad(const FastX& fx, const double x[3], double v, double g[3]) {
+    const int n = fx.n;
+    int i = (int)((v - fx.t_first) * fx.inv_dt);
+    i = min(max(i, 0), n - 2);
+    const double* __restrict__ tp = fx.t + i;
+    const double* __restrict__ yp = fx.y + 3 * i;
+    double ta = __ldg(tp), tb = __ldg(tp + 1);
+    double y0[3], y1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { y0[k] = __ldg(yp + k); y1[k] = __ldg(yp + 3 + k); }
+    // searchsorted(t, v, 'left') - 1 clipped to [0, n-2]: t[i] < v <= t[i+1] inside the table
+    const bool ok = (ta < v || i == 0) && (v <= tb || i == n - 2);
+    if (!ok) {
+        double o[8];
+        fastx_slow(fx.t, fx.y, n, v, o);
+        ta = o[0]; tb = o[1];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { y0[k] = o[2 + k]; y1[k] = o[5 + k]; }
+    }
+    const double ih = frcp(tb - ta), w = (v - ta) * ih, w1 = 1.0 - w;
+    if (fx.type == SSB_UNIFORM_ACC) {                              // gradient = d v_frame / dt = slope of the segment
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g[k] = fma(y1[k] - y0[k], ih, g[k]);
+        return;
+    }
+    double xs[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) xs[k] = x[k] - (w1 * y0[k] + w * y1[k]);
+    const double r2 = fma(xs[0], xs[0], fma(xs[1], xs[1], fma(xs[2], xs[2], fx.soft)));
+    double phi, q, wq;
+    if (fx.type == SSB_PLUMMER) plummer_terms<WANT_GRAD>(fx.GM, fx.a, r2, phi, q, wq);
+    else if (fx.type == SSB_HERNQUIST) hernquist_terms<WANT_GRAD>(fx.GM, fx.a, r2, phi, q, wq);
+    else if (fx.type == SSB_NFW) nfw_terms<WANT_GRAD>(fx.GM, fx.a, r2, phi, q, wq);
+    else isochrone_terms<WANT_GRAD>(fx.GM, fx.a, r2, phi, q, wq);
+    g[0] = fma(q, xs[0], g[0]); g[1] = fma(q, xs[1], g[1]); g[2] = fma(q, xs[2], g[2]);
+}
+// host side: do the components beyond the first `nf` qualify?  returns their number (1 or 2) or 0
+static inline int ssb_fast_extras(const ssb_potential* p, int nf) {
+    const int nx = p->n_comp - nf;
+    if (nx < 1 || nx > 2) return 0;
+    for (int i = nf; i < p->n_comp; ++i) {
+        const ssb_component& c = p->comp[i];
+        const bool kind_ok = c.type == SSB_NFW || c.type == SSB_HERNQUIST || c.type == SSB_PLUMMER || c.type == SSB_ISOCHRONE || c.type == SSB_UNIFORM_ACC;
+        if (!kind_ok || c.track < 0 || p->track[c.track].kind != SSB_TRACK_LINEAR) return 0;
+    }
+    return nx;
 }
 
 // ---------------------------------------------------------------------------------------------
