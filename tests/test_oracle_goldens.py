@@ -188,3 +188,44 @@ def test_tracks():
     assert np.isnan(c[0]).all() and np.isnan(c[-1]).all()                         # interpax extrap=False
     assert np.allclose(c[1:-1, 2], 3 * q[1:-1]) and np.allclose(c[2, 0], q[2] ** 2, atol=1e-12)   # interior knots: FD slopes exact for quadratics
     assert np.allclose(c[1:-1, 1], np.sin(q[1:-1]), atol=0.05)
+
+
+def _fixture():
+    import json
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "notebook_goldens.json")
+    num = re.compile(r"[-+]?\d+\.\d*(?:[eE][-+]?\d+)?")
+    return {g["id"]: (g, np.array([float(x) for x in num.findall(g["output"])])) for g in json.load(open(path))}
+
+
+def test_committed_notebook_fixture_pins_the_oracle():
+    """tests/golden/notebook_goldens.json = the reference's own printed outputs, extracted verbatim by tools/extract_goldens.py.
+    The oracle is checked against the numbers parsed from the fixture (not against hand-copied constants)."""
+    fx = _fixture()
+    assert set(fx) >= {"G1", "D1", "D2", "D3_head", "D4", "D5", "D8"}
+    # G1: pins G
+    x, y, z, q = 1.0, 20.0, 10.0, 1.3
+    rp = np.sqrt(x * x + y * y + (z / q) ** 2)
+    assert abs(-(O.G_KPC_MYR_MSUN * 1e12 / rp) * np.log(1 + rp / 15.0) - fx["G1"][1][0]) < 2e-15
+    # D1: acceleration of NFW(1e12, 20) at (1,2,3) = last three printed numbers
+    nfw = O.Program().nfw(1e12, 20.0)
+    assert np.allclose(-nfw.gradient([1.0, 2.0, 3.0])[0], fx["D1"][1][3:6], rtol=0, atol=5e-9)
+    # D2: dense evaluate at t = 30
+    ys, _, _ = nfw.integrate_orbits([20, 15, 20, .08, .1, -.05], 0.0, 3000.0, ts=[0.0, 30.0, 3000.0])
+    assert np.allclose(ys[0, 1], fx["D2"][1][:6], rtol=0, atol=6e-9)
+    # D3: the printed array shows rows 0..2 and -3..-1 of the 1000 saved rows
+    rows = fx["D3_head"][1][:36].reshape(6, 6)
+    ts = np.linspace(0, 3000, 1000)
+    ys, _, _ = nfw.integrate_orbits([20, 0, 20, 0, .2, 0], 0.0, 3000.0, ts=ts, dtmin=0.5, max_steps=1000)
+    got = ys[0, [0, 1, 2, -3, -2, -1]]
+    tolr = 0.6 * 10.0 ** (np.floor(np.log10(np.maximum(np.abs(rows), 1e-300))) - 8) + 5e-10
+    assert np.all(np.abs(got - rows) <= np.where(rows == 0.0, 1e-12, tolr))
+    # D4 / D5 at tolerance level
+    ys, _, _ = nfw.integrate_orbits([20, 0, 20, 0, .2, 0], 0.0, 3000.0, ts=ts, rtol=1e-6, atol=1e-6)
+    assert abs(ys.sum() - fx["D4"][1][0]) < 5e-3
+    MW = O.Program().miyamoto(6.8e10, 3.0, 0.28).hernquist(5e9, 1.0).hernquist(1.71e9, 0.07).nfw(5.4e11, 15.62)
+    ic, _, _ = MW.integrate_orbits([20, 0, 20, 0, .15, 0], 0.0, -3500.0, ts=[-3500.0])
+    assert np.abs(ic[0, 0] - fx["D5"][1][:6]).max() < 5e-6
+    # D8 (release Jacobian): shape of the printed tensor only - its inputs are not recoverable (DESIGN.md section 5)
+    assert fx["D8"][1].size >= 72

@@ -1,0 +1,56 @@
+"""Extract the reference's own printed results for the hot path from its notebooks into
+tests/golden/notebook_goldens.json.  Run in the build container (needs /root/reference; the GPU box never reads it).
+Each golden records notebook, cell index, the cell source and the printed output verbatim."""
+import json
+import os
+import sys
+
+REF = "/root/reference/streamsculptor/examples"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "notebook_goldens.json")
+# (id, notebook, a number string that identifies the output cell)
+WANTED = [
+    ("G1", "custom_potential.ipynb", "-0.186204177133592"),
+    ("D1", "tests.ipynb", "-0.00238739"),
+    ("D2", "tests.ipynb", "21.9793661"),
+    ("D3_head", "tests.ipynb", "1.99947007e+01"),
+    ("D3_tail", "tests.ipynb", "1.60397604e+01"),
+    ("D4", "tests.ipynb", "-936.42809302"),
+    ("D5", "StreamSubhaloExample.ipynb", "-7.23164146"),
+    ("D7a", "linear_perturbation_stream.ipynb", "(1499, 50, 12)"),
+    ("D8", "tests.ipynb", "9.96418614e-01"),
+]
+
+
+def cell_outputs(cell):
+    txt = []
+    for o in cell.get("outputs", []):
+        if "text" in o:
+            txt.append("".join(o["text"]))
+        elif "data" in o and "text/plain" in o["data"]:
+            txt.append("".join(o["data"]["text/plain"]))
+    return "\n".join(txt)
+
+
+def main():
+    res = []
+    for gid, nbname, needle in WANTED:
+        nb = json.load(open(os.path.join(REF, nbname)))
+        hit = None
+        for idx, cell in enumerate(nb["cells"]):
+            if cell["cell_type"] != "code":
+                continue
+            out = cell_outputs(cell)
+            if needle in out:
+                hit = {"id": gid, "notebook": "streamsculptor/examples/" + nbname, "cell": idx, "source": "".join(cell["source"]), "output": out}
+                break
+        if hit is None:
+            print("NOT FOUND:", gid, nbname, needle, file=sys.stderr)
+            continue
+        res.append(hit)
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    json.dump(res, open(OUT, "w"), indent=1)
+    print(f"wrote {len(res)} goldens to {OUT}")
+
+
+if __name__ == "__main__":
+    main()
