@@ -190,9 +190,13 @@ def run_ours(args, rank, world):
     def step_device():
         lead, trail, status, nsteps = rt.gen_stream(pot, pot, pot._G, ts_d, w0_d, ms_d, SEED, kv, None, ctrl, i_begin=rank, i_stride=world,
                                                     n_local=n_local)
-        if world > 1:
-            lead = par.gather_interleaved(lead, n_rel, rank, world)
-            trail = par.gather_interleaved(trail, n_rel, rank, world)
+        packed = getattr(lead, "_ssb_packed", None)          # [2, n_local, 6] storage shared by lead and trail
+        if world > 1:          # ONE NCCL all-gather of the packed (lead, trail) shares + one permuting copy into global particle order
+            both = par.gather_interleaved(lead if packed is None else packed, n_rel, rank, world, axis=1 if packed is not None else 0)
+            if packed is not None:
+                lead, trail = both[0], both[1]
+            else:
+                lead, trail = both, par.gather_interleaved(trail, n_rel, rank, world)
         return lead, trail, status, nsteps
 
     def barrier():
@@ -303,7 +307,7 @@ def run_ours(args, rank, world):
                                    "(gen_stream_vmapped semantics), jax-threefry release draws",
                        "particles_per_gpu": args.particles, "particle_steps_per_step": psteps, "parallelism": f"dp{world} (particles interleaved over ranks)",
                        "l2": "512 MB buffer zeroed between timed iterations", "time_to_stream_ms": ms_total / args.steps},
-            "clocks": clocks, "gpu_launches": 5 * args.steps,
+            "clocks": clocks, "gpu_launches": 4 * args.steps,      # dense_step, dense_eval, release, orbit kernels per gen_stream call
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * float(te.item()) / args.steps, "call": "ssb_gen_stream_host (C ABI, pinned host buffers)"},
             "roofline": roofline, "cpu_baseline": cpu}

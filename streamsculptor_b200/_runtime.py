@@ -289,7 +289,9 @@ def gen_stream(pot, pot_release, G, ts, prog_w0, Msat, seed, kvals, normals, ctr
     Nts = ts.shape[0]
     i_begin, i_stride = int(i_begin), int(i_stride)
     n = shard_count(Nts - 1, i_begin, i_stride) if n_local is None else int(n_local)
-    lead, trail = empty((n, 6)), empty((n, 6))
+    both = empty((2, n, 6))                       # lead and trail share one buffer: a sharded run gathers them in one collective
+    lead, trail = both[0], both[1]
+    lead._ssb_packed = both
     status, nsteps = empty((2, n), tt.int32), empty((2, n, 3), tt.int32)
     nbytes = _lib.lib().ssb_stream_scratch_bytes(Nts, ctrl.max_steps)
     scratch = empty(((nbytes + 7) // 8,))

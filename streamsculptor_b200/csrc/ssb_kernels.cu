@@ -259,11 +259,13 @@ __global__ void __launch_bounds__(32) dense_step_kernel(const __grid_constant__ 
     }
 }
 
+// ts_stride > 1: row m of ys is the state at ts[ts_begin + m * ts_stride] (a rank's own stripping times of a sharded stream)
 template <int SOLVER>
-__global__ void dense_eval_kernel(const double* scratch, const double* ts, int64_t M, double* ys) {
+__global__ void dense_eval_kernel(const double* scratch, const double* ts, int64_t M, double* ys, int64_t ts_begin = 0, int64_t ts_stride = 1) {
     constexpr int S = Tab<SOLVER>::S;
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
+    ts += ts_begin + m * (ts_stride - 1);               // ts[m] below reads ts[ts_begin + m * ts_stride]
     const int n = (int)scratch[0];
     const double dir = scratch[4];
     const double* rec = scratch + 8;
@@ -402,6 +404,10 @@ struct ReleaseArgs {
     double G;
     double *pos_lead, *pos_trail, *vel_lead, *vel_trail;
     double *w0_packed, *t0_packed;   // optional [2,N,6] / [2,N] in the orbit-kernel layout (lead block, trail block)
+    // sharded streams: thread k handles stripping time g = sel_begin + k * sel_stride; t / Msat / normals / the draw index are read at g,
+    // prog and every output at k (sel_stride = 0: g = k).  t1_packed[2,N] (optional) is filled with *t_end.
+    int64_t sel_begin, sel_stride;
+    double* t1_packed; const double* t_end;
 };
 
 // ---- forward-mode dual numbers for jacfwd(release_model) (perturbative.py:281-296): value + 6 partials d/d(x, v) ----
@@ -468,19 +474,20 @@ __device__ inline void release_draws(const ReleaseArgs& a, int64_t i, double nr[
 __global__ void release_kernel(const __grid_constant__ ssb_potential Pin, const ReleaseArgs a) {
     __shared__ ssb_potential sP;
     stage_potential(&sP, &Pin);
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;        // compact index: prog row, output row
     if (i >= a.N) return;
+    const int64_t gi = a.sel_stride ? a.sel_begin + i * a.sel_stride : i;   // stripping-time index
     const double* w = a.prog + 6 * i;
     const double x[3] = {w[0], w[1], w[2]}, v[3] = {w[3], w[4], w[5]};
-    const double t = a.t[i];
+    const double t = a.t[gi];
     double nr[4];
-    release_draws(a, i, nr);
+    release_draws(a, gi, nr);
     double P, g[3];
     Sym3 Hs;
     pot_eval<WANT_HESS>(sP, x, t, P, g, Hs);
     const double H[3][3] = {{Hs.xx, Hs.xy, Hs.xz}, {Hs.xy, Hs.yy, Hs.yz}, {Hs.xz, Hs.yz, Hs.zz}};
     double out[12];
-    release_math<double>(x, v, H, a.G * a.Msat[i], a.kv, nr, out);
+    release_math<double>(x, v, H, a.G * a.Msat[gi], a.kv, nr, out);
     for (int k = 0; k < 3; ++k) {
         if (a.pos_lead) { a.pos_lead[3 * i + k] = out[k]; a.pos_trail[3 * i + k] = out[3 + k]; a.vel_lead[3 * i + k] = out[6 + k]; a.vel_trail[3 * i + k] = out[9 + k]; }
         if (a.w0_packed) {
@@ -489,6 +496,7 @@ __global__ void release_kernel(const __grid_constant__ ssb_potential Pin, const 
         }
     }
     if (a.t0_packed) { a.t0_packed[i] = t; a.t0_packed[a.N + i] = t; }
+    if (a.t1_packed) { const double te = *a.t_end; a.t1_packed[i] = te; a.t1_packed[a.N + i] = te; }
 }
 
 // ---- Chen+25 release (streamhelpers.py:352-432): 6 correlated normals per stripping time -> (Dr, phi, theta, Dv, alpha, beta) ----
@@ -605,18 +613,6 @@ __global__ void potential_third_kernel(const __grid_constant__ ssb_potential Pin
     for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) for (int k = 0; k < 3; ++k) third[27 * i + 9 * p + 3 * q + k] = third_at(T3, p, q, k);
 }
 
-// gather the [i_begin, i_end) slice of the packed release output into the orbit-kernel input of the stream
-__global__ void stream_pack_kernel(int64_t Nts, int64_t i_begin, int64_t i_stride, int64_t n, const double* w0_packed, const double* ts,
-                                   double* w0, double* t0, double* t1) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= 2 * n) return;
-    const int arm = j >= n;
-    const int64_t i = i_begin + (arm ? j - n : j) * i_stride;
-    const double* src = w0_packed + 6 * ((int64_t)arm * Nts + i);
-    for (int k = 0; k < 6; ++k) w0[6 * j + k] = src[k];
-    t0[j] = ts[i];
-    t1[j] = ts[Nts - 1];
-}
 
 // fp64 peak probe: 8 independent DFMA chains per thread
 __global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, double* sink) {
@@ -781,7 +777,7 @@ size_t ssb_scratch_bytes(int32_t max_steps) { return sizeof(double) * (8 + (size
 
 static int dense_launch(const ssb_potential* pot, const double* w0, double t0, double t1, const double* t0p, const double* t1p,
                         const double* ts, int64_t M, const ssb_ctrl& ctrl, double* ys, int32_t* status, int32_t* nsteps, double* scratch,
-                        cudaStream_t st) {
+                        cudaStream_t st, int64_t ts_begin = 0, int64_t ts_stride = 1) {
     const CtrlDev c = to_dev(ctrl);
     ssb_potential pc;
     const int sig = ssb_canonicalize(pot, &pc);
@@ -791,8 +787,8 @@ static int dense_launch(const ssb_potential* pot, const double* w0, double t0, d
     if (ctrl.solver == 5) SSB_LAUNCH_DENSE_SIG(5); else SSB_LAUNCH_DENSE_SIG(8);
     CKL("dense_step_kernel");
     if (M > 0) {
-        if (ctrl.solver == 5) dense_eval_kernel<5><<<nblk(M, 128), 128, 0, st>>>(scratch, ts, M, ys);
-        else dense_eval_kernel<8><<<nblk(M, 128), 128, 0, st>>>(scratch, ts, M, ys);
+        if (ctrl.solver == 5) dense_eval_kernel<5><<<nblk(M, 128), 128, 0, st>>>(scratch, ts, M, ys, ts_begin, ts_stride);
+        else dense_eval_kernel<8><<<nblk(M, 128), 128, 0, st>>>(scratch, ts, M, ys, ts_begin, ts_stride);
         CKL("dense_eval_kernel");
     }
     return 0;
@@ -908,22 +904,25 @@ int ssb_gen_stream_f64(const ssb_potential* pot, const ssb_potential* pot_releas
     double* t0 = w0 + 12 * Nts;
     double* t1 = t0 + 2 * Nts;
     double* ys = t1 + 2 * Nts;
-    // (1) progenitor at every stripping time: integrate_orbit(prog_w0, ts) with t0 = ts.min, t1 = ts.max (main.py:289, 152-153)
-    if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts, ts + (Nts - 1), ts, Nts, ctrl, prog, nullptr, nullptr, dense, st)) return e;
-    // (2) release at every stripping time (main.py:293-303)
+    if (n == 0) return 0;
+    // (1) progenitor orbit integrate_orbit(prog_w0, ts) with t0 = ts.min, t1 = ts.max (main.py:289, 152-153): ONE serial solve, then its
+    //     dense output at THIS SHARD's stripping times only (ts[i_begin + k i_stride], k < n)
+    if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts, ts + (Nts - 1), ts, n, ctrl, prog, nullptr, nullptr, dense, st, i_begin, i_stride)) return e;
+    // (2) release at those stripping times (main.py:293-303), written straight into the orbit kernel's input layout
+    //     (lead block, trail block) together with the per-orbit start / end times
     ReleaseArgs a;
     memset(&a, 0, sizeof(a));
-    a.N = Nts; a.prog = prog; a.Msat = Msat; a.t = ts; a.normals = normals; a.idx = nullptr; a.G = G;
+    a.N = n; a.prog = prog; a.Msat = Msat; a.t = ts; a.normals = normals; a.idx = nullptr; a.G = G;
+    a.sel_begin = i_begin; a.sel_stride = i_stride;
     int64_t r5[5]; host_randint5(seed, r5);
     for (int q = 0; q < 4; ++q) a.r[q] = r5[q];
     memcpy(a.kv, kvals, sizeof(a.kv));
-    a.w0_packed = w0p;
-    release_kernel<<<nblk(Nts, 128), 128, 0, st>>>(*pot_release, a);
+    a.w0_packed = w0; a.t0_packed = t0; a.t1_packed = t1; a.t_end = ts + (Nts - 1);
+    release_kernel<<<nblk(n, 128), 128, 0, st>>>(*pot_release, a);
     CKL("release_kernel");
-    if (n == 0) return 0;
-    // (3) 2n independent solves from ts[i] to ts[-1], keep the final state (main.py:349-368)
-    stream_pack_kernel<<<nblk(2 * n, 128), 128, 0, st>>>(Nts, i_begin, i_stride, n, w0p, ts, w0, t0, t1);
-    CKL("stream_pack_kernel");
+    // (3) 2n independent solves from ts[i] to ts[-1], keep the final state (main.py:349-368); lead and trail that are adjacent in
+    //     memory (one [2,n,6] buffer) receive the kernel's output directly
+    if (trail == lead + 6 * n) return ssb_orbit_integrate_f64(pot, 2 * n, w0, t0, t1, t1, 1, 1, ctrl, lead, status, nsteps, stream);
     if (int e = ssb_orbit_integrate_f64(pot, 2 * n, w0, t0, t1, t1, 1, 1, ctrl, ys, status, nsteps, stream)) return e;
     CK(cudaMemcpyAsync(lead, ys, sizeof(double) * 6 * n, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(trail, ys + 6 * n, sizeof(double) * 6 * n, cudaMemcpyDeviceToDevice, st));

@@ -39,22 +39,51 @@ def shard_count(n, rank, world):
     return max(0, (n - rank + world - 1) // world)
 
 
-def gather_interleaved(local, n_total, rank, world, group=None):
-    """All-gather per-rank shards (rows k <-> global index rank + k*world) into the global [n_total, ...] order.
-    `local` is a torch tensor on the device the process group works on."""
+_GATHER_BUF = {}
+
+
+def _gather_buffer(shape, dtype, device):
+    """Receive buffers are cached between calls (a 1e6-particle share per GPU is 96 MB; re-allocating it every step costs more
+    than the NVLink transfer itself)."""
+    key = (tuple(shape), dtype, str(device))
+    buf = _GATHER_BUF.get(key)
+    if buf is None:
+        import torch
+        if len(_GATHER_BUF) > 8:
+            _GATHER_BUF.clear()
+        buf = _GATHER_BUF[key] = torch.empty(shape, dtype=dtype, device=device)
+    return buf
+
+
+def gather_interleaved(local, n_total, rank, world, group=None, axis=0):
+    """All-gather per-rank shards (row k of rank r <-> global index r + k*world along `axis`) into the global order.
+    ONE collective (all_gather_into_tensor) and ONE permuting copy; `local` is a torch tensor on the process group's device.
+    axis = 1 gathers a packed [2, n_local, 6] (lead, trail) pair in a single call."""
     import torch
     if world == 1:
         return local
     d = dist()
     n_max = shard_count(n_total, 0, world)
-    pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    d.all_gather(bufs, pad, group=group)
-    out = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    for r in range(world):
-        out[r::world] = bufs[r][: shard_count(n_total, r, world)]
-    return out
+    n_loc = local.shape[axis]
+    src = local.contiguous()
+    if n_loc != n_max:                                    # ragged tail: pad this rank's share to the common length
+        shape = list(local.shape); shape[axis] = n_max
+        src = torch.zeros(shape, dtype=local.dtype, device=local.device)
+        src.narrow(axis, 0, n_loc).copy_(local)
+    buf = _gather_buffer((world,) + tuple(src.shape), src.dtype, src.device)
+    try:
+        d.all_gather_into_tensor(buf, src, group=group)
+    except (RuntimeError, NotImplementedError):           # backends without the flat collective
+        d.all_gather(list(buf.unbind(0)), src, group=group)
+    # buf[r, ..., k, ...] -> out[..., k*world + r, ...]
+    perm = list(range(1, buf.dim()))
+    perm.insert(axis + 1, 0)                              # [..., n_max, world, ...]
+    out = buf.permute(perm)
+    shape = list(local.shape); shape[axis] = n_max * world
+    out = out.reshape(shape)                              # the one permuting copy
+    if out.data_ptr() == buf.data_ptr():                  # degenerate shapes reshape without copying: never hand out the cached buffer
+        out = out.clone()
+    return out if n_max * world == n_total else out.narrow(axis, 0, n_total).contiguous()
 
 
 def gen_stream_sharded(pot, ts, prog_w0, Msat, seed_num, solver, rank, world, kval_arr=1.0, rtol=1e-7, atol=1e-7, dtmin=0.3, dtmax=None,
@@ -76,6 +105,11 @@ def gen_stream_sharded(pot, ts, prog_w0, Msat, seed_num, solver, rank, world, kv
         lead, trail = compute(rank, world, n_local)
     if not gather:
         return lead, trail
+    import torch
+    if isinstance(lead, torch.Tensor) and lead.shape == trail.shape:
+        packed = getattr(lead, "_ssb_packed", None)          # rt.gen_stream writes both arms into one [2, n_local, 6] buffer
+        both = gather_interleaved(torch.stack([lead, trail]) if packed is None else packed, n, rank, world, group, axis=1)   # one collective for both arms
+        return both[0], both[1]
     return gather_interleaved(lead, n, rank, world, group), gather_interleaved(trail, n, rank, world, group)
 
 
