@@ -328,6 +328,8 @@ def main():
         run_reference(args, rank, world)
         return
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # keeps NCCL's banner out of stdout: rank 0 prints ONE JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         from streamsculptor_b200 import parallel as par
         par.init_from_env("nccl")
     run_ours(args, rank, world)
