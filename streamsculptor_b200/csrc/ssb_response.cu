@@ -263,12 +263,17 @@ __device__ __forceinline__ void sweep_items(const BaseShared<Tab<SOLVER>::S>* sb
         const bool closed = (t_lo - t0j >= twj) || (t0j - t_hi >= twj);       // |t - t0| >= tw at every stage (potential.py:826)
         if (closed) {
             const double y[6] = {q[0], q[1], q[2], pp[0], pp[1], pp[2]};
+            const double2* __restrict__ M2 = reinterpret_cast<const double2*>(PhiE);     // 16-byte shared loads: [12 rows][3] double2
             double o[6], e[6];
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 double so = 0.0, se = 0.0;
 #pragma unroll
-                for (int cc = 0; cc < 6; ++cc) { so = fma(PhiE[r * 6 + cc], y[cc], so); se = fma(PhiE[36 + r * 6 + cc], y[cc], se); }
+                for (int c2 = 0; c2 < 3; ++c2) {
+                    const double2 m = M2[r * 3 + c2], me = M2[18 + r * 3 + c2];
+                    so = fma(m.x, y[2 * c2], so); so = fma(m.y, y[2 * c2 + 1], so);
+                    se = fma(me.x, y[2 * c2], se); se = fma(me.y, y[2 * c2 + 1], se);
+                }
                 o[r] = so; e[r] = se;
             }
 #pragma unroll
