@@ -15,21 +15,7 @@ from .fields import integrate_field
 from .solvers import Dopri8
 
 
-def _as_prog_track(interp_prog, n_knots=4097):
-    """`interp_prog` in the reference is a diffrax dense Solution (`.evaluate(t)[:3]`, RestrictedNbody.py:99).  The kernels need a
-    tabulated track: accept LinearTrack/CubicTrack/interpax-like objects as they are; a dense Solution of this package is
-    re-sampled on `n_knots` uniform knots into a cubic-Hermite track."""
-    try:
-        return rt.as_track(interp_prog)
-    except NotImplementedError:
-        pass
-    dense = getattr(interp_prog, "_dense", None)
-    if dense is None:
-        raise NotImplementedError("interp_prog must be a tabulated track or a dense Solution returned by integrate_orbit(dense=True)")
-    ta, tb = dense.t0, dense.t1
-    tk = np.linspace(min(ta, tb), max(ta, tb), n_knots)
-    yk = np.asarray(interp_prog.evaluate(tk))[:, :3]
-    return _pot.CubicTrack(tk, yk)
+_as_prog_track = _pot._track_of_interp      # diffrax dense Solution -> tabulated cubic track (potential.py:152, RestrictedNbody.py:99)
 
 
 class RestrictedNbody_generator:

@@ -298,6 +298,47 @@ class SubhaloLinePotentialCustom_dRadius_fromFunc(_SubhaloLineBase):   # potenti
         self._setup(_profile_of(func), m, r_s)
 
 
+class SubhaloLinePotential_Custom(_SubhaloLineBase):   # potential.py:908-956: ONE potential object `pot` shared by every subhalo
+    """`pot` must be a Plummer / Hernquist / NFW instance (its m and r_s are used for all subhalos)."""
+
+    def __init__(self, pot, subhalo_x0, subhalo_v, subhalo_t0, t_window, units=None):
+        super().__init__(units, {'pot': pot, 'subhalo_x0': subhalo_x0, 'subhalo_v': subhalo_v, 'subhalo_t0': subhalo_t0, 't_window': t_window})
+        n = len(np.atleast_1d(np.asarray(subhalo_t0)))
+        rs = getattr(pot, 'r_s', None)
+        if rs is None:
+            rs = getattr(pot, 'a')
+        self._arrays = rt.SubhaloArrays(_profile_of(type(pot)), pot._G, np.full(n, float(pot.m)), np.full(n, float(rs)), subhalo_x0, subhalo_v,
+                                        subhalo_t0, t_window)
+
+
+def _track_of_interp(interp_func, n_knots=4097):
+    """`interp_func` in the reference is a diffrax dense Solution (`.evaluate(t)[:3]`, potential.py:152).  The kernels need a tabulated
+    track: LinearTrack / CubicTrack / interpax-like objects pass through; a dense Solution of this package is re-sampled on `n_knots`
+    uniform knots into a cubic-Hermite track."""
+    try:
+        return rt.as_track(interp_func)
+    except NotImplementedError:
+        pass
+    dense = getattr(interp_func, "_dense", None)
+    if dense is None:
+        raise NotImplementedError("interp_func must be a tabulated track or a dense Solution returned by integrate_orbit(dense=True)")
+    tk = np.linspace(min(dense.t0, dense.t1), max(dense.t0, dense.t1), n_knots)
+    return CubicTrack(tk, np.asarray(interp_func.evaluate(tk))[:, :3])
+
+
+class ProgenitorPotential(Potential):                 # potential.py:140-153
+    """prog_pot(m, r_s) centred on the progenitor's interpolated trajectory."""
+
+    def __init__(self, m, r_s, interp_func, prog_pot, units=None):
+        super().__init__(units, {'m': m, 'r_s': r_s, 'interp_func': interp_func, 'prog_pot': prog_pot})
+        self.prog_pot = prog_pot(m=self.m, r_s=self.r_s, units=units)
+        self._track = _track_of_interp(interp_func)
+
+    def _lower(self, prog, track):
+        _no_nested(track)
+        self.prog_pot._lower(prog, prog.add_track(self._track))
+
+
 # ---- reference classes deliberately outside the B200 hot path -----------------------------------------------------
 def _out_of_scope(name, why):
     class _X(Potential):

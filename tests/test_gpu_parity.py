@@ -694,3 +694,30 @@ def test_variational_equations(cuda):
     # failure semantics: max_steps -> +inf rows, status 1
     w, M, _, st = F.integrate_variational_batch(mwp, w0[:3], -500.0, 0.0, order=1, rtol=1e-10, atol=1e-10, dtmin=0.01, max_steps=4)
     assert (st == 1).all() and np.isinf(w).all() and np.isinf(M).all()
+
+
+def test_progenitor_and_custom_subhalo_wrappers(cuda):
+    """ProgenitorPotential (potential.py:140-153) and SubhaloLinePotential_Custom (potential.py:908-956) lower onto the same device
+    components as their explicit forms."""
+    import streamsculptor_b200 as ssc
+    P = ssc.potential
+    mw = mw3_product()
+    sol = mw.integrate_orbit(w0=[20., 0, 20, 0, .15, 0], ts=np.array([0.0, -800.0]), t0=0.0, t1=-800.0, dense=True)
+    prog = P.ProgenitorPotential(m=3e4, r_s=0.02, interp_func=sol, prog_pot=P.PlummerPotential, units=ssc.usys)
+    x = np.array([[19.5, 1.0, 19.0], [5.0, -3.0, 2.0]])
+    for t in (-10.0, -400.0):
+        c = np.asarray(sol.evaluate(t))[:3]
+        ref = P.PlummerPotential(m=3e4, r_s=0.02, units=ssc.usys)
+        assert relerr(prog.gradient(x, t), ref.gradient(x - c, t)) < 1e-7          # cubic re-sampling of the dense track: 4097 knots
+        assert relerr(prog.potential(x, t), ref.potential(x - c, t)) < 1e-7
+    tot = P.Potential_Combine([mw, prog], units=ssc.usys)
+    ys = tot.integrate_orbit(w0=[19.9, 0.1, 20.0, 0.0, 0.15, 0.0], ts=np.array([-800.0, 0.0])).ys
+    assert np.isfinite(ys).all()
+    sh = subhalo_set(6, seed=9, tw=300.0)
+    one = P.HernquistPotential(m=2e7, r_s=0.4, units=ssc.usys)
+    cust = P.SubhaloLinePotential_Custom(pot=one, subhalo_x0=sh["x0"], subhalo_v=sh["v"], subhalo_t0=sh["t0"], t_window=300.0, units=ssc.usys)
+    expl = P.SubhaloLinePotentialCustom_fromFunc(func=P.HernquistPotential, m=np.full(6, 2e7), r_s=np.full(6, 0.4), subhalo_x0=sh["x0"], subhalo_v=sh["v"],
+                                                 subhalo_t0=sh["t0"], t_window=300.0, units=ssc.usys)
+    tq = float(sh["t0"][2]) + 20.0
+    assert np.array_equal(cust.potential_per_SH(x[0], tq), expl.potential_per_SH(x[0], tq))
+    assert np.array_equal(cust.gradient(x, np.full(2, tq)), expl.gradient(x, np.full(2, tq)))
