@@ -385,7 +385,9 @@ int ssb_shared_step_orbits_f64(const ssb_potential* pot, int64_t N, const double
                                int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream) {
     if (int e = ssb_validate_potential(pot)) return e;
     if (int e = ssb_validate_ctrl(ctrl)) return e;
-    if (N <= 0 || !w0 || !wout || !status || !nsteps || !scratch) return ssb_set_error(SSB_ERR_ARG, "shared_step_orbits: NULL array or N <= 0");
+    if (N < 0) return ssb_set_error(SSB_ERR_ARG, "shared_step_orbits: negative N");
+    if (N == 0) return 0;
+    if (!w0 || !wout || !status || !nsteps || !scratch) return ssb_set_error(SSB_ERR_ARG, "shared_step_orbits: NULL array");
     if (scratch_bytes < ssb_shared_scratch_bytes(N)) return ssb_set_error(SSB_ERR_SCRATCH, "shared_step_orbits: scratch too small");
     cudaStream_t st = (cudaStream_t)stream;
     SharedCtl* ctl = (SharedCtl*)scratch;

@@ -293,8 +293,9 @@ int ssb_variational_f64(const ssb_potential* pot, int32_t order, int64_t N, cons
     if (int e = ssb_validate_potential(pot)) return e;
     if (int e = ssb_validate_ctrl(ctrl)) return e;
     if (order != 1 && order != 2) return ssb_set_error(SSB_ERR_UNSUPPORTED, "variational: order must be 1 or 2");
-    if (N <= 0 || !w0 || !t0 || !wout || !Mout || !status || !nsteps || (order == 2 && !M2out))
-        return ssb_set_error(SSB_ERR_ARG, "variational: NULL array or N <= 0");
+    if (N < 0) return ssb_set_error(SSB_ERR_ARG, "variational: negative N");
+    if (N == 0) return 0;                               // empty batch is a no-op, like every batched entry point
+    if (!w0 || !t0 || !wout || !Mout || !status || !nsteps || (order == 2 && !M2out)) return ssb_set_error(SSB_ERR_ARG, "variational: NULL array");
     VarArgs a;
     a.N = N; a.w0 = w0; a.M0 = M0; a.M20 = order == 2 ? M20 : nullptr; a.t0 = t0; a.t1 = t1;
     a.c.rtol = ctrl.rtol; a.c.atol = ctrl.atol; a.c.dtmin = ctrl.dtmin; a.c.dtmax = ctrl.dtmax; a.c.max_steps = ctrl.max_steps;

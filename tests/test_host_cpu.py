@@ -162,3 +162,26 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(res.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "particle-steps/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_argument_validation_of_the_round1_entry_points():
+    """A17 / A16 entry points: validation happens before any CUDA call (no GPU needed)."""
+    from streamsculptor_b200 import _lib
+    L = _lib.lib()
+    P = _lib.Potential()
+    P.n_comp = 1
+    P.comp[0].type = _lib.NFW
+    P.comp[0].track = -1
+    ctrl = _lib.Ctrl(solver=8, max_steps=10, rtol=1e-7, atol=1e-7, dtmin=0.3, dtmax=np.inf)
+    bad = _lib.Ctrl(solver=3, max_steps=10, rtol=1e-7, atol=1e-7, dtmin=0.3, dtmax=np.inf)
+    z = C.c_void_p(0)
+    assert L.ssb_variational_f64(C.byref(P), 1, 0, z, z, z, z, 0.0, ctrl, z, z, z, z, z, z) == 0            # empty batch
+    assert L.ssb_variational_f64(C.byref(P), 3, 4, z, z, z, z, 0.0, ctrl, z, z, z, z, z, z) == -2           # order 3 does not exist
+    assert L.ssb_variational_f64(C.byref(P), 1, 4, z, z, z, z, 0.0, ctrl, z, z, z, z, z, z) == -1           # NULL arrays
+    assert L.ssb_variational_f64(C.byref(P), 1, 4, z, z, z, z, 0.0, bad, z, z, z, z, z, z) == -2            # solver
+    assert L.ssb_shared_step_orbits_f64(C.byref(P), 0, z, 0.0, 1.0, ctrl, z, z, z, z, 0, z) == 0
+    assert L.ssb_shared_step_orbits_f64(C.byref(P), 5, z, 0.0, 1.0, ctrl, z, z, z, z, 0, z) == -1
+    assert L.ssb_shared_scratch_bytes(1000) >= 18 * 1000 * 8
+    assert L.ssb_nbody_integrate_f64(None, 2000, z, 1.0, 0.1, z, 0.0, 1.0, z, 1, ctrl, z, z, z, z, 0, z) == -1 and b"1024" in L.ssb_last_error()
+    assert L.ssb_nbody_integrate_f64(None, 3, z, 1.0, 0.1, z, 0.0, 1.0, z, 1, ctrl, z, z, z, z, 0, z) == -1           # NULL masses
+    assert L.ssb_nbody_scratch_bytes(100) == 8 * 3 * 100 * 18
