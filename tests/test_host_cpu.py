@@ -134,6 +134,19 @@ def compute(rank, world, n_local):          # the oracle stands in for the CUDA 
     return torch.from_numpy(lead_all[sel].copy()), torch.from_numpy(trail_all[sel].copy())
 lead, trail = par.gen_stream_sharded(None, ts, w0, 1e4, 0, None, rank, world, compute=compute)
 assert lead.shape == (37, 6) and np.array_equal(lead.numpy(), lead_all) and np.array_equal(trail.numpy(), trail_all)
+# C4 sharding: particles dealt out interleaved, only final states + response summaries are exchanged
+sh = dict(m=np.ones(3), rs=np.array([0.2, 0.3, 0.4]), x0=np.array([[5., 5, 5], [-5, 5, 0], [0, -8, 3]]), v=np.full((3, 3), 0.1), t0=np.array([-500., -300, -100]))
+osh = O.Program().subhalos(O.PR_HERNQUIST, sh["m"], sh["rs"], sh["x0"], sh["v"], sh["t0"], 150.0)
+w0r = np.vstack([lead_all[:9] * 0 + np.asarray(w0)]) + np.arange(9)[:, None] * 1e-3
+t0r = ts[:9].copy()
+w_all, D_all, _, _ = O.linear_response(orc, osh, w0r, t0r, 0.0, solver=5, rtol=1e-7, atol=1e-7)
+def rcompute(w0_l, t0_l):
+    wl, Dl, _, _ = O.linear_response(orc, osh, w0_l.numpy(), t0_l.numpy(), 0.0, solver=5, rtol=1e-7, atol=1e-7)
+    return torch.from_numpy(wl), torch.from_numpy(Dl)
+Msh = np.array([1e6, 3e7, 2e8])
+wg, dg, D_l, sel = par.linear_response_sharded(None, None, torch.from_numpy(w0r), torch.from_numpy(t0r), 0.0, None, rank, world, Msh, dr_s=[0.1, 0.0, -0.2], compute=rcompute)
+ref = np.einsum("s,nsk->nk", Msh, D_all[:, :, :6]) + np.einsum("s,nsk->nk", Msh * np.array([0.1, 0.0, -0.2]), D_all[:, :, 6:])
+assert np.array_equal(wg.numpy(), w_all) and np.allclose(dg.numpy(), ref, rtol=1e-13, atol=0) and np.array_equal(D_l.numpy(), D_all[sel.numpy()])
 s = par.allreduce_sum(torch.tensor([float(rank + 1)]), world)
 assert s.item() == world * (world + 1) / 2
 dist.barrier(); dist.destroy_process_group()
