@@ -141,6 +141,11 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
         h = fmax(h, c.dtmin);
         tnext = fmin(T0 + h, T1);
     }
+    double tq_a = __longlong_as_double(0x7ff0000000000000LL), tq_b = tq_a;      // MODE 0: the next two save times (mirrored time)
+    if (MODE == 0 && valid) {
+        if (M > 0) tq_a = tsp[0] * dir;
+        if (M > 1) tq_b = tsp[1] * dir;
+    }
     for (;;) {
         bool active = valid && status == 0 && tprev < T1;
         if (active && n_steps >= c.max_steps) { status = 1; active = false; }
@@ -178,9 +183,11 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
                         for (int k = 0; k < 3; ++k) r[14 + 3 * l + k] = F[l][k];
                 }
             } else if (MODE == 0) {
-                // SaveAt(ts): every ts[save_idx] <= tnext is interpolated inside this accepted step
+                // SaveAt(ts): every ts[save_idx] <= tnext is interpolated inside this accepted step.  The next two save times are kept
+                // in registers (tq_a, tq_b): a step without a save costs no memory access, and the reload after a save is not needed
+                // until the save after it.
                 while (save_idx < M) {
-                    const double tq = tsp[save_idx] * dir;
+                    const double tq = tq_a;
                     if (!(tq <= tnext)) break;
                     double xo[3], po[3];
                     if (tq == tnext) {
@@ -193,6 +200,8 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
 #pragma unroll
                     for (int k = 0; k < 3; ++k) { o[k] = xo[k]; o[3 + k] = dir * po[k]; }
                     save_idx++;
+                    tq_a = tq_b;
+                    tq_b = (save_idx + 1 < M) ? tsp[save_idx + 1] * dir : __longlong_as_double(0x7ff0000000000000LL);
                 }
             }
 #pragma unroll
