@@ -8,7 +8,9 @@
 #include "ssb_potential.cuh"
 #include "ssb_rk.cuh"
 
+#ifndef SSB_ORBIT_THREADS
 #define SSB_ORBIT_THREADS 128
+#endif
 #ifndef SSB_ORBIT_MIN_BLOCKS
 #define SSB_ORBIT_MIN_BLOCKS 3
 #endif
