@@ -138,6 +138,15 @@ int ssb_orbit_dense_f64(const ssb_potential* pot, const double* w0 /*[6] device*
                         const double* ts, int64_t M, ssb_ctrl ctrl, double* ys /*[M,6]*/, int32_t* status /*[1]*/,
                         int32_t* nsteps /*[3]*/, void* scratch, size_t scratch_bytes, void* stream);
 size_t ssb_scratch_bytes(int32_t max_steps);
+/* A3/A8  batched dense solutions: integrate_orbit(dense=True) under vmap (main.py:139-162, dense branch) as used by
+ * gen_stream_scan_dense / gen_stream_vmapped_dense (main.py:376-430) and streamhelpers.eval_dense_stream (streamhelpers.py:23-53).
+ * Every accepted step of every orbit is recorded (rec_cap slots of 512 B per orbit; more accepted steps than slots -> status 1);
+ * ssb_orbit_record_eval_f64 then evaluates all N interpolants at one common time (per_orbit = 0) or at tq[i]; +inf outside the
+ * integrated interval.  recs >= ssb_record_bytes(N, rec_cap) bytes. */
+int ssb_orbit_record_f64(const ssb_potential* pot, int64_t N, const double* w0, const double* t0, const double* t1, ssb_ctrl ctrl, int32_t rec_cap,
+                         void* recs, size_t rec_bytes, int32_t* status, int32_t* nsteps, void* stream);
+int ssb_orbit_record_eval_f64(int32_t solver, int64_t N, const void* recs, int32_t rec_cap, const double* tq, int32_t per_orbit, double* ys, void* stream);
+size_t ssb_record_bytes(int64_t N, int32_t rec_cap);
 /* Solution.evaluate(t) of a dense=True solve (main.py:131, 141): interpolate M more times inside the steps recorded in `scratch` by a
  * previous ssb_orbit_dense_f64 call with the same solver; ys[M,6] (+inf outside the integrated interval). */
 int ssb_orbit_dense_eval_f64(int32_t solver, const void* scratch, const double* ts, int64_t M, double* ys, void* stream);

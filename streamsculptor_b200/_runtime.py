@@ -434,3 +434,34 @@ def variational_term(pot, order, t, y):
     dy = empty(yd.shape)
     _lib.check(_lib.lib().ssb_variational_term_f64(C.byref(P), int(order), float(t), ptr(yd), ptr(dy), stream_ptr()))
     return dy
+
+
+class DenseOrbits:
+    """N dense solutions living on the device (the vmapped `diffrax.Solution`s of gen_stream_*_dense, main.py:376-430):
+    every accepted step of every orbit recorded by ssb_orbit_record_f64; evaluate(t) interpolates all of them."""
+
+    MAX_BYTES = 64 << 30
+
+    def __init__(self, pot, w0, t0, t1, ctrl, rec_cap=None):
+        tt = torch()
+        P, _keep = lower(pot)
+        self.N, self.solver = int(w0.shape[0]), int(ctrl.solver)
+        self.rec_cap = int(rec_cap if rec_cap is not None else min(int(ctrl.max_steps), 512))
+        nbytes = _lib.lib().ssb_record_bytes(self.N, self.rec_cap)
+        if nbytes > self.MAX_BYTES:
+            raise MemoryError(f"dense solutions of {self.N} orbits x {self.rec_cap} steps need {nbytes / 2**30:.0f} GiB; lower rec_cap or save "
+                              "snapshots (integrate_orbit_batch_vmapped with ts[N,M]) instead")
+        self.recs = empty(((nbytes + 7) // 8,))
+        self.status, self.nsteps = empty((self.N,), tt.int32), empty((self.N, 3), tt.int32)
+        _lib.check(_lib.lib().ssb_orbit_record_f64(C.byref(P), self.N, ptr(w0), ptr(t0), ptr(t1), ctrl, self.rec_cap, ptr(self.recs), nbytes,
+                                                   ptr(self.status), ptr(self.nsteps), stream_ptr()))
+
+    def evaluate(self, t):
+        """States of all N orbits at time t (scalar) or at t[i] (array of length N): device tensor [N, 6]; +inf outside an orbit's interval."""
+        tq = to_dev(np.atleast_1d(np.asarray(t.cpu() if hasattr(t, "cpu") else t, dtype=np.float64)))
+        per = int(tq.shape[0] == self.N and self.N > 1)
+        if not per and tq.shape[0] != 1:
+            raise ValueError("evaluate(t): t must be a scalar or have one entry per orbit")
+        ys = empty((self.N, 6))
+        _lib.check(_lib.lib().ssb_orbit_record_eval_f64(self.solver, self.N, ptr(self.recs), self.rec_cap, ptr(tq), per, ptr(ys), stream_ptr()))
+        return ys

@@ -140,8 +140,8 @@ int ssb_gen_stream_host(const ssb_potential* pot_h, const ssb_potential* pot_rel
     if (int e = pool.up(Msat, 8 * (size_t)Nts, &dms)) return e;
     if (normals) { if (int e = pool.up(normals, 32 * (size_t)Nts, &dnr)) return e; }
     void *dl, *dtr, *dstat, *dns, *scr;
-    if (int e = pool.alloc(&dl, 48 * n)) return e;
-    if (int e = pool.alloc(&dtr, 48 * n)) return e;
+    if (int e = pool.alloc(&dl, 96 * n)) return e;             // lead and trail adjacent: the orbit kernel writes them in place
+    dtr = (char*)dl + 48 * n;
     if (int e = pool.alloc(&dstat, 8 * n)) return e;
     if (int e = pool.alloc(&dns, 24 * n)) return e;
     const size_t sb = ssb_stream_scratch_bytes(Nts, ctrl.max_steps);

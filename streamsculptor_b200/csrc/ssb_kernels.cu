@@ -308,6 +308,66 @@ __global__ void dense_eval_kernel(const double* scratch, const double* ts, int64
     for (int k = 0; k < 3; ++k) { o[k] = xo[k]; o[3 + k] = dir * po[k]; }
 }
 
+// ---- batched dense solutions (gen_stream_*_dense, main.py:376-430; integrate_orbit(dense=True) under vmap) ----
+// record layout per orbit: hdr[8] {n_recorded, status, -, -, dir} + rec[cap][SSB_REC_STRIDE], i.e. the K0 layout repeated N times
+template <int SOLVER, int SIG>
+__global__ void __launch_bounds__(SSB_ORBIT_THREADS, SSB_ORBIT_MIN_BLOCKS) record_kernel(const __grid_constant__ ssb_potential Pin, int64_t N, const double* w0,
+                                                                                         const double* t0, const double* t1, CtrlDev c, double* recs,
+                                                                                         int rec_cap, int32_t* status_out, int32_t* nsteps_out) {
+    __shared__ ssb_potential sP;
+    stage_potential(&sP, &Pin);
+    logtab_init();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < N;
+    const int64_t ii = valid ? i : 0;
+    double* scratch = recs + (size_t)ii * (8 + (size_t)rec_cap * SSB_REC_STRIDE);
+    int status, n_steps, n_acc, n_rej;
+    integrate_one<SOLVER, 1, SIG>(&sP, &Pin, w0 + 6 * ii, t0[ii], t1[ii], nullptr, 0, nullptr, c, valid, status, n_steps, n_acc, n_rej, scratch + 8, rec_cap);
+    if (valid) {
+        if (status == 0 && n_acc > rec_cap) status = 1;             // more accepted steps than record slots: treated like max_steps
+        scratch[0] = (double)min(n_acc, rec_cap); scratch[1] = (double)status; scratch[4] = (t0[ii] < t1[ii]) ? 1.0 : -1.0;
+        status_out[i] = status;
+        nsteps_out[3 * i] = n_steps; nsteps_out[3 * i + 1] = n_acc; nsteps_out[3 * i + 2] = n_rej;
+    }
+}
+// ys[i] = orbit i evaluated at tq[i] (per_orbit) or tq[0]; +inf outside the recorded interval
+template <int SOLVER>
+__global__ void record_eval_kernel(const double* recs, int rec_cap, int64_t N, const double* tq, int per_orbit, double* ys) {
+    constexpr int S = Tab<SOLVER>::S;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double* scratch = recs + (size_t)i * (8 + (size_t)rec_cap * SSB_REC_STRIDE);
+    const int n = (int)scratch[0];
+    const double dir = scratch[4];
+    const double* rec = scratch + 8;
+    const double t = tq[per_orbit ? i : 0] * dir;
+    double* o = ys + 6 * i;
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (rec[(size_t)mid * SSB_REC_STRIDE + 1] < t) lo = mid + 1; else hi = mid; }
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    if (lo >= n || n == 0 || t < rec[0]) {
+        for (int k = 0; k < 6; ++k) o[k] = inf;
+        return;
+    }
+    const double* r = rec + (size_t)lo * SSB_REC_STRIDE;
+    const double ta = r[0], tb = r[1];
+    double x[3], p[3], x1[3], p1[3], F[S][3], xo[3], po[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { x[k] = r[2 + k]; p[k] = r[5 + k]; x1[k] = r[8 + k]; p1[k] = r[11 + k]; }
+#pragma unroll
+    for (int l = 0; l < S; ++l)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) F[l][k] = r[14 + 3 * l + k];
+    if (t == tb) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { xo[k] = x1[k]; po[k] = p1[k]; }
+    } else {
+        rk_dense<SOLVER>(x, p, x1, p1, tb - ta, F, (t - ta) / (tb - ta), xo, po);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[k] = xo[k]; o[3 + k] = dir * po[k]; }
+}
+
 // =============================================================================================
 // field evaluation kernels
 // =============================================================================================
@@ -811,6 +871,41 @@ int ssb_orbit_dense_f64(const ssb_potential* pot, const double* w0, double t0, d
     if (scratch_bytes < ssb_scratch_bytes(ctrl.max_steps)) return ssb_set_error(SSB_ERR_SCRATCH, "orbit_dense: scratch too small");
     cudaStream_t st = (cudaStream_t)stream;
     return dense_launch(pot, w0, t0, t1, nullptr, nullptr, ts, M, ctrl, ys, status, nsteps, (double*)scratch, st);
+}
+
+size_t ssb_record_bytes(int64_t N, int32_t rec_cap) { return sizeof(double) * (size_t)(N > 0 ? N : 1) * (8 + (size_t)(rec_cap > 0 ? rec_cap : 1) * SSB_REC_STRIDE); }
+
+int ssb_orbit_record_f64(const ssb_potential* pot, int64_t N, const double* w0, const double* t0, const double* t1, ssb_ctrl ctrl, int32_t rec_cap,
+                         void* recs, size_t rec_bytes, int32_t* status, int32_t* nsteps, void* stream) {
+    if (int e = ssb_validate_potential(pot)) return e;
+    if (int e = ssb_validate_ctrl(ctrl)) return e;
+    if (N < 0 || rec_cap < 1) return ssb_set_error(SSB_ERR_ARG, "orbit_record: negative N or rec_cap < 1");
+    if (N == 0) return 0;
+    if (!w0 || !t0 || !t1 || !recs || !status || !nsteps) return ssb_set_error(SSB_ERR_ARG, "orbit_record: NULL array");
+    if (rec_bytes < ssb_record_bytes(N, rec_cap)) return ssb_set_error(SSB_ERR_SCRATCH, "orbit_record: record buffer too small (ssb_record_bytes)");
+    const CtrlDev c = to_dev(ctrl);
+    ssb_potential pc;
+    const int sig = ssb_canonicalize(pot, &pc);
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = nblk(N, SSB_ORBIT_THREADS);
+#define SSB_LAUNCH_REC(S, SG) record_kernel<S, SG><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, N, w0, t0, t1, c, (double*)recs, rec_cap, status, nsteps)
+#define SSB_LAUNCH_REC_SIG(S) do { switch (sig) { case SIG_NHM: SSB_LAUNCH_REC(S, SIG_NHM); break; case SIG_NHHM: SSB_LAUNCH_REC(S, SIG_NHHM); break; \
+        default: record_kernel<S, SIG_GENERIC><<<grid, SSB_ORBIT_THREADS, 0, st>>>(*pot, N, w0, t0, t1, c, (double*)recs, rec_cap, status, nsteps); } } while (0)
+    if (ctrl.solver == 5) SSB_LAUNCH_REC_SIG(5); else SSB_LAUNCH_REC_SIG(8);
+    CKL("record_kernel");
+    return 0;
+}
+
+int ssb_orbit_record_eval_f64(int32_t solver, int64_t N, const void* recs, int32_t rec_cap, const double* tq, int32_t per_orbit, double* ys, void* stream) {
+    if (solver != 5 && solver != 8) return ssb_set_error(SSB_ERR_UNSUPPORTED, "solver must be 5 (Dopri5) or 8 (Dopri8)");
+    if (N < 0 || rec_cap < 1) return ssb_set_error(SSB_ERR_ARG, "orbit_record_eval: negative N or rec_cap < 1");
+    if (N == 0) return 0;
+    if (!recs || !tq || !ys) return ssb_set_error(SSB_ERR_ARG, "orbit_record_eval: NULL array");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (solver == 5) record_eval_kernel<5><<<nblk(N, 128), 128, 0, st>>>((const double*)recs, rec_cap, N, tq, per_orbit, ys);
+    else record_eval_kernel<8><<<nblk(N, 128), 128, 0, st>>>((const double*)recs, rec_cap, N, tq, per_orbit, ys);
+    CKL("record_eval_kernel");
+    return 0;
 }
 
 int ssb_orbit_dense_eval_f64(int32_t solver, const void* scratch, const double* ts, int64_t M, double* ys, void* stream) {

@@ -220,10 +220,41 @@ class Potential:
         return self.gen_stream_vmapped(ts=ts, prog_w0=prog_w0, Msat=Msat, seed_num=seed_num, solver=solver, kval_arr=kval_arr, rtol=rtol,
                                        atol=atol, dtmin=dtmin, dtmax=dtmax, max_steps=max_steps, normals=normals)
 
-    def gen_stream_vmapped_dense(self, *a, **k):
-        raise NotImplementedError("dense per-particle stream interpolants (main.py:376-430) are not on the B200 hot path yet")
+    def gen_stream_vmapped_dense(self, ts=None, prog_w0=None, Msat=None, seed_num=None, solver=Dopri5(scan_kind='bounded'), kval_arr=1.0, rtol=1e-7,
+                                 atol=1e-7, dtmin=0.3, dtmax=None, max_steps=10_000, normals=None, rec_cap=None):
+        """Dense stream model (main.py:376-430): every particle's orbit from its release time to ts[-1] as a dense interpolant.
+        Returns a DenseStream; `streamhelpers.eval_dense_stream(t, dense_stream)` gives (lead, trail) at any time (+inf for particles
+        not yet released at t).  rec_cap = record slots per orbit (default min(max_steps, 512) accepted steps)."""
+        tt = rt.torch()
+        ts_d, w0_d, Ms, kv, nr = self._stream_inputs(ts, prog_w0, Msat, kval_arr, normals)
+        pl, pt, vl, vt = self.gen_stream_ics(ts=ts_d, prog_w0=w0_d, Msat=Ms, seed_num=seed_num, solver=solver, kval_arr=kval_arr, rtol=rtol, atol=atol,
+                                             dtmin=dtmin, dtmax=dtmax, max_steps=max_steps, normals=normals)
+        n = ts_d.shape[0] - 1
+        w0 = tt.cat([tt.cat([pl, vl], 1)[:n], tt.cat([pt, vt], 1)[:n]]).contiguous()            # lead block, trail block
+        t0 = tt.cat([ts_d[:n], ts_d[:n]]).contiguous()
+        t1 = ts_d[-1].expand(2 * n).contiguous()
+        ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
+        return DenseStream(rt.DenseOrbits(self, w0, t0, t1, ctrl, rec_cap), n)
 
     gen_stream_scan_dense = gen_stream_vmapped_dense
+
+
+class DenseStream:
+    """What gen_stream_*_dense returns: 2(N-1) dense orbits (lead block, trail block) on the device."""
+
+    def __init__(self, orbits, n):
+        self.orbits, self.n = orbits, n
+
+    def evaluate(self, t):
+        ys = self.orbits.evaluate(t)
+        return ys[: self.n], ys[self.n:]
+
+    def evaluate_id(self, t, idx, lead=True):
+        """One particle's trajectory at the times t (streamhelpers.eval_dense_stream_id)."""
+        tq = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        row = int(idx) + (0 if lead else self.n)
+        out = np.stack([self.orbits.evaluate(float(v))[row].cpu().numpy() for v in tq])
+        return out[0] if np.ndim(t) == 0 else out
 
 
 class _DenseEval:

@@ -4,7 +4,7 @@ import numpy as np
 from . import _runtime as rt
 from .main import DEFAULT_KVALS
 from .potential import Potential_Combine
-from .solvers import Dopri5
+from .solvers import Dopri5, Dopri8
 from .units import usys
 
 
@@ -155,3 +155,51 @@ def gen_stream_vmapped_with_pert_Chen25_fixed_prog(pot_base=None, pot_pert=None,
     ics, orb = gen_stream_ics_Chen25(pot_base=pot_base, ts=ts, prog_w0=prog_w0, Msat=Msat, key=key, solver=solver, max_steps=max_steps, rtol=rtol,
                                      atol=atol, dtmin=dtmin, normals=normals)
     return _chen25_integrate([pot_base, pot_pert], prog_pot, ics, orb, ts, solver, rtol, atol, dtmin, None, max_steps)
+
+
+# ---- dense streams and streaklines (streamhelpers.py:23-53, 656-732) -------------------------------------------------
+def eval_dense_stream(t_eval=None, dense_stream=None):
+    """(lead, trail) of a dense stream model at time t_eval (streamhelpers.py:23-31); device tensors [N-1, 6]."""
+    return dense_stream.evaluate(t_eval)
+
+
+def eval_dense_stream_id(time=None, interp_func=None, idx=None, lead=True):
+    """Trajectory of particle `idx` of a dense stream (streamhelpers.py:33-53)."""
+    return interp_func.evaluate_id(time, idx, lead=lead)
+
+
+def get_Streakline_ICs(pot, prog_w0, Msat, t0, t1, Nstrip, solver=Dopri8(), rtol=1e-6, atol=1e-6):
+    """Streakline initial conditions (streamhelpers.py:656-699): particles leave L1 / L2 with the cluster's angular velocity.
+    The progenitor orbit and the Hessians come from the device; the O(Nstrip) vector algebra is numpy."""
+    ts = np.linspace(t0, t1, Nstrip)
+    prog = np.asarray(pot.integrate_orbit(w0=prog_w0, ts=ts, solver=solver, rtol=rtol, atol=atol).ys)
+    x, v = prog[:, :3], prog[:, 3:]
+    r = np.sqrt(np.sum(x ** 2, axis=1))
+    r_hat = x / r[:, None]
+    H = np.asarray(pot.jacobian_force(x, ts))                                   # Hessian of Phi at the progenitor (main.py:59-65)
+    d2phidr2 = np.einsum("ni,nij,nj->n", r_hat, H, r_hat)                       # main.py:76-85
+    omega = np.linalg.norm(np.cross(x, v), axis=1) / r ** 2                     # main.py:88-96
+    r_tidal = (pot._G * Msat / (omega ** 2 - d2phidr2)) ** (1.0 / 3.0)          # main.py:98-104
+    L_close, L_far = x - r_hat * r_tidal[:, None], x + r_hat * r_tidal[:, None]  # main.py:106-112
+    v_hat = v / np.linalg.norm(v, axis=1)[:, None]
+    sintheta = np.linalg.norm(np.cross(r_hat, v_hat), axis=1)
+
+    def release_velocity(q_rel):
+        return (omega * np.sqrt(np.sum(q_rel ** 2, axis=1)) / sintheta)[:, None] * v_hat
+
+    return L_close, release_velocity(L_close), L_far, release_velocity(L_far), ts
+
+
+def gen_streakline(pot, prog_w0, Msat, t0, t1, Nstrip, solver=Dopri8(), rtol=1e-6, atol=1e-6):
+    """Streakline stream (streamhelpers.py:701-732): every particle integrated from its stripping time to t1."""
+    pos_lead, vel_lead, pos_trail, vel_trail, tstrip = get_Streakline_ICs(pot=pot, prog_w0=prog_w0, Msat=Msat, t0=t0, t1=t1, Nstrip=Nstrip,
+                                                                           solver=solver, rtol=rtol, atol=atol)
+    w0 = np.vstack([np.hstack([pos_lead, vel_lead]), np.hstack([pos_trail, vel_trail])])
+    tt = np.concatenate([tstrip, tstrip])
+    sol = pot.integrate_orbit_batch_vmapped(w0=w0, ts=np.full((len(tt), 1), float(t1)), solver=solver, rtol=rtol, atol=atol, t0=tt,
+                                            t1=np.full(len(tt), float(t1)))
+    ys = np.asarray(sol.ys)[:, 0]
+    # the last particle is released AT t1: a zero-length solve returns its initial condition in the reference
+    zero = tt == t1
+    ys[zero] = w0[zero]
+    return ys[:Nstrip], ys[Nstrip:], tstrip

@@ -721,3 +721,54 @@ def test_progenitor_and_custom_subhalo_wrappers(cuda):
     tq = float(sh["t0"][2]) + 20.0
     assert np.array_equal(cust.potential_per_SH(x[0], tq), expl.potential_per_SH(x[0], tq))
     assert np.array_equal(cust.gradient(x, np.full(2, tq)), expl.gradient(x, np.full(2, tq)))
+
+
+def test_dense_stream_and_streakline(cuda):
+    """gen_stream_vmapped_dense + eval_dense_stream (main.py:409-430, streamhelpers.py:23-53) and gen_streakline
+    (streamhelpers.py:656-732) against the oracle."""
+    import streamsculptor_b200 as ssc
+    orc, prod = mw3_oracle(), mw3_product()
+    prog_today = [20.0, 0.0, 20.0, 0.0, 0.15, 0.0]
+    back, _, _ = orc.integrate_orbits(prog_today, 0.0, -2000.0)
+    ts = np.linspace(-2000.0, 0.0, 201)
+    nr = np.random.Generator(np.random.PCG64(2)).standard_normal((201, 4))
+    kw = dict(ts=ts, prog_w0=back[0, 0], Msat=1e4, seed_num=583, normals=nr, dtmin=1.0, dtmax=1.0)          # fixed 1 Myr steps: exact comparison
+    for solver, sid in ((ssc.Dopri8(), 8), (ssc.Dopri5(), 5)):
+        ds = prod.gen_stream_vmapped_dense(solver=solver, rec_cap=2048, **kw)            # 2000 fixed steps for the oldest particle
+        lead_f, trail_f = prod.gen_stream_vmapped(solver=solver, **kw)
+        le, te = ssc.eval_dense_stream(0.0, ds)
+        assert relerr(le.cpu().numpy(), lead_f) < 1e-12 and relerr(te.cpu().numpy(), trail_f) < 1e-12      # at ts[-1]: the final states
+        # at an interior time: particles released before it are interpolated, the others are +inf
+        t_eval = -733.3
+        le, te = [a.cpu().numpy() for a in ssc.eval_dense_stream(t_eval, ds)]
+        released = ts[:-1] <= t_eval
+        assert np.isinf(le[~released]).all() and np.isfinite(le[released]).all()
+        pl, pt, vl, vt, = orc.gen_stream_ics(ts, back[0, 0], 1e4, 583, solver=sid, normals=nr, dtmin=1.0, dtmax=1.0)[:4]
+        w0l = np.hstack([pl, vl])[:-1][released]
+        yo, sto, _ = orc.integrate_orbits(w0l, ts[:-1][released], 0.0, ts=np.array([t_eval, 0.0]), solver=sid, dtmin=1.0, dtmax=1.0)
+        ok = ts[:-1][released] < t_eval
+        assert relerr(le[released][ok], yo[ok, 0]) < 1e-10
+        one = ssc.eval_dense_stream_id(time=np.array([-500.0, -100.0]), interp_func=ds, idx=10, lead=False)
+        yo1, _, _ = orc.integrate_orbits(np.hstack([pt, vt])[10], ts[10], 0.0, ts=np.array([-500.0, -100.0]), solver=sid, dtmin=1.0, dtmax=1.0)
+        assert relerr(one, yo1[0]) < 1e-10
+    # too few record slots -> status 1 (like max_steps), never silent truncation
+    ds_small = prod.gen_stream_vmapped_dense(solver=ssc.Dopri8(), rec_cap=16, **kw)
+    assert int((ds_small.orbits.status == 1).sum()) > 0
+    # ---- streakline ----
+    Ns = 101
+    Lc, vl_, Lf, vt_, tstrip = ssc.get_Streakline_ICs(prod, back[0, 0], 1e4, -2000.0, 0.0, Ns, solver=ssc.Dopri8(), rtol=1e-9, atol=1e-9)
+    po, _, _ = orc.integrate_orbits(back[0, 0], -2000.0, 0.0, ts=tstrip, rtol=1e-9, atol=1e-9)
+    x, v = po[0, :, :3], po[0, :, 3:]
+    r = np.linalg.norm(x, axis=1); rh = x / r[:, None]
+    H = orc.hessian(x, tstrip)
+    om = np.linalg.norm(np.cross(x, v), axis=1) / r ** 2
+    rt_ = (O.G_KPC_MYR_MSUN * 1e4 / (om ** 2 - np.einsum("ni,nij,nj->n", rh, H, rh))) ** (1 / 3)
+    vh = v / np.linalg.norm(v, axis=1)[:, None]
+    st_ = np.linalg.norm(np.cross(rh, vh), axis=1)
+    Lc_o = x - rh * rt_[:, None]
+    vl_o = (om * np.linalg.norm(Lc_o, axis=1) / st_)[:, None] * vh
+    assert scaled_err(Lc, Lc_o, 1e-8).max() < 10.0 and scaled_err(vl_, vl_o, 1e-8).max() < 10.0
+    lead, trail, tstrip2 = ssc.gen_streakline(prod, back[0, 0], 1e4, -2000.0, 0.0, Ns, solver=ssc.Dopri8(), rtol=1e-9, atol=1e-9)
+    yo, _, _ = orc.integrate_orbits(np.hstack([Lc, vl_])[:-1], tstrip[:-1], 0.0, rtol=1e-9, atol=1e-9)
+    assert lead.shape == (Ns, 6) and np.mean(scaled_err(lead[:-1], yo[:, 0], 1e-9) < 10.0) > 0.85
+    assert np.array_equal(lead[-1], np.hstack([Lc, vl_])[-1])                   # released at t1: zero-length solve
