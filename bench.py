@@ -162,6 +162,17 @@ def ncu_traffic():
     return tot, os.path.relpath(files[-1], ROOT)
 
 
+def ncu_counted_frac():
+    """(2 DFMA + DADD + DMUL) per cycle / DFMA peak of the same committed capture: the counter-based fp64 rate BASELINE.md section 3 names."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*orbit_kernel_ncu.txt")))
+    if not files:
+        return None
+    m = re.search(r"counted fp64 FLOP rate .* = ([0-9.]+)", open(files[-1]).read())
+    return float(m.group(1)) if m else None
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
@@ -290,6 +301,7 @@ def run_ours(args, rank, world):
                 "frac_of_nominal": achieved / FP64_NOMINAL_TFLOPS,
                 "hbm_gbs_of_kernel": (w0_all.numel() * 8 + ys.numel() * 8 + t0_all.numel() * 16 + ns.numel() * 4) / (k_ms * 1e-3) / 1e9}
     roofline["traffic"], roofline["traffic_source"] = ncu_traffic()
+    roofline["ncu_counted_fp64_frac"] = ncu_counted_frac()
     # ---- CPU baseline on this box's host cores: bounded sample of the same workload (rank 0, N = 1 only) ----
     cpu = None
     if world == 1:

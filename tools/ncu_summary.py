@@ -13,5 +13,16 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread",
 for r in rows[2:]:
     print("-----")
     for h, u, v in zip(hdr, rows[1], r):
-        if any(h == w or (w in h and ("stalled" in w)) for w in want) or "issue_stalled" in h and h.endswith("per_issue_active.ratio") or h.startswith("smsp__sass_thread_inst_executed_op_d") and h.endswith(".sum") or "lsu_mem_local" in h and h.endswith(".sum"):
+        if any(h == w or (w in h and ("stalled" in w)) for w in want) or "issue_stalled" in h and h.endswith("per_issue_active.ratio") or h.startswith("smsp__sass_thread_inst_executed_op_d") and h.endswith(".sum") or "lsu_mem_local" in h and h.endswith(".sum") or h.startswith("smsp__sass_thread_inst_executed_op_d") and h.endswith(".sum.per_cycle_elapsed") or h == "sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained":
             print(f"{h} [{u}] = {v}")
+
+# ncu-counted fp64 FLOP rate as a fraction of the DFMA peak: (2 dfma + dadd + dmul) / (2 * peak dfma/cycle)
+for r in rows[2:]:
+    d = dict(zip(hdr, r))
+    try:
+        f = lambda k: float(d[k].replace(",", ""))
+        frac = (2 * f("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed") + f("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed")
+                + f("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed")) / (2 * f("sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained"))
+        print(f"derived: counted fp64 FLOP rate (2 DFMA + DADD + DMUL) / DFMA peak = {frac:.3f}")
+    except Exception:
+        pass
