@@ -251,7 +251,14 @@ int ssb_variational_f64(const ssb_potential* pot, int32_t order, int64_t N, cons
 /* the variational field at one state y[42 | 258] -> dy (device pointers), for unit tests */
 int ssb_variational_term_f64(const ssb_potential* pot, int32_t order, double t, const double* y, double* dy, void* stream);
 
-/* ---- host-pointer conveniences (H2D, launch, D2H, synchronise) - what a CPU-side plugin call looks like ---------- */
+/* ---- host-pointer conveniences (H2D, launch, D2H, synchronise) - what a CPU-side plugin call looks like ----------
+ * Zero-copy outputs: if the final-state outputs are PINNED (page-locked, mapped) host memory the orbit kernel writes them
+ * directly over PCIe while the remaining orbits integrate, and no D2H copy follows:
+ *   ssb_gen_stream_host      - lead and trail are the two halves of ONE pinned [2, n_local, 6] buffer (trail == lead + 6 n_local),
+ *                              status [2 n_local] and nsteps [2 n_local, 3] pinned too;
+ *   ssb_orbit_integrate_host - final-state mode (M == 1, ts_per_orbit, ts == t1) with ys, status, nsteps pinned.
+ * Any other combination (pageable memory, separate lead / trail allocations) takes the staged path: results in HBM, then
+ * cudaMemcpyAsync.  Both paths give identical bytes.  SSB_HOST_ZEROCOPY=0 in the environment forces the staged path. */
 int ssb_orbit_integrate_host(const ssb_potential* pot_hostptrs, int64_t N, const double* w0, const double* t0,
                              const double* t1, const double* ts, int32_t M, int32_t ts_per_orbit, ssb_ctrl ctrl,
                              double* ys, int32_t* status, int32_t* nsteps);

@@ -2,8 +2,14 @@
 // Each call uploads its inputs (stream-ordered allocations from the CUDA memory pool, so repeated calls do not
 // pay cudaMalloc), enqueues the same kernels as the device-pointer entry points, downloads the results and
 // synchronises.  Pinned host buffers make the copies DMA at full PCIe rate; pageable buffers also work.
+//
+// Zero-copy outputs: when the final-state outputs of ssb_gen_stream_host / ssb_orbit_integrate_host are PINNED (page-locked,
+// mapped) host buffers, the orbit kernel receives their device aliases and writes every warp's results straight into host
+// memory as whole 256-byte runs while the other orbits are still integrating - the device-to-host transfer (64 MB for a
+// 1e6-particle stream) disappears from the critical path.  SSB_HOST_ZEROCOPY=0 forces the staged copies (A/B measurement).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -85,6 +91,21 @@ int upload_potential(const ssb_potential* h, ssb_potential* d, Pool& pool) {
     return 0;
 }
 
+// device alias of a pinned + mapped host range [h, h + bytes), or nullptr (pageable memory, device memory, zero-copy disabled)
+void* pinned_alias(const void* h, size_t bytes) {
+    if (!h || !bytes) return nullptr;
+    const char* env = getenv("SSB_HOST_ZEROCOPY");
+    if (env && env[0] == '0') return nullptr;
+    cudaPointerAttributes lo, hi;
+    if (cudaPointerGetAttributes(&lo, h) != cudaSuccess || cudaPointerGetAttributes(&hi, (const char*)h + bytes - 1) != cudaSuccess) {
+        cudaGetLastError();          // older drivers report pageable memory as an error: clear it
+        return nullptr;
+    }
+    if (lo.type != cudaMemoryTypeHost || hi.type != cudaMemoryTypeHost || !lo.devicePointer || !hi.devicePointer) return nullptr;
+    if ((const char*)hi.devicePointer - (const char*)lo.devicePointer != (ptrdiff_t)(bytes - 1)) return nullptr;      // one contiguous mapping
+    return lo.devicePointer;
+}
+
 int down(void* h, const void* d, size_t bytes, cudaStream_t st) {
     if (!bytes) return 0;
     return ssb_cuda_check(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st), "D2H");
@@ -107,16 +128,25 @@ int ssb_orbit_integrate_host(const ssb_potential* pot_h, int64_t N, const double
     if (int e = pool.up(w0, 48 * (size_t)N, &dw0)) return e;
     if (int e = pool.up(t0, 8 * (size_t)N, &dt0)) return e;
     if (int e = pool.up(t1, 8 * (size_t)N, &dt1)) return e;
-    if (int e = pool.up(ts, 8 * (size_t)M * (ts_per_orbit ? (size_t)N : 1), &dts)) return e;
-    void *dys, *dstat, *dns;
-    if (int e = pool.alloc(&dys, 48 * (size_t)N * M)) return e;
-    if (int e = pool.alloc(&dstat, 4 * (size_t)N)) return e;
-    if (int e = pool.alloc(&dns, 12 * (size_t)N)) return e;
+    const bool final_only = (M == 1 && ts_per_orbit && ts == t1);       // same convention as the device entry point: ts aliases t1
+    if (final_only) dts = dt1;
+    else if (int e = pool.up(ts, 8 * (size_t)M * (ts_per_orbit ? (size_t)N : 1), &dts)) return e;
+    // final-state mode with pinned outputs: the kernel writes host memory directly (see the header comment)
+    void *dys = nullptr, *dstat = nullptr, *dns = nullptr;
+    const bool zc = final_only && (dys = pinned_alias(ys, 48 * (size_t)N)) && (dstat = pinned_alias(status, 4 * (size_t)N)) &&
+                    (dns = pinned_alias(nsteps, 12 * (size_t)N));
+    if (!zc) {
+        if (int e = pool.alloc(&dys, 48 * (size_t)N * M)) return e;
+        if (int e = pool.alloc(&dstat, 4 * (size_t)N)) return e;
+        if (int e = pool.alloc(&dns, 12 * (size_t)N)) return e;
+    }
     if (int e = ssb_orbit_integrate_f64(&pd, N, (const double*)dw0, (const double*)dt0, (const double*)dt1, (const double*)dts, M, ts_per_orbit,
                                         ctrl, (double*)dys, (int32_t*)dstat, (int32_t*)dns, st)) return e;
-    if (int e = down(ys, dys, 48 * (size_t)N * M, st)) return e;
-    if (int e = down(status, dstat, 4 * (size_t)N, st)) return e;
-    if (int e = down(nsteps, dns, 12 * (size_t)N, st)) return e;
+    if (!zc) {
+        if (int e = down(ys, dys, 48 * (size_t)N * M, st)) return e;
+        if (int e = down(status, dstat, 4 * (size_t)N, st)) return e;
+        if (int e = down(nsteps, dns, 12 * (size_t)N, st)) return e;
+    }
     CK(cudaStreamSynchronize(st));
     return 0;
 }
@@ -139,19 +169,27 @@ int ssb_gen_stream_host(const ssb_potential* pot_h, const ssb_potential* pot_rel
     if (int e = pool.up(prog_w0, 48, &dw0)) return e;
     if (int e = pool.up(Msat, 8 * (size_t)Nts, &dms)) return e;
     if (normals) { if (int e = pool.up(normals, 32 * (size_t)Nts, &dnr)) return e; }
-    void *dl, *dtr, *dstat, *dns, *scr;
-    if (int e = pool.alloc(&dl, 96 * n)) return e;             // lead and trail adjacent: the orbit kernel writes them in place
+    // lead and trail adjacent in memory (one [2, n, 6] buffer): the orbit kernel writes them in place.  If that buffer and the
+    // status / step-count outputs are pinned host memory, "in place" is the HOST buffer itself (zero-copy, see the header comment).
+    void *dl = nullptr, *dtr, *dstat = nullptr, *dns = nullptr, *scr;
+    const bool zc = n && trail == lead + 6 * n && (dl = pinned_alias(lead, 96 * n)) && (dstat = pinned_alias(status, 8 * n)) &&
+                    (dns = pinned_alias(nsteps, 24 * n));
+    if (!zc) {
+        if (int e = pool.alloc(&dl, 96 * n)) return e;
+        if (int e = pool.alloc(&dstat, 8 * n)) return e;
+        if (int e = pool.alloc(&dns, 24 * n)) return e;
+    }
     dtr = (char*)dl + 48 * n;
-    if (int e = pool.alloc(&dstat, 8 * n)) return e;
-    if (int e = pool.alloc(&dns, 24 * n)) return e;
     const size_t sb = ssb_stream_scratch_bytes(Nts, ctrl.max_steps);
     if (int e = pool.alloc(&scr, sb)) return e;
     if (int e = ssb_gen_stream_f64(&pd, &prd, G, Nts, (const double*)dts, (const double*)dw0, (const double*)dms, seed, kvals,
                                    (const double*)dnr, ctrl, i_begin, i_stride, n_local, (double*)dl, (double*)dtr, (int32_t*)dstat, (int32_t*)dns, scr, sb, st)) return e;
-    if (int e = down(lead, dl, 48 * n, st)) return e;
-    if (int e = down(trail, dtr, 48 * n, st)) return e;
-    if (int e = down(status, dstat, 8 * n, st)) return e;
-    if (int e = down(nsteps, dns, 24 * n, st)) return e;
+    if (!zc) {
+        if (int e = down(lead, dl, 48 * n, st)) return e;
+        if (int e = down(trail, dtr, 48 * n, st)) return e;
+        if (int e = down(status, dstat, 8 * n, st)) return e;
+        if (int e = down(nsteps, dns, 24 * n, st)) return e;
+    }
     CK(cudaStreamSynchronize(st));
     return 0;
 }

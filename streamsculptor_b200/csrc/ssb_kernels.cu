@@ -238,6 +238,33 @@ __global__ void __launch_bounds__(SSB_ORBIT_THREADS, SSB_ORBIT_MIN_BLOCKS) orbit
     const int64_t ii = valid ? i : 0;
     int status, n_steps, n_acc, n_rej;
     const double* tsp = a.ts + (a.ts_per_orbit ? ii * a.M : 0);
+    if (MODE == 2) {
+        // Final-state mode (M == 1): the warp's 32 x 6 doubles and 32 x 3 step counters are contiguous in the outputs.  They are staged
+        // through shared memory and written as whole 256-byte / 128-byte runs, so that the same kernel can write straight into pinned
+        // HOST memory (ssb_gen_stream_host's zero-copy outputs: full PCIe write transactions, overlapped with the running orbits).
+        __shared__ double s_fin[SSB_ORBIT_THREADS * 6];
+        __shared__ int32_t s_cnt[SSB_ORBIT_THREADS * 3];
+        double fin[6] = {0, 0, 0, 0, 0, 0};
+        integrate_one<SOLVER, MODE, SIG, XS>(&sP, &Pin, a.w0 + ii * 6, a.t0[ii], a.t1[ii], tsp, a.M, fin, a.c, valid,
+                                             status, n_steps, n_acc, n_rej, nullptr, 0, sfx);
+        const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+        double* sf = s_fin + wbase * 6;
+        int32_t* sc = s_cnt + wbase * 3;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sf[lane * 6 + k] = fin[k];
+        sc[lane * 3] = n_steps; sc[lane * 3 + 1] = n_acc; sc[lane * 3 + 2] = n_rej;
+        __syncwarp();
+        const int64_t w_first = (int64_t)blockIdx.x * blockDim.x + wbase;          // first orbit of this warp
+        const int64_t n_here = a.N - w_first < 32 ? a.N - w_first : 32;            // valid orbits of this warp (<= 0: none)
+        double* yo = a.ys + (size_t)w_first * 6;
+        int32_t* no = a.nsteps + (size_t)w_first * 3;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { const int q = j * 32 + lane; if (q < n_here * 6) yo[q] = sf[q]; }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { const int q = j * 32 + lane; if (q < n_here * 3) no[q] = sc[q]; }
+        if (valid) a.status[i] = status;
+        return;
+    }
     integrate_one<SOLVER, MODE, SIG, XS>(&sP, &Pin, a.w0 + ii * 6, a.t0[ii], a.t1[ii], tsp, a.M, a.ys + (size_t)ii * a.M * 6, a.c, valid,
                                      status, n_steps, n_acc, n_rej, nullptr, 0, sfx);
     if (valid) {

@@ -20,7 +20,10 @@
 //     warps see coherent window states, and - when the perturbation ICs are zero (perturbative.py:712) and time runs
 //     forwards - the subhalos whose window has not opened yet are still EXACTLY zero with zero error contribution, so
 //     the sweep stops at the last "born" subhalo.  The reference evaluates them (vmapped lax.cond = select); the result
-//     is bit-identical, the work is not.
+//     is bit-identical, the work is not.  Under the same conditions a subhalo whose window CLOSED before the particle was
+//     released (t0 + t_window <= release time) never exerts a force on it: its response is exactly zero for the whole
+//     integration.  In processing order those "dead" subhalos form a prefix (running maximum of the window ends, computed
+//     with the sort), which the sweep of that particle skips as well.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -51,6 +54,7 @@ struct RespArgs {
     unsigned long long* counter;
     const double* sorted;     // [10][n_sh] subhalo parameters gathered in processing order: GM, rs, x0[3], v[3], t0, tw
     const double* start;      // [n_sh] window start t0 - tw, ascending
+    const double* endmax;     // [n_sh] running maximum of the window ends t0 + tw in processing order (non-decreasing)
     const int* order;         // [n_sh] processing position -> user index
     int skip_unborn;          // 1: D0 == NULL (zero ICs): subhalos whose window has not opened are exactly zero
     // SaveAt(ts) for a single trajectory (backward progenitor response, perturbative.py:53-60): N == 1
@@ -175,7 +179,7 @@ __device__ __forceinline__ void load_item_params(const double* __restrict__ tab,
 }
 
 // ---- once per call: processing order (ascending window start) and the gathered parameter table ----
-__global__ void response_sort_kernel(const ssb_subhalos Sh, int npad, int* order, double* start) {
+__global__ void response_sort_kernel(const ssb_subhalos Sh, int npad, int* order, double* start, double* endmax) {
     extern __shared__ unsigned char smem_raw[];
     double* key = reinterpret_cast<double*>(smem_raw);
     int* val = reinterpret_cast<int*>(key + npad);
@@ -196,10 +200,25 @@ __global__ void response_sort_kernel(const ssb_subhalos Sh, int npad, int* order
             __syncthreads();
         }
     for (int i = threadIdx.x; i < Sh.n; i += blockDim.x) { order[i] = val[i]; start[i] = key[i]; }
+    // running maximum of the window ends in processing order (inclusive scan with max, Hillis-Steele on the key array)
+    __syncthreads();
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) key[i] = i < Sh.n ? Sh.t0[val[i]] + Sh.tw[val[i]] : inf;
+    __syncthreads();
+    for (int off = 1; off < npad; off <<= 1) {
+        double mine[(SSB_RESP_MAX_SORT + 1023) / 1024];
+        int q = 0;
+        for (int i = threadIdx.x; i < npad; i += blockDim.x, ++q) mine[q] = i >= off ? fmax(key[i], key[i - off]) : key[i];
+        __syncthreads();
+        q = 0;
+        for (int i = threadIdx.x; i < npad; i += blockDim.x, ++q) key[i] = mine[q];
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < Sh.n; i += blockDim.x) endmax[i] = key[i];
 }
-__global__ void response_identity_kernel(const ssb_subhalos Sh, int* order, double* start) {
+__global__ void response_identity_kernel(const ssb_subhalos Sh, int* order, double* start, double* endmax) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < Sh.n) { order[i] = i; start[i] = -__longlong_as_double(0x7ff0000000000000LL); }
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    if (i < Sh.n) { order[i] = i; start[i] = -inf; endmax[i] = inf; }          // every subhalo counts as born and alive
 }
 __global__ void response_gather_kernel(const ssb_subhalos Sh, const int* order, double* tab) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -232,29 +251,31 @@ __device__ __forceinline__ void item_finish(const double (&q)[3], const double (
 
 template <int SOLVER, int PROFILE>
 __device__ __forceinline__ void sweep_items(const BaseShared<Tab<SOLVER>::S>* sb, const double* __restrict__ PhiE, const double* __restrict__ tab, int n_sh,
-                                            int n_items, int n_act, const double* __restrict__ cur, double* __restrict__ nxt, double dt, const CtrlDev& c,
-                                            double& esq, int& bad_local) {
+                                            int n_items, int n_dead, int n_act, const double* __restrict__ cur, double* __restrict__ nxt, double dt,
+                                            const CtrlDev& c, double& esq, int& bad_local) {
     constexpr int S = Tab<SOLVER>::S;
     const double t_lo = fmin(sb->t[0], sb->t[S - 1]), t_hi = fmax(sb->t[0], sb->t[S - 1]);     // every stage time lies in [t_lo, t_hi]
-    const int n2 = 2 * n_act;
+    // processing positions [n_dead, n_act) of both blocks: idx -> (blk, j)
+    const int n_span = n_act > n_dead ? n_act - n_dead : 0;
+    const int n2 = 2 * n_span;
     const double* __restrict__ t0tab = tab + (size_t)8 * n_sh;
     const double* __restrict__ twtab = tab + (size_t)9 * n_sh;
     // software-pipelined: the state of the NEXT item (L2-resident scratch, ~1 us away) is requested before the current one is processed
     int idx = threadIdx.x;
     double yn[6] = {0, 0, 0, 0, 0, 0}, t0n = 0.0, twn = 0.0;
     if (idx < n2) {
-        const int blk = idx >= n_act, j = idx - blk * n_act, it = blk * n_sh + j;
+        const int blk = idx >= n_span, j = n_dead + idx - blk * n_span, it = blk * n_sh + j;
 #pragma unroll
         for (int k = 0; k < 6; ++k) yn[k] = cur[(size_t)k * n_items + it];
         t0n = __ldg(t0tab + j); twn = __ldg(twtab + j);
     }
     while (idx < n2) {
-        const int blk = idx >= n_act, j = idx - blk * n_act, it = blk * n_sh + j;
+        const int blk = idx >= n_span, j = n_dead + idx - blk * n_span, it = blk * n_sh + j;
         const double q[3] = {yn[0], yn[1], yn[2]}, pp[3] = {yn[3], yn[4], yn[5]};
         const double t0j = t0n, twj = twn;
         const int idn = idx + blockDim.x;
         if (idn < n2) {
-            const int blkn = idn >= n_act, jn = idn - blkn * n_act, itn = blkn * n_sh + jn;
+            const int blkn = idn >= n_span, jn = n_dead + idn - blkn * n_span, itn = blkn * n_sh + jn;
 #pragma unroll
             for (int k = 0; k < 6; ++k) yn[k] = cur[(size_t)k * n_items + itn];
             t0n = __ldg(t0tab + jn); twn = __ldg(twtab + jn);
@@ -332,7 +353,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
     __shared__ BaseShared<S> sb;
     __shared__ double sred[32];
     __shared__ __align__(16) double sPhiE[72];         // propagator Phi[6][6] and error map E[6][6] of the current attempt (homogeneous items)
-    __shared__ int s_nact;
+    __shared__ int s_nact, s_ndead;
     __shared__ long long s_part;
     stage_potential(&sP, &Pin);
     logtab_init();
@@ -354,6 +375,11 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
         double* cur = buf0;
         double* nxt = buf1;
         const bool skip = a.skip_unborn && dir > 0.0;
+        if (tid == 0) {            // subhalos whose window closed before the release of this particle: exact zeros throughout (see the header)
+            int nd = 0;
+            if (skip) { int lo = 0, hi = n_sh; while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.endmax[mid] <= T0) lo = mid + 1; else hi = mid; } nd = lo; }
+            s_ndead = nd;
+        }
         // ---- load item state (SoA [6][n_items], item = blk * n_sh + processing position); momentum-like rows carry dir ----
         for (int it = tid; it < n_items; it += blockDim.x) {
             const int j = it % n_sh, blk = it / n_sh, o = a.order[j];
@@ -509,7 +535,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
             n_act_run = max(n_act_run, s_nact);
             const int n_act = n_act_run;
             // ---- item sweep over the born subhalos: mass block, then radius block ----
-            sweep_items<SOLVER, PROFILE>(&sb, sPhiE, a.sorted, n_sh, n_items, n_act, cur, nxt, dt, c, esq, bad_local);
+            sweep_items<SOLVER, PROFILE>(&sb, sPhiE, a.sorted, n_sh, n_items, s_ndead, n_act, cur, nxt, dt, c, esq, bad_local);
             const double err = sqrt(block_sum(esq, sred) / ncomp);
             const int any_bad = __syncthreads_or(bad_local);
             double hn; bool bad;
@@ -612,9 +638,9 @@ static int resp_grid(int64_t N) {
 
 extern "C" {
 
-// scratch layout: [256 B header: work counter] [sorted table 10*n] [start n] [order n (int)] [ping-pong state per persistent CTA]
+// scratch layout: [256 B header: work counter] [sorted table 10*n] [start n] [endmax n] [order n (int)] [ping-pong state per persistent CTA]
 #define SSB_RESP_MAX_CTAS (160 * SSB_RESP_CTAS_PER_SM)
-static size_t resp_table_bytes(int32_t n_sh) { const size_t n = (size_t)(n_sh > 0 ? n_sh : 1); return ((sizeof(double) * 11 * n + sizeof(int) * n + 255) / 256) * 256; }
+static size_t resp_table_bytes(int32_t n_sh) { const size_t n = (size_t)(n_sh > 0 ? n_sh : 1); return ((sizeof(double) * 12 * n + sizeof(int) * n + 255) / 256) * 256; }
 size_t ssb_response_scratch_bytes(int32_t n_sh) {
     const size_t per_cta = sizeof(double) * 2 * 6 * 2 * (size_t)(n_sh > 0 ? n_sh : 1);
     return 256 + resp_table_bytes(n_sh) + per_cta * (size_t)SSB_RESP_MAX_CTAS;
@@ -640,8 +666,9 @@ static int response_impl(const ssb_potential* pot_base, const ssb_subhalos* sh, 
     a.counter = (unsigned long long*)scratch;
     double* tab = (double*)((char*)scratch + 256);
     double* start = tab + (size_t)10 * sh->n;
-    int* order = (int*)(start + sh->n);
-    a.sorted = tab; a.start = start; a.order = order;
+    double* endmax = start + sh->n;
+    int* order = (int*)(endmax + sh->n);
+    a.sorted = tab; a.start = start; a.endmax = endmax; a.order = order;
     a.scratch = (double*)((char*)scratch + 256 + resp_table_bytes(sh->n));
     a.skip_unborn = (D0 == nullptr && M == 0) ? 1 : 0;
     a.ts_save = ts_save; a.M = M; a.wsave = wsave; a.Dsave = Dsave;
@@ -649,10 +676,10 @@ static int response_impl(const ssb_potential* pot_base, const ssb_subhalos* sh, 
     if (sh->n > 0) {
         if (sh->n <= SSB_RESP_MAX_SORT) {
             int npad = 1; while (npad < sh->n) npad <<= 1;
-            response_sort_kernel<<<1, 1024, (size_t)npad * 12, st>>>(*sh, npad, order, start);
+            response_sort_kernel<<<1, 1024, (size_t)npad * 12, st>>>(*sh, npad, order, start, endmax);
             CKL("response_sort_kernel");
         } else {                                   // identity order; every subhalo counts as born
-            response_identity_kernel<<<(sh->n + 127) / 128, 128, 0, st>>>(*sh, order, start);
+            response_identity_kernel<<<(sh->n + 127) / 128, 128, 0, st>>>(*sh, order, start, endmax);
             CKL("response_identity_kernel");
         }
         response_gather_kernel<<<(sh->n + 127) / 128, 128, 0, st>>>(*sh, order, tab);

@@ -345,6 +345,51 @@ def test_cubic_track_and_host_entry_points(cuda):
     assert np.array_equal(ys, sol.ys) and (st == 0).all()
 
 
+def test_host_entry_points_zero_copy_outputs(cuda):
+    """ssb_gen_stream_host / ssb_orbit_integrate_host with PINNED outputs (the orbit kernel writes host memory directly, csrc/ssb_host.cu)
+    against pageable outputs (staged copies) and the device-pointer path: bit-identical, including partially filled warps."""
+    import ctypes as C
+    import torch
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import _lib, _runtime as rt
+    pot = mw3_product()
+    Pst, keep = rt.lower(pot)
+    host = _lib.Potential.from_buffer_copy(Pst)
+    ctrl = rt.make_ctrl(ssc.Dopri8(), 1e-7, 1e-7, 0.3, None, 10_000)
+    L = _lib.lib()
+    hp = lambda t: C.c_void_p(t.data_ptr())
+    for nts in (78, 2, 1026):                      # 2 n = 154, 2, 2050 orbits: none a multiple of the warp size
+        n = nts - 1
+        ts = np.linspace(-1500.0, 0.0, nts)
+        w0 = np.array([-3.0, 14.0, 8.0, 0.14, 0.02, -0.07])
+        ms = np.full(nts, 1e4)
+        kv = (C.c_double * 8)(*ssc.main.DEFAULT_KVALS)
+        tt, tw, tm = torch.from_numpy(ts), torch.from_numpy(w0), torch.from_numpy(ms)
+        res = []
+        for pinned in (True, False):
+            out = torch.full((2, n, 6), -7.0, dtype=torch.float64)
+            st = torch.full((2, n), -7, dtype=torch.int32)
+            ns = torch.full((2, n, 3), -7, dtype=torch.int32)
+            if pinned:
+                out, st, ns = out.pin_memory(), st.pin_memory(), ns.pin_memory()
+            _lib.check(L.ssb_gen_stream_host(C.byref(host), C.byref(host), pot._G, nts, hp(tt), hp(tw), hp(tm), 583, kv, None, ctrl, 0, 1, n,
+                                             hp(out[0]), hp(out[1]), hp(st), hp(ns)))
+            res.append((out.clone(), st.clone(), ns.clone()))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+        assert (res[0][1] == 0).all() and (res[0][2][..., 0] == res[0][2][..., 1] + res[0][2][..., 2]).all()
+        lead, trail = pot.gen_stream_vmapped(ts=ts, prog_w0=w0, Msat=1e4, seed_num=583, solver=ssc.Dopri8())
+        assert np.array_equal(res[0][0][0].numpy(), np.asarray(lead)) and np.array_equal(res[0][0][1].numpy(), np.asarray(trail))
+    # batch of orbits, final state only (ts aliases t1), pinned outputs
+    N = 77
+    w0 = torch.from_numpy(random_orbits(N, seed=8)); t0 = torch.full((N,), -1500.0, dtype=torch.float64); t1 = torch.zeros(N, dtype=torch.float64)
+    ys = torch.full((N, 1, 6), -7.0, dtype=torch.float64).pin_memory()
+    st = torch.full((N,), -7, dtype=torch.int32).pin_memory(); ns = torch.full((N, 3), -7, dtype=torch.int32).pin_memory()
+    _lib.check(L.ssb_orbit_integrate_host(C.byref(host), N, hp(w0), hp(t0), hp(t1), hp(t1), 1, 1, ctrl, hp(ys), hp(st), hp(ns)))
+    sol = pot.integrate_orbit_batch_vmapped(w0=w0.numpy(), ts=np.zeros((N, 1)), t0=t0.numpy(), t1=t1.numpy())
+    assert (st == 0).all() and relerr(ys.numpy(), sol.ys) < 1e-12       # final-state kernel vs SaveAt kernel: same steps, t1 row
+    assert (ns[:, 0] == ns[:, 1] + ns[:, 2]).all() and (ns[:, 0] > 10).all()
+
+
 def test_third_derivatives_and_release_jacobian(cuda):
     """A15: closed-form third derivatives and jacfwd(release_model) (perturbative.py:281-296) vs the oracle's nested autodiff."""
     import streamsculptor_b200 as ssc
