@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ssb_common.cuh"
@@ -40,6 +41,10 @@ using namespace ssb;
 #define SSB_RESP_CTAS_PER_SM 3      // 168 registers/thread: three 128-thread CTAs (three particles) per SM overlap base and item phases
 #endif
 #define SSB_RESP_MAX_SORT 4096
+#define SSB_RESP_MAX_NP 4           // response_kernel_mp: particle slots per CTA (eight lanes of warp 0 each)
+#ifndef SSB_RESP_DEFAULT_NP
+#define SSB_RESP_DEFAULT_NP 2
+#endif
 #define CK(call) do { int _e = ssb_cuda_check((call), #call); if (_e) return _e; } while (0)
 #define CKL(what) do { int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
 
@@ -57,6 +62,7 @@ struct RespArgs {
     const double* endmax;     // [n_sh] running maximum of the window ends t0 + tw in processing order (non-decreasing)
     const int* order;         // [n_sh] processing position -> user index
     int skip_unborn;          // 1: D0 == NULL (zero ICs): subhalos whose window has not opened are exactly zero
+    int np;                   // response_kernel_mp: particles in flight per CTA (1..SSB_RESP_MAX_NP)
     // SaveAt(ts) for a single trajectory (backward progenitor response, perturbative.py:53-60): N == 1
     const double* ts_save; int M; double* wsave; double* Dsave;
 };
@@ -377,8 +383,8 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
         const bool skip = a.skip_unborn && dir > 0.0;
         if (tid == 0) {            // subhalos whose window closed before the release of this particle: exact zeros throughout (see the header)
             int nd = 0;
-            if (skip) { int lo = 0, hi = n_sh; while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.endmax[mid] <= T0) lo = mid + 1; else hi = mid; } nd = lo; }
-            s_ndead = nd;
+            if (skip) { int lo = 0, hi = n_sh; while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.endmax[mid] <= T0) lo = mid + 1; else hi = mid; } nd = lo & ~15; }
+            s_ndead = nd;                                    // multiple of 16 items: the sweep's 128-byte segments stay aligned
         }
         // ---- load item state (SoA [6][n_items], item = blk * n_sh + processing position); momentum-like rows carry dir ----
         for (int it = tid; it < n_items; it += blockDim.x) {
@@ -600,6 +606,350 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
     }
 }
 
+
+// =============================================================================================
+// K3-mp: the same computation with SEVERAL particles in flight per CTA.
+//
+// ncu (profiles/r1_response_kernel_source.txt) shows what bounds response_kernel: the base-orbit phase of an attempt is a serial,
+// latency-bound instruction stream of ONE warp (13 force + Hessian evaluations, ~4.7 k instructions at ~5 cycles each) during
+// which the other warps of the CTA wait at the barrier - 45 % of every attempt.  SIMT makes that stream free to share: here
+// warp 0 advances the base orbits (and propagator columns) of up to four particles AT ONCE, eight lanes per particle slot
+// (lane 8q: base orbit of slot q, lanes 8q+1..8q+6: unit vectors), so the serial phase costs the same for np particles as
+// for one; the item sweeps of the slots then run back to back on all threads.  Every slot keeps its own controller, scratch
+// buffers, window bookkeeping and work-queue position; slots finish and refill independently.  Per-slot control state lives
+// in shared memory and is advanced by thread 0 between two barriers.  With np = 1 the arithmetic (including the order of the
+// error reduction) is that of response_kernel.
+// =============================================================================================
+struct RespSlot {
+    long long part;                 // particle index; -1: free (refill from the queue); -2: queue exhausted
+    double dir, T0, T1, tprev, tnext;
+    int status, n_steps, n_acc, n_rej;
+    int at_dtmin, accepted, finishing, flip;
+    int n_act_run, n_dead, skip, pad;
+};
+
+// lanes of one slot follow the slot leader's base point; `sh` is the slot's stage record (or the trash record of idle lanes)
+template <int S, int SIG>
+struct BaseGroupForce {
+    const ssb_potential* P; const ssb_potential* Pc; BaseShared<S>* sh; double dir; int stage; int src; bool base;
+    __device__ __forceinline__ void operator()(const double X[3], double tau, double A[3]) {
+        const double bx = __shfl_sync(0xffffffffu, X[0], src), by = __shfl_sync(0xffffffffu, X[1], src), bz = __shfl_sync(0xffffffffu, X[2], src);
+        const double3 a = base_force_call<S, SIG>(P, Pc, sh, stage, bx, by, bz, tau * dir);
+        __syncwarp();
+        const double* T = sh->T[stage];
+        A[0] = base ? a.x : (T[0] * X[0] + T[3] * X[1] + T[4] * X[2]);
+        A[1] = base ? a.y : (T[3] * X[0] + T[1] * X[1] + T[5] * X[2]);
+        A[2] = base ? a.z : (T[4] * X[0] + T[5] * X[1] + T[2] * X[2]);
+        stage++;
+    }
+};
+
+template <int SOLVER, int SIG, int PROFILE>
+__global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) response_kernel_mp(const __grid_constant__ ssb_potential Pin, const ssb_subhalos Sh,
+                                                                                             const RespArgs a) {
+    typedef Tab<SOLVER> T;
+    constexpr int S = T::S;
+    constexpr int NPX = SSB_RESP_MAX_NP;
+    __shared__ ssb_potential sP;
+    __shared__ BaseShared<S> sb[NPX + 1];                     // [NPX]: trash record of the idle lanes of warp 0
+    __shared__ __align__(16) double sPhiE[NPX + 1][72];
+    __shared__ double sred[32], sred_q[NPX][32];
+    __shared__ RespSlot slot[NPX];
+    __shared__ int s_nact[NPX + 1], s_bad[NPX + 1];
+    __shared__ double s_besq[NPX + 1];                        // squared scaled error of the base orbit's attempt
+    __shared__ int s_service, s_live;
+    stage_potential(&sP, &Pin);
+    logtab_init();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    const int NP = a.np;
+    const int n_sh = Sh.n, n_items = 2 * n_sh, ncomp = 6 + 12 * n_sh;
+    const CtrlDev c = a.c;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    // warp 0: lane = 8 * slot + role; role 0 = base orbit, 1..6 = propagator columns, 7 = idle
+    const int col = (lane & 7) - 1;
+    const int my_slot = (tid < 32 && (lane >> 3) < NP && col < 6) ? (lane >> 3) : NPX;
+    double x[3] = {8.0, 0.0, 0.0}, p[3] = {0, 0, 0}, F[S][3], x1[3] = {8.0, 0.0, 0.0}, p1[3] = {0, 0, 0};
+#pragma unroll
+    for (int l = 0; l < S; ++l) F[l][0] = F[l][1] = F[l][2] = 0.0;
+    if (tid < NPX) {
+        RespSlot& s = slot[tid];
+        s.part = tid < NP ? -1 : -2; s.dir = 1.0; s.T0 = s.T1 = s.tprev = s.tnext = 0.0; s.status = s.n_steps = s.n_acc = s.n_rej = 0;
+        s.at_dtmin = s.accepted = s.finishing = s.flip = s.n_act_run = s.n_dead = s.skip = s.pad = 0;
+    }
+    if (tid <= NPX) { s_nact[tid] = 0; s_bad[tid] = 0; }
+    if (tid == 0) { s_service = 1; s_live = 1; }
+    double* const cta_buf = a.scratch + (size_t)blockIdx.x * NPX * 2 * 6 * n_items;
+
+    for (;;) {
+        __syncthreads();                                       // slot state written by thread 0 is visible
+        // ---- commit the attempts accepted in the previous round (FSAL): base lanes only ----
+        if (my_slot < NPX && col == -1 && slot[my_slot].part >= 0 && slot[my_slot].accepted) {
+            BaseShared<S>& r = sb[my_slot];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { x[k] = x1[k]; p[k] = p1[k]; F[0][k] = F[S - 1][k]; r.X[0][k] = r.X[S - 1][k]; }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) r.T[0][k] = r.T[S - 1][k];
+            r.t[0] = r.t[S - 1];
+        }
+        // ---- service: write out finished particles, refill their slots from the queue, start the new particles ----
+        while (s_service) {                                    // uniform
+            __syncthreads();
+            for (int q = 0; q < NP; ++q) {
+                if (!(slot[q].part >= 0 && slot[q].finishing)) continue;
+                // outputs: final state if the end was reached, +inf otherwise (diffrax SaveAt semantics)
+                const long long part = slot[q].part;
+                const double dir = slot[q].dir;
+                const bool ok = (slot[q].status == 0) && (slot[q].T0 < slot[q].T1);
+                const double* cur = cta_buf + (size_t)(2 * q + slot[q].flip) * 6 * n_items;
+                for (int it = tid; it < n_items; it += blockDim.x) {
+                    const int j = it % n_sh, blk = it / n_sh, o = a.order[j];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        double v = cur[(size_t)k * n_items + it];
+                        if (k >= 3) v *= dir;
+                        a.Dout[((size_t)part * n_sh + o) * 12 + blk * 6 + k] = ok ? v : inf;
+                    }
+                }
+                if (tid == 8 * q) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { a.wout[6 * part + k] = ok ? x[k] : inf; a.wout[6 * part + 3 + k] = ok ? dir * p[k] : inf; }
+                    a.status[part] = slot[q].status;
+                    a.nsteps[3 * part] = slot[q].n_steps; a.nsteps[3 * part + 1] = slot[q].n_acc; a.nsteps[3 * part + 2] = slot[q].n_rej;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                s_service = 0;
+                for (int q = 0; q < NP; ++q) {
+                    RespSlot& s = slot[q];
+                    if (s.part >= 0 && s.finishing) { s.part = -1; s.finishing = 0; s.accepted = 0; }
+                    if (s.part == -1) {
+                        const long long nx = (long long)atomicAdd(a.counter, 1ULL);
+                        s.part = nx < a.N ? nx : -2;
+                        s.finishing = s.part >= 0 ? 2 : 0;        // 2: needs start-up
+                    }
+                }
+            }
+            __syncthreads();
+            for (int q = 0; q < NP; ++q) {
+                if (!(slot[q].part >= 0 && slot[q].finishing == 2)) continue;
+                // ================= start-up of slot q: state load + HNW initial step over the whole coupled state =================
+                const long long part = slot[q].part;
+                const double t0_in = a.t0[part], t1_in = a.t1;
+                const double dir = (t0_in < t1_in) ? 1.0 : -1.0;
+                const double T0 = t0_in * dir, T1 = t1_in * dir;
+                double* cur = cta_buf + (size_t)(2 * q) * 6 * n_items;
+                double* nxt = cur + (size_t)6 * n_items;
+                for (int it = tid; it < n_items; it += blockDim.x) {
+                    const int j = it % n_sh, blk = it / n_sh, o = a.order[j];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        double v = a.D0 ? a.D0[((size_t)part * n_sh + o) * 12 + blk * 6 + k] : 0.0;
+                        if (k >= 3) v *= dir;
+                        cur[(size_t)k * n_items + it] = v;
+                        nxt[(size_t)k * n_items + it] = v;         // unborn / dead subhalos are never written again: both buffers hold their zeros
+                    }
+                }
+                BaseForce<S, SIG> bforce{&sP, &Pin, &sb[q], dir, 0};
+                double d0s = 0.0, d1s = 0.0;
+                if (tid == 8 * q) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { x[k] = a.w0[6 * part + k]; p[k] = dir * a.w0[6 * part + 3 + k]; }
+                    bforce.stage = 0;
+                    bforce(x, T0, F[0]);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const double sx = fma(c.rtol, fabs(x[k]), c.atol), sp = fma(c.rtol, fabs(p[k]), c.atol);
+                        double r;
+                        r = x[k] / sx; d0s = fma(r, r, d0s); r = p[k] / sp; d0s = fma(r, r, d0s);
+                        r = p[k] / sx; d1s = fma(r, r, d1s); r = F[0][k] / sp; d1s = fma(r, r, d1s);
+                    }
+                }
+                __syncthreads();
+                for (int it = tid; it < n_items; it += blockDim.x) {
+                    ItemParams ip; load_item_params(a.sorted, Sh.profile, it % n_sh, it / n_sh, n_sh, ip);
+                    ItemForce<S> f{&sb[q], &ip, 0};
+                    double qq[3], pp[3], G[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { qq[k] = cur[(size_t)k * n_items + it]; pp[k] = cur[(size_t)(3 + k) * n_items + it]; }
+                    f.at(0, qq, G);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const double sx = fma(c.rtol, fabs(qq[k]), c.atol), sp = fma(c.rtol, fabs(pp[k]), c.atol);
+                        double r;
+                        r = qq[k] / sx; d0s = fma(r, r, d0s); r = pp[k] / sp; d0s = fma(r, r, d0s);
+                        r = pp[k] / sx; d1s = fma(r, r, d1s); r = G[k] / sp; d1s = fma(r, r, d1s);
+                    }
+                }
+                const double d0 = sqrt(block_sum(d0s, sred) / ncomp);
+                const double d1 = sqrt(block_sum(d1s, sred) / ncomp);
+                const double h0 = hnw_h0(d0, d1);
+                double d2s = 0.0;
+                if (tid == 8 * q) {
+                    double X1[3], F1[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) X1[k] = fma(h0, p[k], x[k]);
+                    bforce.stage = 1;
+                    bforce(X1, T0 + h0, F1);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const double sx = fma(c.rtol, fabs(x[k]), c.atol), sp = fma(c.rtol, fabs(p[k]), c.atol);
+                        double r;
+                        r = (fma(h0, F[0][k], p[k]) - p[k]) / sx; d2s = fma(r, r, d2s);
+                        r = (F1[k] - F[0][k]) / sp; d2s = fma(r, r, d2s);
+                    }
+                }
+                __syncthreads();
+                for (int it = tid; it < n_items; it += blockDim.x) {
+                    ItemParams ip; load_item_params(a.sorted, Sh.profile, it % n_sh, it / n_sh, n_sh, ip);
+                    ItemForce<S> f{&sb[q], &ip, 0};
+                    double qq[3], pp[3], G0[3], G1[3], q1[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { qq[k] = cur[(size_t)k * n_items + it]; pp[k] = cur[(size_t)(3 + k) * n_items + it]; }
+                    f.at(0, qq, G0);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) q1[k] = fma(h0, pp[k], qq[k]);
+                    f.at(1, q1, G1);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const double sx = fma(c.rtol, fabs(qq[k]), c.atol), sp = fma(c.rtol, fabs(pp[k]), c.atol);
+                        double r;
+                        r = (fma(h0, G0[k], pp[k]) - pp[k]) / sx; d2s = fma(r, r, d2s);
+                        r = (G1[k] - G0[k]) / sp; d2s = fma(r, r, d2s);
+                    }
+                }
+                const double d2 = sqrt(block_sum(d2s, sred) / ncomp) / h0;
+                if (tid == 0) {
+                    RespSlot& s = slot[q];
+                    double h = fmin(hnw_h1<T::ORDER>(h0, d1, d2), c.dtmax);
+                    s.at_dtmin = h <= c.dtmin;
+                    h = fmax(h, c.dtmin);
+                    s.dir = dir; s.T0 = T0; s.T1 = T1; s.tprev = T0; s.tnext = fmin(T0 + h, T1);
+                    s.status = 0; s.n_steps = s.n_acc = s.n_rej = 0; s.accepted = 0; s.flip = 0; s.n_act_run = 0;
+                    s.skip = (a.skip_unborn && dir > 0.0) ? 1 : 0;
+                    int nd = 0;       // subhalos whose window closed before the release of this particle: exact zeros throughout (see the header)
+                    if (s.skip) { int lo = 0, hi = n_sh; while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.endmax[mid] <= T0) lo = mid + 1; else hi = mid; } nd = lo & ~15; }
+                    s.n_dead = nd;
+                    s.finishing = 0;
+                    if (!(T0 < T1)) { s.finishing = 1; s_service = 1; }                    // nothing to integrate: rows stay +inf
+                    else if (c.max_steps <= 0) { s.status = 1; s.finishing = 1; s_service = 1; }
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                int live = 0;
+                for (int q = 0; q < NP; ++q) live |= slot[q].part >= 0;
+                s_live = live;
+            }
+            __syncthreads();
+        }
+        if (!s_live) break;                                    // uniform
+        // ---- serial phase, shared by the slots: base orbits + propagator columns of this round's attempts (warp 0) ----
+        if (tid < 32) {
+            const bool act = my_slot < NPX && slot[my_slot].part >= 0;
+            const int rec = act ? my_slot : NPX;
+            const double tp = act ? slot[rec].tprev : 0.0, dt = act ? slot[rec].tnext - tp : 1.0, dir = act ? slot[rec].dir : 1.0;
+            if (col >= 0) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { x[k] = (col == k) ? 1.0 : 0.0; p[k] = (col == 3 + k) ? 1.0 : 0.0; }
+                const double* T0m = sb[rec].T[0];
+                F[0][0] = T0m[0] * x[0] + T0m[3] * x[1] + T0m[4] * x[2];
+                F[0][1] = T0m[3] * x[0] + T0m[1] * x[1] + T0m[5] * x[2];
+                F[0][2] = T0m[4] * x[0] + T0m[5] * x[1] + T0m[2] * x[2];
+            }
+            double ex[3], ep[3];
+            BaseGroupForce<S, SIG> gforce{&sP, &Pin, &sb[rec], dir, 1, lane & ~7, col == -1};
+            // stage 0 of the record (X, T, t at tprev) is already in place: FSAL copy above / start-up evaluation
+            rk_stages<SOLVER>(gforce, x, p, tp, dt, F);
+            rk_candidate<SOLVER>(x, p, dt, F, x1, p1);
+            gforce.stage = S - 1;
+            gforce(x1, tp + T::c(S - 1) * dt, F[S - 1]);
+            rk_error<SOLVER>(p, dt, F, ex, ep);
+            if (act && col == -1) {
+                bool nan_cand = false, finite = true;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    nan_cand |= isnan(x1[k]) | isnan(p1[k]);
+                    finite &= isfinite(x1[k]) & isfinite(p1[k]);
+                }
+                if (!finite) s_bad[rec] = 1;
+                s_besq[rec] = err_sq6(x, p, x1, p1, ex, ep, c.rtol, c.atol, nan_cand);
+                // number of subhalos whose window start lies before the end of this attempt (sorted ascending)
+                int na = n_sh;
+                if (slot[rec].skip) {
+                    const double tn = slot[rec].tnext;
+                    int lo = 0, hi = n_sh;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.start[mid] < tn) lo = mid + 1; else hi = mid; }
+                    na = lo;
+                }
+                s_nact[rec] = na;
+            } else if (act && col < 6) {
+                double* PE = sPhiE[rec];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    PE[k * 6 + col] = x1[k]; PE[(3 + k) * 6 + col] = p1[k];
+                    PE[36 + k * 6 + col] = ex[k]; PE[36 + (3 + k) * 6 + col] = ep[k];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- item sweeps of the slots, one after the other, on all threads ----
+#pragma unroll 1
+        for (int q = 0; q < NP; ++q) {
+            if (slot[q].part < 0) continue;                    // uniform
+            // monotone within a particle: a subhalo touched by a (possibly rejected) attempt has a candidate in `nxt` that must be
+            // overwritten by every later attempt, even one that ends before its window opens
+            const int n_act = max(slot[q].n_act_run, s_nact[q]);
+            const double* cur = cta_buf + (size_t)(2 * q + slot[q].flip) * 6 * n_items;
+            double* nxt = cta_buf + (size_t)(2 * q + (slot[q].flip ^ 1)) * 6 * n_items;
+            double esq = (tid == 0) ? s_besq[q] : 0.0;          // same summation order as response_kernel, whatever the slot
+            int bad_local = 0;
+            sweep_items<SOLVER, PROFILE>(&sb[q], sPhiE[q], a.sorted, n_sh, n_items, slot[q].n_dead, n_act, cur, nxt, slot[q].tnext - slot[q].tprev, c, esq,
+                                         bad_local);
+            if (bad_local) s_bad[q] = 1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) esq += __shfl_xor_sync(0xffffffffu, esq, o);
+            if (lane == 0) sred_q[q][wid] = esq;
+        }
+        __syncthreads();
+        // ---- controllers (thread 0): accept / reject, next step, completion ----
+        if (tid == 0) {
+            for (int q = 0; q < NP; ++q) {
+                RespSlot& s = slot[q];
+                if (s.part < 0) continue;
+                double tot = 0.0;
+                for (int i = 0; i < nw; ++i) tot += sred_q[q][i];
+                const double err = sqrt(tot / ncomp);
+                const double dt = s.tnext - s.tprev;
+                const int any_bad = s_bad[q];
+                s_bad[q] = 0;
+                s.n_act_run = max(s.n_act_run, s_nact[q]);
+                double hn; bool bad;
+                bool at_dtmin = s.at_dtmin != 0;
+                const bool keep = pid_update<T::ORDER>(err, dt, c, at_dtmin, hn, bad);
+                s.at_dtmin = at_dtmin;
+                s.n_steps++;
+                s.accepted = 0;
+                if (bad) { s.status = 2; s.n_rej++; }
+                else if (keep) {
+                    s.n_acc++;
+                    if (any_bad) s.status = 2;
+                    else { s.flip ^= 1; s.accepted = 1; s.tprev = s.tnext; }
+                } else s.n_rej++;
+                if (s.status == 0) {
+                    s.tprev = fmin(s.tprev, s.T1);
+                    double tn = s.tprev + hn;
+                    if (tn > s.T1 - 1e-10) tn = keep ? s.T1 : s.tprev + 0.5 * (s.T1 - s.tprev);
+                    s.tnext = tn;
+                    if (!(s.tprev < s.T1)) s.finishing = 1;
+                    else if (s.n_steps >= c.max_steps) { s.status = 1; s.finishing = 1; }
+                } else s.finishing = 1;
+                if (s.finishing) s_service = 1;
+            }
+        }
+    }
+}
+
 // RHS of the coupled field at one state (fields.py:175-206): y = [w(6), D(n_sh,12)]
 __global__ void response_term_kernel(const __grid_constant__ ssb_potential Pin, const ssb_subhalos Sh, double t, const double* y, double* dy) {
     __shared__ ssb_potential sP;
@@ -628,12 +978,24 @@ __global__ void response_term_kernel(const __grid_constant__ ssb_potential Pin, 
     }
 }
 
-static int resp_grid(int64_t N) {
+static int resp_grid(int64_t N, int np = 1) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t g = (int64_t)sms * SSB_RESP_CTAS_PER_SM;
-    return (int)(N < g ? N : g);
+    const int64_t g = (int64_t)sms * SSB_RESP_CTAS_PER_SM, want = (N + np - 1) / np;
+    return (int)(want < g ? want : g);
+}
+
+// particles in flight per CTA (response_kernel_mp).  SSB_RESP_NP in the environment overrides the default for A/B runs:
+// 0 = the one-particle-per-CTA kernel, 1..4 = slots per CTA.
+static int resp_np(int64_t N, int grid_cap) {
+    if (const char* e = getenv("SSB_RESP_NP")) {                   // explicit choice: taken as is (tests force 2 and 4 slots on small batches)
+        const int np = atoi(e);
+        return np <= 0 ? 0 : (np > SSB_RESP_MAX_NP ? SSB_RESP_MAX_NP : np);
+    }
+    int np = SSB_RESP_DEFAULT_NP;
+    while (np > 1 && N < (int64_t)grid_cap * np) np >>= 1;         // too few particles to fill every slot of every CTA: fewer slots, more CTAs
+    return np;
 }
 
 extern "C" {
@@ -642,8 +1004,8 @@ extern "C" {
 #define SSB_RESP_MAX_CTAS (160 * SSB_RESP_CTAS_PER_SM)
 static size_t resp_table_bytes(int32_t n_sh) { const size_t n = (size_t)(n_sh > 0 ? n_sh : 1); return ((sizeof(double) * 12 * n + sizeof(int) * n + 255) / 256) * 256; }
 size_t ssb_response_scratch_bytes(int32_t n_sh) {
-    const size_t per_cta = sizeof(double) * 2 * 6 * 2 * (size_t)(n_sh > 0 ? n_sh : 1);
-    return 256 + resp_table_bytes(n_sh) + per_cta * (size_t)SSB_RESP_MAX_CTAS;
+    const size_t per_slot = sizeof(double) * 2 * 6 * 2 * (size_t)(n_sh > 0 ? n_sh : 1);           // ping-pong state of one particle in flight
+    return 256 + resp_table_bytes(n_sh) + per_slot * (size_t)SSB_RESP_MAX_NP * (size_t)SSB_RESP_MAX_CTAS;
 }
 
 static int response_impl(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0, const double* D0,
@@ -658,7 +1020,9 @@ static int response_impl(const ssb_potential* pot_base, const ssb_subhalos* sh, 
     if (!w0 || !t0 || !wout || !status || !nsteps || !scratch || (sh->n > 0 && !Dout)) return ssb_set_error(SSB_ERR_ARG, "linear_response: NULL array");
     if (scratch_bytes < ssb_response_scratch_bytes(sh->n)) return ssb_set_error(SSB_ERR_SCRATCH, "linear_response: scratch too small");
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = resp_grid(N);
+    const int grid_cap = resp_grid(INT64_MAX / 8);
+    const int np = (M > 0) ? 0 : resp_np(N, grid_cap);
+    const int grid = resp_grid(N, np > 0 ? np : 1);
     if (grid > SSB_RESP_MAX_CTAS) return ssb_set_error(SSB_ERR_SCRATCH, "linear_response: more SMs than the scratch layout assumes");
     RespArgs a;
     a.N = N; a.w0 = w0; a.D0 = D0; a.t0 = t0; a.t1 = t1; a.c.rtol = ctrl.rtol; a.c.atol = ctrl.atol; a.c.dtmin = ctrl.dtmin; a.c.dtmax = ctrl.dtmax;
@@ -671,6 +1035,7 @@ static int response_impl(const ssb_potential* pot_base, const ssb_subhalos* sh, 
     a.sorted = tab; a.start = start; a.endmax = endmax; a.order = order;
     a.scratch = (double*)((char*)scratch + 256 + resp_table_bytes(sh->n));
     a.skip_unborn = (D0 == nullptr && M == 0) ? 1 : 0;
+    a.np = np;
     a.ts_save = ts_save; a.M = M; a.wsave = wsave; a.Dsave = Dsave;
     CK(cudaMemsetAsync(scratch, 0, 256, st));
     if (sh->n > 0) {
@@ -698,6 +1063,13 @@ static int response_impl(const ssb_potential* pot_base, const ssb_subhalos* sh, 
 #define SSB_LAUNCH_SAVE_PR(S) do { switch (sh->profile) { case SSB_PROFILE_PLUMMER: SSB_LAUNCH_SAVE(S, SSB_PROFILE_PLUMMER); break; \
         case SSB_PROFILE_HERNQUIST: SSB_LAUNCH_SAVE(S, SSB_PROFILE_HERNQUIST); break; default: SSB_LAUNCH_SAVE(S, SSB_PROFILE_NFW); } } while (0)
         if (ctrl.solver == 5) SSB_LAUNCH_SAVE_PR(5); else SSB_LAUNCH_SAVE_PR(8);
+    } else if (np > 0) {      // several particles in flight per CTA (shared serial phase)
+#define SSB_LAUNCH_MP(S, SG, PR) response_kernel_mp<S, SG, PR><<<grid, SSB_RESP_THREADS, 0, st>>>(sig == SG ? pc : *pot_base, *sh, a)
+#define SSB_LAUNCH_MP_SIG(S, PR) do { switch (sig) { case SIG_NHM: SSB_LAUNCH_MP(S, SIG_NHM, PR); break; \
+        case SIG_NHHM: SSB_LAUNCH_MP(S, SIG_NHHM, PR); break; default: SSB_LAUNCH_MP(S, SIG_GENERIC, PR); } } while (0)
+#define SSB_LAUNCH_MP_PR(S) do { switch (sh->profile) { case SSB_PROFILE_PLUMMER: SSB_LAUNCH_MP_SIG(S, SSB_PROFILE_PLUMMER); break; \
+        case SSB_PROFILE_HERNQUIST: SSB_LAUNCH_MP_SIG(S, SSB_PROFILE_HERNQUIST); break; default: SSB_LAUNCH_MP_SIG(S, SSB_PROFILE_NFW); } } while (0)
+        if (ctrl.solver == 5) SSB_LAUNCH_MP_PR(5); else SSB_LAUNCH_MP_PR(8);
     } else {
         if (ctrl.solver == 5) SSB_LAUNCH_RESP_PR(5); else SSB_LAUNCH_RESP_PR(8);
     }

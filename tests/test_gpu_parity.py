@@ -286,6 +286,60 @@ def test_response_c4_scale_fixed_step(cuda):
     assert np.abs(D2.cpu().numpy() - D_g).max() <= 1e-10 * np.abs(D_g).max()
 
 
+def test_response_multi_slot_kernel_bit_identical(cuda):
+    """response_kernel_mp keeps several particles in flight per CTA (shared base-orbit phase, csrc/ssb_response.cu).  Every particle's arithmetic
+    is independent of the slot and CTA it lands in, so 1, 2 and 4 slots per CTA and the one-particle-per-CTA kernel must agree bit for bit -
+    adaptive steps, zero and non-zero perturbation ICs, forward and backward integration, failures included."""
+    import os
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import _runtime as rt
+    P = ssc.potential
+    nsh = 70
+    sh = subhalo_set(nsh, seed=5, t_lo=-2000.0, tw=200.0)
+    sh["tw"][::7] = 60.0                                        # unequal windows: the dead-prefix logic must use the running maximum of the ends
+    base = mw3_product()
+    pert = P.SubhaloLinePotentialCustom_fromFunc(func=P.HernquistPotential, m=sh["m"], r_s=sh["rs"], subhalo_x0=sh["x0"], subhalo_v=sh["v"],
+                                                 subhalo_t0=sh["t0"], t_window=sh["tw"], units=ssc.usys)
+    N = 37
+    w0 = halo_orbits(N, seed=11)
+    t0 = np.linspace(-2500.0, -5.0, N)
+    t0[5] = 0.0                                                 # nothing to integrate: +inf rows
+    rng = np.random.default_rng(2)
+    D0 = rng.normal(size=(N, nsh, 12)) * 1e-6
+    cases = [(ssc.Dopri8(), 1e-8, None, 0.0, 10_000), (ssc.Dopri5(), 1e-7, D0, 0.0, 10_000), (ssc.Dopri8(), 1e-9, None, -3000.0, 10_000),
+             (ssc.Dopri8(), 1e-10, None, 0.0, 40)]             # last: max_steps reached by the long orbits
+    try:
+        for solver, tol, d0, t1, max_steps in cases:
+            ctrl = rt.make_ctrl(solver, tol, tol, 0.01, None, max_steps)
+            out = {}
+            for np_slots in (0, 1, 2, 4):
+                os.environ["SSB_RESP_NP"] = str(np_slots)
+                w, D, st, ns = rt.linear_response(base, pert._arrays, rt.to_dev(w0), None if d0 is None else rt.to_dev(d0), rt.to_dev(t0), t1, ctrl)
+                out[np_slots] = (w.cpu().numpy(), D.cpu().numpy(), st.cpu().numpy(), ns.cpu().numpy())
+            ref = out[0]
+            if max_steps == 40:
+                assert (ref[2] == 1).any() and (ref[2] == 0).any()
+            else:
+                assert (ref[2] == 0).all()
+            assert np.isinf(ref[0][5]).all() == (t1 == 0.0)
+            for np_slots in (1, 2, 4):
+                for a, b in zip(out[np_slots], ref):
+                    assert np.array_equal(a, b), f"{np_slots} slots per CTA differ from the one-particle kernel"
+    finally:
+        os.environ.pop("SSB_RESP_NP", None)
+    # default slot count at a batch large enough to use it: same bits as the one-particle kernel
+    N2 = 1200
+    w0b = halo_orbits(N2, seed=12); t0b = np.linspace(-1000.0, -5.0, N2)
+    ctrl = rt.make_ctrl(ssc.Dopri8(), 1e-7, 1e-7, 0.01, None, 10_000)
+    wa, Da, sa, na = rt.linear_response(base, pert._arrays, rt.to_dev(w0b), None, rt.to_dev(t0b), 0.0, ctrl)
+    os.environ["SSB_RESP_NP"] = "0"
+    try:
+        wb, Db, sb_, nb = rt.linear_response(base, pert._arrays, rt.to_dev(w0b), None, rt.to_dev(t0b), 0.0, ctrl)
+    finally:
+        os.environ.pop("SSB_RESP_NP", None)
+    assert bool((Da == Db).all()) and bool((wa == wb).all()) and bool((na == nb).all()) and int((sa != 0).sum()) == 0
+
+
 def test_response_generator_api(cuda):
     """GenerateMassRadiusPerturbation_Chen25.compute_perturbation_OTF shape contract (golden D7) + oracle parity."""
     import streamsculptor_b200 as ssc
