@@ -38,6 +38,13 @@ def workload(n_release):
     return ts, np.full(n_release + 1, MSAT)
 
 
+def workload_name(particles_per_gpu, world):
+    """config.workload of both arms (the reference arm times a bounded sample of this workload on the host cores)."""
+    return (f"C2: {particles_per_gpu}-particle mock stream per GPU ({particles_per_gpu * world} total), static MW3 "
+            "(Hernquist+MiyamotoNagai+NFW), 3 Gyr, adaptive Dopri8 rtol=atol=1e-7 dtmin=0.3, final state kept "
+            "(gen_stream_vmapped semantics), jax-threefry release draws")
+
+
 def prog_start():
     """Progenitor state 3 Gyr ago, computed ONCE on the device (not part of the timed step)."""
     import streamsculptor_b200 as ssc
@@ -136,8 +143,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "fp64 particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: 1e6-particle mock stream per GPU, static MW3 (Hernquist+MiyamotoNagai+NFW), adaptive Dopri8 rtol=atol=1e-7, "
-                                   "final state kept; CPU arm runs a bounded sample of it", "particles_per_step": 2 * n_rel},
+            "config": {"workload": workload_name(args.particles, world), "particles_per_gpu": args.particles,
+                       "sample": f"each step = {2 * n_rel} particles of that stream on the host cores", "particles_per_step": 2 * n_rel},
             "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample,
                              "note": "C++ restatement of the reference algorithm (oracle/), NOT jax[cpu]: jax/diffrax are not installable offline"},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -327,9 +334,7 @@ def run_ours(args, rank, world):
                "note": "C++ restatement of the reference algorithm (oracle/), NOT jax[cpu]: jax/diffrax are not installable offline"}
     line = {"metric": "fp64 particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C2: {args.particles}-particle mock stream per GPU ({args.particles * world} total), static MW3 "
-                                   "(Hernquist+MiyamotoNagai+NFW), 3 Gyr, adaptive Dopri8 rtol=atol=1e-7 dtmin=0.3, final state kept "
-                                   "(gen_stream_vmapped semantics), jax-threefry release draws",
+            "config": {"workload": workload_name(args.particles, world),
                        "particles_per_gpu": args.particles, "particle_steps_per_step": psteps, "parallelism": f"dp{world} (particles interleaved over ranks)",
                        "l2": "512 MB buffer zeroed between timed iterations", "time_to_stream_ms": ms_total / args.steps},
             "clocks": clocks, "gpu_launches": 4 * args.steps,      # dense_step, dense_eval, release, orbit kernels per gen_stream call

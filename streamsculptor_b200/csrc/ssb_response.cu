@@ -43,7 +43,7 @@ using namespace ssb;
 #define SSB_RESP_MAX_SORT 4096
 #define SSB_RESP_MAX_NP 4           // response_kernel_mp: particle slots per CTA (eight lanes of warp 0 each)
 #ifndef SSB_RESP_DEFAULT_NP
-#define SSB_RESP_DEFAULT_NP 2
+#define SSB_RESP_DEFAULT_NP 4
 #endif
 #define CK(call) do { int _e = ssb_cuda_check((call), #call); if (_e) return _e; } while (0)
 #define CKL(what) do { int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
