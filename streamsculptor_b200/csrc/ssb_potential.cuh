@@ -231,8 +231,11 @@ __device__ __forceinline__ void add_subhalos(const ssb_subhalos& S, const double
 // ---------------------------------------------------------------------------------------------
 // total field: sum over the program (Potential_Combine.gradient_func, potential.py:1291-1296)
 // ---------------------------------------------------------------------------------------------
+// `frozen` (optional): [SSB_MAX_TRACK][6] = value c[3] and derivative dc[3] of every track ALREADY evaluated at this t - used where many
+// evaluation points share one time (the shared-step kernels), so that the segment search and interpolation run once per stage, not per tracer.
 template <int MODE>
-__device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x[3], double t, double& P, double g[3], Sym3& H, int first = 0) {
+__device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x[3], double t, double& P, double g[3], Sym3& H, int first = 0,
+                                         const double* frozen = nullptr) {
     if (MODE & WANT_PHI) P = 0.0;
     if (MODE & WANT_GRAD) { g[0] = g[1] = g[2] = 0.0; }
     if (MODE & WANT_HESS) { H.xx = H.yy = H.zz = H.xy = H.xz = H.yz = 0.0; }
@@ -243,7 +246,8 @@ __device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x
         if (type == SSB_UNIFORM_ACC) {                              // potential.py:497-499
             if (MODE & WANT_GRAD) {
                 double cv[3], dv[3];
-                track_eval<true>(Pt.track[c.track], t, cv, dv);
+                if (frozen) { dv[0] = frozen[6 * c.track + 3]; dv[1] = frozen[6 * c.track + 4]; dv[2] = frozen[6 * c.track + 5]; }
+                else track_eval<true>(Pt.track[c.track], t, cv, dv);
                 g[0] += dv[0]; g[1] += dv[1]; g[2] += dv[2];
             }
             continue;
@@ -251,7 +255,8 @@ __device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x
         double xs[3] = {x[0], x[1], x[2]};
         if (c.track >= 0) {                                         // potential.py:460-462
             double ctr[3];
-            track_eval<false>(Pt.track[c.track], t, ctr, ctr);
+            if (frozen) { ctr[0] = frozen[6 * c.track]; ctr[1] = frozen[6 * c.track + 1]; ctr[2] = frozen[6 * c.track + 2]; }
+            else track_eval<false>(Pt.track[c.track], t, ctr, ctr);
             xs[0] -= ctr[0]; xs[1] -= ctr[1]; xs[2] -= ctr[2];
         }
         double phi = 0, q = 0, w = 0;

@@ -113,26 +113,70 @@ __global__ void shared_init_ctl2(int64_t N, SharedCtl* ctl, CtrlDev c) {
     ctl->done = !(ctl->tprev < ctl->T1);
 }
 
+// Force of the step-attempt kernel.  Every tracer is at the SAME time in every stage, so the time-dependent part of the program
+// (track centres of translating components, frame accelerations) is evaluated once per stage and CTA into `frozen` and the
+// tracers only subtract a centre; the static galaxy in front of the program (SIG != 0) is the fused inline signature of K1.
+__device__ __noinline__ double3 shared_accel_frozen(const ssb_potential* P, int first, double x, double y, double z, double t, const double* frozen) {
+    const double X[3] = {x, y, z};
+    double phi, g[3];
+    Sym3 H;
+    pot_eval<WANT_GRAD>(*P, X, t, phi, g, H, first, frozen);
+    return make_double3(-g[0], -g[1], -g[2]);
+}
+template <int SIG>
+struct SharedStageForce {
+    const ssb_potential* P; const ssb_potential* Pc; double dir; const double* frozen; int stage; bool extra;
+    __device__ __forceinline__ void operator()(const double X[3], double tau, double A[3]) {
+        const double* fz = frozen + stage * (6 * SSB_MAX_TRACK);
+        if (SIG == SIG_GENERIC) {
+            const double3 a = shared_accel_frozen(P, 0, X[0], X[1], X[2], tau * dir, fz);
+            A[0] = a.x; A[1] = a.y; A[2] = a.z;
+        } else {
+            double g[3];
+            fused_grad<SIG>(*Pc, X, g);
+            A[0] = -g[0]; A[1] = -g[1]; A[2] = -g[2];
+            if (extra) {
+                const double3 a = shared_accel_frozen(P, SigInfo<SIG>::NF, X[0], X[1], X[2], tau * dir, fz);
+                A[0] += a.x; A[1] += a.y; A[2] += a.z;
+            }
+        }
+        stage++;
+    }
+};
+
 // one step attempt for every tracer
-template <int SOLVER>
+template <int SOLVER, int SIG>
 __global__ void __launch_bounds__(128) shared_attempt(const __grid_constant__ ssb_potential Pin, int64_t N, double* buf0, double* buf1, SharedCtl* ctl, CtrlDev c) {
     typedef Tab<SOLVER> T;
     constexpr int S = T::S;
     __shared__ ssb_potential sP;
+    __shared__ double s_frozen[S][6 * SSB_MAX_TRACK];
     stage_potential(&sP, &Pin);
+    logtab_init();
     if (ctl->done) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const double tprev = ctl->tprev, dt = ctl->tnext - ctl->tprev, dir = ctl->dir;
+    // tracks at the S stage times of this attempt (the same expressions rk_stages / the last-stage call below hand to the force)
+    for (int q = threadIdx.x; q < S * sP.n_track; q += blockDim.x) {
+        const int st = q / sP.n_track, k = q - st * sP.n_track;
+        const double tau = tprev + T::c(st) * dt;
+        double cv[3], dv[3];
+        track_eval<true>(sP.track[k], tau * dir, cv, dv);
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { s_frozen[st][6 * k + m] = cv[m]; s_frozen[st][6 * k + 3 + m] = dv[m]; }
+    }
+    __syncthreads();
     const double* cur = ctl->which ? buf1 : buf0;
     double* nxt = ctl->which ? buf0 : buf1;
     double esq = 0.0;
     int bad = 0;
     if (i < N) {
-        SharedForce f{&sP, dir};
+        SharedStageForce<SIG> f{&sP, &Pin, dir, &s_frozen[0][0], 1, Pin.n_comp > SigInfo<SIG>::NF};
         double x[3], p[3], F[S][3], x1[3], p1[3], ex[3], ep[3];
         for (int k = 0; k < 3; ++k) { x[k] = cur[3 * i + k]; p[k] = cur[3 * N + 3 * i + k]; F[0][k] = cur[6 * N + 3 * i + k]; }
         rk_stages<SOLVER>(f, x, p, tprev, dt, F);
         rk_candidate<SOLVER>(x, p, dt, F, x1, p1);
+        f.stage = S - 1;
         f(x1, tprev + T::c(S - 1) * dt, F[S - 1]);
         rk_error<SOLVER>(p, dt, F, ex, ep);
         bool nanc = false;
@@ -407,10 +451,15 @@ int ssb_shared_step_orbits_f64(const ssb_potential* pot, int64_t N, const double
     CKL("shared_init");
     // batches of attempts; poll the done flag between batches
     const int batch = N >= 1000000 ? 4 : 32;
+    ssb_potential pc;
+    const int sig = ssb_canonicalize(pot, &pc);          // fused static galaxy in front (as in K1), the rest through the interpreter
+#define SSB_LAUNCH_ATT(S, SG) shared_attempt<S, SG><<<grid, 128, 0, st>>>(sig == SG ? pc : *pot, N, buf0, buf1, ctl, c)
+#define SSB_LAUNCH_ATT_SIG(S) do { switch (sig) { case SIG_NHM: SSB_LAUNCH_ATT(S, SIG_NHM); break; case SIG_NHHM: SSB_LAUNCH_ATT(S, SIG_NHHM); break; \
+        default: SSB_LAUNCH_ATT(S, SIG_GENERIC); } } while (0)
     for (int64_t launched = 0; launched <= (int64_t)ctrl.max_steps + batch;) {
         for (int b = 0; b < batch; ++b) {
-            if (ctrl.solver == 5) { shared_attempt<5><<<grid, 128, 0, st>>>(*pot, N, buf0, buf1, ctl, c); shared_control<5><<<1, 1, 0, st>>>(N, ctl, c); }
-            else { shared_attempt<8><<<grid, 128, 0, st>>>(*pot, N, buf0, buf1, ctl, c); shared_control<8><<<1, 1, 0, st>>>(N, ctl, c); }
+            if (ctrl.solver == 5) { SSB_LAUNCH_ATT_SIG(5); shared_control<5><<<1, 1, 0, st>>>(N, ctl, c); }
+            else { SSB_LAUNCH_ATT_SIG(8); shared_control<8><<<1, 1, 0, st>>>(N, ctl, c); }
         }
         launched += batch;
         CKL("shared_attempt");
