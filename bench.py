@@ -38,6 +38,26 @@ def workload(n_release):
     return ts, np.full(n_release + 1, MSAT)
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Rank 0 must print ONE JSON line: everything else written to fd 1 by libraries (NCCL prints its version banner there) is sent
+    to stderr for the duration of the run; emit() writes the result line to the real stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def workload_name(particles_per_gpu, world):
     """config.workload of both arms (the reference arm times a bounded sample of this workload on the host cores)."""
     return (f"C2: {particles_per_gpu}-particle mock stream per GPU ({particles_per_gpu * world} total), static MW3 "
@@ -148,7 +168,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample,
                              "note": "C++ restatement of the reference algorithm (oracle/), NOT jax[cpu]: jax/diffrax are not installable offline"},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def ncu_traffic():
@@ -342,7 +362,7 @@ def run_ours(args, rank, world):
                     "ms_per_step": 1e3 * e2e_s / args.steps, "call": "ssb_gen_stream_host (C ABI, pinned host buffers; results written by the orbit "
                     "kernel directly into the pinned output buffer)", "ms_per_step_staged_d2h": 1e3 * e2e_staged_s / args.steps},
             "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -355,6 +375,7 @@ def main():
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

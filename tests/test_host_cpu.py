@@ -172,9 +172,12 @@ def test_bench_reference_arm_runs_on_cpu():
                          text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     import json
-    line = json.loads(res.stdout.strip().splitlines()[-1])
+    out = res.stdout.strip().splitlines()
+    assert len(out) == 1, "bench.py must print exactly ONE line on stdout (library chatter goes to stderr)"
+    line = json.loads(out[0])
     assert line["impl"] == "reference" and line["unit"] == "particle-steps/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["config"]["workload"].startswith("C2: 1000000-particle mock stream per GPU") and line["metric"] == "fp64 particle-steps/sec"
 
 
 def test_argument_validation_of_the_round1_entry_points():
