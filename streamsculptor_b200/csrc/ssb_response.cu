@@ -651,12 +651,12 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
     constexpr int S = T::S;
     constexpr int NPX = SSB_RESP_MAX_NP;
     __shared__ ssb_potential sP;
-    __shared__ BaseShared<S> sb[NPX + 1];                     // [NPX]: trash record of the idle lanes of warp 0
-    __shared__ __align__(16) double sPhiE[NPX + 1][72];
+    __shared__ BaseShared<S> sb[2 * NPX];                     // [NPX + g]: scratch record of lane group g of warp 0 while it has no particle
+    __shared__ __align__(16) double sPhiE[NPX][72];
     __shared__ double sred[32], sred_q[NPX][32];
     __shared__ RespSlot slot[NPX];
-    __shared__ int s_nact[NPX + 1], s_bad[NPX + 1];
-    __shared__ double s_besq[NPX + 1];                        // squared scaled error of the base orbit's attempt
+    __shared__ int s_nact[NPX], s_bad[NPX];
+    __shared__ double s_besq[NPX];                            // squared scaled error of the base orbit's attempt
     __shared__ int s_service, s_live;
     stage_potential(&sP, &Pin);
     logtab_init();
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     // warp 0: lane = 8 * slot + role; role 0 = base orbit, 1..6 = propagator columns, 7 = idle
     const int col = (lane & 7) - 1;
-    const int my_slot = (tid < 32 && (lane >> 3) < NP && col < 6) ? (lane >> 3) : NPX;
+    const int my_slot = (tid < 32 && (lane >> 3) < NP) ? (lane >> 3) : NPX;        // NPX: this lane group carries no slot
     double x[3] = {8.0, 0.0, 0.0}, p[3] = {0, 0, 0}, F[S][3], x1[3] = {8.0, 0.0, 0.0}, p1[3] = {0, 0, 0};
 #pragma unroll
     for (int l = 0; l < S; ++l) F[l][0] = F[l][1] = F[l][2] = 0.0;
@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
         s.part = tid < NP ? -1 : -2; s.dir = 1.0; s.T0 = s.T1 = s.tprev = s.tnext = 0.0; s.status = s.n_steps = s.n_acc = s.n_rej = 0;
         s.at_dtmin = s.accepted = s.finishing = s.flip = s.n_act_run = s.n_dead = s.skip = s.pad = 0;
     }
-    if (tid <= NPX) { s_nact[tid] = 0; s_bad[tid] = 0; }
+    if (tid < NPX) { s_nact[tid] = 0; s_bad[tid] = 0; s_besq[tid] = 0.0; }
     if (tid == 0) { s_service = 1; s_live = 1; }
     double* const cta_buf = a.scratch + (size_t)blockIdx.x * NPX * 2 * 6 * n_items;
 
@@ -846,8 +846,11 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
         if (!s_live) break;                                    // uniform
         // ---- serial phase, shared by the slots: base orbits + propagator columns of this round's attempts (warp 0) ----
         if (tid < 32) {
+            __syncwarp();                                      // the FSAL commit of the base lanes (stage-0 record) is visible to the column lanes
+            // all eight lanes of a group evaluate the group leader's point and store the SAME record; a group without a particle
+            // works on its own scratch record
             const bool act = my_slot < NPX && slot[my_slot].part >= 0;
-            const int rec = act ? my_slot : NPX;
+            const int rec = act ? my_slot : NPX + (lane >> 3);
             const double tp = act ? slot[rec].tprev : 0.0, dt = act ? slot[rec].tnext - tp : 1.0, dir = act ? slot[rec].dir : 1.0;
             if (col >= 0) {
 #pragma unroll
@@ -883,7 +886,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
                     na = lo;
                 }
                 s_nact[rec] = na;
-            } else if (act && col < 6) {
+            } else if (act && col >= 0 && col < 6) {
                 double* PE = sPhiE[rec];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {

@@ -1,3 +1,5 @@
+# One gpurun call that validates a build on a B200 box: GPU parity tests, smoke(), bench.py, the ncu launch list of the bench, one
+# full ncu capture of the orbit kernel and the per-config throughput tools.  Usage: gpurun --timeout 900 -- bash tools/gpu_validate.sh
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out

@@ -1,0 +1,49 @@
+"""Small invocations of the kernels touched in session 3, sized for compute-sanitizer (memcheck / racecheck):
+response_kernel_mp with 4 particle slots per CTA, the zero-copy host outputs of the orbit kernel, the shared-step attempt kernel
+with once-per-stage track evaluation.  Usage: compute-sanitizer --tool racecheck python tools/sanitize_new_kernels.py"""
+import os, sys
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
+import ctypes as C
+import numpy as np, torch
+import streamsculptor_b200 as ssc
+from streamsculptor_b200 import _lib, _runtime as rt, RestrictedNbody as RN
+from common import mw3_product, halo_orbits, subhalo_set
+
+P = ssc.potential
+base = mw3_product()
+# (1) K3-mp, 4 slots per CTA, zero and non-zero perturbation ICs
+os.environ["SSB_RESP_NP"] = "4"
+nsh = 40
+sh = subhalo_set(nsh, seed=5, t_lo=-300.0, tw=60.0)
+pert = P.SubhaloLinePotentialCustom_fromFunc(func=P.HernquistPotential, m=sh["m"], r_s=sh["rs"], subhalo_x0=sh["x0"], subhalo_v=sh["v"],
+                                             subhalo_t0=sh["t0"], t_window=sh["tw"], units=ssc.usys)
+N = 10
+w0, t0 = halo_orbits(N, seed=11), np.linspace(-300.0, -5.0, N)
+D0 = np.random.default_rng(2).normal(size=(N, nsh, 12)) * 1e-6
+for solver, d0 in ((ssc.Dopri8(), None), (ssc.Dopri5(), D0)):
+    ctrl = rt.make_ctrl(solver, 1e-7, 1e-7, 0.01, None, 10_000)
+    w, D, st, ns = rt.linear_response(base, pert._arrays, rt.to_dev(w0), None if d0 is None else rt.to_dev(d0), rt.to_dev(t0), 0.0, ctrl)
+    assert int((st != 0).sum().item()) == 0
+print("response_kernel_mp ok", ns[:, 0].cpu().numpy())
+# (2) zero-copy host outputs
+Pst, keep = rt.lower(base)
+host = _lib.Potential.from_buffer_copy(Pst)
+nts = 78; n = nts - 1
+ts = torch.from_numpy(np.linspace(-300.0, 0.0, nts)); pw = torch.from_numpy(np.array([-3.0, 14.0, 8.0, 0.14, 0.02, -0.07])); ms = torch.full((nts,), 1e4, dtype=torch.float64)
+out = torch.empty((2, n, 6), dtype=torch.float64).pin_memory(); st = torch.empty((2, n), dtype=torch.int32).pin_memory(); nsb = torch.empty((2, n, 3), dtype=torch.int32).pin_memory()
+hp = lambda t: C.c_void_p(t.data_ptr())
+ctrl = rt.make_ctrl(ssc.Dopri8(), 1e-7, 1e-7, 0.3, None, 10_000)
+_lib.check(_lib.lib().ssb_gen_stream_host(C.byref(host), C.byref(host), base._G, nts, hp(ts), hp(pw), hp(ms), 583, (C.c_double * 8)(*ssc.main.DEFAULT_KVALS), None,
+                                          ctrl, 0, 1, n, hp(out[0]), hp(out[1]), hp(st), hp(nsb)))
+assert (st == 0).all() and torch.isfinite(out).all()
+print("zero-copy host outputs ok")
+# (3) shared-step tracers: fused galaxy + progenitor on a cubic track evaluated once per stage
+tk = np.linspace(-60.0, 0.0, 31)
+yk = base.integrate_orbit(w0=[20.0, 0.0, 20.0, 0.0, 0.15, 0.0], ts=tk[::-1].copy(), t0=0.0, t1=-60.0).ys[::-1].copy()
+field = RN.RestrictedNbody_generator(potential=base, progenitor_potential=P.PlummerPotential, interp_prog=ssc.CubicTrack(tk, yk[:, :3].copy()), init_mass=2e4,
+                                     init_rs=0.01, r_esc=0.05)
+rng = np.random.default_rng(5)
+wt = np.hstack([yk[0, :3] + rng.normal(size=(300, 3)) * 0.02, yk[0, 3:] + rng.normal(size=(300, 3)) * 5e-4])
+sol = ssc.integrate_field(w0=wt, ts=np.array([-60.0, -40.0]), solver=ssc.Dopri8(), field=field, rtol=1e-8, atol=1e-8, dtmin=0.05, max_steps=500)
+assert np.isfinite(sol.ys).all()
+print("shared-step kernels ok", int(sol.stats["num_steps"]))
