@@ -2,11 +2,11 @@
 tangent ODEs along every orbit (K7) and a live softened N-body field of 100 bodies (K6).  CUDA events, best of 3.
 Usage: python tools/bench_c5.py [n_tracers] [n_variational]"""
 import os, sys
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tools"))
 import numpy as np, torch
 import streamsculptor_b200 as ssc
 from streamsculptor_b200 import RestrictedNbody as RN
-from common import mw3_product, halo_orbits
+from _workloads import mw3_product, halo_orbits
 
 n_tr = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000
 n_var = int(float(sys.argv[2])) if len(sys.argv) > 2 else 1_000_000

@@ -1,11 +1,11 @@
 """Throughput of the BASELINE.json configs other than the bench.py headline (C2): C1, C3, C2 with 64 saved snapshots.
 Usage: python tools/bench_configs.py [n_particles]   (prints one line per config; CUDA events, 3 warm-ups, best of 3)"""
 import os, sys
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tools"))
 import numpy as np, torch
 import streamsculptor_b200 as ssc
 from streamsculptor_b200 import _runtime as rt
-from common import mw3_product
+from _workloads import mw3_product
 
 n_part = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 P = ssc.potential

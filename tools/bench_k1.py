@@ -1,11 +1,11 @@
 """K1 A/B microbenchmark: C2 stream (1e6 particles, Dopri8 1e-7) through gen_stream_vmapped; CUDA events, best of 5.
 Usage: SSB_LIB_PATH=build/variants/x.so python tools/bench_k1.py [n_particles] [solver]"""
 import os, sys
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tools"))
 import numpy as np, torch
 import streamsculptor_b200 as ssc
 from streamsculptor_b200 import _runtime as rt
-from common import mw3_product
+from _workloads import mw3_product
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 solver = ssc.Dopri5() if (len(sys.argv) > 2 and sys.argv[2] == "5") else ssc.Dopri8()

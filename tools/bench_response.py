@@ -1,16 +1,15 @@
 """C4 measurement: first-order response of a C1-like stream to N_sh Hernquist subhalos.
-Usage: python tools/bench_response.py [n_particles] [n_sh] [tol] [check]"""
-import os, sys, time
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
+Usage: python tools/bench_response.py [n_particles] [n_sh] [tol]   (parity against the oracle lives in tests/test_gpu_parity.py)"""
+import os, sys
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tools"))
 import numpy as np, torch
 import streamsculptor_b200 as ssc
 from streamsculptor_b200 import _runtime as rt
-from common import mw3_product, mw3_oracle
+from _workloads import mw3_product
 
 n_p = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 n_sh = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 tol = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-6
-check = len(sys.argv) > 4
 pot = mw3_product()
 P = ssc.potential
 back = pot.integrate_orbit(w0=[20.0, 0.0, 20.0, 0.0, 0.15, 0.0], ts=np.array([0.0, -3000.0]), t0=0.0, t1=-3000.0).ys[-1]
@@ -41,20 +40,3 @@ for it in range(3):
 steps = int(ns[:, 0].sum().item())
 print(f"C4: {len(w0)} particles x {n_sh} subhalos, Dopri8 tol={tol}: {ms:.1f} ms, particle-steps {steps}, pair-steps/s {steps * n_sh / ms * 1e3:.3e}, "
       f"status!=0: {int((st != 0).sum().item())}, mean steps {steps / len(w0):.1f}, flop/s (2.85 kflop/pair-step) {2850.0 * steps * n_sh / ms * 1e3 / 1e12:.2f} TF")
-if check:
-    import oracle as O
-    orc = mw3_oracle()
-    osh = O.Program().subhalos(O.PR_HERNQUIST, np.ones(n_sh), rs, x0, v, t_imp, 150.0)
-    sel = np.linspace(0, len(w0) - 2, 8).astype(int)
-    t = time.time()
-    wo, Do, so, nso = O.linear_response(orc, osh, w0[sel], t0[sel], 0.0, solver=8, rtol=tol, atol=tol, dtmin=0.01, threads=8)
-    dt = time.time() - t
-    Dg = D.cpu().numpy()[sel]
-    print("oracle: %.1f s for 8 particles -> pair-steps/s %.3e (8 threads)" % (dt, nso[:, 0].sum() * n_sh / dt))
-    print("steps gpu", ns.cpu().numpy()[sel, 0], "oracle", nso[:, 0])
-    print("max |D_gpu - D_orc| / max|D_orc| per particle", (np.abs(Dg - Do).reshape(8, -1).max(1) / np.abs(Do).reshape(8, -1).max(1)))
-    wt, Dt, _, nst = O.linear_response(orc, osh, w0[sel], t0[sel], 0.0, solver=8, rtol=1e-13, atol=1e-16, dtmin=1e-4, max_steps=1_000_000, threads=8)
-    print("truth steps", nst[:, 0], "max|D_truth|", np.abs(Dt).reshape(8, -1).max(1))
-    print("|D_orc - truth|/max|truth|", (np.abs(Do - Dt).reshape(8, -1).max(1) / np.abs(Dt).reshape(8, -1).max(1)))
-    print("|D_gpu - truth|/max|truth|", (np.abs(Dg - Dt).reshape(8, -1).max(1) / np.abs(Dt).reshape(8, -1).max(1)))
-    print("|w_orc - truth|", np.abs(wo - wt).max(1), "|w_gpu - truth|", np.abs(w.cpu().numpy()[sel] - wt).max(1))

@@ -1,11 +1,11 @@
 """C4 on N GPUs (weak scaling: n_p particles per GPU x n_sh subhalos, particles interleaved over ranks, only final states and
 response summaries all-gathered).  Launch: python -m torch.distributed.run --nproc-per-node N tools/bench_response_multi.py [n_p] [n_sh] [tol]"""
 import os, sys
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tools"))
 import numpy as np, torch
 import streamsculptor_b200 as ssc
 from streamsculptor_b200 import _runtime as rt, parallel as par
-from common import mw3_product
+from _workloads import mw3_product
 
 n_p = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 n_sh = int(sys.argv[2]) if len(sys.argv) > 2 else 1000

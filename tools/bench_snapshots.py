@@ -1,11 +1,11 @@
 """C2 with M saved snapshots per particle (integrate_orbit_batch_vmapped, ts[N,M]): output-heavy variant of the stream hot path.
 Usage: python tools/bench_snapshots.py [n_particles] [M]"""
 import os, sys
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tools"))
 import numpy as np, torch
 import streamsculptor_b200 as ssc
 from streamsculptor_b200 import _runtime as rt
-from common import mw3_product
+from _workloads import mw3_product
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 64

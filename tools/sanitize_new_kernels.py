@@ -2,12 +2,12 @@
 response_kernel_mp with 4 particle slots per CTA, the zero-copy host outputs of the orbit kernel, the shared-step attempt kernel
 with once-per-stage track evaluation.  Usage: compute-sanitizer --tool racecheck python tools/sanitize_new_kernels.py"""
 import os, sys
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tools"))
 import ctypes as C
 import numpy as np, torch
 import streamsculptor_b200 as ssc
 from streamsculptor_b200 import _lib, _runtime as rt, RestrictedNbody as RN
-from common import mw3_product, halo_orbits, subhalo_set
+from _workloads import mw3_product, halo_orbits, subhalo_set
 
 P = ssc.potential
 base = mw3_product()
