@@ -357,7 +357,9 @@ def run_ours(args, rank, world):
             "config": {"workload": workload_name(args.particles, world),
                        "particles_per_gpu": args.particles, "particle_steps_per_step": psteps, "parallelism": f"dp{world} (particles interleaved over ranks)",
                        "l2": "512 MB buffer zeroed between timed iterations", "time_to_stream_ms": ms_total / args.steps},
-            "clocks": clocks, "gpu_launches": 4 * args.steps,      # dense_step, dense_eval, release, orbit kernels per gen_stream call
+            # kernels per gen_stream call: dense_step, dense_eval, release, orbit - or, for streams large enough for the two-part pipeline
+            # (csrc/ssb_kernels.cu, >= 32768 particles per arm), 2 x (dense_step, dense_eval, release) + 4 orbit launches
+            "clocks": clocks, "gpu_launches": (10 if n_local >= 32768 and os.environ.get("SSB_STREAM_SPLIT", "1")[0] != "0" else 4) * args.steps,
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / args.steps, "call": "ssb_gen_stream_host (C ABI, pinned host buffers; results written by the orbit "
                     "kernel directly into the pinned output buffer)", "ms_per_step_staged_d2h": 1e3 * e2e_staged_s / args.steps},

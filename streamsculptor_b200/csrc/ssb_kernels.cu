@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <limits>
@@ -93,7 +94,7 @@ template <int SOLVER, int MODE, int SIG, int XS = 0>
 __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_potential* Pc, const double* w0, double t0_in, double t1_in,
                                               const double* tsp, int M, double* ys, const CtrlDev& c, bool valid,
                                               int& status, int& n_steps, int& n_acc, int& n_rej, double* rec, int rec_cap,
-                                              const FastX* fxp = nullptr) {
+                                              const FastX* fxp = nullptr, double t_stop = HUGE_VAL) {
     typedef Tab<SOLVER> T;
     constexpr int S = T::S;
     const double dir = (t0_in < t1_in) ? 1.0 : -1.0;              // diffrax: direction = where(t0 < t1, 1, -1)
@@ -148,6 +149,7 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
     }
     for (;;) {
         bool active = valid && status == 0 && tprev < T1;
+        if (MODE == 1) active = active && tprev < t_stop;            // K0 part runs (t_stop in mirrored time): same steps as the full solve, cut short
         if (active && n_steps >= c.max_steps) { status = 1; active = false; }
         if (!__any_sync(0xffffffffu, active)) break;
         if (!active) continue;
@@ -280,14 +282,16 @@ __global__ void __launch_bounds__(SSB_ORBIT_THREADS, SSB_ORBIT_MIN_BLOCKS) orbit
 template <int SOLVER, int SIG>
 __global__ void __launch_bounds__(32) dense_step_kernel(const __grid_constant__ ssb_potential Pin, const double* w0, double t0, double t1,
                                                         const double* t0p, const double* t1p, CtrlDev c, double* scratch, int rec_cap,
-                                                        int32_t* status_out, int32_t* nsteps_out) {
+                                                        int32_t* status_out, int32_t* nsteps_out, const double* tstop_p = nullptr) {
     __shared__ ssb_potential sP;
     stage_potential(&sP, &Pin);
     logtab_init();
     if (t0p) { t0 = *t0p; t1 = *t1p; }              // interval ends read on the device (no host round trip in gen_stream)
     const bool valid = threadIdx.x == 0;
     int status, n_steps, n_acc, n_rej;
-    integrate_one<SOLVER, 1, SIG>(&sP, &Pin, w0, t0, t1, nullptr, 0, nullptr, c, valid, status, n_steps, n_acc, n_rej, scratch + 8, rec_cap);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const double t_stop = tstop_p ? *tstop_p * ((t0 < t1) ? 1.0 : -1.0) : inf;      // mirrored time, as integrate_one runs
+    integrate_one<SOLVER, 1, SIG>(&sP, &Pin, w0, t0, t1, nullptr, 0, nullptr, c, valid, status, n_steps, n_acc, n_rej, scratch + 8, rec_cap, nullptr, t_stop);
     if (valid) {
         scratch[0] = (double)min(n_acc, rec_cap); scratch[1] = (double)status; scratch[4] = (t0 < t1) ? 1.0 : -1.0;
         if (status_out) *status_out = status;
@@ -504,6 +508,7 @@ struct ReleaseArgs {
     // prog and every output at k (sel_stride = 0: g = k).  t1_packed[2,N] (optional) is filled with *t_end.
     int64_t sel_begin, sel_stride;
     double* t1_packed; const double* t_end;
+    int64_t i0, cnt;              // cnt > 0: this launch handles the compact indices [i0, i0 + cnt) of the N (gen_stream's two-part pipeline)
 };
 
 // ---- forward-mode dual numbers for jacfwd(release_model) (perturbative.py:281-296): value + 6 partials d/d(x, v) ----
@@ -570,7 +575,9 @@ __device__ inline void release_draws(const ReleaseArgs& a, int64_t i, double nr[
 __global__ void release_kernel(const __grid_constant__ ssb_potential Pin, const ReleaseArgs a) {
     __shared__ ssb_potential sP;
     stage_potential(&sP, &Pin);
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;        // compact index: prog row, output row
+    const int64_t k0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.cnt > 0 && k0 >= a.cnt) return;
+    const int64_t i = a.i0 + k0;                                             // compact index: prog row, output row
     if (i >= a.N) return;
     const int64_t gi = a.sel_stride ? a.sel_begin + i * a.sel_stride : i;   // stripping-time index
     const double* w = a.prog + 6 * i;
@@ -873,11 +880,11 @@ size_t ssb_scratch_bytes(int32_t max_steps) { return sizeof(double) * (8 + (size
 
 static int dense_launch(const ssb_potential* pot, const double* w0, double t0, double t1, const double* t0p, const double* t1p,
                         const double* ts, int64_t M, const ssb_ctrl& ctrl, double* ys, int32_t* status, int32_t* nsteps, double* scratch,
-                        cudaStream_t st, int64_t ts_begin = 0, int64_t ts_stride = 1) {
+                        cudaStream_t st, int64_t ts_begin = 0, int64_t ts_stride = 1, const double* tstop_p = nullptr) {
     const CtrlDev c = to_dev(ctrl);
     ssb_potential pc;
     const int sig = ssb_canonicalize(pot, &pc);
-#define SSB_LAUNCH_DENSE(S, SG) dense_step_kernel<S, SG><<<1, 32, 0, st>>>(pc, w0, t0, t1, t0p, t1p, c, scratch, ctrl.max_steps, status, nsteps)
+#define SSB_LAUNCH_DENSE(S, SG) dense_step_kernel<S, SG><<<1, 32, 0, st>>>(pc, w0, t0, t1, t0p, t1p, c, scratch, ctrl.max_steps, status, nsteps, tstop_p)
 #define SSB_LAUNCH_DENSE_SIG(S) do { switch (sig) { case SIG_N: SSB_LAUNCH_DENSE(S, SIG_N); break; case SIG_NHM: SSB_LAUNCH_DENSE(S, SIG_NHM); break; \
         case SIG_NHHM: SSB_LAUNCH_DENSE(S, SIG_NHHM); break; default: SSB_LAUNCH_DENSE(S, SIG_GENERIC); } } while (0)
     if (ctrl.solver == 5) SSB_LAUNCH_DENSE_SIG(5); else SSB_LAUNCH_DENSE_SIG(8);
@@ -1012,7 +1019,38 @@ int ssb_potential_third_f64(const ssb_potential* pot, int64_t n, const double* x
 
 // scratch layout of gen_stream: [dense scratch | prog Nts*6 | w0_packed 2*Nts*6 | w0 2n*6 | t0 2n | t1 2n | ys 2n*6]
 size_t ssb_stream_scratch_bytes(int64_t Nts, int32_t max_steps) {
-    return ssb_scratch_bytes(max_steps) + sizeof(double) * (size_t)Nts * (6 + 12 + 12 + 2 + 2 + 12) + 256;
+    return 2 * ssb_scratch_bytes(max_steps) + sizeof(double) * (size_t)Nts * (6 + 12 + 12 + 2 + 2 + 12) + 256;
+}
+
+// ---- two-part pipeline of gen_stream ----
+// The progenitor orbit is ONE serial solve (~0.7 ms for 3 Gyr) that every release waits for.  For large streams the particles
+// are cut into an early part A (the first eighth of the stripping times = the longest orbits) and the rest B:
+//   caller's stream : progenitor only until it has passed A's last stripping time (~0.1 ms) -> release A -> orbits A (lead, trail)
+//   internal stream : the whole progenitor orbit again (its own record buffer)          -> release B -> orbits B (lead, trail)
+// so the orbit kernels start after ~0.1 ms and B's serial phase hides behind A's orbits.  Both progenitor solves take the same
+// steps (the early stop only ends the loop), every particle sees the same bits as in the one-part pipeline.
+#ifndef SSB_STREAM_SPLIT_MIN
+#define SSB_STREAM_SPLIT_MIN 32768          // particles per arm below which the one-part pipeline is used
+#endif
+struct StreamAux { bool ok; cudaStream_t s2; cudaEvent_t e0, e1; };
+static StreamAux* stream_aux() {
+    static thread_local StreamAux aux[64];
+    static thread_local bool tried[64];
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!tried[dev]) {
+        tried[dev] = true;
+        StreamAux& x = aux[dev];
+        x.ok = cudaStreamCreateWithFlags(&x.s2, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&x.e0, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&x.e1, cudaEventDisableTiming) == cudaSuccess;
+        if (!x.ok) cudaGetLastError();
+    }
+    return aux[dev].ok ? &aux[dev] : nullptr;
+}
+static bool stream_split_enabled() {
+    const char* e = getenv("SSB_STREAM_SPLIT");
+    return !(e && e[0] == '0');
 }
 
 int ssb_gen_stream_f64(const ssb_potential* pot, const ssb_potential* pot_release, double G, int64_t Nts, const double* ts, const double* prog_w0,
@@ -1035,7 +1073,43 @@ int ssb_gen_stream_f64(const ssb_potential* pot, const ssb_potential* pot_releas
     double* t0 = w0 + 12 * Nts;
     double* t1 = t0 + 2 * Nts;
     double* ys = t1 + 2 * Nts;
+    double* dense2 = ys + 12 * Nts;
     if (n == 0) return 0;
+    int64_t r5[5]; host_randint5(seed, r5);
+    StreamAux* ax = (n >= SSB_STREAM_SPLIT_MIN && trail == lead + 6 * n && stream_split_enabled()) ? stream_aux() : nullptr;
+    if (ax) {
+        const int64_t na = ((n / 8 + 127) / 128) * 128, nb = n - na;      // part A: the first eighth of this shard's stripping times
+        cudaStream_t s2 = ax->s2;
+        ReleaseArgs a;
+        memset(&a, 0, sizeof(a));
+        a.N = n; a.prog = prog; a.Msat = Msat; a.t = ts; a.normals = normals; a.idx = nullptr; a.G = G;
+        a.sel_begin = i_begin; a.sel_stride = i_stride;
+        for (int q = 0; q < 4; ++q) a.r[q] = r5[q];
+        memcpy(a.kv, kvals, sizeof(a.kv));
+        a.w0_packed = w0; a.t0_packed = t0; a.t1_packed = t1; a.t_end = ts + (Nts - 1);
+        CK(cudaEventRecord(ax->e0, st));                                   // the inputs are ready in the caller's stream order
+        CK(cudaStreamWaitEvent(s2, ax->e0, 0));
+        // part B on the internal stream: whole progenitor orbit -> its dense output at B's stripping times -> release -> orbits
+        if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts, ts + (Nts - 1), ts, nb, ctrl, prog + 6 * na, nullptr, nullptr, dense2, s2,
+                                 i_begin + na * i_stride, i_stride)) return e;
+        a.i0 = na; a.cnt = nb;
+        release_kernel<<<nblk(nb, 128), 128, 0, s2>>>(*pot_release, a);
+        CKL("release_kernel");
+        if (int e = ssb_orbit_integrate_f64(pot, nb, w0 + 6 * na, t0 + na, t1 + na, t1 + na, 1, 1, ctrl, lead + 6 * na, status + na, nsteps + 3 * na, s2)) return e;
+        if (int e = ssb_orbit_integrate_f64(pot, nb, w0 + 6 * (n + na), t0 + n + na, t1 + n + na, t1 + n + na, 1, 1, ctrl, lead + 6 * (n + na),
+                                            status + n + na, nsteps + 3 * (n + na), s2)) return e;
+        CK(cudaEventRecord(ax->e1, s2));
+        // part A on the caller's stream: the progenitor only until it has passed A's last stripping time
+        if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts, ts + (Nts - 1), ts, na, ctrl, prog, nullptr, nullptr, dense, st, i_begin, i_stride,
+                                 ts + (i_begin + (na - 1) * i_stride))) return e;
+        a.i0 = 0; a.cnt = na;
+        release_kernel<<<nblk(na, 128), 128, 0, st>>>(*pot_release, a);
+        CKL("release_kernel");
+        if (int e = ssb_orbit_integrate_f64(pot, na, w0, t0, t1, t1, 1, 1, ctrl, lead, status, nsteps, st)) return e;
+        if (int e = ssb_orbit_integrate_f64(pot, na, w0 + 6 * n, t0 + n, t1 + n, t1 + n, 1, 1, ctrl, lead + 6 * n, status + n, nsteps + 3 * n, st)) return e;
+        CK(cudaStreamWaitEvent(st, ax->e1, 0));                            // join: the caller's stream continues after both parts
+        return 0;
+    }
     // (1) progenitor orbit integrate_orbit(prog_w0, ts) with t0 = ts.min, t1 = ts.max (main.py:289, 152-153): ONE serial solve, then its
     //     dense output at THIS SHARD's stripping times only (ts[i_begin + k i_stride], k < n)
     if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts, ts + (Nts - 1), ts, n, ctrl, prog, nullptr, nullptr, dense, st, i_begin, i_stride)) return e;
@@ -1045,7 +1119,6 @@ int ssb_gen_stream_f64(const ssb_potential* pot, const ssb_potential* pot_releas
     memset(&a, 0, sizeof(a));
     a.N = n; a.prog = prog; a.Msat = Msat; a.t = ts; a.normals = normals; a.idx = nullptr; a.G = G;
     a.sel_begin = i_begin; a.sel_stride = i_stride;
-    int64_t r5[5]; host_randint5(seed, r5);
     for (int q = 0; q < 4; ++q) a.r[q] = r5[q];
     memcpy(a.kv, kvals, sizeof(a.kv));
     a.w0_packed = w0; a.t0_packed = t0; a.t1_packed = t1; a.t_end = ts + (Nts - 1);

@@ -444,6 +444,34 @@ def test_host_entry_points_zero_copy_outputs(cuda):
     assert (ns[:, 0] == ns[:, 1] + ns[:, 2]).all() and (ns[:, 0] > 10).all()
 
 
+def test_two_part_stream_pipeline_bit_identical(cuda):
+    """Large streams run gen_stream as two concurrent parts (early particles behind a cut-short progenitor solve, the rest behind the full one,
+    csrc/ssb_kernels.cu).  Same bits as the one-part pipeline, also for a sharded selection and through the host entry point."""
+    import os
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import _runtime as rt
+    pot = mw3_product()
+    nts = 40_001                                                # 40 000 particles per arm: above the split threshold
+    ts = rt.to_dev(np.linspace(-2000.0, 0.0, nts))
+    w0 = rt.to_dev(np.array([-3.0, 14.0, 8.0, 0.14, 0.02, -0.07]))
+    ms = rt.to_dev(np.full(nts, 1e4))
+    ctrl = rt.make_ctrl(ssc.Dopri8(), 1e-7, 1e-7, 0.3, None, 10_000)
+    kv = ssc.main.DEFAULT_KVALS
+    res = {}
+    try:
+        for mode in ("1", "0"):
+            os.environ["SSB_STREAM_SPLIT"] = mode
+            full = rt.gen_stream(pot, pot, pot._G, ts, w0, ms, 583, kv, None, ctrl)
+            shard = rt.gen_stream(pot, pot, pot._G, ts, w0, ms, 583, kv, None, ctrl, i_begin=0, i_stride=1, n_local=36_000)
+            res[mode] = [t.cpu().numpy().copy() for t in full] + [t.cpu().numpy().copy() for t in shard]
+    finally:
+        os.environ.pop("SSB_STREAM_SPLIT", None)
+    for a, b in zip(res["1"], res["0"]):
+        assert np.array_equal(a, b)
+    assert (res["1"][2] == 0).all() and np.isfinite(res["1"][0]).all() and res["1"][0].shape == (nts - 1, 6)
+    assert np.array_equal(res["1"][4], res["1"][0][:36_000])   # a prefix selection equals the prefix of the whole stream
+
+
 def test_third_derivatives_and_release_jacobian(cuda):
     """A15: closed-form third derivatives and jacfwd(release_model) (perturbative.py:281-296) vs the oracle's nested autodiff."""
     import streamsculptor_b200 as ssc
