@@ -211,6 +211,18 @@ class GenerateMassRadiusPerturbation_Chen25(_ResponseGenerator):          # pert
     def compute_base_stream(self, cpu=True):
         return self.base_stream.gen_stream()
 
+    def run_nonlinear_sim(self, pot_pert=None, solver=Dopri8(scan_kind='bounded'), rtol=1e-6, atol=1e-6, dtmin=0.05, max_steps=10_000):
+        """The full non-linear simulation of the stream in base + perturbation, without perturbation theory (perturbative.py:775-813):
+        gen_stream_vmapped_with_pert_Chen25_fixed_prog with this model's stream parameters; returns vstack([lead, trail]) [2(N-1), 6]."""
+        from .streamhelpers import gen_stream_vmapped_with_pert_Chen25_fixed_prog
+        if pot_pert is None:
+            pot_pert = self.potential_perturbation
+        bm = self.BaseStreamModel
+        lead, trail = gen_stream_vmapped_with_pert_Chen25_fixed_prog(pot_base=self.potential_base, pot_pert=pot_pert, prog_pot=bm.prog_pot,
+                                                                     prog_w0=self.base_stream.prog_w0, ts=bm.ts, key=bm.key, Msat=bm.Msat,
+                                                                     max_steps=max_steps, atol=atol, rtol=rtol, solver=solver, dtmin=dtmin)
+        return np.vstack([np.asarray(lead), np.asarray(trail)])
+
     def compute_perturbation_second_order_OTF(self, cpu=True, solver=Dopri8(scan_kind='bounded'), rtol=1e-6, atol=1e-6, dtmin=0.05, max_steps=10_000,
                                               dtmax=None):
         """[w (N-1,6), D (N-1,N_sh,12), E (N-1,N_sh,6)] (perturbative.py:757-772); zero perturbation ICs (perturbative.py:715)."""

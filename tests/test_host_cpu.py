@@ -201,3 +201,28 @@ def test_argument_validation_of_the_round1_entry_points():
     assert L.ssb_nbody_integrate_f64(None, 2000, z, 1.0, 0.1, z, 0.0, 1.0, z, 1, ctrl, z, z, z, z, 0, z) == -1 and b"1024" in L.ssb_last_error()
     assert L.ssb_nbody_integrate_f64(None, 3, z, 1.0, 0.1, z, 0.0, 1.0, z, 1, ctrl, z, z, z, z, 0, z) == -1           # NULL masses
     assert L.ssb_nbody_scratch_bytes(100) == 8 * 3 * 100 * 18
+
+
+def test_run_nonlinear_sim_forwards_the_model_parameters(monkeypatch):
+    """GenerateMassRadiusPerturbation_Chen25.run_nonlinear_sim (perturbative.py:775-813) is glue: the stream parameters of the base model go to
+    gen_stream_vmapped_with_pert_Chen25_fixed_prog and (lead, trail) come back stacked.  Checked without a GPU by intercepting the call."""
+    import types
+    import numpy as np
+    from streamsculptor_b200 import perturbative as pt, streamhelpers as sh
+    seen = {}
+
+    def fake(**kw):
+        seen.update(kw)
+        return np.zeros((3, 6)), np.ones((3, 6))
+    monkeypatch.setattr(sh, "gen_stream_vmapped_with_pert_Chen25_fixed_prog", fake)
+    gen = object.__new__(pt.GenerateMassRadiusPerturbation_Chen25)
+    gen.potential_base, gen.potential_perturbation = "BASE", "PERT"
+    gen.BaseStreamModel = types.SimpleNamespace(prog_pot="PROG", ts=np.linspace(-10.0, 0.0, 4), key=7, Msat=1e4)
+    gen.base_stream = types.SimpleNamespace(prog_w0=[1.0, 2, 3, 4, 5, 6])
+    out = gen.run_nonlinear_sim(rtol=1e-8, atol=1e-9, dtmin=0.02, max_steps=123)
+    assert out.shape == (6, 6) and (out[:3] == 0).all() and (out[3:] == 1).all()
+    assert seen["pot_base"] == "BASE" and seen["pot_pert"] == "PERT" and seen["prog_pot"] == "PROG" and seen["key"] == 7 and seen["Msat"] == 1e4
+    assert seen["prog_w0"] == [1.0, 2, 3, 4, 5, 6] and seen["rtol"] == 1e-8 and seen["atol"] == 1e-9 and seen["dtmin"] == 0.02 and seen["max_steps"] == 123
+    assert type(seen["solver"]).__name__ == "Dopri8"
+    gen.run_nonlinear_sim(pot_pert="OTHER")
+    assert seen["pot_pert"] == "OTHER"
