@@ -151,9 +151,24 @@ class GenerateMassRadiusPerturbation_CustomBase(_ResponseGenerator):      # pert
         self.base_stream = BaseStreamModel
         self.base_realspace_ICs = self.base_stream.streamICs
         if perturbation_ICs is None:
-            raise NotImplementedError("the backward-integrated progenitor response (perturbative.py:391-399) needs saved responses at "
-                                      "every stripping time, which the device path does not provide yet; pass perturbation_ICs= explicitly")
+            # perturbative.py:388-399: the progenitor's own response, integrated backwards from the observed position and saved at every
+            # stripping time (ssb_linear_response_saveat_f64), mapped through the release Jacobian
+            from . import fields
+            self.field_wobs = [np.asarray(BaseStreamModel.prog_loc_fwd)[-1], np.zeros((self.num_pert, 12))]
+            flipped_times = np.flip(np.asarray(BaseStreamModel.ts, dtype=np.float64))
+            prog_fieldICs = fields.integrate_field(w0=self.field_wobs, ts=flipped_times, field=fields.MassRadiusPerturbation_OTF(self),
+                                                   backwards_int=True, **kwargs)
+            self.prog_base = prog_fieldICs
+            self.prog_fieldICs = np.flipud(prog_fieldICs.ys[1])
+            perturbation_ICs = self.compute_perturbation_ICs()
         self.perturbation_ICs = perturbation_ICs
+
+    def compute_base_stream(self, cpu=True):          # perturbative.py:405-410
+        return self.base_stream.gen_stream()
+
+    def compute_perturbation_ICs(self):               # perturbative.py:413-422: [N_star, N_sh, 12]
+        J, F = np.asarray(self.base_stream.dRel_dIC), self.prog_fieldICs
+        return np.dstack([np.einsum('ijk,ilk->ilj', J, F[:, :, :6]), np.einsum('ijk,ilk->ilj', J, F[:, :, 6:])])
 
 
 class BaseStreamModelChen25(Potential):               # perturbative.py:588-658

@@ -537,6 +537,38 @@ def test_saved_response_trajectory_and_classic_generator(cuda):
     assert scaled_err(sol.ys[0], ws2, 1e-8).max() < 10.0 and scaled_err(sol.ys[1].reshape(nts, -1), Ds2.reshape(nts, -1), 1e-8).max() < 10.0
 
 
+def test_custom_base_generator_perturbation_ics(cuda):
+    """GenerateMassRadiusPerturbation_CustomBase without explicit ICs (perturbative.py:375-454): the progenitor's backward response saved at
+    every stripping time becomes the particles' perturbation ICs (the additive release has an identity Jacobian), then the responses."""
+    import streamsculptor_b200 as ssc
+    P, pt = ssc.potential, ssc.perturbative
+    nsh, nts = 6, 25
+    sh = subhalo_set(nsh, seed=23, t_lo=-700.0)
+    sh["x0"] = sh["x0"] * 0.3 + np.array([12.0, 3.0, -6.0])
+    base, orc_base = mw3_product(), mw3_oracle()
+    ts = np.linspace(-800.0, 0.0, nts)
+    prog_w0 = [12.0, 3.0, -6.0, -0.05, 0.15, 0.03]
+    rng = np.random.default_rng(3)
+    pos_rel, vel_rel = rng.normal(size=(nts, 3)) * 0.05, rng.normal(size=(nts, 3)) * 1e-3
+    pert = P.SubhaloLinePotentialCustom_fromFunc(func=P.HernquistPotential, m=sh["m"], r_s=sh["rs"], subhalo_x0=sh["x0"], subhalo_v=sh["v"],
+                                                 subhalo_t0=sh["t0"], t_window=150.0, units=ssc.usys)
+    orc_sh = O.Program().subhalos(O.PR_HERNQUIST, sh["m"], sh["rs"], sh["x0"], sh["v"], sh["t0"], 150.0)
+    fixed = dict(rtol=1e-8, atol=1e-8, dtmin=2.0, dtmax=2.0)
+    model = pt.CustomBaseStreamModel(potential_base=base, prog_w0=prog_w0, ts=ts, pos_rel=pos_rel, vel_rel=vel_rel, solver=ssc.Dopri8(), units=ssc.usys,
+                                     **fixed)
+    gen = pt.GenerateMassRadiusPerturbation_CustomBase(potential_base=base, potential_perturbation=pert, BaseStreamModel=model, units=ssc.usys,
+                                                       solver=ssc.Dopri8(), max_steps=5000, **fixed)
+    prog_o, _, _ = orc_base.integrate_orbits(prog_w0, ts[0], ts[-1], ts=ts, solver=8, **fixed)
+    ws_o, Ds_o, st_o, _ = O.linear_response_saveat(orc_base, orc_sh, prog_o[0, -1], ts[-1], ts[0], ts[::-1].copy(), solver=8, max_steps=5000, **fixed)
+    F_o = Ds_o[::-1]
+    assert st_o[0] == 0 and gen.perturbation_ICs.shape == (nts, nsh, 12)
+    assert np.abs(gen.perturbation_ICs - F_o).max() <= 1e-9 * np.abs(F_o).max()
+    w, D = gen.compute_perturbation_OTF(cpu=False, solver=ssc.Dopri8(), **fixed)
+    ics = np.hstack([prog_o[0][:, :3] + pos_rel, prog_o[0][:, 3:] + vel_rel])
+    w_o, D_o, _, _ = O.linear_response(orc_base, orc_sh, ics[:-1], ts[:-1], 0.0, D0=F_o[:-1], solver=8, **fixed)
+    assert scaled_err(w, w_o, 1e-9).max() < 1.0 and np.abs(D - D_o).max() <= 1e-8 * np.abs(D_o).max()
+
+
 def test_chen25_release_and_streams(cuda):
     """A9: release_model_Chen25 / gen_stream_ics_Chen25 / gen_stream_vmapped_Chen25 (streamhelpers.py:352-545) incl. the progenitor's
     own Plummer potential on an interpax-'cubic' track, vs the oracle.  Fixed steps -> 1e-10."""
