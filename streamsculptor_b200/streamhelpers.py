@@ -203,3 +203,41 @@ def gen_streakline(pot, prog_w0, Msat, t0, t1, Nstrip, solver=Dopri8(), rtol=1e-
     zero = tt == t1
     ys[zero] = w0[zero]
     return ys[:Nstrip], ys[Nstrip:], tstrip
+
+
+# ---- track summaries of a finished stream (streamhelpers.py:201-304): O(N) post-processing of the kernels' output ---------------
+def _host(a):
+    return np.asarray(a.cpu() if hasattr(a, "cpu") else a, dtype=np.float64)
+
+
+def computed_binned_track(stream, phi1, bins=20):
+    """Mean phase-space position in phi1 bins (streamhelpers.py:201-228), [bins-1, 6] with NaN for empty bins.  The reference's
+    conventions are kept: edges = linspace(min, max, bins), `digitize` indices start at 1, so row 0 is always NaN, rows 1..bins-2 hold
+    the particles with edges[r-1] <= phi1 < edges[r], and the particles of the last interval (and the maximum itself) are not used."""
+    stream, phi1 = _host(stream), _host(phi1)
+    edges = np.linspace(phi1.min(), phi1.max(), bins)
+    dig = np.digitize(phi1, edges)
+    out = np.full((len(edges) - 1, 6), np.nan)
+    for b in range(len(edges) - 1):
+        mask = dig == b
+        if mask.any():
+            out[b] = stream[mask].mean(axis=0)
+    out[out == 0] = np.nan                               # streamhelpers.py:227
+    return out
+
+
+def compute_stream_length(stream, phi1, bins=20):
+    """Length of the binned track: sum of the distances between consecutive bin means (streamhelpers.py:230-242)."""
+    pos = computed_binned_track(stream, phi1, bins)[:, :3]
+    return float(np.nansum(np.linalg.norm(pos[1:] - pos[:-1], axis=1)))
+
+
+def compute_length_oscillations(pot, prog_today, first_stripped_lead, first_stripped_trail, t_age, length_today):
+    """Stream length versus time from the separations of the progenitor and the first stripped stars integrated backwards
+    (streamhelpers.py:245-304): dict(ts[2000] ascending from -t_age to 0, length_func[2000])."""
+    ts = np.linspace(0.0, -float(t_age), 2_000)
+    w0 = np.stack([_host(first_stripped_lead), _host(first_stripped_trail), _host(prog_today)])
+    ys = np.asarray(pot.integrate_orbit_batch_vmapped(w0=w0, ts=ts, t0=0.0, t1=-float(t_age)).ys)          # three orbits, one launch
+    diff = np.sqrt(np.sum((ys[0, :, :3] - ys[2, :, :3]) ** 2 + (ys[1, :, :3] - ys[2, :, :3]) ** 2, axis=1))
+    diff_flip = diff[::-1]
+    return dict(ts=ts[::-1].copy(), length_func=float(length_today) * diff_flip / diff_flip[-1])

@@ -226,3 +226,41 @@ def test_run_nonlinear_sim_forwards_the_model_parameters(monkeypatch):
     assert type(seen["solver"]).__name__ == "Dopri8"
     gen.run_nonlinear_sim(pot_pert="OTHER")
     assert seen["pot_pert"] == "OTHER"
+
+
+def test_track_summaries_follow_the_reference_conventions():
+    """computed_binned_track / compute_stream_length / compute_length_oscillations (streamhelpers.py:201-304): host post-processing of the
+    kernels' output, checked against a particle-by-particle restatement of the reference's digitize / scan / nanmean recipe."""
+    import types
+    import numpy as np
+    import streamsculptor_b200 as ssc
+    rng = np.random.default_rng(0)
+    n, bins = 500, 12
+    stream, phi1 = rng.normal(size=(n, 6)), rng.uniform(-40.0, 25.0, n)
+    edges = np.linspace(phi1.min(), phi1.max(), bins)
+    want = np.full((bins - 1, 6), np.nan)
+    sums, cnt = np.zeros((bins + 1, 6)), np.zeros(bins + 1)
+    for x, w in zip(phi1, stream):
+        d = int(np.searchsorted(edges, x, side="right"))        # jnp.digitize: edges[d-1] <= x < edges[d]
+        sums[d] += w; cnt[d] += 1
+    for b in range(bins - 1):                                   # the scan visits bin indices 0 .. bins-2 only
+        if cnt[b] > 0:
+            want[b] = sums[b] / cnt[b]
+    got = ssc.computed_binned_track(stream, phi1, bins=bins)
+    assert got.shape == (bins - 1, 6) and np.isnan(got[0]).all() and np.allclose(got[1:], want[1:], rtol=1e-13, atol=0, equal_nan=True)
+    seg = np.linalg.norm(want[1:, :3] - want[:-1, :3], axis=1)
+    assert np.isclose(ssc.compute_stream_length(stream, phi1, bins=bins), np.nansum(seg), rtol=1e-13)
+    # length oscillations: three orbits integrated backwards in one batch; a fake potential supplies known separations
+    calls = {}
+
+    def batch(w0=None, ts=None, t0=None, t1=None):
+        calls.update(w0=np.asarray(w0), ts=np.asarray(ts), t0=t0, t1=t1)
+        ys = np.zeros((3, len(ts), 6))
+        ys[0, :, 0] = 3.0 * (1.0 - ts / 100.0)                  # lead - progenitor separation grows into the past
+        ys[1, :, 1] = 4.0 * (1.0 - ts / 100.0)
+        return types.SimpleNamespace(ys=ys)
+    pot = types.SimpleNamespace(integrate_orbit_batch_vmapped=batch)
+    res = ssc.compute_length_oscillations(pot, np.arange(6.0), np.ones(6), 2 * np.ones(6), t_age=500.0, length_today=10.0)
+    assert calls["t0"] == 0.0 and calls["t1"] == -500.0 and calls["w0"].shape == (3, 6) and np.array_equal(calls["w0"][2], np.arange(6.0))
+    assert res["ts"][0] == -500.0 and res["ts"][-1] == 0.0 and len(res["ts"]) == 2000
+    assert np.isclose(res["length_func"][-1], 10.0) and np.isclose(res["length_func"][0], 10.0 * 6.0)     # sqrt(3^2 + 4^2) * (1 + 5) / 5
