@@ -12,4 +12,7 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:orbit_kernel -s 4 -c 1 -f -o gpurun_out/orbit_k1 python bench.py --steps 2 --warmup 1 > gpurun_out/b_ncu2.log 2>&1
 ( timeout 300 python tools/bench_configs.py; timeout 100 python tools/bench_response.py 2000 1000 1e-11; timeout 100 python tools/bench_response.py 10000 1000 1e-6; timeout 100 python tools/bench_response.py 100000 1000 1e-6 ) > gpurun_out/configs.log 2>&1
 cat gpurun_out/configs.log
+# A/B of the two-part gen_stream pipeline on this box
+( SSB_STREAM_SPLIT=0 timeout 100 python tools/bench_k1.py; SSB_STREAM_SPLIT=1 timeout 100 python tools/bench_k1.py ) > gpurun_out/split.log 2>&1
+cat gpurun_out/split.log
 ls -la gpurun_out
