@@ -92,8 +92,9 @@ class Program:
         lib().orc_add_comp(self._h, typ, _p(p), int(track))
         return self
 
-    def nfw(self, m, r_s, track=-1):
-        return self._comp(NFW, [self.G * m, r_s], track)
+    def nfw(self, m, r_s, track=-1, soft=0.0):
+        """soft: r -> sqrt(r^2 + soft).  0 = the reference today; 1e-3 = the revision that printed the notebook goldens D8 / S1."""
+        return self._comp(NFW, [self.G * m, r_s, soft], track)
 
     def hernquist(self, m, r_s, soft=0.0, track=-1):
         return self._comp(HERNQUIST, [self.G * m, r_s, soft], track)

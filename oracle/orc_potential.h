@@ -14,7 +14,7 @@
 namespace orc {
 
 enum CompType {
-    C_NFW = 0,          // potential.py:74-84   p = {G*m, r_s}
+    C_NFW = 0,          // potential.py:74-84   p = {G*m, r_s, soft (0 today; 1e-3 in the notebook-era revision)}
     C_HERNQUIST = 1,    // potential.py:132-138 p = {G*m, r_s, soft}
     C_MIYAMOTO = 2,     // potential.py:66-72   p = {G*m, a, b}
     C_PLUMMER = 3,      // potential.py:124-130 p = {G*m, r_s}
@@ -106,9 +106,12 @@ struct Program {
 };
 
 // ---- leaf potentials; T = coordinate scalar type, P = parameter scalar type (double or T) ----
-template <class T, class P> inline T phi_nfw(const P& GM, const P& rs, const T* x) {
+// soft: 0 for the reference as it is today (potential.py:83 has no softening).  The notebook outputs D8 / S1 were produced by an earlier
+// revision whose NFW radius was sqrt(r^2 + 0.001); the golden tests select it with soft = 1e-3 (adding 0.0 leaves today's arithmetic
+// bit-identical).
+template <class T, class P> inline T phi_nfw(const P& GM, const P& rs, const T* x, double soft = 0.0) {
     P v_h2 = -GM / rs;                                                    // potential.py:82
-    T m = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]) / rs;             // potential.py:83 (no softening)
+    T m = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + soft) / rs;      // potential.py:83
     return v_h2 * log(1.0 + m) / m;                                       // potential.py:84
 }
 template <class T, class P> inline T phi_hernquist(const P& GM, const P& rs, double soft, const T* x) {
@@ -163,7 +166,7 @@ template <class T> inline T phi_total(const Program& P, const T* x, double t) {
             for (int k = 0; k < 3; ++k) xs[k] = x[k] - ctr[k];                        // potential.py:460-462
         }
         switch (c.type) {
-            case C_NFW: acc += phi_nfw<T, double>(c.p[0], c.p[1], xs); break;
+            case C_NFW: acc += phi_nfw<T, double>(c.p[0], c.p[1], xs, c.p[2]); break;
             case C_HERNQUIST: acc += phi_hernquist<T, double>(c.p[0], c.p[1], c.p[2], xs); break;
             case C_MIYAMOTO: acc += phi_miyamoto<T, double>(c.p[0], c.p[1], c.p[2], xs); break;
             case C_PLUMMER: acc += phi_plummer<T, double>(c.p[0], c.p[1], xs); break;

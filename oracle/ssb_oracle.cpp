@@ -10,7 +10,9 @@
 //   release_model / gen_stream    below                        (main.py:209-368)
 //   linear-response field         below                        (fields.py:159-206, perturbative.py:101-135,726-755)
 // PARITY STATUS: jax/diffrax cannot run in this environment, so the oracle is pinned only by the
-// reference's notebook goldens (tests/test_oracle_goldens.py); at 1e-10 it is "parity unpinned".
+// reference's notebook goldens (tests/test_oracle_goldens.py): G (G1), the force (D1), the solver / controller / dense output
+// (D2-D5), and - through the printed release Jacobian D8 - release_model, its derivative and the jax.random recipe, to the
+// 9 printed digits.  At 1e-10 against diffrax itself it is "parity unpinned".
 #include <cstdint>
 #include <cstring>
 #include <vector>

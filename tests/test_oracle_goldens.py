@@ -203,7 +203,7 @@ def test_committed_notebook_fixture_pins_the_oracle():
     """tests/golden/notebook_goldens.json = the reference's own printed outputs, extracted verbatim by tools/extract_goldens.py.
     The oracle is checked against the numbers parsed from the fixture (not against hand-copied constants)."""
     fx = _fixture()
-    assert set(fx) >= {"G1", "D1", "D2", "D3_head", "D4", "D5", "D8"}
+    assert set(fx) >= {"G1", "D1", "D2", "D3_head", "D4", "D5", "D8", "S1"}
     # G1: pins G
     x, y, z, q = 1.0, 20.0, 10.0, 1.3
     rp = np.sqrt(x * x + y * y + (z / q) ** 2)
@@ -227,5 +227,63 @@ def test_committed_notebook_fixture_pins_the_oracle():
     MW = O.Program().miyamoto(6.8e10, 3.0, 0.28).hernquist(5e9, 1.0).hernquist(1.71e9, 0.07).nfw(5.4e11, 15.62)
     ic, _, _ = MW.integrate_orbits([20, 0, 20, 0, .15, 0], 0.0, -3500.0, ts=[-3500.0])
     assert np.abs(ic[0, 0] - fx["D5"][1][:6]).max() < 5e-6
-    # D8 (release Jacobian): shape of the printed tensor only - its inputs are not recoverable
-    assert fx["D8"][1].size >= 72
+    # D8 (release Jacobian) has its own test below
+    assert fx["D8"][1].size == 6 * 72
+
+
+def test_release_jacobian_golden_pins_release_model_and_jax_random():
+    """D8: `BaseStreamModel(pot_NFW, prog_w0=w0, ts=ts, Msat=1e4, seednum=493).dRel_dIC` printed by tests.ipynb cell 156 = the blocks of
+    stripping times 0, 1, 2 and 1497, 1498, 1499 (numpy's summarised print), each [2, 6, 6] = d(release_model)/d(progenitor state) for the
+    leading and the trailing particle (perturbative.py:281-296).  The notebook's `w0` and `ts` are not recoverable from its out-of-order
+    cells, so each block's progenitor state is recovered by least squares (6 unknowns against 72 printed numbers); everything else
+    is the oracle's own: the release algebra with the tidal radius and its derivative (third derivatives of the NFW potential), and the
+    jax.random recipe of main.py:220-228, 263-266 - threefry PRNGKey(seed), randint(key, (5,), 0, 1000), keys PRNGKey(i * r_k),
+    normal(key, (1,)) - whose draws are NOT fitted.  All six blocks are reproduced to the printed precision (<= 5e-9) in the revision of
+    the reference that printed them: dispersions sigma_kr = sigma_kvphi = 0.5 (today 0.4, main.py:214; `kval_arr` selects them) and the
+    NFW radius softened by 0.001 (the revision SURVEY.md Appendix D row S1 identifies; oracle `nfw(..., soft=1e-3)`).  The fit lands on
+    the orbit the other cells integrate: [20, 0, 20, 0, 0.2, 0] at the last stripping time to 2e-5, the time-reversed end point of
+    golden D3 at the first.  With today's dispersions, without the softening, or with the draws of another seed, the same fit misses
+    by one to five orders of magnitude."""
+    from scipy.optimize import least_squares
+    fx = _fixture()
+    blocks = fx["D8"][1].reshape(6, 2, 6, 6)
+    assert np.allclose(blocks[:, 0] + blocks[:, 1], 2.0 * np.eye(6), rtol=0, atol=2e-8)      # lead and trail offsets are opposite
+    nfw = O.Program().nfw(1e12, 20.0, soft=1e-3)
+    nfw_today = O.Program().nfw(1e12, 20.0)
+    kv_notebook = [2.0, 0.3, 0.0, 0.0, 0.5, 0.5, 0.5, 0.5]
+    kv_today = [2.0, 0.3, 0.0, 0.0, 0.4, 0.4, 0.5, 0.5]
+
+    def fit(block, idx, seed, kv, start, pot=nfw):
+        res = lambda w: (pot.release(w.reshape(1, 6), 1e4, np.array([idx]), np.array([0.0]), seed, kvals=kv, jacobian=True)[0] - block).ravel()
+        r = least_squares(res, np.asarray(start, dtype=np.float64), x_scale=[10, 10, 10, .1, .1, .1], xtol=1e-15, ftol=1e-15, gtol=1e-15, max_nfev=200)
+        return r.x, np.abs(r.fun).max()
+    today = np.array([20.0, 0.0, 20.0, 0.0, 0.2, 0.0])
+    d3_end = fx["D3_tail"][1][-6:] * np.array([1, -1, 1, -1, 1, -1])          # the orbit of D3 run backwards: y, vx, vz change sign
+    states = {}
+    for b, idx, start in ((5, 1499, today), (4, 1498, today), (3, 1497, today), (0, 0, d3_end), (1, 1, d3_end), (2, 2, d3_end)):
+        w, miss = fit(blocks[b], idx, 493, kv_notebook, start)
+        assert miss < 8e-9, f"block {b} (stripping time {idx}): {miss:.2e}"    # 9 printed digits of numbers <= 1
+        states[idx] = w
+    assert np.abs(states[1499] - today).max() < 2e-4                           # the notebook integrated back and forth at rtol 1e-7
+    assert np.abs(states[0] - d3_end).max() < 3e-3
+    # consecutive blocks are 3000/1499 Myr apart on ONE orbit
+    dt = 3000.0 / 1499.0
+    nxt, _, _ = nfw.integrate_orbits(np.array([states[0], states[1497]]), 0.0, 2 * dt, ts=[dt, 2 * dt], rtol=1e-10, atol=1e-10, dtmin=1e-3)
+    assert np.abs(nxt[0, 0] - states[1]).max() < 1e-4 and np.abs(nxt[0, 1] - states[2]).max() < 1e-4
+    assert np.abs(nxt[1, 0] - states[1498]).max() < 1e-4 and np.abs(nxt[1, 1] - states[1499]).max() < 1e-4
+    # sensitivity: today's dispersions or another seed's draws cannot be absorbed by the six fitted numbers
+    assert fit(blocks[5], 1499, 493, kv_today, today)[1] > 1e-4
+    assert fit(blocks[5], 1499, 494, kv_notebook, today)[1] > 1e-4
+    assert fit(blocks[5], 1499, 493, kv_notebook, today, pot=nfw_today)[1] > 5e-8
+    # S1 (tests.ipynb cell 151, same revision): MassRadiusPerturbation_OTF.term at an all-ones state (fields.py:175-206) - the base
+    # acceleration and the tidal term -Hess(Phi) . 1 of every response row.  (The rows' last digits carry the forces of the notebook's ten
+    # random subhalos, ~3e-12, which are not recoverable.)
+    s1 = fx["S1"][1]
+    acc = -nfw.gradient([1.0, 1.0, 1.0])[0]
+    tid = -(np.asarray(nfw.hessian([1.0, 1.0, 1.0])[0]).reshape(3, 3) @ np.ones(3))
+    assert np.allclose(s1[:6], [1, 1, 1, *acc], rtol=0, atol=6e-9)
+    rows = s1[6:126].reshape(10, 12)
+    assert np.array_equal(rows[:, [0, 1, 2, 6, 7, 8]], np.ones((10, 6)))
+    assert np.abs(rows[:, [3, 4, 5, 9, 10, 11]] - tid[0]).max() < 6e-12 and np.ptp(tid) < 1e-18
+    tid_today = -(np.asarray(nfw_today.hessian([1.0, 1.0, 1.0])[0]).reshape(3, 3) @ np.ones(3))
+    assert abs(tid_today[0] - rows[0, 3]) > 1e-6                                # today's unsoftened NFW: 3.1086e-4 (SURVEY.md App. D, S1)
