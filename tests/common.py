@@ -90,3 +90,30 @@ def assert_adaptive_close(gpu, orc, truth, tol, min_frac=0.85, what="", slack=1.
         a, b = np.percentile(d_at, q), np.percentile(d_bt, q)
         assert a <= slack * fac * b + 10.0, f"{what}: CUDA error percentile {q} = {a:.1f} x tol vs oracle {b:.1f} x tol"
     return frac
+
+
+def orphan_chenab_prog_today():
+    """Present-day phase-space position of the Orphan-Chenab progenitor exactly as examples/OrphanChenab_mw_lmc_example.ipynb cells 2-3
+    compute it, without astropy / jax: (phi1, phi2) -> ICRS with the notebook's rotation matrix, position through the reference's
+    JaxCoords.alpha_delta_to_simcart (JaxCoords.py:48-85), velocity through astropy's ICRS -> Galactocentric with its v4.0 defaults -
+    the same rotation R and tilt H, solar motion (12.9, 245.6, 7.78) km/s - and astropy's unit conversions."""
+    alpha_gc, delta_gc, eta, d_gc, z_sun = np.deg2rad(266.4051), np.deg2rad(-28.936175), np.deg2rad(58.5986320306), 8.122, 0.0208
+    R1 = np.array([[np.cos(delta_gc), 0, np.sin(delta_gc)], [0, 1.0, 0], [-np.sin(delta_gc), 0, np.cos(delta_gc)]])
+    R2 = np.array([[np.cos(alpha_gc), np.sin(alpha_gc), 0.0], [-np.sin(alpha_gc), np.cos(alpha_gc), 0.0], [0, 0, 1.0]])
+    R3 = np.array([[1.0, 0, 0], [0, np.cos(eta), np.sin(eta)], [0, -np.sin(eta), np.cos(eta)]])
+    R = R3 @ (R1 @ R2)
+    th = np.arcsin(z_sun / d_gc)
+    H = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]])
+    R_oc = np.array([[-0.44761231, -0.08785756, -0.88990128], [-0.84246097, 0.37511331, 0.38671632], [0.29983786, 0.92280606, -0.2419219]])
+    phi1, phi2 = np.deg2rad(6.34), np.deg2rad(-0.441)                      # column 1 of arXiv:1812.08192 (notebook cell 3)
+    dist, vr, pmdec, pmra = 18.764, 107.573, 2.880, -3.681                 # kpc, km/s, mas/yr, mas/yr (pm_ra_cosdec)
+    w = np.linalg.inv(R_oc) @ np.array([np.cos(phi1) * np.cos(phi2), np.sin(phi1) * np.cos(phi2), np.sin(phi2)])
+    a, de = np.arctan2(w[1], w[0]), np.arcsin(w[2])
+    a, de = np.deg2rad(np.rad2deg(a)), np.deg2rad(np.rad2deg(de))          # the notebook goes through degrees
+    e_r = np.array([np.cos(a) * np.cos(de), np.sin(a) * np.cos(de), np.sin(de)])
+    e_a = np.array([-np.sin(a), np.cos(a), 0.0])
+    e_d = np.array([-np.cos(a) * np.sin(de), -np.sin(a) * np.sin(de), np.cos(de)])
+    q = H @ (R @ (dist * e_r) - d_gc * np.array([1.0, 0, 0]))
+    k_pm = 4.740470463533348                                               # km/s per (mas/yr x kpc)
+    v = H @ (R @ (vr * e_r + k_pm * dist * (pmra * e_a + pmdec * e_d))) + np.array([12.9, 245.6, 7.78])
+    return np.hstack([q, v * 1.0227121650537077e-3])                      # km/s -> kpc/Myr

@@ -931,3 +931,32 @@ def test_dense_stream_and_streakline(cuda):
     yo, _, _ = orc.integrate_orbits(np.hstack([Lc, vl_])[:-1], tstrip[:-1], 0.0, rtol=1e-9, atol=1e-9)
     assert lead.shape == (Ns, 6) and np.mean(scaled_err(lead[:-1], yo[:, 0], 1e-9) < 10.0) > 0.85
     assert np.array_equal(lead[-1], np.hstack([Lc, vl_])[-1])                   # released at t1: zero-length solve
+
+
+def test_reference_printed_stream_through_the_product_api(cuda):
+    """Golden OC (examples/OrphanChenab_mw_lmc_example.ipynb cells 3-6): the reference's own printed `stream_lead` of the Orphan-Chenab stream
+    in the static GalaMilkyWayPotential, reproduced by the CUDA path through the public API with the notebook's calls - integrate_orbit back
+    4 Gyr, gen_stream_vmapped(3001 stripping times, Msat=1e6, seed_num=9302, max_steps=1000), default Dopri5, rtol = atol = 1e-7.
+    The oracle reproduces the 36 printed numbers to 4e-7 (tests/test_oracle_goldens.py); the CUDA path follows the same adaptive step
+    sequences up to rounding-level decisions, hence the tolerance: 2e-2 kpc / 2e-4 kpc/Myr is two orders of magnitude
+    below what a wrong PRNG draw, dispersion or potential parameter does to these rows (>= 1e-2 kpc/Myr-scale, kiloparsecs in position)."""
+    import json
+    import os
+    import re
+    import warnings
+    import streamsculptor_b200 as ssc
+    from common import orphan_chenab_prog_today
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "notebook_goldens.json")
+    oc = [g for g in json.load(open(path)) if g["id"] == "OC"][0]
+    want = np.array([float(x) for x in re.findall(r"[-+]?\d+\.\d+e[-+]\d+", oc["output"])]).reshape(6, 6)
+    mw = ssc.potential.GalaMilkyWayPotential(units=ssc.usys)
+    ic = np.asarray(mw.integrate_orbit(w0=orphan_chenab_prog_today(), ts=np.array([0.0, -4000.0]), t0=0.0, t1=-4000.0).ys[-1])
+    ts = np.hstack([np.linspace(-4000.0, -150.0, 3000), [0.0]])
+    lead, trail = mw.gen_stream_vmapped(ts=ts, prog_w0=ic, Msat=1e6, seed_num=9302, max_steps=1000)
+    lead = np.asarray(lead)
+    assert lead.shape == (3000, 6) and np.isfinite(lead).all()
+    got = lead[[0, 1, 2, -3, -2, -1]]
+    dpos, dvel = np.abs(got[:, :3] - want[:, :3]).max(), np.abs(got[:, 3:] - want[:, 3:]).max()
+    warnings.warn(f"CUDA stream vs the reference's printed stream: max |dx| = {dpos:.2e} kpc, max |dv| = {dvel:.2e} kpc/Myr")
+    assert dpos < 2e-2 and dvel < 2e-4
+

@@ -287,3 +287,31 @@ def test_release_jacobian_golden_pins_release_model_and_jax_random():
     assert np.abs(rows[:, [3, 4, 5, 9, 10, 11]] - tid[0]).max() < 6e-12 and np.ptp(tid) < 1e-18
     tid_today = -(np.asarray(nfw_today.hessian([1.0, 1.0, 1.0])[0]).reshape(3, 3) @ np.ones(3))
     assert abs(tid_today[0] - rows[0, 3]) > 1e-6                                # today's unsoftened NFW: 3.1086e-4
+
+
+def test_orphan_chenab_stream_golden_pins_the_stream_pipeline():
+    """OC: `stream_lead` printed by examples/OrphanChenab_mw_lmc_example.ipynb cell 6 = rows 0, 1, 2 and 2997, 2998, 2999 of the stream the
+    reference generated in the static GalaMilkyWayPotential (cells 3-5): progenitor today from sky coordinates, integrate_orbit back
+    4 Gyr (Dopri8), `gen_stream_vmapped(prog_w0, ts = [linspace(-4000, -150, 3000), 0], Msat=1e6, seed_num=9302, max_steps=1000)` with
+    its default Dopri5 at rtol = atol = 1e-7.  Nothing is fitted: the whole path - backward solve, progenitor with Dopri5 dense output at
+    3001 stripping times, release_model with its jax.random draws, 2 x 3000 adaptive solves of up to 4 Gyr - is the oracle's, and all 36
+    printed numbers come out to <= 4e-7 (1e-8 of the stream's size; the 9 printed digits are 5e-8, the rest is the reconstruction of
+    astropy's velocity transform amplified by 8 Gyr of integration).  This is the reference's own end-to-end answer for the hot path."""
+    from common import orphan_chenab_prog_today
+    fx = _fixture()
+    want = fx["OC"][1].reshape(6, 6)
+    mw = O.Program().miyamoto(6.8e10, 3.0, 0.28).hernquist(5e9, 1.0).hernquist(1.71e9, 0.07).nfw(5.4e11, 15.62)
+    today = orphan_chenab_prog_today()
+    ic, st0, _ = mw.integrate_orbits(today, 0.0, -4000.0, ts=[-4000.0])                       # integrate_orbit defaults (main.py:125-137)
+    ts = np.hstack([np.linspace(-4000.0, -150.0, 3000), [0.0]])
+    lead, trail, st, ns = mw.gen_stream(ts, ic[0, 0], 1e6, 9302, solver=5, max_steps=1000, threads=8)
+    assert st0[0] == 0 and (st == 0).all() and lead.shape == (3000, 6)
+    got = lead[[0, 1, 2, -3, -2, -1]]
+    assert np.abs(got - want).max() < 4e-7, np.abs(got - want).max(axis=1)
+    # sensitivity: particle 0 draws from PRNGKey(0 * r_k) whatever the seed, particles 1 and 2 from PRNGKey(i * r_k): another seed (other
+    # r_k) leaves row 0 alone and moves rows 1, 2 by a good fraction of a kiloparsec; so do the previous revision's dispersions (golden D8)
+    other, _, _, _ = mw.gen_stream(ts[[0, 1, 2, -1]], ic[0, 0], 1e6, 9303, solver=5, max_steps=1000)
+    assert np.abs(other[0] - want[0]).max() < 4e-7 and np.abs(other[1] - want[1]).max() > 1e-2 and np.abs(other[2] - want[2]).max() > 1e-2
+    old, _, _, _ = mw.gen_stream(ts[[0, 1, 2, -1]], ic[0, 0], 1e6, 9302, solver=5, max_steps=1000, kvals=[2.0, 0.3, 0.0, 0.0, 0.5, 0.5, 0.5, 0.5])
+    assert np.abs(old[:3] - want[:3]).max() > 1e-2
+
