@@ -117,3 +117,12 @@ def orphan_chenab_prog_today():
     k_pm = 4.740470463533348                                               # km/s per (mas/yr x kpc)
     v = H @ (R @ (vr * e_r + k_pm * dist * (pmra * e_a + pmdec * e_d))) + np.array([12.9, 245.6, 7.78])
     return np.hstack([q, v * 1.0227121650537077e-3])                      # km/s -> kpc/Myr
+
+
+def notebook_batch_ics():
+    """The 1000 initial conditions of tests.ipynb cells 12 + 15: numpy's legacy generator (np.random.seed(4934202); frozen stream) around
+    sol.evaluate(0.0) = w0 = [20, 15, 20, .08, .1, -.05]."""
+    rs = np.random.RandomState(4934202)
+    n = 1000
+    ics = np.hstack([rs.normal(loc=0, scale=.01, size=(n, 3)), rs.normal(loc=0, scale=.005, size=(n, 3))])
+    return ics + np.array([20.0, 15.0, 20.0, 0.08, 0.1, -0.05])
