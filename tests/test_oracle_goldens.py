@@ -335,4 +335,11 @@ def test_thousand_orbit_batch_golden_pins_the_adaptive_driver():
     ys_t, _, _ = nfw.integrate_orbits(notebook_batch_ics()[:50], 0.0, 3000.0, ts=[0.0, 3000.0], rtol=1e-13, atol=1e-13, dtmin=1e-3, max_steps=400_000)
     own = np.abs(ys_t[:, -1, 3] - want[:50]).max()
     assert 1e-8 < own < 1e-5 and own > 20 * d[:50].max()
+    # R1 (cell 21): RestrictedNbody_generator.term (RestrictedNbody.py:93-106) at t = 3000 on the two saved states of orbit 0 = [v, -grad of
+    # NFW + the Plummer(1000, 0.01) progenitor centred on the end point of the dense `sol` orbit]; 8 printed decimals
+    r1 = fx["R1"][1].reshape(2, 6)
+    prog, _, _ = nfw.integrate_orbits([20.0, 15.0, 20.0, 0.08, 0.1, -0.05], 0.0, 3000.0, ts=np.linspace(0.0, 3000.0, 500))
+    plummer = O.Program().plummer(1000.0, 0.01)
+    term = np.array([np.hstack([w[3:], -nfw.gradient(w[:3])[0] - plummer.gradient(w[:3] - prog[0, -1, :3])[0]]) for w in ys[0]])
+    assert np.abs(term - r1).max() < 6e-9
 
