@@ -947,7 +947,8 @@ def test_reference_printed_stream_through_the_product_api(cuda):
     import streamsculptor_b200 as ssc
     from common import orphan_chenab_prog_today
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "notebook_goldens.json")
-    oc = [g for g in json.load(open(path)) if g["id"] == "OC"][0]
+    with open(path) as fh:
+        oc = [g for g in json.load(fh) if g["id"] == "OC"][0]
     want = np.array([float(x) for x in re.findall(r"[-+]?\d+\.\d+e[-+]\d+", oc["output"])]).reshape(6, 6)
     mw = ssc.potential.GalaMilkyWayPotential(units=ssc.usys)
     ic = np.asarray(mw.integrate_orbit(w0=orphan_chenab_prog_today(), ts=np.array([0.0, -4000.0]), t0=0.0, t1=-4000.0).ys[-1])
@@ -973,7 +974,8 @@ def test_reference_printed_batch_of_orbits_through_the_product_api(cuda):
     import streamsculptor_b200 as ssc
     from common import notebook_batch_ics
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "notebook_goldens.json")
-    b1 = [g for g in json.load(open(path)) if g["id"] == "B1"][0]
+    with open(path) as fh:
+        b1 = [g for g in json.load(fh) if g["id"] == "B1"][0]
     want = np.array([float(x) for x in re.findall(r"[-+]?\d+\.\d+e[-+]\d+", b1["output"])])
     assert want.shape == (1000,)
     nfw = ssc.potential.NFWPotential(m=1e12, r_s=20.0, units=ssc.usys)
