@@ -20,6 +20,8 @@ WANTED = [
     ("D8", "tests.ipynb", "9.96418614e-01"),
     ("B1", "tests.ipynb", "-1.10464897e-02"),                          # out_batch.ys[:, -1, 3]: 1000 orbits of integrate_orbit_batch_scan (cells 12, 15, 20, 22)
     ("R1", "tests.ipynb", "0.07882516"),                               # RestrictedNbody_generator.term at the two saved states of orbit 0 (cell 21)
+    ("SS_impact", "StreamSubhaloExample.ipynb", "Impact location"),    # mean of a stream patch integrated back to the impact time (cells 1-7)
+    ("SS_pot", "StreamSubhaloExample.ipynb", "Plummer subhalo potential"),   # SubhaloLinePotential[_Custom] values at (1,2,3), t = -850 (cell 9)
     ("OC", "OrphanChenab_mw_lmc_example.ipynb", "-2.19073895e+01"),   # stream_lead of the static-potential Orphan-Chenab stream (cells 3-6)
     ("S1", "tests.ipynb", "3.09774548e-04"),      # printed by an earlier revision (softened NFW): usable with the oracle's nfw(soft=1e-3)
 ]
