@@ -2,7 +2,7 @@
 
 The oracle restates, on the CPU, the algorithm the reference (jnibauer/streamsculptor)
 executes on its hot path; see the header of oracle/ssb_oracle.cpp for the file:line map and
-for its PARITY STATUS ("unpinned at 1e-10; pinned by the reference's notebook goldens").
+for its PARITY STATUS (pinned by the reference's notebook goldens to the 9 digits they print; no runnable reference beyond that).
 
 Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline leg / --impl reference) may
 import this package.  The product package `streamsculptor_b200` never does.

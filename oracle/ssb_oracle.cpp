@@ -13,7 +13,8 @@
 // reference's notebook goldens (tests/test_oracle_goldens.py): G (G1), the force (D1), the solver / controller / dense output
 // (D2-D5), and - through the printed release Jacobian D8 - release_model, its derivative and the jax.random recipe, to the
 // 9 printed digits; OC, the reference's printed Orphan-Chenab stream, pins the whole stream pipeline end to end (36 numbers to
-// 4e-7, nothing fitted).  At 1e-10 against diffrax itself it is "parity unpinned".
+// 4e-7, nothing fitted); B1, the printed final velocities of 1000 adaptive Dopri8 orbits, to 5e-10.  Pinned to the printed digits;
+// beyond them (1e-10 against a live diffrax run) there is nothing to compare with.
 #include <cstdint>
 #include <cstring>
 #include <vector>
