@@ -11,7 +11,7 @@ from .streamhelpers import (custom_release_model, gen_stream_ics_pert, gen_strea
                             gen_stream_scan_with_pert, gen_stream_vmapped_with_pert_fixed_prog, gen_stream_ics_Chen25,
                             gen_stream_ics_pert_Chen25, gen_stream_vmapped_Chen25, gen_stream_vmapped_with_pert_Chen25,
                             gen_stream_vmapped_with_pert_Chen25_fixed_prog, eval_dense_stream, eval_dense_stream_id, get_Streakline_ICs,
-                            gen_streakline, computed_binned_track, compute_stream_length, compute_length_oscillations)
+                            gen_streakline, computed_binned_track, compute_stream_length, compute_length_oscillations, sample_from_1D_pdf)
 from . import fields  # noqa: F401
 from .fields import integrate_field  # noqa: F401
 from . import perturbative  # noqa: F401

@@ -241,3 +241,41 @@ def compute_length_oscillations(pot, prog_today, first_stripped_lead, first_stri
     diff = np.sqrt(np.sum((ys[0, :, :3] - ys[2, :, :3]) ** 2 + (ys[1, :, :3] - ys[2, :, :3]) ** 2, axis=1))
     diff_flip = diff[::-1]
     return dict(ts=ts[::-1].copy(), length_func=float(length_today) * diff_flip / diff_flip[-1])
+
+
+# ---- sample_from_1D_pdf (streamhelpers.py:306-349): inverse-CDF sampling with jax.random.uniform's draws -----------------------
+def _threefry2x32(k0, k1, c0, c1):
+    """Threefry-2x32, 20 rounds (the generator behind jax.random), vectorised over the counter arrays c0, c1 (uint32)."""
+    rot = ((13, 15, 26, 6), (17, 29, 16, 24))
+    m = np.uint64(0xFFFFFFFF)
+    ks = [np.uint64(k0) & m, np.uint64(k1) & m, (np.uint64(k0) ^ np.uint64(k1) ^ np.uint64(0x1BD11BDA)) & m]
+    x0 = (np.asarray(c0, dtype=np.uint64) + ks[0]) & m
+    x1 = (np.asarray(c1, dtype=np.uint64) + ks[1]) & m
+    for g in range(5):
+        for r in rot[g & 1]:
+            x0 = (x0 + x1) & m
+            x1 = ((x1 << np.uint64(r)) | (x1 >> np.uint64(32 - r))) & m
+            x1 = x1 ^ x0
+        x0 = (x0 + ks[(g + 1) % 3]) & m
+        x1 = (x1 + ks[(g + 2) % 3] + np.uint64(g + 1)) & m
+    return x0, x1
+
+
+def jax_uniform(key, n):
+    """jax.random.uniform(key, (n,)) in float64: 64 random bits per sample (counter pairs (j, n + j)), 52 of them as the mantissa of a
+    number in [1, 2), minus 1."""
+    k0, k1 = key_words(key)
+    j = np.arange(n, dtype=np.uint64)
+    hi, lo = _threefry2x32(k0, k1, j, j + np.uint64(n))
+    bits = ((hi << np.uint64(32)) | lo) >> np.uint64(12) | np.uint64(0x3FF0000000000000)
+    return bits.view(np.float64) - 1.0
+
+
+def sample_from_1D_pdf(x, y, key, num_samples):
+    """Random values from the 1-D density y(x) by the inverse-CDF method (streamhelpers.py:306-349): cumulative sum of the normalised
+    density, linear interpolation of its inverse, jax.random.uniform draws for `key` (int seed or two key words)."""
+    x, y = _host(x), _host(y)
+    pdf = y / np.trapezoid(y, x)
+    cdf = np.cumsum(pdf)
+    cdf = cdf / cdf[-1]
+    return np.interp(jax_uniform(key, int(num_samples)), cdf, x)

@@ -264,3 +264,28 @@ def test_track_summaries_follow_the_reference_conventions():
     assert calls["t0"] == 0.0 and calls["t1"] == -500.0 and calls["w0"].shape == (3, 6) and np.array_equal(calls["w0"][2], np.arange(6.0))
     assert res["ts"][0] == -500.0 and res["ts"][-1] == 0.0 and len(res["ts"]) == 2000
     assert np.isclose(res["length_func"][-1], 10.0) and np.isclose(res["length_func"][0], 10.0 * 6.0)     # sqrt(3^2 + 4^2) * (1 + 5) / 5
+
+
+def test_sample_from_1d_pdf_uses_jax_uniform_draws():
+    """sample_from_1D_pdf (streamhelpers.py:306-349).  The host-side threefry / uniform recipe is checked against the oracle's generator,
+    which the reference's printed release Jacobian and stream pin (goldens D8, OC): same Threefry-2x32 words, and the uniform it builds
+    maps to the oracle's jax.random.normal through sqrt(2) erfinv(u (1 - lo) + lo)."""
+    import numpy as np
+    from scipy.special import erfinv
+    import oracle as O
+    from streamsculptor_b200 import streamhelpers as sh
+    for k0, k1, c0, c1 in ((0, 0, 0, 0), (0x13198a2e, 0x03707344, 0x243f6a88, 0x85a308d3), (0xffffffff,) * 4):
+        a = sh._threefry2x32(k0, k1, np.array([c0]), np.array([c1]))
+        assert [int(a[0][0]), int(a[1][0])] == [int(v) for v in O.threefry2x32(k0, k1, c0, c1)]
+    lo = np.nextafter(-1.0, 0.0)
+    for seed in (0, 493, 90 * 1499, 2**40 + 17):
+        u = sh.jax_uniform(seed, 1)[0]
+        assert 0.0 <= u < 1.0 and abs(np.sqrt(2.0) * erfinv(max(lo, u * (1.0 - lo) + lo)) - O.normal1(seed)) < 1e-14
+    # inverse-CDF sampling: a flat density returns the draws themselves on the grid's scale; a one-sided density stays in its support
+    x = np.linspace(2.0, 6.0, 4001)
+    s = sh.sample_from_1D_pdf(x, np.ones_like(x), key=7, num_samples=1000)
+    assert np.abs(s - (2.0 + 4.0 * sh.jax_uniform(7, 1000))).max() < 2e-3
+    y = np.where(x > 4.0, (x - 4.0) ** 2, 0.0)
+    s = sh.sample_from_1D_pdf(x, y, key=(0, 7), num_samples=2000)
+    assert s.min() >= 4.0 and s.max() <= 6.0 and abs(s.mean() - 5.5) < 0.03       # mean of 3 (x-4)^2 / 8 on [4, 6]
+    assert np.array_equal(s, sh.sample_from_1D_pdf(x, y, key=7, num_samples=2000))  # PRNGKey(7) == key words (0, 7)
