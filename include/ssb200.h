@@ -147,6 +147,12 @@ int ssb_orbit_record_f64(const ssb_potential* pot, int64_t N, const double* w0, 
                          void* recs, size_t rec_bytes, int32_t* status, int32_t* nsteps, void* stream);
 int ssb_orbit_record_eval_f64(int32_t solver, int64_t N, const void* recs, int32_t rec_cap, const double* tq, int32_t per_orbit, double* ys, void* stream);
 size_t ssb_record_bytes(int64_t N, int32_t rec_cap);
+/* Diagnostics for the lock-step parity tests (tests/test_gpu_lockstep.py): the controller's view of every step ATTEMPT of N adaptive
+ * solves with the same stepper code as ssb_orbit_integrate_f64 - trace[N,trace_cap,4] = {t_prev, dt, err, keep} in mirrored time
+ * (t * direction; rows beyond an orbit's attempt count are left untouched) - and the final states yfin[N,6].  What it mirrors in the
+ * reference: the (tprev, tnext, y_error norm, keep_step) carried by diffrax's adaptive loop under main.py:139-162. */
+int ssb_orbit_trace_f64(const ssb_potential* pot, int64_t N, const double* w0, const double* t0, const double* t1, ssb_ctrl ctrl,
+                        int32_t trace_cap, double* trace, double* yfin, int32_t* status, int32_t* nsteps, void* stream);
 /* Solution.evaluate(t) of a dense=True solve (main.py:131, 141): interpolate M more times inside the steps recorded in `scratch` by a
  * previous ssb_orbit_dense_f64 call with the same solver; ys[M,6] (+inf outside the integrated interval). */
 int ssb_orbit_dense_eval_f64(int32_t solver, const void* scratch, const double* ts, int64_t M, double* ys, void* stream);

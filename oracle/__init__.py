@@ -199,6 +199,15 @@ class Program:
                                   int(max_steps), cap, _p(tg), _p(yg))
         return tg[: n + 1], yg[: n + 1]
 
+    def orbit_trace(self, w0, t0, t1, solver=8, rtol=1e-7, atol=1e-7, dtmin=0.3, dtmax=None, max_steps=10_000):
+        """Every step ATTEMPT of one adaptive solve: array [n_attempts, 4] = (tprev, dt, err, keep) in mirrored time, and the final state."""
+        cap = max_steps + 1
+        out, yfin = np.empty((cap, 4)), np.empty(6)
+        w0 = _d(w0)
+        n = lib().orc_orbit_trace(self._h, _p(w0), C.c_double(t0), C.c_double(t1), int(solver), C.c_double(rtol), C.c_double(atol),
+                                  C.c_double(dtmin), C.c_double(np.inf if dtmax is None else dtmax), int(max_steps), cap, _p(out), _p(yfin))
+        return out[:min(n, cap)].copy(), yfin
+
     # ---- release model ----------------------------------------------------------------------
     def release(self, xv, Msat, idx, t, seed, kvals=None, normals=None, jacobian=False):
         """release_model (main.py:209-280) for a batch; returns pos_lead, pos_trail, v_lead, v_trail [n,3]

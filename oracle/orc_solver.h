@@ -36,6 +36,7 @@ struct Ctrl {
     double rtol = 1e-7, atol = 1e-7, dtmin = 0.3;
     double dtmax = std::numeric_limits<double>::infinity();   // None
     int max_steps = 10000;
+    std::vector<double>* trace = nullptr;   // optional: one record {tprev, dt, err, keep} per step ATTEMPT (mirrored time), for the lock-step parity tests
 };
 struct Stats { int status = 0, n_steps = 0, n_acc = 0, n_rej = 0; };   // status: 0 ok, 1 max_steps, 2 non-finite
 
@@ -127,6 +128,7 @@ Stats solve(F& f_user, int n, double t0_in, double t1_in, const double* y0_in, c
         }
         double err = rms(yerr.data(), sc.data(), n);
         bool keep = (err < 1.0) || at_dtmin;
+        if (ctl.trace) { ctl.trace->push_back(tprev); ctl.trace->push_back(dt); ctl.trace->push_back(err); ctl.trace->push_back(keep ? 1.0 : 0.0); }
         double factor = 0.9 * std::pow(1.0 / err, 1.0 / rk.order);   // icoeff=1 only; err==0 -> inf -> clipped to 10
         double fmin = keep ? 1.0 : 0.2;
         if (std::isnan(factor)) { st.status = 2; st.n_steps++; st.n_rej++; break; }   // NaN field: the reference spins to max_steps, outputs stay +inf

@@ -338,6 +338,21 @@ int orc_orbit_steps(void* h, const double* w0, double t0, double t1, int solver,
     return cnt;
 }
 
+// one orbit, every step ATTEMPT traced: out[cap][4] = {tprev, dt, err, keep} in mirrored time; returns the number of attempts
+int orc_orbit_trace(void* h, const double* w0, double t0, double t1, int solver, double rtol, double atol, double dtmin,
+                    double dtmax, int max_steps, int cap, double* out, double* yfin /*[6]*/) {
+    const Program& P = *(Program*)h;
+    Ctrl c; c.solver = solver; c.rtol = rtol; c.atol = atol; c.dtmin = dtmin; c.dtmax = dtmax; c.max_steps = max_steps;
+    std::vector<double> tr;
+    c.trace = &tr;
+    OrbitField f{&P};
+    double tsd = t1;
+    solve(f, 6, t0, t1, w0, &tsd, 1, c, yfin);
+    const int n = (int)(tr.size() / 4);
+    std::memcpy(out, tr.data(), sizeof(double) * 4 * (size_t)(n < cap ? n : cap));
+    return n;
+}
+
 void orc_threefry(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t* out) { threefry2x32(k0, k1, c0, c1, out, out + 1); }
 void orc_randint5(int64_t seed, int64_t lo, int64_t hi, int64_t* out) { randint5(prng_key(seed), lo, hi, out); }
 double orc_normal1(int64_t seed) { return random_normal1(prng_key(seed)); }

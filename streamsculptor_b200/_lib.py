@@ -85,6 +85,7 @@ _SIGNATURES = {
     "ssb_orbit_dense_f64": ([_PP, _dp, _dbl, _dbl, _dp, _i64, Ctrl, _dp, _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
     "ssb_scratch_bytes": ([_i32], C.c_size_t),
     "ssb_orbit_record_f64": ([_PP, _i64, _dp, _dp, _dp, Ctrl, _i32, _dp, C.c_size_t, _dp, _dp, _dp], C.c_int),
+    "ssb_orbit_trace_f64": ([_PP, _i64, _dp, _dp, _dp, Ctrl, _i32, _dp, _dp, _dp, _dp, _dp], C.c_int),
     "ssb_orbit_record_eval_f64": ([_i32, _i64, _dp, _i32, _dp, _i32, _dp, _dp], C.c_int),
     "ssb_record_bytes": ([_i64, _i32], C.c_size_t),
     "ssb_orbit_dense_eval_f64": ([_i32, _dp, _dp, _i64, _dp, _dp], C.c_int),

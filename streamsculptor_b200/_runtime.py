@@ -219,6 +219,20 @@ def orbit_integrate(pot, w0, t0, t1, ts, ctrl, ts_per_orbit):
     return ys, status, nsteps
 
 
+def orbit_trace(pot, w0, t0, t1, ctrl, trace_cap=None):
+    """Every step attempt of N adaptive solves (diagnostics): trace[N,cap,4] = (tprev, dt, err, keep) in mirrored time (NaN-filled beyond
+    an orbit's attempts), yfin[N,6], status[N], nsteps[N,3]."""
+    t = torch()
+    P, _keep = lower(pot)
+    N = w0.shape[0]
+    cap = int(trace_cap if trace_cap is not None else ctrl.max_steps)
+    trace = t.full((N, cap, 4), float("nan"), dtype=t.float64, device=device())
+    yfin, status, nsteps = empty((N, 6)), empty((N,), t.int32), empty((N, 3), t.int32)
+    _lib.check(_lib.lib().ssb_orbit_trace_f64(C.byref(P), N, ptr(w0), ptr(t0), ptr(t1), ctrl, cap, ptr(trace), ptr(yfin), ptr(status), ptr(nsteps),
+                                              stream_ptr()))
+    return trace, yfin, status, nsteps
+
+
 def orbit_dense(pot, w0, t0, t1, ts, ctrl):
     """One orbit: returns ys[M,6], status[1], nsteps[3], scratch (kept for later dense evaluation)."""
     t = torch()
@@ -446,7 +460,12 @@ class DenseOrbits:
         tt = torch()
         P, _keep = lower(pot)
         self.N, self.solver = int(w0.shape[0]), int(ctrl.solver)
-        self.rec_cap = int(rec_cap if rec_cap is not None else min(int(ctrl.max_steps), 512))
+        if rec_cap is None:
+            # size the record from a step-count pre-pass (the final-state kernel: same stepper, same step sequences), so that no orbit
+            # can run out of slots - the reference's dense Solution holds up to max_steps steps
+            _, _, ns = orbit_integrate(pot, w0, t0, t1, t1.reshape(-1, 1), ctrl, ts_per_orbit=1)
+            rec_cap = max(1, int(ns[:, 1].max().item())) if self.N > 0 else 1
+        self.rec_cap = int(rec_cap)
         nbytes = _lib.lib().ssb_record_bytes(self.N, self.rec_cap)
         if nbytes > self.MAX_BYTES:
             raise MemoryError(f"dense solutions of {self.N} orbits x {self.rec_cap} steps need {nbytes / 2**30:.0f} GiB; lower rec_cap or save "
@@ -455,6 +474,11 @@ class DenseOrbits:
         self.status, self.nsteps = empty((self.N,), tt.int32), empty((self.N, 3), tt.int32)
         _lib.check(_lib.lib().ssb_orbit_record_f64(C.byref(P), self.N, ptr(w0), ptr(t0), ptr(t1), ctrl, self.rec_cap, ptr(self.recs), nbytes,
                                                    ptr(self.status), ptr(self.nsteps), stream_ptr()))
+        n_over = int((self.nsteps[:, 1] > self.rec_cap).sum().item()) if self.N > 0 else 0
+        if n_over:            # only possible with an explicit rec_cap: those orbits carry status 1 and evaluate to +inf past their last slot
+            import warnings
+            warnings.warn(f"DenseOrbits: {n_over} of {self.N} orbits took more than rec_cap = {self.rec_cap} accepted steps; they have status 1 and "
+                          "evaluate to +inf beyond the recorded part (raise rec_cap, or leave it None to size it automatically)")
 
     def evaluate(self, t):
         """States of all N orbits at time t (scalar) or at t[i] (array of length N): device tensor [N, 6]; +inf outside an orbit's interval."""

@@ -43,4 +43,11 @@ int ssb_set_error(int code, const char* msg);
 int ssb_cuda_check(cudaError_t e, const char* what);
 int ssb_validate_potential(const ssb_potential* p);
 int ssb_validate_ctrl(const ssb_ctrl& c);
+// ssb_gen_stream_f64 on COMPACT per-shard inputs (internal; used by ssb_gen_stream_host so that a rank uploads only its own stripping
+// times): ts_c[n_local + 2] = the shard's stripping times, then the first and last stripping time of the whole stream; Msat_c[n_local],
+// normals_c[n_local,4] (or NULL) likewise.  scratch >= ssb_stream_scratch_bytes(n_local + 2, max_steps).
+extern "C" int ssb_gen_stream_compact(const ssb_potential* pot, const ssb_potential* pot_release, double G, int64_t Nts, const double* ts_c,
+                                      const double* prog_w0, const double* Msat_c, int64_t seed, const double* kvals, const double* normals_c, ssb_ctrl ctrl,
+                                      int64_t i_begin, int64_t i_stride, int64_t n_local, double* lead, double* trail, int32_t* status, int32_t* nsteps,
+                                      void* scratch, size_t scratch_bytes, void* stream);
 #endif

@@ -105,7 +105,9 @@ template <> __device__ __forceinline__ double inv_root<8>(double x) {
     const double a = x * frsqrt(x);        // x^(1/2)
     const double b = a * frsqrt(a);        // x^(1/4)
     const double r = frsqrt(b);            // x^(-1/8)
-    return x == 0.0 ? __longlong_as_double(0x7ff0000000000000LL) : r;
+    // err == +inf (overflowing error estimate): diffrax's (1/inf)^(1/8) = 0 -> factor clipped to factormin, the step is rejected
+    // and retried; rsqrt.approx(inf) = 0 would turn the refinement into inf * 0 = NaN (status 2) instead
+    return x == 0.0 ? __longlong_as_double(0x7ff0000000000000LL) : (x == __longlong_as_double(0x7ff0000000000000LL) ? 0.0 : r);
 }
 template <> __device__ __forceinline__ double inv_root<5>(double x) { return exp(-0.2 * log(x)); }
 

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <vector>
 
 #include "ssb_common.cuh"
@@ -24,15 +25,15 @@ struct Pool {                       // stream-ordered device allocations release
     cudaStream_t st;
     std::vector<void*> ptrs;
     explicit Pool(cudaStream_t s) : st(s) {
-        static bool tuned = false;
-        if (!tuned) {               // keep freed blocks cached in the pool between calls
-            int dev = 0; cudaGetDevice(&dev);
+        // keep freed blocks cached in the device's default pool between calls: once per DEVICE, safe under concurrent callers
+        static std::atomic<bool> tuned[64];
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !tuned[dev].exchange(true, std::memory_order_acq_rel)) {
             cudaMemPool_t mp;
             if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
                 uint64_t thr = UINT64_MAX;
                 cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
             }
-            tuned = true;
         }
     }
     ~Pool() { for (void* p : ptrs) cudaFreeAsync(p, st); }
@@ -89,6 +90,21 @@ int upload_potential(const ssb_potential* h, ssb_potential* d, Pool& pool) {
     for (int i = 0; i < h->n_sh; ++i)
         if (int e = upload_subhalos(&h->sh[i], &d->sh[i], pool)) return e;
     return 0;
+}
+
+// per-thread pinned staging buffer (grown on demand, kept between calls): the strided slices a shard needs are gathered here on the
+// host and uploaded with one DMA instead of uploading the whole arrays on every rank
+double* staging(size_t doubles) {
+    static thread_local double* buf = nullptr;
+    static thread_local size_t cap = 0;
+    if (doubles > cap) {
+        if (buf) cudaFreeHost(buf);
+        buf = nullptr; cap = 0;
+        const size_t want = doubles + doubles / 2 + 1024;
+        if (cudaHostAlloc((void**)&buf, want * sizeof(double), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); buf = nullptr; return nullptr; }
+        cap = want;
+    }
+    return buf;
 }
 
 // device alias of a pinned + mapped host range [h, h + bytes), or nullptr (pageable memory, device memory, zero-copy disabled)
@@ -165,10 +181,28 @@ int ssb_gen_stream_host(const ssb_potential* pot_h, const ssb_potential* pot_rel
     if (pot_release_h == pot_h) prd = pd;
     else if (int e = upload_potential(pot_release_h, &prd, pool)) return e;
     const void *dts, *dw0, *dms, *dnr = nullptr;
-    if (int e = pool.up(ts, 8 * (size_t)Nts, &dts)) return e;
     if (int e = pool.up(prog_w0, 48, &dw0)) return e;
-    if (int e = pool.up(Msat, 8 * (size_t)Nts, &dms)) return e;
-    if (normals) { if (int e = pool.up(normals, 32 * (size_t)Nts, &dnr)) return e; }
+    // A shard (i_stride > 1) needs only its own n_local stripping times (+ the two ends of the progenitor interval): gather them on
+    // the host and upload the compact arrays - h2d bytes per rank stay ~ 1/world of the arrays however many ranks share the stream.
+    bool compact = i_stride > 1 && n > 0 && i_begin >= 0 && i_begin + (int64_t)(n - 1) * i_stride <= Nts - 2;
+    double* stg = compact ? staging((n + 2) + n + (normals ? 4 * n : 0)) : nullptr;
+    if (!stg) compact = false;
+    if (compact) {
+        double *c_ts = stg, *c_ms = stg + (n + 2), *c_nr = c_ms + n;
+        for (size_t k = 0; k < n; ++k) {
+            const size_t g = (size_t)i_begin + k * (size_t)i_stride;
+            c_ts[k] = ts[g]; c_ms[k] = Msat[g];
+            if (normals) { c_nr[4 * k] = normals[4 * g]; c_nr[4 * k + 1] = normals[4 * g + 1]; c_nr[4 * k + 2] = normals[4 * g + 2]; c_nr[4 * k + 3] = normals[4 * g + 3]; }
+        }
+        c_ts[n] = ts[0]; c_ts[n + 1] = ts[Nts - 1];
+        if (int e = pool.up(c_ts, 8 * (n + 2), &dts)) return e;
+        if (int e = pool.up(c_ms, 8 * n, &dms)) return e;
+        if (normals) { if (int e = pool.up(c_nr, 32 * n, &dnr)) return e; }
+    } else {
+        if (int e = pool.up(ts, 8 * (size_t)Nts, &dts)) return e;
+        if (int e = pool.up(Msat, 8 * (size_t)Nts, &dms)) return e;
+        if (normals) { if (int e = pool.up(normals, 32 * (size_t)Nts, &dnr)) return e; }
+    }
     // lead and trail adjacent in memory (one [2, n, 6] buffer): the orbit kernel writes them in place.  If that buffer and the
     // status / step-count outputs are pinned host memory, "in place" is the HOST buffer itself (zero-copy, see the header comment).
     void *dl = nullptr, *dtr, *dstat = nullptr, *dns = nullptr, *scr;
@@ -180,9 +214,9 @@ int ssb_gen_stream_host(const ssb_potential* pot_h, const ssb_potential* pot_rel
         if (int e = pool.alloc(&dns, 24 * n)) return e;
     }
     dtr = (char*)dl + 48 * n;
-    const size_t sb = ssb_stream_scratch_bytes(Nts, ctrl.max_steps);
+    const size_t sb = ssb_stream_scratch_bytes(compact ? (int64_t)n + 2 : Nts, ctrl.max_steps);
     if (int e = pool.alloc(&scr, sb)) return e;
-    if (int e = ssb_gen_stream_f64(&pd, &prd, G, Nts, (const double*)dts, (const double*)dw0, (const double*)dms, seed, kvals,
+    if (int e = (compact ? ssb_gen_stream_compact : ssb_gen_stream_f64)(&pd, &prd, G, Nts, (const double*)dts, (const double*)dw0, (const double*)dms, seed, kvals,
                                    (const double*)dnr, ctrl, i_begin, i_stride, n_local, (double*)dl, (double*)dtr, (int32_t*)dstat, (int32_t*)dns, scr, sb, st)) return e;
     if (!zc) {
         if (int e = down(lead, dl, 48 * n, st)) return e;

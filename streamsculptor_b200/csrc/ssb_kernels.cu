@@ -76,6 +76,109 @@ struct OrbitForce {
 };
 
 // =============================================================================================
+// warp-cooperative dense output of the saving orbit kernel (K1 MODE 0: integrate_orbit_batch_vmapped with ts[N,M], main.py:186-202)
+// =============================================================================================
+// srec: the CTA's step records, field f of thread t at srec[f * SSB_ORBIT_THREADS + t]:
+//   0 tprev, 1 tnext (mirrored time), 2..4 x, 5..7 p (step start), 8..10 x1, 11..13 p1 (step end), 14 + 3 l + k: force stage l.
+// nsave: save times of THIS lane inside its published step (0: none); they are ts[save_idx .. save_idx + nsave) of its row tsp and go
+// to rows save_idx.. of its output block ys.  Task j of the warp (j < sum of nsave) belongs to the lane s with excl_s <= j < incl_s
+// (inclusive scan); tasks are dealt out j = lane, lane + 32, ...: every pass keeps all lanes busy and the lanes that serve one orbit
+// write adjacent 48-byte rows.
+template <int SOLVER>
+__device__ __forceinline__ void coop_dense(const double* __restrict__ srec, int nsave, int save_idx, const double* tsp, double* ys, double dir) {
+    constexpr int NT = SSB_ORBIT_THREADS;
+    constexpr int S = Tab<SOLVER>::S;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    int incl = nsave;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(full, incl, o); if (lane >= o) incl += v; }
+    const int total = __shfl_sync(full, incl, 31);
+    const int excl = incl - nsave;
+    for (int j0 = 0; j0 < total; j0 += 32) {
+        const int j = j0 + lane;
+        int lo = 0, hi = 31;                                  // smallest s with incl_s > j
+#pragma unroll
+        for (int it = 0; it < 5; ++it) { const int mid = (lo + hi) >> 1; const int v = __shfl_sync(full, incl, mid); if (v > j) hi = mid; else lo = mid + 1; }
+        const int s = lo;
+        const int r = j - __shfl_sync(full, excl, s);
+        const int m = __shfl_sync(full, save_idx, s) + r;
+        const double* ts_s = reinterpret_cast<const double*>(__shfl_sync(full, reinterpret_cast<unsigned long long>(tsp), s));
+        double* ys_s = reinterpret_cast<double*>(__shfl_sync(full, reinterpret_cast<unsigned long long>(ys), s));
+        const double dir_s = __shfl_sync(full, dir, s);
+        if (j >= total) continue;
+        const double* R = srec + wbase + s;
+        const double tq = ts_s[m] * dir_s;
+        const double ta = R[0], tb = R[NT], h = tb - ta;
+        double xo[3], po[3];
+        if (tq == tb) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { xo[k] = R[(8 + k) * NT]; po[k] = R[(11 + k) * NT]; }
+        } else {
+            const double theta = (tq - ta) / h;
+            double x0[3], p0[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { x0[k] = R[(2 + k) * NT]; p0[k] = R[(5 + k) * NT]; }
+            if constexpr (SOLVER == 5) {
+                // diffrax Dopri5: quartic through y0, y1, k1 = h f0, k7 = h f1 and y_mid = y0 + h sum cmid_i f_i (as rk_dense<5>)
+                double mx[3] = {0, 0, 0}, mp[3] = {0, 0, 0};
+#pragma unroll 1
+                for (int l = 0; l < S; ++l) {
+                    const double ca = ssb_tab::d5_cmida[l], cb = ssb_tab::d5_cmid[l];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { const double f = R[(14 + 3 * l + k) * NT]; mx[k] = fma(ca, f, mx[k]); mp[k] = fma(cb, f, mp[k]); }
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double x1k = R[(8 + k) * NT], p1k = R[(11 + k) * NT];
+                    const double xm = fma(h, fma(h, mx[k], ssb_tab::d5_cmidsum * p0[k]), x0[k]);
+                    const double pm = fma(h, mp[k], p0[k]);
+                    {
+                        const double f0 = h * p0[k], f1 = h * p1k, y0 = x0[k], y1 = x1k;
+                        const double a = 2 * (f1 - f0) - 8 * (y1 + y0) + 16 * xm;
+                        const double b = 5 * f0 - 3 * f1 + 18 * y0 + 14 * y1 - 32 * xm;
+                        const double cc = f1 - 4 * f0 - 11 * y0 - 5 * y1 + 16 * xm;
+                        xo[k] = (((a * theta + b) * theta + cc) * theta + f0) * theta + y0;
+                    }
+                    {
+                        const double f0 = h * R[(14 + k) * NT], f1 = h * R[(14 + 3 * (S - 1) + k) * NT], y0 = p0[k], y1 = p1k;
+                        const double a = 2 * (f1 - f0) - 8 * (y1 + y0) + 16 * pm;
+                        const double b = 5 * f0 - 3 * f1 + 18 * y0 + 14 * y1 - 32 * pm;
+                        const double cc = f1 - 4 * f0 - 11 * y0 - 5 * y1 + 16 * pm;
+                        po[k] = (((a * theta + b) * theta + cc) * theta + f0) * theta + y0;
+                    }
+                }
+            } else {
+                // our C1 5th-order continuous extension of RK8(7)13M (tools/derive_dopri8_dense.py), stage weights by Horner in theta:
+                // rolled loop over the stages, coefficients from the constant tables, stage forces from the shared record
+                double accx[3] = {0, 0, 0}, accp[3] = {0, 0, 0};
+#pragma unroll 1
+                for (int l = 0; l < S; ++l) {
+                    double wa = 0.0, wb = 0.0;
+#pragma unroll
+                    for (int q = 6; q >= 0; --q) { wa = fma(wa, theta, ssb_tab::d8_dense_a[l][q]); wb = fma(wb, theta, ssb_tab::d8_dense[l][q]); }
+                    wa *= theta; wb *= theta;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { const double f = R[(14 + 3 * l + k) * NT]; accx[k] = fma(wa, f, accx[k]); accp[k] = fma(wb, f, accp[k]); }
+                }
+                double wsum = 0.0;
+#pragma unroll
+                for (int q = 6; q >= 0; --q) wsum = fma(wsum, theta, ssb_tab::d8_dense_sum[q]);
+                wsum *= theta;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    xo[k] = fma(h, fma(h, accx[k], wsum * p0[k]), x0[k]);
+                    po[k] = fma(h, accp[k], p0[k]);
+                }
+            }
+        }
+        double* o = ys_s + (size_t)m * 6;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { o[k] = xo[k]; o[3 + k] = dir_s * po[k]; }
+    }
+}
+
+// =============================================================================================
 // K1: batch of independent adaptive solves
 // =============================================================================================
 struct OrbitArgs {
@@ -94,7 +197,8 @@ template <int SOLVER, int MODE, int SIG, int XS = 0>
 __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_potential* Pc, const double* w0, double t0_in, double t1_in,
                                               const double* tsp, int M, double* ys, const CtrlDev& c, bool valid,
                                               int& status, int& n_steps, int& n_acc, int& n_rej, double* rec, int rec_cap,
-                                              const FastX* fxp = nullptr, double t_stop = HUGE_VAL) {
+                                              const FastX* fxp = nullptr, double t_stop = HUGE_VAL, double* trace = nullptr, int trace_cap = 0,
+                                              double* srec = nullptr) {
     typedef Tab<SOLVER> T;
     constexpr int S = T::S;
     const double dir = (t0_in < t1_in) ? 1.0 : -1.0;              // diffrax: direction = where(t0 < t1, 1, -1)
@@ -142,10 +246,86 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
         h = fmax(h, c.dtmin);
         tnext = fmin(T0 + h, T1);
     }
-    double tq_a = __longlong_as_double(0x7ff0000000000000LL), tq_b = tq_a;      // MODE 0: the next two save times (mirrored time)
-    if (MODE == 0 && valid) {
-        if (M > 0) tq_a = tsp[0] * dir;
-        if (M > 1) tq_b = tsp[1] * dir;
+    double tq_a = __longlong_as_double(0x7ff0000000000000LL);      // MODE 0: the next save time (mirrored time)
+    if (MODE == 0 && valid && M > 0) tq_a = tsp[0] * dir;
+    if constexpr (MODE == 0) {
+        // SaveAt(ts) with WARP-COOPERATIVE dense output.  A lane whose accepted step covers save times publishes the step (times,
+        // end points, force stages) in its shared-memory record; the (orbit, save time) pairs of the whole warp are then dealt out
+        // evenly over the 32 lanes (coop_dense), so the interpolation runs converged whatever the lanes' step sequences are and
+        // adjacent rows of one orbit are written by adjacent lanes.
+        constexpr int NT = SSB_ORBIT_THREADS;
+        double* myrec = srec + threadIdx.x;
+        for (;;) {
+            bool active = valid && status == 0 && tprev < T1;
+            if (active && n_steps >= c.max_steps) { status = 1; active = false; }
+            if (!__any_sync(0xffffffffu, active)) break;
+            int nsave = 0;
+            if (active) {
+                const double dt = tnext - tprev;
+                double x1[3], p1[3], ex[3], ep[3];
+                rk_stages<SOLVER>(force, x, p, tprev, dt, F);
+                rk_candidate<SOLVER>(x, p, dt, F, x1, p1);
+                force(x1, tprev + T::c(S - 1) * dt, F[S - 1]);
+                rk_error<SOLVER>(p, dt, F, ex, ep);
+                bool nan_cand = false, finite = true;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    nan_cand |= isnan(x1[k]) | isnan(p1[k]);
+                    finite &= isfinite(x1[k]) & isfinite(p1[k]);
+                }
+                const double err = sqrt(err_sq6(x, p, x1, p1, ex, ep, c.rtol, c.atol, nan_cand) / 6.0);
+                double hn; bool bad;
+                const bool keep = pid_update<T::ORDER>(err, dt, c, at_dtmin, hn, bad);
+                n_steps++;
+                if (bad) { status = 2; n_rej++; }
+                else {
+                    if (keep) {
+                        n_acc++;
+                        if (!finite) status = 2;
+                        else {
+                            if (tq_a <= tnext) {           // every ts[save_idx + r] <= tnext is interpolated inside this accepted step
+                                myrec[0] = tprev; myrec[NT] = tnext;
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) {
+                                    myrec[(2 + k) * NT] = x[k]; myrec[(5 + k) * NT] = p[k]; myrec[(8 + k) * NT] = x1[k]; myrec[(11 + k) * NT] = p1[k];
+                                }
+#pragma unroll
+                                for (int l = 0; l < S; ++l)
+#pragma unroll
+                                    for (int k = 0; k < 3; ++k) myrec[(14 + 3 * l + k) * NT] = F[l][k];
+                                // number of save times inside the step: gallop, then bisect (ts is monotone)
+                                const int left = M - save_idx;
+                                int hi = 1;
+                                while (hi < left && tsp[save_idx + hi] * dir <= tnext) hi <<= 1;
+                                int lo = hi >> 1;                       // row lo is inside the step (lo = 0: known from tq_a) ...
+                                if (hi > left) hi = left;               // ... row hi is outside (or the end of the list)
+                                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tsp[save_idx + mid] * dir <= tnext) lo = mid; else hi = mid; }
+                                nsave = hi;
+                            }
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) { x[k] = x1[k]; p[k] = p1[k]; F[0][k] = F[S - 1][k]; }    // FSAL
+                            tprev = tnext;
+                        }
+                    } else {
+                        n_rej++;
+                    }
+                    if (status == 0) {
+                        tprev = fmin(tprev, T1);
+                        double tn = tprev + hn;
+                        if (tn > T1 - 1e-10) tn = keep ? T1 : tprev + 0.5 * (T1 - tprev);     // diffrax _clip_to_end (f64)
+                        tnext = tn;
+                    }
+                }
+            }
+            if (__any_sync(0xffffffffu, nsave > 0)) {
+                __syncwarp();
+                coop_dense<SOLVER>(srec, nsave, save_idx, tsp, ys, dir);
+                __syncwarp();
+                save_idx += nsave;
+                tq_a = (valid && save_idx < M) ? tsp[save_idx] * dir : __longlong_as_double(0x7ff0000000000000LL);
+            }
+        }
+        return;
     }
     for (;;) {
         bool active = valid && status == 0 && tprev < T1;
@@ -168,6 +348,10 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
         const double err = sqrt(err_sq6(x, p, x1, p1, ex, ep, c.rtol, c.atol, nan_cand) / 6.0);
         double hn; bool bad;
         const bool keep = pid_update<T::ORDER>(err, dt, c, at_dtmin, hn, bad);
+        if (MODE == 1 && trace && n_steps < trace_cap) {        // lock-step parity tests: every ATTEMPT {tprev, dt, err, keep} (mirrored time)
+            double* q = trace + 4 * (size_t)n_steps;
+            q[0] = tprev; q[1] = dt; q[2] = err; q[3] = keep ? 1.0 : 0.0;
+        }
         n_steps++;
         if (bad) { status = 2; n_rej++; continue; }
         if (keep) {
@@ -184,27 +368,6 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
 #pragma unroll
                         for (int k = 0; k < 3; ++k) r[14 + 3 * l + k] = F[l][k];
                 }
-            } else if (MODE == 0) {
-                // SaveAt(ts): every ts[save_idx] <= tnext is interpolated inside this accepted step.  The next two save times are kept
-                // in registers (tq_a, tq_b): a step without a save costs no memory access, and the reload after a save is not needed
-                // until the save after it.
-                while (save_idx < M) {
-                    const double tq = tq_a;
-                    if (!(tq <= tnext)) break;
-                    double xo[3], po[3];
-                    if (tq == tnext) {
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) { xo[k] = x1[k]; po[k] = p1[k]; }
-                    } else {
-                        rk_dense<SOLVER>(x, p, x1, p1, dt, F, (tq - tprev) / dt, xo, po);
-                    }
-                    double* o = ys + (size_t)save_idx * 6;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) { o[k] = xo[k]; o[3 + k] = dir * po[k]; }
-                    save_idx++;
-                    tq_a = tq_b;
-                    tq_b = (save_idx + 1 < M) ? tsp[save_idx + 1] * dir : __longlong_as_double(0x7ff0000000000000LL);
-                }
             }
 #pragma unroll
             for (int k = 0; k < 3; ++k) { x[k] = x1[k]; p[k] = p1[k]; F[0][k] = F[S - 1][k]; }    // FSAL
@@ -217,7 +380,7 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
         if (tn > T1 - 1e-10) tn = keep ? T1 : tprev + 0.5 * (T1 - tprev);     // diffrax _clip_to_end (f64)
         tnext = tn;
     }
-    if (MODE == 2 && valid) {              // final state (or +inf if the end was not reached: diffrax leaves unsaved rows at inf)
+    if ((MODE == 2 || (MODE == 1 && ys != nullptr)) && valid) {              // final state (or +inf if the end was not reached: diffrax leaves unsaved rows at inf)
         const bool done = status == 0 && tprev >= T1 && T0 < T1;
         const double inf = __longlong_as_double(0x7ff0000000000000LL);
 #pragma unroll
@@ -267,11 +430,34 @@ __global__ void __launch_bounds__(SSB_ORBIT_THREADS, SSB_ORBIT_MIN_BLOCKS) orbit
         if (valid) a.status[i] = status;
         return;
     }
+    extern __shared__ double s_steprec[];          // MODE 0: one published step record per thread (coop_dense), (14 + 3 S) x SSB_ORBIT_THREADS doubles
     integrate_one<SOLVER, MODE, SIG, XS>(&sP, &Pin, a.w0 + ii * 6, a.t0[ii], a.t1[ii], tsp, a.M, a.ys + (size_t)ii * a.M * 6, a.c, valid,
-                                     status, n_steps, n_acc, n_rej, nullptr, 0, sfx);
+                                     status, n_steps, n_acc, n_rej, nullptr, 0, sfx, HUGE_VAL, nullptr, 0, s_steprec);
     if (valid) {
         a.status[i] = status;
         a.nsteps[3 * i] = n_steps; a.nsteps[3 * i + 1] = n_acc; a.nsteps[3 * i + 2] = n_rej;
+    }
+}
+
+// lock-step parity diagnostics: every step ATTEMPT of every orbit {tprev, dt, err, keep} (mirrored time) + the final state
+template <int SOLVER, int SIG>
+__global__ void __launch_bounds__(SSB_ORBIT_THREADS, SSB_ORBIT_MIN_BLOCKS) trace_kernel(const __grid_constant__ ssb_potential Pin, int64_t N, const double* w0,
+                                                                                        const double* t0, const double* t1, CtrlDev c, double* trace,
+                                                                                        int trace_cap, double* yfin, int32_t* status_out, int32_t* nsteps_out) {
+    __shared__ ssb_potential sP;
+    stage_potential(&sP, &Pin);
+    logtab_init();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < N;
+    const int64_t ii = valid ? i : 0;
+    int status, n_steps, n_acc, n_rej;
+    double fin[6] = {0, 0, 0, 0, 0, 0};
+    integrate_one<SOLVER, 1, SIG>(&sP, &Pin, w0 + 6 * ii, t0[ii], t1[ii], nullptr, 0, fin, c, valid, status, n_steps, n_acc, n_rej, nullptr, 0, nullptr, HUGE_VAL,
+                                  trace + (size_t)ii * 4 * trace_cap, trace_cap);
+    if (valid) {
+        for (int k = 0; k < 6; ++k) yfin[6 * i + k] = fin[k];
+        status_out[i] = status;
+        nsteps_out[3 * i] = n_steps; nsteps_out[3 * i + 1] = n_acc; nsteps_out[3 * i + 2] = n_rej;
     }
 }
 
@@ -509,6 +695,9 @@ struct ReleaseArgs {
     int64_t sel_begin, sel_stride;
     double* t1_packed; const double* t_end;
     int64_t i0, cnt;              // cnt > 0: this launch handles the compact indices [i0, i0 + cnt) of the N (gen_stream's two-part pipeline)
+    // compact inputs (ssb_gen_stream_host on a shard): t / Msat / normals hold ONLY this shard's stripping times, row k <-> stripping
+    // index draw_begin + k * draw_stride (the index that seeds jax.random, main.py:223-228).  draw_stride = 0: the array index itself.
+    int64_t draw_begin, draw_stride;
 };
 
 // ---- forward-mode dual numbers for jacfwd(release_model) (perturbative.py:281-296): value + 6 partials d/d(x, v) ----
@@ -569,7 +758,7 @@ __device__ inline void release_math(const T x[3], const T v[3], const T H[3][3],
 
 __device__ inline void release_draws(const ReleaseArgs& a, int64_t i, double nr[4]) {
     if (a.normals) { for (int q = 0; q < 4; ++q) nr[q] = a.normals[4 * i + q]; }
-    else { const int64_t id = a.idx ? a.idx[i] : i; for (int q = 0; q < 4; ++q) nr[q] = jax_normal1(id * a.r[q]); }
+    else { const int64_t id = a.idx ? a.idx[i] : (a.draw_stride ? a.draw_begin + i * a.draw_stride : i); for (int q = 0; q < 4; ++q) nr[q] = jax_normal1(id * a.r[q]); }
 }
 
 __global__ void release_kernel(const __grid_constant__ ssb_potential Pin, const ReleaseArgs a) {
@@ -863,7 +1052,10 @@ int ssb_orbit_integrate_f64(const ssb_potential* pot, int64_t N, const double* w
     const int sig = ssb_canonicalize(pot, &pc);
     // XS = number of "fast extras" (linear-track moving perturbers / frame acceleration) next to a fused MW signature, final-state mode
     const int xs = (final_only && (sig == SIG_NHM || sig == SIG_NHHM)) ? ssb_fast_extras(&pc, sig == SIG_NHM ? 3 : 4) : 0;
-#define SSB_LAUNCH_ORBIT(S, MD, SG) orbit_kernel<S, MD, SG, 0><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a)
+    // MODE 0 (SaveAt with dense output): one step record of (14 + 3 stages) doubles per thread in dynamic shared memory (coop_dense)
+#define SSB_LAUNCH_ORBIT(S, MD, SG) do { const size_t shm = (MD) == 0 ? sizeof(double) * (14 + 3 * ((S) == 5 ? 7 : 14)) * SSB_ORBIT_THREADS : 0; \
+        if (shm > 48 * 1024) CK(cudaFuncSetAttribute(orbit_kernel<S, MD, SG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); \
+        orbit_kernel<S, MD, SG, 0><<<grid, SSB_ORBIT_THREADS, shm, st>>>(pc, a); } while (0)
 #define SSB_LAUNCH_SIG(S, MD) do { switch (sig) { case SIG_N: SSB_LAUNCH_ORBIT(S, MD, SIG_N); break; case SIG_NHM: SSB_LAUNCH_ORBIT(S, MD, SIG_NHM); break; \
         case SIG_NHHM: SSB_LAUNCH_ORBIT(S, MD, SIG_NHHM); break; default: SSB_LAUNCH_ORBIT(S, MD, SIG_GENERIC); } } while (0)
 #define SSB_LAUNCH_XS(S) do { if (sig == SIG_NHM) { if (xs == 1) orbit_kernel<S, 2, SIG_NHM, 1><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
@@ -927,6 +1119,26 @@ int ssb_orbit_record_f64(const ssb_potential* pot, int64_t N, const double* w0, 
         default: record_kernel<S, SIG_GENERIC><<<grid, SSB_ORBIT_THREADS, 0, st>>>(*pot, N, w0, t0, t1, c, (double*)recs, rec_cap, status, nsteps); } } while (0)
     if (ctrl.solver == 5) SSB_LAUNCH_REC_SIG(5); else SSB_LAUNCH_REC_SIG(8);
     CKL("record_kernel");
+    return 0;
+}
+
+int ssb_orbit_trace_f64(const ssb_potential* pot, int64_t N, const double* w0, const double* t0, const double* t1, ssb_ctrl ctrl, int32_t trace_cap,
+                        double* trace, double* yfin, int32_t* status, int32_t* nsteps, void* stream) {
+    if (int e = ssb_validate_potential(pot)) return e;
+    if (int e = ssb_validate_ctrl(ctrl)) return e;
+    if (N < 0 || trace_cap < 1) return ssb_set_error(SSB_ERR_ARG, "orbit_trace: negative N or trace_cap < 1");
+    if (N == 0) return 0;
+    if (!w0 || !t0 || !t1 || !trace || !yfin || !status || !nsteps) return ssb_set_error(SSB_ERR_ARG, "orbit_trace: NULL array");
+    const CtrlDev c = to_dev(ctrl);
+    ssb_potential pc;
+    const int sig = ssb_canonicalize(pot, &pc);
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = nblk(N, SSB_ORBIT_THREADS);
+#define SSB_LAUNCH_TRACE(S, SG) trace_kernel<S, SG><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, N, w0, t0, t1, c, trace, trace_cap, yfin, status, nsteps)
+#define SSB_LAUNCH_TRACE_SIG(S) do { switch (sig) { case SIG_N: SSB_LAUNCH_TRACE(S, SIG_N); break; case SIG_NHM: SSB_LAUNCH_TRACE(S, SIG_NHM); break; \
+        case SIG_NHHM: SSB_LAUNCH_TRACE(S, SIG_NHHM); break; default: SSB_LAUNCH_TRACE(S, SIG_GENERIC); } } while (0)
+    if (ctrl.solver == 5) SSB_LAUNCH_TRACE_SIG(5); else SSB_LAUNCH_TRACE_SIG(8);
+    CKL("trace_kernel");
     return 0;
 }
 
@@ -1053,28 +1265,55 @@ static bool stream_split_enabled() {
     return !(e && e[0] == '0');
 }
 
+// compact != 0 (internal, ssb_gen_stream_host on a shard): ts / Msat / normals hold only the shard's n_local stripping times (row k <->
+// stripping index i_begin + k i_stride) followed, in ts, by the two ends of the progenitor interval: ts[n_local] = first, ts[n_local + 1] =
+// last stripping time of the WHOLE stream.
+static int gen_stream_impl(const ssb_potential* pot, const ssb_potential* pot_release, double G, int64_t Nts, const double* ts, const double* prog_w0,
+                           const double* Msat, int64_t seed, const double* kvals, const double* normals, ssb_ctrl ctrl, int64_t i_begin, int64_t i_stride,
+                           int64_t n_local, double* lead, double* trail, int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream,
+                           int compact);
+
 int ssb_gen_stream_f64(const ssb_potential* pot, const ssb_potential* pot_release, double G, int64_t Nts, const double* ts, const double* prog_w0,
                        const double* Msat, int64_t seed, const double* kvals, const double* normals, ssb_ctrl ctrl, int64_t i_begin, int64_t i_stride,
                        int64_t n_local, double* lead, double* trail, int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream) {
+    return gen_stream_impl(pot, pot_release, G, Nts, ts, prog_w0, Msat, seed, kvals, normals, ctrl, i_begin, i_stride, n_local, lead, trail, status, nsteps,
+                           scratch, scratch_bytes, stream, 0);
+}
+int ssb_gen_stream_compact(const ssb_potential* pot, const ssb_potential* pot_release, double G, int64_t Nts, const double* ts_c, const double* prog_w0,
+                           const double* Msat_c, int64_t seed, const double* kvals, const double* normals_c, ssb_ctrl ctrl, int64_t i_begin, int64_t i_stride,
+                           int64_t n_local, double* lead, double* trail, int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream) {
+    return gen_stream_impl(pot, pot_release, G, Nts, ts_c, prog_w0, Msat_c, seed, kvals, normals_c, ctrl, i_begin, i_stride, n_local, lead, trail, status,
+                           nsteps, scratch, scratch_bytes, stream, 1);
+}
+
+static int gen_stream_impl(const ssb_potential* pot, const ssb_potential* pot_release, double G, int64_t Nts, const double* ts, const double* prog_w0,
+                           const double* Msat, int64_t seed, const double* kvals, const double* normals, ssb_ctrl ctrl, int64_t i_begin, int64_t i_stride,
+                           int64_t n_local, double* lead, double* trail, int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream,
+                           int compact) {
     if (int e = ssb_validate_potential(pot)) return e;
     if (int e = ssb_validate_potential(pot_release)) return e;
     if (int e = ssb_validate_ctrl(ctrl)) return e;
     if (Nts < 2 || !ts || !prog_w0 || !Msat || !kvals || !scratch) return ssb_set_error(SSB_ERR_ARG, "gen_stream: NULL array or Nts < 2");
     if (i_begin < 0 || i_stride < 1 || n_local < 0 || (n_local > 0 && i_begin + (n_local - 1) * i_stride > Nts - 2))
         return ssb_set_error(SSB_ERR_ARG, "gen_stream: particle selection outside [0, Nts-1)");
-    if (scratch_bytes < ssb_stream_scratch_bytes(Nts, ctrl.max_steps)) return ssb_set_error(SSB_ERR_SCRATCH, "gen_stream: scratch too small");
     const int64_t n = n_local;
+    const int64_t Nlay = compact ? n + 2 : Nts;             // rows the scratch layout is sized for
+    if (scratch_bytes < ssb_stream_scratch_bytes(Nlay, ctrl.max_steps)) return ssb_set_error(SSB_ERR_SCRATCH, "gen_stream: scratch too small");
     if (n > 0 && (!lead || !trail || !status || !nsteps)) return ssb_set_error(SSB_ERR_ARG, "gen_stream: NULL output");
     cudaStream_t st = (cudaStream_t)stream;
     double* dense = (double*)scratch;
     double* prog = dense + ssb_scratch_bytes(ctrl.max_steps) / sizeof(double);
-    double* w0p = prog + 6 * Nts;
-    double* w0 = w0p + 12 * Nts;
-    double* t0 = w0 + 12 * Nts;
-    double* t1 = t0 + 2 * Nts;
-    double* ys = t1 + 2 * Nts;
-    double* dense2 = ys + 12 * Nts;
+    double* w0p = prog + 6 * Nlay;
+    double* w0 = w0p + 12 * Nlay;
+    double* t0 = w0 + 12 * Nlay;
+    double* t1 = t0 + 2 * Nlay;
+    double* ys = t1 + 2 * Nlay;
+    double* dense2 = ys + 12 * Nlay;
     if (n == 0) return 0;
+    // where this shard's stripping times live: the full arrays (row i_begin + k i_stride) or compact ones (row k)
+    const double* ts_first = compact ? ts + n : ts;
+    const double* ts_last = compact ? ts + n + 1 : ts + (Nts - 1);
+    const int64_t tb = compact ? 0 : i_begin, tstr = compact ? 1 : i_stride;
     int64_t r5[5]; host_randint5(seed, r5);
     StreamAux* ax = (n >= SSB_STREAM_SPLIT_MIN && trail == lead + 6 * n && stream_split_enabled()) ? stream_aux() : nullptr;
     if (ax) {
@@ -1083,15 +1322,16 @@ int ssb_gen_stream_f64(const ssb_potential* pot, const ssb_potential* pot_releas
         ReleaseArgs a;
         memset(&a, 0, sizeof(a));
         a.N = n; a.prog = prog; a.Msat = Msat; a.t = ts; a.normals = normals; a.idx = nullptr; a.G = G;
-        a.sel_begin = i_begin; a.sel_stride = i_stride;
+        a.sel_begin = tb; a.sel_stride = tstr;
+        if (compact) { a.draw_begin = i_begin; a.draw_stride = i_stride; }
         for (int q = 0; q < 4; ++q) a.r[q] = r5[q];
         memcpy(a.kv, kvals, sizeof(a.kv));
-        a.w0_packed = w0; a.t0_packed = t0; a.t1_packed = t1; a.t_end = ts + (Nts - 1);
+        a.w0_packed = w0; a.t0_packed = t0; a.t1_packed = t1; a.t_end = ts_last;
         CK(cudaEventRecord(ax->e0, st));                                   // the inputs are ready in the caller's stream order
         CK(cudaStreamWaitEvent(s2, ax->e0, 0));
         // part B on the internal stream: whole progenitor orbit -> its dense output at B's stripping times -> release -> orbits
-        if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts, ts + (Nts - 1), ts, nb, ctrl, prog + 6 * na, nullptr, nullptr, dense2, s2,
-                                 i_begin + na * i_stride, i_stride)) return e;
+        if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts_first, ts_last, ts, nb, ctrl, prog + 6 * na, nullptr, nullptr, dense2, s2,
+                                 tb + na * tstr, tstr)) return e;
         a.i0 = na; a.cnt = nb;
         release_kernel<<<nblk(nb, 128), 128, 0, s2>>>(*pot_release, a);
         CKL("release_kernel");
@@ -1100,8 +1340,8 @@ int ssb_gen_stream_f64(const ssb_potential* pot, const ssb_potential* pot_releas
                                             status + n + na, nsteps + 3 * (n + na), s2)) return e;
         CK(cudaEventRecord(ax->e1, s2));
         // part A on the caller's stream: the progenitor only until it has passed A's last stripping time
-        if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts, ts + (Nts - 1), ts, na, ctrl, prog, nullptr, nullptr, dense, st, i_begin, i_stride,
-                                 ts + (i_begin + (na - 1) * i_stride))) return e;
+        if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts_first, ts_last, ts, na, ctrl, prog, nullptr, nullptr, dense, st, tb, tstr,
+                                 ts + (tb + (na - 1) * tstr))) return e;
         a.i0 = 0; a.cnt = na;
         release_kernel<<<nblk(na, 128), 128, 0, st>>>(*pot_release, a);
         CKL("release_kernel");
@@ -1112,16 +1352,17 @@ int ssb_gen_stream_f64(const ssb_potential* pot, const ssb_potential* pot_releas
     }
     // (1) progenitor orbit integrate_orbit(prog_w0, ts) with t0 = ts.min, t1 = ts.max (main.py:289, 152-153): ONE serial solve, then its
     //     dense output at THIS SHARD's stripping times only (ts[i_begin + k i_stride], k < n)
-    if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts, ts + (Nts - 1), ts, n, ctrl, prog, nullptr, nullptr, dense, st, i_begin, i_stride)) return e;
+    if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts_first, ts_last, ts, n, ctrl, prog, nullptr, nullptr, dense, st, tb, tstr)) return e;
     // (2) release at those stripping times (main.py:293-303), written straight into the orbit kernel's input layout
     //     (lead block, trail block) together with the per-orbit start / end times
     ReleaseArgs a;
     memset(&a, 0, sizeof(a));
     a.N = n; a.prog = prog; a.Msat = Msat; a.t = ts; a.normals = normals; a.idx = nullptr; a.G = G;
-    a.sel_begin = i_begin; a.sel_stride = i_stride;
+    a.sel_begin = tb; a.sel_stride = tstr;
+        if (compact) { a.draw_begin = i_begin; a.draw_stride = i_stride; }
     for (int q = 0; q < 4; ++q) a.r[q] = r5[q];
     memcpy(a.kv, kvals, sizeof(a.kv));
-    a.w0_packed = w0; a.t0_packed = t0; a.t1_packed = t1; a.t_end = ts + (Nts - 1);
+    a.w0_packed = w0; a.t0_packed = t0; a.t1_packed = t1; a.t_end = ts_last;
     release_kernel<<<nblk(n, 128), 128, 0, st>>>(*pot_release, a);
     CKL("release_kernel");
     // (3) 2n independent solves from ts[i] to ts[-1], keep the final state (main.py:349-368); lead and trail that are adjacent in

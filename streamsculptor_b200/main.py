@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _lib
 from . import _runtime as rt
-from .solvers import Dopri5, Dopri8
+from .solvers import Dopri5, Dopri8, solver_id
 from .units import dimensionless, resolve_G, usys  # noqa: F401  (usys re-exported like the reference)
 
 DEFAULT_KVALS = (2.0, 0.3, 0.0, 0.0, 0.4, 0.4, 0.5, 0.5)   # main.py:214
@@ -216,15 +216,31 @@ class Potential:
 
     def gen_stream_scan(self, ts=None, prog_w0=None, Msat=None, seed_num=None, solver=Dopri5(scan_kind='bounded'), kval_arr=1.0, rtol=1e-7,
                         atol=1e-7, dtmin=0.3, dtmax=None, max_steps=10_000, normals=None):
-        """Same result as gen_stream_vmapped (main.py:312-340 is its sequential schedule)."""
-        return self.gen_stream_vmapped(ts=ts, prog_w0=prog_w0, Msat=Msat, seed_num=seed_num, solver=solver, kval_arr=kval_arr, rtol=rtol,
-                                       atol=atol, dtmin=dtmin, dtmax=dtmax, max_steps=max_steps, normals=normals)
+        """The sequential schedule of gen_stream_vmapped (main.py:312-340).  One quirk of the reference is kept: gen_stream_scan calls
+        gen_stream_ics WITHOUT its `solver` (main.py:318), so the progenitor orbit and the release use the default Dopri5 whatever solver
+        integrates the particles.  With solver = Dopri5 this is gen_stream_vmapped exactly (one fused enqueue); otherwise the release ICs
+        come from a Dopri5 progenitor and the particles are integrated with `solver`."""
+        if solver_id(solver) == 5:
+            return self.gen_stream_vmapped(ts=ts, prog_w0=prog_w0, Msat=Msat, seed_num=seed_num, solver=solver, kval_arr=kval_arr, rtol=rtol,
+                                           atol=atol, dtmin=dtmin, dtmax=dtmax, max_steps=max_steps, normals=normals)
+        dev_in = rt.is_dev(ts)
+        tt = rt.torch()
+        ts_d = rt.to_dev(ts).reshape(-1)
+        pl, pt, vl, vt = self.gen_stream_ics(ts=ts_d, prog_w0=prog_w0, Msat=Msat, seed_num=seed_num, solver=Dopri5(scan_kind='bounded'), kval_arr=kval_arr,
+                                             rtol=rtol, atol=atol, dtmin=dtmin, dtmax=dtmax, max_steps=max_steps, normals=normals)
+        n = ts_d.shape[0] - 1
+        w0 = tt.cat([tt.cat([pl, vl], 1)[:n], tt.cat([pt, vt], 1)[:n]]).contiguous()            # lead block, trail block
+        t0 = tt.cat([ts_d[:n], ts_d[:n]]).contiguous()
+        t1 = ts_d[-1].expand(2 * n).contiguous()
+        ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
+        ys, _, _ = rt.orbit_integrate(self, w0, t0, t1, t1.reshape(-1, 1), ctrl, ts_per_orbit=1)
+        return rt.out(ys[:n, 0].contiguous(), dev_in), rt.out(ys[n:, 0].contiguous(), dev_in)
 
     def gen_stream_vmapped_dense(self, ts=None, prog_w0=None, Msat=None, seed_num=None, solver=Dopri5(scan_kind='bounded'), kval_arr=1.0, rtol=1e-7,
                                  atol=1e-7, dtmin=0.3, dtmax=None, max_steps=10_000, normals=None, rec_cap=None):
         """Dense stream model (main.py:376-430): every particle's orbit from its release time to ts[-1] as a dense interpolant.
         Returns a DenseStream; `streamhelpers.eval_dense_stream(t, dense_stream)` gives (lead, trail) at any time (+inf for particles
-        not yet released at t).  rec_cap = record slots per orbit (default min(max_steps, 512) accepted steps)."""
+        not yet released at t).  rec_cap = record slots per orbit (default: sized from a step-count pre-pass so that no orbit overflows)."""
         tt = rt.torch()
         ts_d, w0_d, Ms, kv, nr = self._stream_inputs(ts, prog_w0, Msat, kval_arr, normals)
         pl, pt, vl, vt = self.gen_stream_ics(ts=ts_d, prog_w0=w0_d, Msat=Ms, seed_num=seed_num, solver=solver, kval_arr=kval_arr, rtol=rtol, atol=atol,
@@ -244,6 +260,11 @@ class DenseStream:
 
     def __init__(self, orbits, n):
         self.orbits, self.n = orbits, n
+
+    @property
+    def status(self):
+        """Per-orbit solver status [2(N-1)] (0 ok, 1 max_steps / record slots exhausted, 2 non-finite): lead block, trail block."""
+        return self.orbits.status
 
     def evaluate(self, t):
         ys = self.orbits.evaluate(t)

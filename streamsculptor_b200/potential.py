@@ -304,6 +304,11 @@ class SubhaloLinePotential_Custom(_SubhaloLineBase):   # potential.py:908-956: O
     def __init__(self, pot, subhalo_x0, subhalo_v, subhalo_t0, t_window, units=None):
         super().__init__(units, {'pot': pot, 'subhalo_x0': subhalo_x0, 'subhalo_v': subhalo_v, 'subhalo_t0': subhalo_t0, 't_window': t_window})
         n = len(np.atleast_1d(np.asarray(subhalo_t0)))
+        if float(getattr(pot, 'soft', 0.0) or 0.0) != 0.0:
+            # the reference evaluates self.pot.potential(), softening included (potential.py:136-138, 908-956); the subhalo arrays of the
+            # kernels (ssb_subhalos) carry no softening, so a softened profile must not be evaluated silently with soft = 0
+            raise NotImplementedError("SubhaloLinePotential_Custom: a softened `pot` (soft != 0) is not supported by the subhalo kernels; "
+                                      "use soft=0 or add the subhalo as a translating HernquistPotential component")
         rs = getattr(pot, 'r_s', None)
         if rs is None:
             rs = getattr(pot, 'a')
