@@ -30,10 +30,14 @@ _ip = C.POINTER(C.c_int)
 _lp = C.POINTER(C.c_int64)
 
 
-def build(force=False):
-    """Compile oracle/_build/libssb_oracle.so with the committed Makefile."""
+_VARIANTS = {None: ("all", "libssb_oracle.so"), "fma": ("fma", "libssb_oracle_fma.so"), "bench": ("bench", "libssb_oracle_bench.so")}
+
+
+def build(force=False, variant=None):
+    """Compile oracle/_build/libssb_oracle[_fma|_bench].so with the committed Makefile."""
     import fcntl
-    args = ["make", "-C", _HERE] + (["-B"] if force else [])
+    target, name = _VARIANTS[variant]
+    args = ["make", "-C", _HERE, target] + (["-B"] if force else [])
     os.makedirs(os.path.join(_HERE, "_build"), exist_ok=True)
     with open(os.path.join(_HERE, "_build", ".lock"), "w") as lock:      # several test ranks may import at once
         fcntl.flock(lock, fcntl.LOCK_EX)
@@ -41,21 +45,49 @@ def build(force=False):
             subprocess.run(args, check=True, stdout=subprocess.DEVNULL)
         finally:
             fcntl.flock(lock, fcntl.LOCK_UN)
-    return os.path.join(_HERE, "_build", "libssb_oracle.so")
+    return os.path.join(_HERE, "_build", name)
+
+
+def _load(path):
+    L = C.CDLL(path)
+    L.orc_program_new.restype = C.c_void_p
+    L.orc_normal1.restype = C.c_double
+    L.orc_erfinv.restype = C.c_double
+    L.orc_erfinv.argtypes = [C.c_double]
+    L.orc_normal1.argtypes = [C.c_int64]
+    return L
 
 
 def lib():
     global _LIB
     if _LIB is None:
-        path = build()
-        L = C.CDLL(path)
-        L.orc_program_new.restype = C.c_void_p
-        L.orc_normal1.restype = C.c_double
-        L.orc_erfinv.restype = C.c_double
-        L.orc_erfinv.argtypes = [C.c_double]
-        L.orc_normal1.argtypes = [C.c_int64]
-        _LIB = L
+        _LIB = _load(build())
     return _LIB
+
+
+_VARIANT_LIBS = {}
+
+
+class variant:
+    """Context manager: inside it every oracle call runs in another BUILD of the same sources (oracle/Makefile): "fma" = FMA contraction
+    and AVX2 code generation (another legal rounding of the same algorithm), "bench" = the -O3 build bench.py times as the CPU baseline.
+    Programs must be built and used inside the same context."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        global _LIB
+        lib()
+        if self.name not in _VARIANT_LIBS:
+            _VARIANT_LIBS[self.name] = _load(build(variant=self.name))
+        self._prev, _LIB = _LIB, _VARIANT_LIBS[self.name]
+        return self
+
+    def __exit__(self, *exc):
+        global _LIB
+        _LIB = self._prev
+        return False
 
 
 def _d(a):
