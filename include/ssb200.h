@@ -108,6 +108,7 @@ typedef struct {
 
 int ssb_abi_version(void);
 const char* ssb_last_error(void); /* thread-local text of the last SSB_ERR_CUDA / SSB_ERR_ARG */
+unsigned long long ssb_launch_count(void); /* kernels this library has launched in this process so far (bench.py: gpu_launches) */
 
 /* A1/A5  Potential.potential / gradient / jacobian_force (main.py:37-65) at n points.
  * Any of phi[n], grad[n,3], hess[n,3,3] may be NULL.  SSB_UNIFORM_ACC contributes to grad only. */

@@ -77,6 +77,7 @@ _PP, _SP = C.POINTER(Potential), C.POINTER(Subhalos)
 _SIGNATURES = {
     "ssb_abi_version": ([], C.c_int),
     "ssb_last_error": ([], C.c_char_p),
+    "ssb_launch_count": ([], C.c_ulonglong),
     "ssb_potential_eval_f64": ([_PP, _i64, _dp, _dp, _dp, _dp, _dp, _dp], C.c_int),
     "ssb_subhalo_eval_f64": ([_SP, C.c_int, C.POINTER(C.c_double), _dbl, _dp, _dp, _dp], C.c_int),
     "ssb_track_slopes_f64": ([_i64, _dp, _dp, _dp, _dp], C.c_int),

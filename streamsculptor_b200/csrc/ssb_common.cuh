@@ -43,6 +43,7 @@ int ssb_set_error(int code, const char* msg);
 int ssb_cuda_check(cudaError_t e, const char* what);
 int ssb_validate_potential(const ssb_potential* p);
 int ssb_validate_ctrl(const ssb_ctrl& c);
+void ssb_count_launch();     // every kernel launch of the library bumps a process-wide counter (ssb_launch_count, read by bench.py's gpu_launches)
 // ssb_gen_stream_f64 on COMPACT per-shard inputs (internal; used by ssb_gen_stream_host so that a rank uploads only its own stripping
 // times): ts_c[n_local + 2] = the shard's stripping times, then the first and last stripping time of the whole stream; Msat_c[n_local],
 // normals_c[n_local,4] (or NULL) likewise.  scratch >= ssb_stream_scratch_bytes(n_local + 2, max_steps).

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <limits>
 #include <vector>
 
@@ -925,6 +926,8 @@ __global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, double* sink
 // host side: C ABI
 // =============================================================================================
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+void ssb_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int ssb_set_error(int code, const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); return code; }
 int ssb_cuda_check(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return 0;
@@ -932,7 +935,7 @@ int ssb_cuda_check(cudaError_t e, const char* what) {
     return SSB_ERR_CUDA;
 }
 #define CK(call) do { int _e = ssb_cuda_check((call), #call); if (_e) return _e; } while (0)
-#define CKL(what) do { int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
+#define CKL(what) do { ssb_count_launch(); int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
 
 int ssb_validate_potential(const ssb_potential* p) {
     if (!p) return ssb_set_error(SSB_ERR_ARG, "potential is NULL");
@@ -1000,6 +1003,7 @@ static void host_randint5(int64_t seed, int64_t* out) {
 extern "C" {
 
 int ssb_abi_version(void) { return SSB_ABI_VERSION; }
+unsigned long long ssb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* ssb_last_error(void) { return g_err; }
 
 int ssb_potential_eval_f64(const ssb_potential* pot, int64_t n, const double* xyz, const double* t, double* phi, double* grad,

@@ -46,7 +46,7 @@ using namespace ssb;
 #define SSB_RESP_DEFAULT_NP 4
 #endif
 #define CK(call) do { int _e = ssb_cuda_check((call), #call); if (_e) return _e; } while (0)
-#define CKL(what) do { int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
+#define CKL(what) do { ssb_count_launch(); int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
 
 struct RespArgs {
     int64_t N;

@@ -19,7 +19,7 @@
 using namespace ssb;
 
 #define CK(call) do { int _e = ssb_cuda_check((call), #call); if (_e) return _e; } while (0)
-#define CKL(what) do { int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
+#define CKL(what) do { ssb_count_launch(); int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
 
 struct SharedCtl {            // device control block
     double tprev, tnext, T1, dir, acc, acc2, h0, d1;

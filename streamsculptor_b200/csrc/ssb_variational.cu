@@ -23,7 +23,7 @@
 
 using namespace ssb;
 
-#define CKL(what) do { int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
+#define CKL(what) do { ssb_count_launch(); int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
 #define SSB_VAR_THREADS 128
 #define FULLMASK 0xffffffffu
 

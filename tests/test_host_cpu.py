@@ -177,7 +177,8 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out[0])
     assert line["impl"] == "reference" and line["unit"] == "particle-steps/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
-    assert line["config"]["workload"].startswith("C2: 1000000-particle mock stream per GPU") and line["metric"] == "fp64 particle-steps/sec"
+    assert line["config"]["workload"].startswith("C2: ONE 1000000-particle mock stream") and line["metric"] == "fp64 particle-steps/sec"
+    assert line["scaling"] == "strong"
 
 
 def test_argument_validation_of_the_round1_entry_points():
