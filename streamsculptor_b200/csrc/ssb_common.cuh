@@ -14,6 +14,9 @@
 #ifndef SSB_ORBIT_MIN_BLOCKS
 #define SSB_ORBIT_MIN_BLOCKS 3
 #endif
+#ifndef SSB_SNAP_MIN_BLOCKS
+#define SSB_SNAP_MIN_BLOCKS 3   // saving kernel (MODE 0): CTAs per SM the register budget is set for (A/B: 2 = 255 registers, no spills)
+#endif
 #ifndef SSB_FUSED_INLINE
 #define SSB_FUSED_INLINE 1
 #endif

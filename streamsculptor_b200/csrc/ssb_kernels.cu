@@ -86,7 +86,7 @@ struct OrbitForce {
 // (inclusive scan); tasks are dealt out j = lane, lane + 32, ...: every pass keeps all lanes busy and the lanes that serve one orbit
 // write adjacent 48-byte rows.
 template <int SOLVER>
-__device__ __forceinline__ void coop_dense(const double* __restrict__ srec, int nsave, int save_idx, const double* tsp, double* ys, double dir) {
+__device__ __noinline__ void coop_dense(const double* __restrict__ srec, int nsave, int save_idx, const double* tsp, double* ys, double dir) {
     constexpr int NT = SSB_ORBIT_THREADS;
     constexpr int S = Tab<SOLVER>::S;
     const unsigned full = 0xffffffffu;
@@ -213,12 +213,6 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
     if (valid) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) { x[k] = w0[k]; p[k] = dir * w0[3 + k]; }
-        if (MODE == 0) {
-            const double inf = __longlong_as_double(0x7ff0000000000000LL);
-            for (int m = 0; m < M; ++m)
-#pragma unroll
-                for (int k = 0; k < 6; ++k) ys[(size_t)m * 6 + k] = inf;
-        }
         // ---- PIDController.init: Hairer-Norsett-Wanner initial step ----
         force(x, T0, F[0]);
         double sx[3], sp[3], d0 = 0.0, d1 = 0.0;
@@ -247,8 +241,11 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
         h = fmax(h, c.dtmin);
         tnext = fmin(T0 + h, T1);
     }
-    double tq_a = __longlong_as_double(0x7ff0000000000000LL);      // MODE 0: the next save time (mirrored time)
-    if (MODE == 0 && valid && M > 0) tq_a = tsp[0] * dir;
+    double tq_a = __longlong_as_double(0x7ff0000000000000LL), tq_b = tq_a;      // MODE 0: the next two save times (mirrored time)
+    if (MODE == 0 && valid) {
+        if (M > 0) tq_a = tsp[0] * dir;
+        if (M > 1) tq_b = tsp[1] * dir;
+    }
     if constexpr (MODE == 0) {
         // SaveAt(ts) with WARP-COOPERATIVE dense output.  A lane whose accepted step covers save times publishes the step (times,
         // end points, force stages) in its shared-memory record; the (orbit, save time) pairs of the whole warp are then dealt out
@@ -294,14 +291,18 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
                                 for (int l = 0; l < S; ++l)
 #pragma unroll
                                     for (int k = 0; k < 3; ++k) myrec[(14 + 3 * l + k) * NT] = F[l][k];
-                                // number of save times inside the step: gallop, then bisect (ts is monotone)
-                                const int left = M - save_idx;
-                                int hi = 1;
-                                while (hi < left && tsp[save_idx + hi] * dir <= tnext) hi <<= 1;
-                                int lo = hi >> 1;                       // row lo is inside the step (lo = 0: known from tq_a) ...
-                                if (hi > left) hi = left;               // ... row hi is outside (or the end of the list)
-                                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tsp[save_idx + mid] * dir <= tnext) lo = mid; else hi = mid; }
-                                nsave = hi;
+                                // number of save times inside the step (ts is monotone).  The common cases - one save time, the next one
+                                // beyond the step - are decided from the two prefetched values; otherwise gallop, then bisect
+                                nsave = 1;
+                                if (tq_b <= tnext) {
+                                    const int left = M - save_idx;
+                                    int hi = 2;
+                                    while (hi < left && tsp[save_idx + hi] * dir <= tnext) hi <<= 1;
+                                    int lo = hi >> 1;                   // row lo is inside the step ...
+                                    if (hi > left) hi = left;           // ... row hi is outside (or the end of the list)
+                                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tsp[save_idx + mid] * dir <= tnext) lo = mid; else hi = mid; }
+                                    nsave = hi;
+                                }
                             }
 #pragma unroll
                             for (int k = 0; k < 3; ++k) { x[k] = x1[k]; p[k] = p1[k]; F[0][k] = F[S - 1][k]; }    // FSAL
@@ -322,9 +323,18 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
                 __syncwarp();
                 coop_dense<SOLVER>(srec, nsave, save_idx, tsp, ys, dir);
                 __syncwarp();
-                save_idx += nsave;
-                tq_a = (valid && save_idx < M) ? tsp[save_idx] * dir : __longlong_as_double(0x7ff0000000000000LL);
+                if (nsave > 0) {           // reload the two look-ahead save times: not needed before the end of the next step
+                    save_idx += nsave;
+                    tq_a = (save_idx < M) ? tsp[save_idx] * dir : __longlong_as_double(0x7ff0000000000000LL);
+                    tq_b = (save_idx + 1 < M) ? tsp[save_idx + 1] * dir : __longlong_as_double(0x7ff0000000000000LL);
+                }
             }
+        }
+        if (valid) {               // rows never reached stay +inf (diffrax SaveAt semantics); every saved row was written exactly once
+            const double inf = __longlong_as_double(0x7ff0000000000000LL);
+            for (int m = save_idx; m < M; ++m)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) ys[(size_t)m * 6 + k] = inf;
         }
         return;
     }
@@ -390,7 +400,7 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
 }
 
 template <int SOLVER, int MODE, int SIG, int XS>
-__global__ void __launch_bounds__(SSB_ORBIT_THREADS, SSB_ORBIT_MIN_BLOCKS) orbit_kernel(const __grid_constant__ ssb_potential Pin, const OrbitArgs a) {
+__global__ void __launch_bounds__(SSB_ORBIT_THREADS, MODE == 0 ? SSB_SNAP_MIN_BLOCKS : SSB_ORBIT_MIN_BLOCKS) orbit_kernel(const __grid_constant__ ssb_potential Pin, const OrbitArgs a) {
     __shared__ ssb_potential sP;
     stage_potential(&sP, &Pin);
     logtab_init();

@@ -63,6 +63,11 @@ struct RespArgs {
     const int* order;         // [n_sh] processing position -> user index
     int skip_unborn;          // 1: D0 == NULL (zero ICs): subhalos whose window has not opened are exactly zero
     int np;                   // response_kernel_mp: particles in flight per CTA (1..SSB_RESP_MAX_NP)
+    // retired items (response_kernel_mp, see the kernel's header): per particle slot a log of step propagators [log_cap][36] and the
+    // log position at which each subhalo retired [n_sh]
+    int retire, log_cap;
+    double* plog;             // [grid][SSB_RESP_MAX_NP][log_cap][36]
+    int* rstep;               // [grid][SSB_RESP_MAX_NP][n_sh]
     // SaveAt(ts) for a single trajectory (backward progenitor response, perturbative.py:53-60): N == 1
     const double* ts_save; int M; double* wsave; double* Dsave;
 };
@@ -257,7 +262,7 @@ __device__ __forceinline__ void item_finish(const double (&q)[3], const double (
 
 template <int SOLVER, int PROFILE>
 __device__ __forceinline__ void sweep_items(const BaseShared<Tab<SOLVER>::S>* sb, const double* __restrict__ PhiE, const double* __restrict__ tab, int n_sh,
-                                            int n_items, int n_dead, int n_act, const double* __restrict__ cur, double* __restrict__ nxt, double dt,
+                                            int n_items, int n_dead /* first position swept: dead or retired prefix */, int n_act, const double* __restrict__ cur, double* __restrict__ nxt, double dt,
                                             const CtrlDev& c, double& esq, int& bad_local) {
     constexpr int S = Tab<SOLVER>::S;
     const double t_lo = fmin(sb->t[0], sb->t[S - 1]), t_hi = fmax(sb->t[0], sb->t[S - 1]);     // every stage time lies in [t_lo, t_hi]
@@ -620,13 +625,69 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
 // in shared memory and is advanced by thread 0 between two barriers.  With np = 1 the arithmetic (including the order of the
 // error reduction) is that of response_kernel.
 // =============================================================================================
+//
+// RETIRED ITEMS.  With zero perturbation ICs and forward time a subhalo is unborn (exact zeros), then open (window |t - t0| < t_window:
+// 13-stage items), then closed FOR GOOD.  From then on its items obey the homogeneous system q'' = T(t) q: every accepted step maps
+// them by the step's 6x6 propagator Phi_n, and their share of the error norm is sum (E_n y)^2 / scale^2.  Such items are RETIRED
+// (in processing order they form a prefix: running maximum of the window ends, chunks of 16 positions) and never swept again:
+//   * their state is frozen at retirement (y_c, kept in both ping-pong buffers) together with the position in the particle's LOG of
+//     step propagators; at the end (or when the log is full) the suffix products R_i = Phi_N ... Phi_{i+1} are formed once and every
+//     retired item gets y_final = R_i y_c - algebraically the step-by-step application, one 6x6 mat-vec instead of one per step;
+//   * their error contribution needs only the 6x6 second-moment matrix C = sum y y^T of the retired set, advanced by C <- Phi C Phi^T
+//     per accepted step: sum_items |E y|^2_k = (E C E^T)_kk.  The scale of a retired component is taken as atol (the exact
+//     atol + rtol max(|y0|, |y1|) would need every item): the response to a unit-mass subhalo is ~1e-8 or smaller, so the relative
+//     deviation of the norm is ~rtol |y| / atol ~ 1e-8; the kernel checks the bound rtol sqrt(max_k C_kk) <= 5e-4 atol at every attempt
+//     and, should it ever fail (huge subhalo masses), restarts that particle with retirement switched off.
+// ~80 % of the item-steps of a C4 run (1000 subhalos, t_window = 150 Myr over 3 Gyr) are retired ones: the sweep, and with it the
+// item-state traffic (52 GB per launch before), shrinks to the open windows.  SSB_RESP_RETIRE=0 switches the path off (A/B, tests).
 struct RespSlot {
     long long part;                 // particle index; -1: free (refill from the queue); -2: queue exhausted
     double dir, T0, T1, tprev, tnext;
     int status, n_steps, n_acc, n_rej;
-    int at_dtmin, accepted, finishing, flip;
+    int at_dtmin, accepted, finishing, flip;     // finishing: 1 = write out and free the slot, 2 = (re)start the particle in `part`
     int n_act_run, n_dead, skip, pad;
+    int n_ret, log_len, retire_on, no_retire, need_flush, pad2;
 };
+
+#define SSB_RESP_LOG_BLK 16         // log entries staged in shared memory per pass of the suffix-product chain
+
+// R_i = L[len-1] ... L[i] for i = len-1 .. 0, in place (L: [len][36] row-major 6x6, global memory).  Uniform over the CTA: all threads
+// move blocks of SSB_RESP_LOG_BLK entries through shared memory, warp 0 runs the chain.
+__device__ __forceinline__ void suffix_products(double* __restrict__ L, int len, double* sBlk /*[BLK*36]*/, double* sR /*[2][36]*/) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid < 36) sR[tid] = (tid / 6 == tid % 6) ? 1.0 : 0.0;
+    int cur = 0;
+    for (int blk_end = len; blk_end > 0; blk_end -= SSB_RESP_LOG_BLK) {
+        const int b0 = blk_end > SSB_RESP_LOG_BLK ? blk_end - SSB_RESP_LOG_BLK : 0, nb = blk_end - b0;
+        __syncthreads();
+        for (int e = tid; e < nb * 36; e += blockDim.x) sBlk[e] = L[(size_t)b0 * 36 + e];
+        __syncthreads();
+        if (wid == 0) {
+            for (int i = nb - 1; i >= 0; --i) {
+                const double* Rc = sR + cur * 36;
+                double* Li = sBlk + i * 36;
+                double acc[2] = {0.0, 0.0};
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int e = lane + 32 * u;
+                    if (e < 36) {
+                        const int r = e / 6, c = e % 6;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) acc[u] = fma(Rc[r * 6 + k], Li[k * 6 + c], acc[u]);
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < 2; ++u) { const int e = lane + 32 * u; if (e < 36) { sR[(cur ^ 1) * 36 + e] = acc[u]; Li[e] = acc[u]; } }
+                cur ^= 1;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < nb * 36; e += blockDim.x) L[(size_t)b0 * 36 + e] = sBlk[e];
+    }
+    __syncthreads();
+}
 
 // lanes of one slot follow the slot leader's base point; `sh` is the slot's stage record (or the trash record of idle lanes)
 template <int S, int SIG>
@@ -658,6 +719,9 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
     __shared__ int s_nact[NPX], s_bad[NPX];
     __shared__ double s_besq[NPX];                            // squared scaled error of the base orbit's attempt
     __shared__ int s_service, s_live;
+    __shared__ double sC[NPX][36], sT[NPX][36];               // second-moment matrix of each slot's retired items (+ scratch for Phi C)
+    __shared__ double sLogBlk[SSB_RESP_LOG_BLK * 36], sR[2 * 36];
+    __shared__ int s_guard[NPX];
     stage_potential(&sP, &Pin);
     logtab_init();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
@@ -675,13 +739,81 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
         RespSlot& s = slot[tid];
         s.part = tid < NP ? -1 : -2; s.dir = 1.0; s.T0 = s.T1 = s.tprev = s.tnext = 0.0; s.status = s.n_steps = s.n_acc = s.n_rej = 0;
         s.at_dtmin = s.accepted = s.finishing = s.flip = s.n_act_run = s.n_dead = s.skip = s.pad = 0;
+        s.n_ret = s.log_len = s.retire_on = s.no_retire = s.need_flush = s.pad2 = 0;
     }
-    if (tid < NPX) { s_nact[tid] = 0; s_bad[tid] = 0; s_besq[tid] = 0.0; }
+    if (tid < NPX) { s_nact[tid] = 0; s_bad[tid] = 0; s_besq[tid] = 0.0; s_guard[tid] = 0; }
+    const double inv_atol2 = c.atol > 0.0 ? 1.0 / (c.atol * c.atol) : 0.0;
+    const double guard_lim = 2.5e-7 * c.atol * c.atol;         // rtol^2 max_k C_kk <= (5e-4 atol)^2
     if (tid == 0) { s_service = 1; s_live = 1; }
     double* const cta_buf = a.scratch + (size_t)blockIdx.x * NPX * 2 * 6 * n_items;
+    double* const cta_log = a.plog + (size_t)blockIdx.x * NPX * (size_t)a.log_cap * 36;
+    int* const cta_rstep = a.rstep + (size_t)blockIdx.x * NPX * n_sh;
 
     for (;;) {
         __syncthreads();                                       // slot state written by thread 0 is visible
+        // ---- retired items of the slots whose attempt was accepted (warp w serves slot w): log the step's propagator, advance the moment
+        //      matrix C <- Phi C Phi^T, then retire the chunks of 16 positions whose windows are now closed for good ----
+        if (wid < NP && slot[wid].part >= 0 && slot[wid].accepted && slot[wid].retire_on) {
+            const int q = wid;
+            int n_ret = slot[q].n_ret, len = slot[q].log_len;
+            const double* PE = sPhiE[q];
+            double* Cq = sC[q];
+            if (n_ret > slot[q].n_dead) {
+                double* Lq = cta_log + ((size_t)q * a.log_cap + len) * 36;
+                for (int e = lane; e < 36; e += 32) Lq[e] = PE[e];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {                  // T = Phi C
+                    const int e = lane + 32 * u;
+                    if (e < 36) {
+                        const int r = e / 6, cc = e % 6;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) acc = fma(PE[r * 6 + k], Cq[k * 6 + cc], acc);
+                        sT[q][e] = acc;
+                    }
+                }
+                __syncwarp();
+                if (lane < 21) {                               // C = T Phi^T, upper triangle mirrored: exactly symmetric
+                    int r = 0, rem = lane;
+                    while (rem >= 6 - r) { rem -= 6 - r; ++r; }
+                    const int cc = r + rem;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) acc = fma(sT[q][r * 6 + k], PE[cc * 6 + k], acc);
+                    Cq[r * 6 + cc] = acc; Cq[cc * 6 + r] = acc;
+                }
+                __syncwarp();
+                len++;
+            }
+            if (!slot[q].finishing) {
+                const double tp = slot[q].tprev;
+                double* cur = cta_buf + (size_t)(2 * q + slot[q].flip) * 6 * n_items;
+                double* nxt = cta_buf + (size_t)(2 * q + (slot[q].flip ^ 1)) * 6 * n_items;
+                while (n_ret + 16 <= n_sh && a.endmax[n_ret + 15] <= tp) {
+                    const int j = n_ret + (lane & 15), blk = lane >> 4, it = blk * n_sh + j;
+                    double y[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) { y[k] = cur[(size_t)k * n_items + it]; nxt[(size_t)k * n_items + it] = y[k]; }
+                    if (blk == 0) cta_rstep[q * n_sh + j] = len;
+#pragma unroll
+                    for (int r = 0; r < 6; ++r)
+#pragma unroll
+                        for (int cc = r; cc < 6; ++cc) {
+                            double v = y[r] * y[cc];
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                            if (lane == 0) { const double t = Cq[r * 6 + cc] + v; Cq[r * 6 + cc] = t; Cq[cc * 6 + r] = t; }
+                        }
+                    n_ret += 16;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) {
+                slot[q].n_ret = n_ret; slot[q].log_len = len;
+                if (len >= a.log_cap && !slot[q].finishing) { slot[q].need_flush = 1; s_service = 1; }
+            }
+        }
+        __syncthreads();
         // ---- commit the attempts accepted in the previous round (FSAL): base lanes only ----
         if (my_slot < NPX && col == -1 && slot[my_slot].part >= 0 && slot[my_slot].accepted) {
             BaseShared<S>& r = sb[my_slot];
@@ -695,7 +827,42 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
         while (s_service) {                                    // uniform
             __syncthreads();
             for (int q = 0; q < NP; ++q) {
-                if (!(slot[q].part >= 0 && slot[q].finishing)) continue;
+                const bool fin = slot[q].part >= 0 && slot[q].finishing == 1;
+                const bool flush = slot[q].part >= 0 && slot[q].need_flush && !fin;
+                if (!fin && !flush) continue;                  // uniform
+                // retired items: bring the states frozen at retirement to the current time with the suffix products of the logged propagators
+                const int n_dead = slot[q].n_dead, n_ret = slot[q].n_ret, len = slot[q].log_len;
+                double* Lq = cta_log + (size_t)q * a.log_cap * 36;
+                const int* rs = cta_rstep + q * n_sh;
+                const bool apply = slot[q].retire_on && n_ret > n_dead && len > 0;
+                if (apply) suffix_products(Lq, len, sLogBlk, sR);
+                if (flush) {                                   // log full: apply now, restart the log at the current step
+                    double* b0 = cta_buf + (size_t)(2 * q) * 6 * n_items;
+                    double* b1 = b0 + (size_t)6 * n_items;
+                    for (int idx = tid; idx < 2 * (n_ret - n_dead); idx += blockDim.x) {
+                        const int blk = idx >= (n_ret - n_dead), j = n_dead + idx - blk * (n_ret - n_dead), it = blk * n_sh + j;
+                        const int i = rs[j];
+                        if (apply && i < len) {
+                            double y[6], o6[6];
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) y[k] = b0[(size_t)k * n_items + it];
+                            const double* R = Lq + (size_t)i * 36;
+#pragma unroll
+                            for (int r = 0; r < 6; ++r) {
+                                double acc = 0.0;
+#pragma unroll
+                                for (int k = 0; k < 6; ++k) acc = fma(R[r * 6 + k], y[k], acc);
+                                o6[r] = acc;
+                            }
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) { b0[(size_t)k * n_items + it] = o6[k]; b1[(size_t)k * n_items + it] = o6[k]; }
+                        }
+                    }
+                    __syncthreads();
+                    for (int j = n_dead + tid; j < n_ret; j += blockDim.x) cta_rstep[q * n_sh + j] = 0;
+                    if (tid == 0) { slot[q].log_len = 0; slot[q].need_flush = 0; }
+                    continue;
+                }
                 // outputs: final state if the end was reached, +inf otherwise (diffrax SaveAt semantics)
                 const long long part = slot[q].part;
                 const double dir = slot[q].dir;
@@ -703,11 +870,29 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
                 const double* cur = cta_buf + (size_t)(2 * q + slot[q].flip) * 6 * n_items;
                 for (int it = tid; it < n_items; it += blockDim.x) {
                     const int j = it % n_sh, blk = it / n_sh, o = a.order[j];
+                    double v[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) v[k] = cur[(size_t)k * n_items + it];
+                    if (apply && j >= n_dead && j < n_ret) {
+                        const int i = rs[j];
+                        if (i < len) {
+                            const double* R = Lq + (size_t)i * 36;
+                            double o6[6];
+#pragma unroll
+                            for (int r = 0; r < 6; ++r) {
+                                double acc = 0.0;
+#pragma unroll
+                                for (int k = 0; k < 6; ++k) acc = fma(R[r * 6 + k], v[k], acc);
+                                o6[r] = acc;
+                            }
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) v[k] = o6[k];
+                        }
+                    }
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
-                        double v = cur[(size_t)k * n_items + it];
-                        if (k >= 3) v *= dir;
-                        a.Dout[((size_t)part * n_sh + o) * 12 + blk * 6 + k] = ok ? v : inf;
+                        const double w = k >= 3 ? v[k] * dir : v[k];
+                        a.Dout[((size_t)part * n_sh + o) * 12 + blk * 6 + k] = ok ? w : inf;
                     }
                 }
                 if (tid == 8 * q) {
@@ -722,11 +907,12 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
                 s_service = 0;
                 for (int q = 0; q < NP; ++q) {
                     RespSlot& s = slot[q];
-                    if (s.part >= 0 && s.finishing) { s.part = -1; s.finishing = 0; s.accepted = 0; }
+                    if (s.part >= 0 && s.finishing == 1) { s.part = -1; s.finishing = 0; s.accepted = 0; }
                     if (s.part == -1) {
                         const long long nx = (long long)atomicAdd(a.counter, 1ULL);
                         s.part = nx < a.N ? nx : -2;
                         s.finishing = s.part >= 0 ? 2 : 0;        // 2: needs start-up
+                        s.no_retire = 0;
                     }
                 }
             }
@@ -830,6 +1016,10 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
                     int nd = 0;       // subhalos whose window closed before the release of this particle: exact zeros throughout (see the header)
                     if (s.skip) { int lo = 0, hi = n_sh; while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.endmax[mid] <= T0) lo = mid + 1; else hi = mid; } nd = lo & ~15; }
                     s.n_dead = nd;
+                    s.n_ret = nd; s.log_len = 0; s.need_flush = 0;
+                    s.retire_on = (s.skip && a.retire && c.atol > 0.0 && !s.no_retire) ? 1 : 0;
+                    for (int e = 0; e < 36; ++e) sC[q][e] = 0.0;
+                    s_guard[q] = 0;
                     s.finishing = 0;
                     if (!(T0 < T1)) { s.finishing = 1; s_service = 1; }                    // nothing to integrate: rows stay +inf
                     else if (c.max_steps <= 0) { s.status = 1; s.finishing = 1; s_service = 1; }
@@ -907,9 +1097,25 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
             double* nxt = cta_buf + (size_t)(2 * q + (slot[q].flip ^ 1)) * 6 * n_items;
             double esq = (tid == 0) ? s_besq[q] : 0.0;          // same summation order as response_kernel, whatever the slot
             int bad_local = 0;
-            sweep_items<SOLVER, PROFILE>(&sb[q], sPhiE[q], a.sorted, n_sh, n_items, slot[q].n_dead, n_act, cur, nxt, slot[q].tnext - slot[q].tprev, c, esq,
+            sweep_items<SOLVER, PROFILE>(&sb[q], sPhiE[q], a.sorted, n_sh, n_items, slot[q].n_ret, n_act, cur, nxt, slot[q].tnext - slot[q].tprev, c, esq,
                                          bad_local);
             if (bad_local) s_bad[q] = 1;
+            if (slot[q].n_ret > slot[q].n_dead && wid == (nw > 1 ? 1 : 0) && lane < 6) {
+                // retired items: sum over them of (E y)_k^2 = (E C E^T)_kk, scale atol (see the header); always by the same lanes, whatever the
+                // slot, so that a particle's error sum does not depend on where it runs
+                const double* E = sPhiE[q] + 36;
+                const double* Cq = sC[q];
+                double v = 0.0;
+#pragma unroll
+                for (int cc = 0; cc < 6; ++cc) {
+                    double u = 0.0;
+#pragma unroll
+                    for (int l = 0; l < 6; ++l) u = fma(E[lane * 6 + l], Cq[l * 6 + cc], u);
+                    v = fma(u, E[lane * 6 + cc], v);
+                }
+                esq += fmax(v, 0.0) * inv_atol2;
+                if (c.rtol * c.rtol * Cq[lane * 6 + lane] > guard_lim) s_guard[q] = 1;
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) esq += __shfl_xor_sync(0xffffffffu, esq, o);
             if (lane == 0) sred_q[q][wid] = esq;
@@ -926,6 +1132,11 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
                 const double dt = s.tnext - s.tprev;
                 const int any_bad = s_bad[q];
                 s_bad[q] = 0;
+                if (s_guard[q]) {                              // the atol-only scale of the retired items is not good enough here: start this particle over
+                    s_guard[q] = 0;                            // with every item swept (exact scales)
+                    s.no_retire = 1; s.accepted = 0; s.finishing = 2; s_service = 1;
+                    continue;
+                }
                 s.n_act_run = max(s.n_act_run, s_nact[q]);
                 double hn; bool bad;
                 bool at_dtmin = s.at_dtmin != 0;
@@ -1006,9 +1217,18 @@ extern "C" {
 // scratch layout: [256 B header: work counter] [sorted table 10*n] [start n] [endmax n] [order n (int)] [ping-pong state per persistent CTA]
 #define SSB_RESP_MAX_CTAS (160 * SSB_RESP_CTAS_PER_SM)
 static size_t resp_table_bytes(int32_t n_sh) { const size_t n = (size_t)(n_sh > 0 ? n_sh : 1); return ((sizeof(double) * 12 * n + sizeof(int) * n + 255) / 256) * 256; }
+#define SSB_RESP_LOG_CAP 512        // logged step propagators per particle slot before the log is applied and restarted
+// per particle slot: ping-pong item state, the log of step propagators and the retirement positions (rounded to 256 bytes)
+static size_t resp_state_bytes(int32_t n_sh) { return sizeof(double) * 2 * 6 * 2 * (size_t)(n_sh > 0 ? n_sh : 1); }
+static size_t resp_log_bytes() { return sizeof(double) * 36 * (size_t)SSB_RESP_LOG_CAP; }
+static size_t resp_rstep_bytes(int32_t n_sh) { return ((sizeof(int) * (size_t)(n_sh > 0 ? n_sh : 1) + 255) / 256) * 256; }
 size_t ssb_response_scratch_bytes(int32_t n_sh) {
-    const size_t per_slot = sizeof(double) * 2 * 6 * 2 * (size_t)(n_sh > 0 ? n_sh : 1);           // ping-pong state of one particle in flight
+    const size_t per_slot = resp_state_bytes(n_sh) + resp_log_bytes() + resp_rstep_bytes(n_sh);
     return 256 + resp_table_bytes(n_sh) + per_slot * (size_t)SSB_RESP_MAX_NP * (size_t)SSB_RESP_MAX_CTAS;
+}
+static bool resp_retire_enabled() {
+    const char* e = getenv("SSB_RESP_RETIRE");
+    return !(e && e[0] == '0');
 }
 
 static int response_impl(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0, const double* D0,
@@ -1037,7 +1257,14 @@ static int response_impl(const ssb_potential* pot_base, const ssb_subhalos* sh, 
     int* order = (int*)(endmax + sh->n);
     a.sorted = tab; a.start = start; a.endmax = endmax; a.order = order;
     a.scratch = (double*)((char*)scratch + 256 + resp_table_bytes(sh->n));
+    {
+        const size_t slots = (size_t)SSB_RESP_MAX_NP * (size_t)SSB_RESP_MAX_CTAS;
+        a.plog = (double*)((char*)a.scratch + resp_state_bytes(sh->n) * slots);
+        a.rstep = (int*)((char*)a.plog + resp_log_bytes() * slots);
+        a.log_cap = SSB_RESP_LOG_CAP;
+    }
     a.skip_unborn = (D0 == nullptr && M == 0) ? 1 : 0;
+    a.retire = (a.skip_unborn && np > 0 && resp_retire_enabled()) ? 1 : 0;
     a.np = np;
     a.ts_save = ts_save; a.M = M; a.wsave = wsave; a.Dsave = Dsave;
     CK(cudaMemsetAsync(scratch, 0, 256, st));

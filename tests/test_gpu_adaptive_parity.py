@@ -56,7 +56,7 @@ def test_controller_in_lock_step_with_the_oracle(cuda, solver, tol):
         # (A1) while in lock step the two error estimators are the same function of the same state: relative 1e-3 above the noise floor
         e_o, e_g = a[:k, 2], b[:k, 2]
         assert np.all(np.abs(e_g - e_o) <= 1e-3 * e_o + 1e-5), (i, k, np.abs(e_g - e_o).max())
-        assert np.all(np.abs(a[:k, 0] - b[:k, 0]) <= 1e-9 * (1.0 + np.abs(a[:k, 0])))          # same step start times
+        assert np.all(np.abs(a[:k, 0] - b[:k, 0]) <= 2e-6 * (1.0 + np.abs(a[:k, 0] - a[0, 0])))          # same step start times (sums of the step sizes)
         if k == m and len(a) == len(b):
             n_lock += 1
             d = scaled_err(y_g[i][None], y_o[None], tol)[0]

@@ -11,7 +11,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 mw3 = mw3_product()
 back = mw3.gen_stream_ics  # noqa
-w_then = rt.to_dev(np.array([-3.02958, 14.05466, 8.23232, 0.13775, 0.02224, -0.07224]))      # progenitor 3 Gyr ago (any bound orbit does)
+# the bench.py stream (C2): progenitor today [20, 0, 20, 0, 0.15, 0] integrated back 3 Gyr
+w_then = rt.to_dev(np.asarray(mw3.integrate_orbit(w0=[20.0, 0.0, 20.0, 0.0, 0.15, 0.0], ts=np.array([0.0, -3000.0]), t0=0.0, t1=-3000.0, solver=ssc.Dopri8()).ys[-1]))
 ts = np.linspace(-3000.0, 0.0, n // 2 + 1)
 pl, pt, vl, vt = mw3.gen_stream_ics(ts=rt.to_dev(ts), prog_w0=w_then, Msat=1e4, seed_num=583, solver=ssc.Dopri8())
 w0 = torch.cat([torch.cat([pl, vl], 1)[:-1], torch.cat([pt, vt], 1)[:-1]]).contiguous()
