@@ -264,6 +264,18 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
                 rk_stages<SOLVER>(force, x, p, tprev, dt, F);
                 rk_candidate<SOLVER>(x, p, dt, F, x1, p1);
                 force(x1, tprev + T::c(S - 1) * dt, F[S - 1]);
+                // the attempt is published BEFORE the controller runs (56 shared-memory stores, ~2 % of a step): the force stages are still
+                // live for the error estimate here, whereas keeping them for a conditional store after the accept / reject logic would
+                // stretch 39 doubles over the controller code and spill; a rejected attempt's record is simply never read
+                myrec[0] = tprev; myrec[NT] = tnext;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    myrec[(2 + k) * NT] = x[k]; myrec[(5 + k) * NT] = p[k]; myrec[(8 + k) * NT] = x1[k]; myrec[(11 + k) * NT] = p1[k];
+                }
+#pragma unroll
+                for (int l = 0; l < S; ++l)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) myrec[(14 + 3 * l + k) * NT] = F[l][k];
                 rk_error<SOLVER>(p, dt, F, ex, ep);
                 bool nan_cand = false, finite = true;
 #pragma unroll
@@ -282,15 +294,6 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
                         if (!finite) status = 2;
                         else {
                             if (tq_a <= tnext) {           // every ts[save_idx + r] <= tnext is interpolated inside this accepted step
-                                myrec[0] = tprev; myrec[NT] = tnext;
-#pragma unroll
-                                for (int k = 0; k < 3; ++k) {
-                                    myrec[(2 + k) * NT] = x[k]; myrec[(5 + k) * NT] = p[k]; myrec[(8 + k) * NT] = x1[k]; myrec[(11 + k) * NT] = p1[k];
-                                }
-#pragma unroll
-                                for (int l = 0; l < S; ++l)
-#pragma unroll
-                                    for (int k = 0; k < 3; ++k) myrec[(14 + 3 * l + k) * NT] = F[l][k];
                                 // number of save times inside the step (ts is monotone).  The common cases - one save time, the next one
                                 // beyond the step - are decided from the two prefetched values; otherwise gallop, then bisect
                                 nsave = 1;

@@ -41,9 +41,9 @@ using namespace ssb;
 #define SSB_RESP_CTAS_PER_SM 3      // 168 registers/thread: three 128-thread CTAs (three particles) per SM overlap base and item phases
 #endif
 #define SSB_RESP_MAX_SORT 4096
-#define SSB_RESP_MAX_NP 4           // response_kernel_mp: particle slots per CTA (eight lanes of warp 0 each)
+#define SSB_RESP_MAX_NP 16          // response_kernel_mp: particle slots per CTA (eight lanes each: four slots per warp)
 #ifndef SSB_RESP_DEFAULT_NP
-#define SSB_RESP_DEFAULT_NP 4
+#define SSB_RESP_DEFAULT_NP 8
 #endif
 #define CK(call) do { int _e = ssb_cuda_check((call), #call); if (_e) return _e; } while (0)
 #define CKL(what) do { ssb_count_launch(); int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
@@ -712,14 +712,18 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
     constexpr int S = T::S;
     constexpr int NPX = SSB_RESP_MAX_NP;
     __shared__ ssb_potential sP;
-    __shared__ BaseShared<S> sb[2 * NPX];                     // [NPX + g]: scratch record of lane group g of warp 0 while it has no particle
-    __shared__ __align__(16) double sPhiE[NPX][72];
-    __shared__ double sred[32], sred_q[NPX][32];
+    // dynamic shared memory (resp_mp_smem_bytes): stage records [2 NPX] ([NPX + 4 w + g]: scratch record of lane group g of warp w while it
+    // has no particle), propagator + error map [NPX][72], moment matrices sC, sT [NPX][36]
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    BaseShared<S>* const sb = reinterpret_cast<BaseShared<S>*>(s_dyn);
+    double (*const sPhiE)[72] = reinterpret_cast<double (*)[72]>(s_dyn + sizeof(BaseShared<S>) * 2 * NPX);
+    double (*const sC)[36] = reinterpret_cast<double (*)[36]>(s_dyn + sizeof(BaseShared<S>) * 2 * NPX + sizeof(double) * 72 * NPX);
+    double (*const sT)[36] = sC + NPX;
+    __shared__ double sred[32], sred_q[NPX][SSB_RESP_THREADS / 32];
     __shared__ RespSlot slot[NPX];
     __shared__ int s_nact[NPX], s_bad[NPX];
     __shared__ double s_besq[NPX];                            // squared scaled error of the base orbit's attempt
     __shared__ int s_service, s_live;
-    __shared__ double sC[NPX][36], sT[NPX][36];               // second-moment matrix of each slot's retired items (+ scratch for Phi C)
     __shared__ double sLogBlk[SSB_RESP_LOG_BLK * 36], sR[2 * 36];
     __shared__ int s_guard[NPX];
     stage_potential(&sP, &Pin);
@@ -731,7 +735,8 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     // warp 0: lane = 8 * slot + role; role 0 = base orbit, 1..6 = propagator columns, 7 = idle
     const int col = (lane & 7) - 1;
-    const int my_slot = (tid < 32 && (lane >> 3) < NP) ? (lane >> 3) : NPX;        // NPX: this lane group carries no slot
+    const int my_slot = (4 * wid + (lane >> 3) < NP) ? 4 * wid + (lane >> 3) : NPX;        // NPX: this lane group carries no slot
+    auto base_tid = [](int q) { return 32 * (q >> 2) + 8 * (q & 3); };             // thread that carries the base orbit of slot q
     double x[3] = {8.0, 0.0, 0.0}, p[3] = {0, 0, 0}, F[S][3], x1[3] = {8.0, 0.0, 0.0}, p1[3] = {0, 0, 0};
 #pragma unroll
     for (int l = 0; l < S; ++l) F[l][0] = F[l][1] = F[l][2] = 0.0;
@@ -753,8 +758,8 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
         __syncthreads();                                       // slot state written by thread 0 is visible
         // ---- retired items of the slots whose attempt was accepted (warp w serves slot w): log the step's propagator, advance the moment
         //      matrix C <- Phi C Phi^T, then retire the chunks of 16 positions whose windows are now closed for good ----
-        if (wid < NP && slot[wid].part >= 0 && slot[wid].accepted && slot[wid].retire_on) {
-            const int q = wid;
+        for (int q = wid; q < NP; q += nw) {
+            if (!(slot[q].part >= 0 && slot[q].accepted && slot[q].retire_on)) continue;
             int n_ret = slot[q].n_ret, len = slot[q].log_len;
             const double* PE = sPhiE[q];
             double* Cq = sC[q];
@@ -895,7 +900,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
                         a.Dout[((size_t)part * n_sh + o) * 12 + blk * 6 + k] = ok ? w : inf;
                     }
                 }
-                if (tid == 8 * q) {
+                if (tid == base_tid(q)) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) { a.wout[6 * part + k] = ok ? x[k] : inf; a.wout[6 * part + 3 + k] = ok ? dir * p[k] : inf; }
                     a.status[part] = slot[q].status;
@@ -938,7 +943,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
                 }
                 BaseForce<S, SIG> bforce{&sP, &Pin, &sb[q], dir, 0};
                 double d0s = 0.0, d1s = 0.0;
-                if (tid == 8 * q) {
+                if (tid == base_tid(q)) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) { x[k] = a.w0[6 * part + k]; p[k] = dir * a.w0[6 * part + 3 + k]; }
                     bforce.stage = 0;
@@ -971,7 +976,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
                 const double d1 = sqrt(block_sum(d1s, sred) / ncomp);
                 const double h0 = hnw_h0(d0, d1);
                 double d2s = 0.0;
-                if (tid == 8 * q) {
+                if (tid == base_tid(q)) {
                     double X1[3], F1[3];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) X1[k] = fma(h0, p[k], x[k]);
@@ -1035,12 +1040,12 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
         }
         if (!s_live) break;                                    // uniform
         // ---- serial phase, shared by the slots: base orbits + propagator columns of this round's attempts (warp 0) ----
-        if (tid < 32) {
+        if (4 * wid < NP) {                                    // every warp advances the base orbits of its (up to four) slots
             __syncwarp();                                      // the FSAL commit of the base lanes (stage-0 record) is visible to the column lanes
             // all eight lanes of a group evaluate the group leader's point and store the SAME record; a group without a particle
             // works on its own scratch record
             const bool act = my_slot < NPX && slot[my_slot].part >= 0;
-            const int rec = act ? my_slot : NPX + (lane >> 3);
+            const int rec = act ? my_slot : NPX + 4 * wid + (lane >> 3);
             const double tp = act ? slot[rec].tprev : 0.0, dt = act ? slot[rec].tnext - tp : 1.0, dir = act ? slot[rec].dir : 1.0;
             if (col >= 0) {
 #pragma unroll
@@ -1121,22 +1126,20 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
             if (lane == 0) sred_q[q][wid] = esq;
         }
         __syncthreads();
-        // ---- controllers (thread 0): accept / reject, next step, completion ----
-        if (tid == 0) {
-            for (int q = 0; q < NP; ++q) {
-                RespSlot& s = slot[q];
-                if (s.part < 0) continue;
-                double tot = 0.0;
-                for (int i = 0; i < nw; ++i) tot += sred_q[q][i];
-                const double err = sqrt(tot / ncomp);
-                const double dt = s.tnext - s.tprev;
-                const int any_bad = s_bad[q];
-                s_bad[q] = 0;
-                if (s_guard[q]) {                              // the atol-only scale of the retired items is not good enough here: start this particle over
-                    s_guard[q] = 0;                            // with every item swept (exact scales)
-                    s.no_retire = 1; s.accepted = 0; s.finishing = 2; s_service = 1;
-                    continue;
-                }
+        // ---- controllers (thread q serves slot q): accept / reject, next step, completion ----
+        if (tid < NP && slot[tid].part >= 0) {
+            const int q = tid;
+            RespSlot& s = slot[q];
+            double tot = 0.0;
+            for (int i = 0; i < nw; ++i) tot += sred_q[q][i];
+            const double err = sqrt(tot / ncomp);
+            const double dt = s.tnext - s.tprev;
+            const int any_bad = s_bad[q];
+            s_bad[q] = 0;
+            if (s_guard[q]) {                              // the atol-only scale of the retired items is not good enough here: start this particle over
+                s_guard[q] = 0;                            // with every item swept (exact scales)
+                s.no_retire = 1; s.accepted = 0; s.finishing = 2; s_service = 1;
+            } else {
                 s.n_act_run = max(s.n_act_run, s_nact[q]);
                 double hn; bool bad;
                 bool at_dtmin = s.at_dtmin != 0;
@@ -1294,7 +1297,10 @@ static int response_impl(const ssb_potential* pot_base, const ssb_subhalos* sh, 
         case SSB_PROFILE_HERNQUIST: SSB_LAUNCH_SAVE(S, SSB_PROFILE_HERNQUIST); break; default: SSB_LAUNCH_SAVE(S, SSB_PROFILE_NFW); } } while (0)
         if (ctrl.solver == 5) SSB_LAUNCH_SAVE_PR(5); else SSB_LAUNCH_SAVE_PR(8);
     } else if (np > 0) {      // several particles in flight per CTA (shared serial phase)
-#define SSB_LAUNCH_MP(S, SG, PR) response_kernel_mp<S, SG, PR><<<grid, SSB_RESP_THREADS, 0, st>>>(sig == SG ? pc : *pot_base, *sh, a)
+        // dynamic shared memory of the multi-slot kernel: stage records, propagators, moment matrices of SSB_RESP_MAX_NP slots
+#define SSB_LAUNCH_MP(S, SG, PR) do { const size_t shm = (sizeof(BaseShared<((S) == 5 ? 7 : 14)>) * 2 + sizeof(double) * (72 + 72)) * SSB_RESP_MAX_NP; \
+        CK(cudaFuncSetAttribute(response_kernel_mp<S, SG, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); \
+        response_kernel_mp<S, SG, PR><<<grid, SSB_RESP_THREADS, shm, st>>>(sig == SG ? pc : *pot_base, *sh, a); } while (0)
 #define SSB_LAUNCH_MP_SIG(S, PR) do { switch (sig) { case SIG_NHM: SSB_LAUNCH_MP(S, SIG_NHM, PR); break; \
         case SIG_NHHM: SSB_LAUNCH_MP(S, SIG_NHHM, PR); break; default: SSB_LAUNCH_MP(S, SIG_GENERIC, PR); } } while (0)
 #define SSB_LAUNCH_MP_PR(S) do { switch (sh->profile) { case SSB_PROFILE_PLUMMER: SSB_LAUNCH_MP_SIG(S, SSB_PROFILE_PLUMMER); break; \

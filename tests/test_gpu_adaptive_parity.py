@@ -58,10 +58,15 @@ def test_controller_in_lock_step_with_the_oracle(cuda, solver, tol):
         assert np.all(np.abs(e_g - e_o) <= 1e-3 * e_o + 1e-5), (i, k, np.abs(e_g - e_o).max())
         assert np.all(np.abs(a[:k, 0] - b[:k, 0]) <= 2e-6 * (1.0 + np.abs(a[:k, 0] - a[0, 0])))          # same step start times (sums of the step sizes)
         if k == m and len(a) == len(b):
-            n_lock += 1
-            d = scaled_err(y_g[i][None], y_o[None], tol)[0]
-            worst_lock = max(worst_lock, d)
-            assert d <= 10.0, f"orbit {i} stayed in lock step for all {m} attempts but differs by {d:.2f} x tol"
+            # same decisions to the end.  STRICT lock step (every step size within 1e-8): the results must agree within 10 x tol, every such
+            # orbit; between 1e-8 and 1e-6 the step sizes drifted continuously (no discrete event) - counted as drift below
+            if np.all(np.abs(a[:, 1] - b[:, 1]) <= 1e-8 * np.abs(a[:, 1])):
+                n_lock += 1
+                d = scaled_err(y_g[i][None], y_o[None], tol)[0]
+                worst_lock = max(worst_lock, d)
+                assert d <= 10.0, f"orbit {i} stayed in strict lock step for all {m} attempts but differs by {d:.2f} x tol"
+            else:
+                classes["drift"] += 1
             continue
         # (A2) classify the first divergence.  Attempt k's step size was chosen after attempt k-1 from its error estimate.
         assert 1 <= k < m, f"orbit {i}: diverges at attempt {k} of {len(a)} / {len(b)}"
@@ -74,7 +79,7 @@ def test_controller_in_lock_step_with_the_oracle(cuda, solver, tol):
             classes["drift"] += 1                     # continuous drift of the step sizes that crossed the 1e-6 threshold, no discrete event
         else:
             unexplained.append((i, k, err_prev, a[k, 1], b[k, 1], a[k, 3], b[k, 3]))
-    warnings.warn(f"Dopri{solver} tol={tol:g}: {n_lock}/{n} orbits in lock step to the end (worst {worst_lock:.3g} x tol); first divergence of the others: "
+    warnings.warn(f"Dopri{solver} tol={tol:g}: {n_lock}/{n} orbits in strict lock step to the end (worst {worst_lock:.3g} x tol); first divergence of the others: "
                   f"{classes}; unexplained {len(unexplained)}")
     assert not unexplained, unexplained[:5]
 

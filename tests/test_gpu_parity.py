@@ -314,7 +314,7 @@ def test_response_multi_slot_kernel_bit_identical(cuda):
             out = {}
             for retire in (0, 1):
                 os.environ["SSB_RESP_RETIRE"] = str(retire)
-                for np_slots in (0, 1, 2, 4):
+                for np_slots in (0, 1, 2, 4, 8, 16):
                     os.environ["SSB_RESP_NP"] = str(np_slots)
                     w, D, st, ns = rt.linear_response(base, pert._arrays, rt.to_dev(w0), None if d0 is None else rt.to_dev(d0), rt.to_dev(t0), t1, ctrl)
                     out[retire, np_slots] = (w.cpu().numpy(), D.cpu().numpy(), st.cpu().numpy(), ns.cpu().numpy())
@@ -324,10 +324,10 @@ def test_response_multi_slot_kernel_bit_identical(cuda):
             else:
                 assert (ref[2] == 0).all()
             assert np.isinf(ref[0][5]).all() == (t1 == 0.0)
-            for np_slots in (1, 2, 4):            # every item swept (SSB_RESP_RETIRE=0): the one-particle kernel's bits
+            for np_slots in (1, 2, 4, 8, 16):     # every item swept (SSB_RESP_RETIRE=0): the one-particle kernel's bits
                 for a, b in zip(out[0, np_slots], ref):
                     assert np.array_equal(a, b), f"{np_slots} slots per CTA differ from the one-particle kernel"
-            for np_slots in (2, 4):               # retired items (the default): independent of the slot count as well
+            for np_slots in (2, 4, 8, 16):        # retired items (the default): independent of the slot count as well
                 for a, b in zip(out[1, np_slots], out[1, 1]):
                     assert np.array_equal(a, b), f"{np_slots} slots per CTA differ from one slot (retired items)"
             # retired vs swept: the same step sequences up to the atol-only scale of the retired items in the error norm (relative 1e-8),
@@ -350,13 +350,18 @@ def test_response_multi_slot_kernel_bit_identical(cuda):
     N2 = 1200
     w0b = halo_orbits(N2, seed=12); t0b = np.linspace(-1000.0, -5.0, N2)
     ctrl = rt.make_ctrl(ssc.Dopri8(), 1e-7, 1e-7, 0.01, None, 10_000)
-    wa, Da, sa, na = rt.linear_response(base, pert._arrays, rt.to_dev(w0b), None, rt.to_dev(t0b), 0.0, ctrl)
-    os.environ["SSB_RESP_NP"] = "0"
+    wr, Dr, sr, nr_ = rt.linear_response(base, pert._arrays, rt.to_dev(w0b), None, rt.to_dev(t0b), 0.0, ctrl)      # the default configuration
     try:
+        os.environ["SSB_RESP_RETIRE"] = "0"
+        wa, Da, sa, na = rt.linear_response(base, pert._arrays, rt.to_dev(w0b), None, rt.to_dev(t0b), 0.0, ctrl)
+        os.environ["SSB_RESP_NP"] = "0"
         wb, Db, sb_, nb = rt.linear_response(base, pert._arrays, rt.to_dev(w0b), None, rt.to_dev(t0b), 0.0, ctrl)
     finally:
         os.environ.pop("SSB_RESP_NP", None)
+        os.environ.pop("SSB_RESP_RETIRE", None)
     assert bool((Da == Db).all()) and bool((wa == wb).all()) and bool((na == nb).all()) and int((sa != 0).sum()) == 0
+    assert int((sr != 0).sum()) == 0 and int((nr_ - nb).abs().max()) <= 2
+    assert float(((wr - wb).abs() / (1e-7 * (1 + wb.abs()))).max()) < 1e-2 and float((Dr - Db).abs().max()) <= 1e-10 * (1.0 + float(Db.abs().max()))
 
 
 def test_response_generator_api(cuda):

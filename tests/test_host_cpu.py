@@ -290,3 +290,45 @@ def test_sample_from_1d_pdf_uses_jax_uniform_draws():
     s = sh.sample_from_1D_pdf(x, y, key=(0, 7), num_samples=2000)
     assert s.min() >= 4.0 and s.max() <= 6.0 and abs(s.mean() - 5.5) < 0.03       # mean of 3 (x-4)^2 / 8 on [4, 6]
     assert np.array_equal(s, sh.sample_from_1D_pdf(x, y, key=7, num_samples=2000))  # PRNGKey(7) == key words (0, 7)
+
+
+def test_xla_ffi_shim_compiles_against_the_api_stub():
+    """csrc/ssb_xla_ffi.cc cannot be built for real here (no jaxlib headers); it must at least parse and type-check against the stub of the
+    public XLA FFI API in tools/xla_ffi_stub (Buffer / RemainingArgs / Span / Error / Bind() builder)."""
+    src = os.path.join(ROOT, "streamsculptor_b200", "csrc", "ssb_xla_ffi.cc")
+    res = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wno-comment", "-Werror", "-I", os.path.join(ROOT, "tools", "xla_ffi_stub"),
+                          "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    # and the guard really is what keeps it out of normal builds: without the include path the translation unit is empty
+    res = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+
+
+def test_jax_plugin_flattens_programs_without_jax_or_cuda():
+    """jax_plugin.flatten_program: pointer-free attribute bytes + table operands in the order the FFI handlers consume them."""
+    import ctypes as C
+    import numpy as np
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import _lib, jax_plugin as jp
+    P = ssc.potential
+    t = np.linspace(-3000.0, 0.0, 50)
+    y = np.stack([np.sin(t / 500.0), np.cos(t / 700.0), t / 3000.0], axis=1)
+    nsh = 7
+    pot = P.Potential_Combine([
+        P.NFWPotential(m=5.4e11, r_s=15.62, units=ssc.usys),
+        P.TimeDepTranslatingPotential(P.PlummerPotential(m=1.5e11, r_s=10.8, units=ssc.usys), ssc.CubicTrack(t, y), units=ssc.usys),
+        P.SubhaloLinePotentialCustom_fromFunc(func=P.HernquistPotential, m=np.ones(nsh), r_s=np.full(nsh, 0.3), subhalo_x0=np.zeros((nsh, 3)),
+                                              subhalo_v=np.ones((nsh, 3)), subhalo_t0=np.linspace(-2000, -100, nsh), t_window=150.0, units=ssc.usys)],
+        units=ssc.usys)
+    attr, tables = jp.flatten_program(pot)
+    assert attr.dtype == np.uint8 and attr.size == C.sizeof(jp.FfiProgram) == 16 + C.sizeof(_lib.Component) * _lib.MAX_COMP + 8 * _lib.MAX_TRACK + 16 * _lib.MAX_SH
+    prog = jp.FfiProgram.from_buffer_copy(attr.tobytes())
+    assert (prog.n_comp, prog.n_track, prog.n_sh) == (3, 1, 1)
+    assert prog.comp[0].type == _lib.NFW and prog.comp[1].type == _lib.PLUMMER and prog.comp[1].track == 0 and prog.comp[2].type == _lib.SUBHALOS
+    assert prog.track_kind[0] == _lib.TRACK_CUBIC and prog.track_n[0] == 50 and prog.sh_n[0] == nsh and prog.sh_profile[0] == _lib.PROFILE_HERNQUIST
+    assert len(tables) == 3 + 6 and tables[0].shape == (50,) and tables[1].shape == (50, 3) and tables[2].shape == (50, 3) and tables[5].shape == (nsh, 3)
+    # knot slopes: the interpax 'cubic' rule (what ssb_track_slopes_f64 computes on the device)
+    s = tables[2]
+    assert np.allclose(s[0], (y[1] - y[0]) / (t[1] - t[0])) and np.allclose(s[10], 0.5 * ((y[10] - y[9]) / (t[10] - t[9]) + (y[11] - y[10]) / (t[11] - t[10])))
+    with pytest.raises(ImportError):
+        jp.register("libssb200_ffi.so")
