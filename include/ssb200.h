@@ -190,10 +190,10 @@ int ssb_potential_third_f64(const ssb_potential* pot, int64_t n, const double* x
  * gen_stream_vmapped_with_pert, streamhelpers.py:56-116).  Only the n_local particles i = i_begin + k*i_stride
  * (k = 0..n_local-1, all < Nts-1) are integrated - interleaved multi-GPU sharding, every rank sees the same mix of
  * integration spans; outputs are indexed by k.  scratch >= ssb_stream_scratch_bytes().
- * Streams with n_local >= 32768 whose lead and trail are the halves of one [2, n_local, 6] buffer run as two concurrent parts
- * (early particles behind a cut-short progenitor solve on `stream`, the rest behind the full solve on a library-owned
- * stream that forks from and joins `stream` through events): same results, the serial progenitor solve leaves the critical
- * path.  Work enqueued on `stream` after the call is ordered after both parts. */
+ * Streams with n_local >= 32768 whose lead and trail are the halves of one [2, n_local, 6] buffer run as up to four concurrent parts
+ * (the earliest particles behind a cut-short progenitor solve on `stream`, the later ones behind longer solves on library-owned
+ * streams that fork from and join `stream` through events): same results, the serial progenitor solve leaves the critical path.
+ * Work enqueued on `stream` after the call is ordered after all parts. */
 int ssb_gen_stream_f64(const ssb_potential* pot, const ssb_potential* pot_release, double G, int64_t Nts,
                        const double* ts, const double* prog_w0 /*[6]*/, const double* Msat /*[Nts]*/, int64_t seed,
                        const double* kvals /*host[8]*/, const double* normals /*[Nts,4] or NULL*/, ssb_ctrl ctrl,

@@ -20,6 +20,9 @@
 #ifndef SSB_FUSED_INLINE
 #define SSB_FUSED_INLINE 1
 #endif
+#ifndef SSB_SNAP_FUSED_INLINE
+#define SSB_SNAP_FUSED_INLINE 0 // saving kernel (MODE 0): one out-of-line copy of the fused force keeps its larger step loop inside the instruction cache
+#endif
 #define SSB_REC_STRIDE 64   // doubles per recorded step: ta, tb, x, p, x1, p1 (14) + up to 14 force stages (42)
 
 namespace ssb {

@@ -41,7 +41,7 @@ __device__ __noinline__ double3 fused_call(const ssb_potential* P, double x, dou
 }
 // Potential.velocity_acceleration (main.py:116-120) in mirrored time.  SIG != 0: the leading NF components are a fused
 // static signature evaluated inline from the constant bank (Pc); any remaining components go through the interpreter (P).
-template <int SIG, int XS = 0>
+template <int SIG, int XS = 0, int INL = SSB_FUSED_INLINE>
 struct OrbitForce {
     const ssb_potential* P;      // shared-memory copy (dynamic indexing)
     const ssb_potential* Pc;     // kernel parameter (constant bank)
@@ -53,14 +53,14 @@ struct OrbitForce {
             const double3 a = accel_call(P, 0, X[0], X[1], X[2], tau * dir);
             A[0] = a.x; A[1] = a.y; A[2] = a.z;
         } else {
-#if SSB_FUSED_INLINE
-            double g[3];
-            fused_grad<SIG>(*Pc, X, g);
-            A[0] = -g[0]; A[1] = -g[1]; A[2] = -g[2];
-#else
-            const double3 f = fused_call<SIG>(P, X[0], X[1], X[2]);
-            A[0] = f.x; A[1] = f.y; A[2] = f.z;
-#endif
+            if (INL) {         // 13 inlined copies of the fused force: fastest while the unrolled step loop still fits the instruction cache (final-state kernel)
+                double g[3];
+                fused_grad<SIG>(*Pc, X, g);
+                A[0] = -g[0]; A[1] = -g[1]; A[2] = -g[2];
+            } else {           // one out-of-line copy: 16 KB less code in the step loop (the saving kernel's loop + dense output would overflow the cache)
+                const double3 f = fused_call<SIG>(Pc, X[0], X[1], X[2]);
+                A[0] = f.x; A[1] = f.y; A[2] = f.z;
+            }
             if (extra) {
                 if (XS > 0) {
                     double g2[3] = {0.0, 0.0, 0.0};
@@ -204,7 +204,7 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
     constexpr int S = T::S;
     const double dir = (t0_in < t1_in) ? 1.0 : -1.0;              // diffrax: direction = where(t0 < t1, 1, -1)
     const double T0 = t0_in * dir, T1 = t1_in * dir;
-    OrbitForce<SIG, XS> force{P, Pc, dir, Pc->n_comp > SigInfo<SIG>::NF, fxp};
+    OrbitForce<SIG, XS, (MODE == 0 ? SSB_SNAP_FUSED_INLINE : SSB_FUSED_INLINE)> force{P, Pc, dir, Pc->n_comp > SigInfo<SIG>::NF, fxp};
     double x[3], p[3], F[S][3];
     status = 0; n_steps = 0; n_acc = 0; n_rej = 0;
     double tprev = T0, tnext = T0, h = 0.0;
@@ -264,18 +264,20 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
                 rk_stages<SOLVER>(force, x, p, tprev, dt, F);
                 rk_candidate<SOLVER>(x, p, dt, F, x1, p1);
                 force(x1, tprev + T::c(S - 1) * dt, F[S - 1]);
-                // the attempt is published BEFORE the controller runs (56 shared-memory stores, ~2 % of a step): the force stages are still
-                // live for the error estimate here, whereas keeping them for a conditional store after the accept / reject logic would
-                // stretch 39 doubles over the controller code and spill; a rejected attempt's record is simply never read
-                myrec[0] = tprev; myrec[NT] = tnext;
+                // an attempt that would cover a save time (known before it is computed) is published BEFORE the controller runs: the force
+                // stages are still live for the error estimate here, whereas a store after the accept / reject logic would stretch 39
+                // doubles over the controller code and spill; the record of a rejected attempt is simply never read
+                if (tq_a <= tnext) {
+                    myrec[0] = tprev; myrec[NT] = tnext;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    myrec[(2 + k) * NT] = x[k]; myrec[(5 + k) * NT] = p[k]; myrec[(8 + k) * NT] = x1[k]; myrec[(11 + k) * NT] = p1[k];
+                    for (int k = 0; k < 3; ++k) {
+                        myrec[(2 + k) * NT] = x[k]; myrec[(5 + k) * NT] = p[k]; myrec[(8 + k) * NT] = x1[k]; myrec[(11 + k) * NT] = p1[k];
+                    }
+#pragma unroll
+                    for (int l = 0; l < S; ++l)
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) myrec[(14 + 3 * l + k) * NT] = F[l][k];
                 }
-#pragma unroll
-                for (int l = 0; l < S; ++l)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) myrec[(14 + 3 * l + k) * NT] = F[l][k];
                 rk_error<SOLVER>(p, dt, F, ex, ep);
                 bool nan_cand = false, finite = true;
 #pragma unroll
@@ -1246,22 +1248,25 @@ int ssb_potential_third_f64(const ssb_potential* pot, int64_t n, const double* x
     return 0;
 }
 
-// scratch layout of gen_stream: [dense scratch | prog Nts*6 | w0_packed 2*Nts*6 | w0 2n*6 | t0 2n | t1 2n | ys 2n*6]
+// scratch layout of gen_stream: [dense record | prog Nts*6 | w0_packed 2*Nts*6 | w0 2n*6 | t0 2n | t1 2n | ys 2n*6 | dense records of parts 1..3]
 size_t ssb_stream_scratch_bytes(int64_t Nts, int32_t max_steps) {
-    return 2 * ssb_scratch_bytes(max_steps) + sizeof(double) * (size_t)Nts * (6 + 12 + 12 + 2 + 2 + 12) + 256;
+    return 4 * ssb_scratch_bytes(max_steps) + sizeof(double) * (size_t)Nts * (6 + 12 + 12 + 2 + 2 + 12) + 256;      // 4 = SSB_STREAM_PARTS record buffers
 }
 
-// ---- two-part pipeline of gen_stream ----
-// The progenitor orbit is ONE serial solve (~0.7 ms for 3 Gyr) that every release waits for.  For large streams the particles
-// are cut into an early part A (the first eighth of the stripping times = the longest orbits) and the rest B:
-//   caller's stream : progenitor only until it has passed A's last stripping time (~0.1 ms) -> release A -> orbits A (lead, trail)
-//   internal stream : the whole progenitor orbit again (its own record buffer)          -> release B -> orbits B (lead, trail)
-// so the orbit kernels start after ~0.1 ms and B's serial phase hides behind A's orbits.  Both progenitor solves take the same
-// steps (the early stop only ends the loop), every particle sees the same bits as in the one-part pipeline.
+// ---- multi-part pipeline of gen_stream ----
+// The progenitor orbit is ONE serial solve (~0.75 ms for 3 Gyr) that every release waits for.  For large streams the particles are cut
+// into up to SSB_STREAM_PARTS parts by stripping time (1/8, 2/8, 2/8, 3/8 of the shard: the earliest = longest orbits first):
+//   caller's stream    : progenitor only until it has passed part 0's last stripping time (~0.1 ms) -> release -> orbits of part 0
+//   internal stream k  : the progenitor again, until part k's last stripping time (its own record buffer) -> release -> orbits of part k
+// All progenitor solves take the same steps (the early stop only ends the loop), so every particle sees the same bits as in the one-part
+// pipeline.  The orbit kernels start after ~0.1 ms and are fed part by part faster than they drain (the progenitor reaches stripping
+// fraction f after f x 0.75 ms), so the serial solve leaves the critical path - which is what a stream SPLIT OVER SEVERAL GPUs needs:
+// at 125 k particles per GPU the orbits take ~1.3 ms, and a 0.75 ms serial prefix would cost a third of the step.
 #ifndef SSB_STREAM_SPLIT_MIN
 #define SSB_STREAM_SPLIT_MIN 32768          // particles per arm below which the one-part pipeline is used
 #endif
-struct StreamAux { bool ok; cudaStream_t s2; cudaEvent_t e0, e1; };
+#define SSB_STREAM_PARTS 4
+struct StreamAux { bool ok; cudaStream_t s[SSB_STREAM_PARTS - 1]; cudaEvent_t e0, e[SSB_STREAM_PARTS - 1]; };
 static StreamAux* stream_aux() {
     static thread_local StreamAux aux[64];
     static thread_local bool tried[64];
@@ -1270,9 +1275,10 @@ static StreamAux* stream_aux() {
     if (!tried[dev]) {
         tried[dev] = true;
         StreamAux& x = aux[dev];
-        x.ok = cudaStreamCreateWithFlags(&x.s2, cudaStreamNonBlocking) == cudaSuccess &&
-               cudaEventCreateWithFlags(&x.e0, cudaEventDisableTiming) == cudaSuccess &&
-               cudaEventCreateWithFlags(&x.e1, cudaEventDisableTiming) == cudaSuccess;
+        x.ok = cudaEventCreateWithFlags(&x.e0, cudaEventDisableTiming) == cudaSuccess;
+        for (int k = 0; k < SSB_STREAM_PARTS - 1; ++k)
+            x.ok = x.ok && cudaStreamCreateWithFlags(&x.s[k], cudaStreamNonBlocking) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&x.e[k], cudaEventDisableTiming) == cudaSuccess;
         if (!x.ok) cudaGetLastError();
     }
     return aux[dev].ok ? &aux[dev] : nullptr;
@@ -1334,8 +1340,10 @@ static int gen_stream_impl(const ssb_potential* pot, const ssb_potential* pot_re
     int64_t r5[5]; host_randint5(seed, r5);
     StreamAux* ax = (n >= SSB_STREAM_SPLIT_MIN && trail == lead + 6 * n && stream_split_enabled()) ? stream_aux() : nullptr;
     if (ax) {
-        const int64_t na = ((n / 8 + 127) / 128) * 128, nb = n - na;      // part A: the first eighth of this shard's stripping times
-        cudaStream_t s2 = ax->s2;
+        // part boundaries in units of this shard's stripping times (multiples of 128 releases = whole CTAs)
+        auto r128 = [](int64_t v) { return ((v + 127) / 128) * 128; };
+        const int64_t b[SSB_STREAM_PARTS + 1] = {0, r128(n / 8), r128(3 * n / 8), r128(5 * n / 8), n};
+        const size_t dense_doubles = ssb_scratch_bytes(ctrl.max_steps) / sizeof(double);
         ReleaseArgs a;
         memset(&a, 0, sizeof(a));
         a.N = n; a.prog = prog; a.Msat = Msat; a.t = ts; a.normals = normals; a.idx = nullptr; a.G = G;
@@ -1345,26 +1353,28 @@ static int gen_stream_impl(const ssb_potential* pot, const ssb_potential* pot_re
         memcpy(a.kv, kvals, sizeof(a.kv));
         a.w0_packed = w0; a.t0_packed = t0; a.t1_packed = t1; a.t_end = ts_last;
         CK(cudaEventRecord(ax->e0, st));                                   // the inputs are ready in the caller's stream order
-        CK(cudaStreamWaitEvent(s2, ax->e0, 0));
-        // part B on the internal stream: whole progenitor orbit -> its dense output at B's stripping times -> release -> orbits
-        if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts_first, ts_last, ts, nb, ctrl, prog + 6 * na, nullptr, nullptr, dense2, s2,
-                                 tb + na * tstr, tstr)) return e;
-        a.i0 = na; a.cnt = nb;
-        release_kernel<<<nblk(nb, 128), 128, 0, s2>>>(*pot_release, a);
-        CKL("release_kernel");
-        if (int e = ssb_orbit_integrate_f64(pot, nb, w0 + 6 * na, t0 + na, t1 + na, t1 + na, 1, 1, ctrl, lead + 6 * na, status + na, nsteps + 3 * na, s2)) return e;
-        if (int e = ssb_orbit_integrate_f64(pot, nb, w0 + 6 * (n + na), t0 + n + na, t1 + n + na, t1 + n + na, 1, 1, ctrl, lead + 6 * (n + na),
-                                            status + n + na, nsteps + 3 * (n + na), s2)) return e;
-        CK(cudaEventRecord(ax->e1, s2));
-        // part A on the caller's stream: the progenitor only until it has passed A's last stripping time
-        if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts_first, ts_last, ts, na, ctrl, prog, nullptr, nullptr, dense, st, tb, tstr,
-                                 ts + (tb + (na - 1) * tstr))) return e;
-        a.i0 = 0; a.cnt = na;
-        release_kernel<<<nblk(na, 128), 128, 0, st>>>(*pot_release, a);
-        CKL("release_kernel");
-        if (int e = ssb_orbit_integrate_f64(pot, na, w0, t0, t1, t1, 1, 1, ctrl, lead, status, nsteps, st)) return e;
-        if (int e = ssb_orbit_integrate_f64(pot, na, w0 + 6 * n, t0 + n, t1 + n, t1 + n, 1, 1, ctrl, lead + 6 * n, status + n, nsteps + 3 * n, st)) return e;
-        CK(cudaStreamWaitEvent(st, ax->e1, 0));                            // join: the caller's stream continues after both parts
+        // the parts with the longest serial prefix are enqueued first; part 0 runs on the caller's stream
+        for (int k = SSB_STREAM_PARTS - 1; k >= 0; --k) {
+            const int64_t p0 = b[k], cnt = b[k + 1] - b[k];
+            if (cnt <= 0) continue;
+            cudaStream_t sk = k == 0 ? st : ax->s[k - 1];
+            if (k > 0) CK(cudaStreamWaitEvent(sk, ax->e0, 0));
+            double* rec = k == 0 ? dense : dense2 + (size_t)(k - 1) * dense_doubles;
+            // progenitor until it has passed this part's last stripping time (the last part: the whole orbit), its dense output at the
+            // part's stripping times, release, orbits (lead block, trail block)
+            const double* tstop = (k == SSB_STREAM_PARTS - 1) ? nullptr : ts + (tb + (b[k + 1] - 1) * tstr);
+            if (int e = dense_launch(pot, prog_w0, 0.0, 0.0, ts_first, ts_last, ts, cnt, ctrl, prog + 6 * p0, nullptr, nullptr, rec, sk, tb + p0 * tstr, tstr, tstop))
+                return e;
+            a.i0 = p0; a.cnt = cnt;
+            release_kernel<<<nblk(cnt, 128), 128, 0, sk>>>(*pot_release, a);
+            CKL("release_kernel");
+            if (int e = ssb_orbit_integrate_f64(pot, cnt, w0 + 6 * p0, t0 + p0, t1 + p0, t1 + p0, 1, 1, ctrl, lead + 6 * p0, status + p0, nsteps + 3 * p0, sk)) return e;
+            if (int e = ssb_orbit_integrate_f64(pot, cnt, w0 + 6 * (n + p0), t0 + n + p0, t1 + n + p0, t1 + n + p0, 1, 1, ctrl, lead + 6 * (n + p0),
+                                                status + n + p0, nsteps + 3 * (n + p0), sk)) return e;
+            if (k > 0) CK(cudaEventRecord(ax->e[k - 1], sk));
+        }
+        for (int k = 1; k < SSB_STREAM_PARTS; ++k)
+            if (b[k + 1] - b[k] > 0) CK(cudaStreamWaitEvent(st, ax->e[k - 1], 0));      // join: the caller's stream continues after every part
         return 0;
     }
     // (1) progenitor orbit integrate_orbit(prog_w0, ts) with t0 = ts.min, t1 = ts.max (main.py:289, 152-153): ONE serial solve, then its

@@ -43,7 +43,7 @@ using namespace ssb;
 #define SSB_RESP_MAX_SORT 4096
 #define SSB_RESP_MAX_NP 16          // response_kernel_mp: particle slots per CTA (eight lanes each: four slots per warp)
 #ifndef SSB_RESP_DEFAULT_NP
-#define SSB_RESP_DEFAULT_NP 8
+#define SSB_RESP_DEFAULT_NP 16      // measured (B200, 1000 subhalos): 1e5 particles 367 / 334 / 304 ms with 4 / 8 / 16 slots; small batches get fewer (resp_np)
 #endif
 #define CK(call) do { int _e = ssb_cuda_check((call), #call); if (_e) return _e; } while (0)
 #define CKL(what) do { ssb_count_launch(); int _e = ssb_cuda_check(cudaGetLastError(), what); if (_e) return _e; } while (0)
@@ -263,7 +263,7 @@ __device__ __forceinline__ void item_finish(const double (&q)[3], const double (
 template <int SOLVER, int PROFILE>
 __device__ __forceinline__ void sweep_items(const BaseShared<Tab<SOLVER>::S>* sb, const double* __restrict__ PhiE, const double* __restrict__ tab, int n_sh,
                                             int n_items, int n_dead /* first position swept: dead or retired prefix */, int n_act, const double* __restrict__ cur, double* __restrict__ nxt, double dt,
-                                            const CtrlDev& c, double& esq, int& bad_local) {
+                                            const CtrlDev& c, double& esq, int& bad_local, int rot = 0) {
     constexpr int S = Tab<SOLVER>::S;
     const double t_lo = fmin(sb->t[0], sb->t[S - 1]), t_hi = fmax(sb->t[0], sb->t[S - 1]);     // every stage time lies in [t_lo, t_hi]
     // processing positions [n_dead, n_act) of both blocks: idx -> (blk, j)
@@ -272,7 +272,10 @@ __device__ __forceinline__ void sweep_items(const BaseShared<Tab<SOLVER>::S>* sb
     const double* __restrict__ t0tab = tab + (size_t)8 * n_sh;
     const double* __restrict__ twtab = tab + (size_t)9 * n_sh;
     // software-pipelined: the state of the NEXT item (L2-resident scratch, ~1 us away) is requested before the current one is processed
-    int idx = threadIdx.x;
+    // `rot` rotates which warp takes which 32 items of a pass: the first positions of the range are closed windows waiting for their
+    // chunk to retire (cheap propagator path), the rest open ones (13 stages) - without the rotation warp 0 would get the cheap ones of
+    // every particle.  Callers derive it from the PARTICLE index, so a particle's arithmetic does not depend on where it runs.
+    int idx = (int)((threadIdx.x + 32u * (unsigned)rot) % blockDim.x);
     double yn[6] = {0, 0, 0, 0, 0, 0}, t0n = 0.0, twn = 0.0;
     if (idx < n2) {
         const int blk = idx >= n_span, j = n_dead + idx - blk * n_span, it = blk * n_sh + j;
@@ -1103,7 +1106,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
             double esq = (tid == 0) ? s_besq[q] : 0.0;          // same summation order as response_kernel, whatever the slot
             int bad_local = 0;
             sweep_items<SOLVER, PROFILE>(&sb[q], sPhiE[q], a.sorted, n_sh, n_items, slot[q].n_ret, n_act, cur, nxt, slot[q].tnext - slot[q].tprev, c, esq,
-                                         bad_local);
+                                         bad_local, a.retire ? (int)(slot[q].part & 3) : 0);
             if (bad_local) s_bad[q] = 1;
             if (slot[q].n_ret > slot[q].n_dead && wid == (nw > 1 ? 1 : 0) && lane < 6) {
                 // retired items: sum over them of (E y)_k^2 = (E C E^T)_kk, scale atol (see the header); always by the same lanes, whatever the
