@@ -299,7 +299,7 @@ def run_c4(args, rank, world, dev, flush, barrier):
     if world == 1:          # CPU port on a bounded sample of the same workload
         import oracle as O
         threads = O.num_threads()
-        n_cpu = max(threads, 8)
+        n_cpu = 60 * max(threads, 1)                # ~10-15 s of host work at ~0.2 s per particle and core
         w0, t0, pert, M_sh, sh = c4_workload(pot, 2 * (C4["n_particles"] // 2), C4["n_sh"])
         pick = np.linspace(0, len(w0) - 1, n_cpu).astype(int)
         with O.variant("bench"):

@@ -21,7 +21,7 @@
 #define SSB_FUSED_INLINE 1
 #endif
 #ifndef SSB_SNAP_FUSED_INLINE
-#define SSB_SNAP_FUSED_INLINE 0 // saving kernel (MODE 0): one out-of-line copy of the fused force keeps its larger step loop inside the instruction cache
+#define SSB_SNAP_FUSED_INLINE 1 // saving kernel (MODE 0): 0 = one out-of-line copy of the fused force (16 KB less code; measured 7 % slower: 24.1 vs 22.5 ms)
 #endif
 #define SSB_REC_STRIDE 64   // doubles per recorded step: ta, tb, x, p, x1, p1 (14) + up to 14 force stages (42)
 

@@ -85,8 +85,22 @@ struct OrbitForce {
 // to rows save_idx.. of its output block ys.  Task j of the warp (j < sum of nsave) belongs to the lane s with excl_s <= j < incl_s
 // (inclusive scan); tasks are dealt out j = lane, lane + 32, ...: every pass keeps all lanes busy and the lanes that serve one orbit
 // write adjacent 48-byte rows.
+// Coefficient tables of the dense output staged in shared memory (s_coef: Dopri8 d8_dense_a[14][7], d8_dense[14][7], d8_dense_sum[7];
+// Dopri5 d5_cmida[7], d5_cmid[7]): the rolled stage loop indexes them dynamically, and indexed loads from the constant bank miss the
+// small constant cache that the step loop's kernel parameters occupy (measured: ~10 k cycles per pass before, as long as a whole step).
 template <int SOLVER>
-__device__ __noinline__ void coop_dense(const double* __restrict__ srec, int nsave, int save_idx, const double* tsp, double* ys, double dir) {
+__device__ __forceinline__ void dense_coef_init(double* s_coef) {
+    if constexpr (SOLVER == 8) {
+        for (int i = threadIdx.x; i < 98; i += blockDim.x) { s_coef[i] = ssb_tab::d8_dense_a[i / 7][i % 7]; s_coef[98 + i] = ssb_tab::d8_dense[i / 7][i % 7]; }
+        if (threadIdx.x < 7) s_coef[196 + threadIdx.x] = ssb_tab::d8_dense_sum[threadIdx.x];
+    } else {
+        if (threadIdx.x < 7) { s_coef[threadIdx.x] = ssb_tab::d5_cmida[threadIdx.x]; s_coef[7 + threadIdx.x] = ssb_tab::d5_cmid[threadIdx.x]; }
+    }
+    __syncthreads();
+}
+template <int SOLVER>
+__device__ __noinline__ void coop_dense(const double* __restrict__ srec, const double* __restrict__ s_coef, int nsave, int save_idx, const double* tsp, double* ys,
+                                        double dir) {
     constexpr int NT = SSB_ORBIT_THREADS;
     constexpr int S = Tab<SOLVER>::S;
     const unsigned full = 0xffffffffu;
@@ -125,7 +139,7 @@ __device__ __noinline__ void coop_dense(const double* __restrict__ srec, int nsa
                 double mx[3] = {0, 0, 0}, mp[3] = {0, 0, 0};
 #pragma unroll 1
                 for (int l = 0; l < S; ++l) {
-                    const double ca = ssb_tab::d5_cmida[l], cb = ssb_tab::d5_cmid[l];
+                    const double ca = s_coef[l], cb = s_coef[7 + l];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) { const double f = R[(14 + 3 * l + k) * NT]; mx[k] = fma(ca, f, mx[k]); mp[k] = fma(cb, f, mp[k]); }
                 }
@@ -157,14 +171,14 @@ __device__ __noinline__ void coop_dense(const double* __restrict__ srec, int nsa
                 for (int l = 0; l < S; ++l) {
                     double wa = 0.0, wb = 0.0;
 #pragma unroll
-                    for (int q = 6; q >= 0; --q) { wa = fma(wa, theta, ssb_tab::d8_dense_a[l][q]); wb = fma(wb, theta, ssb_tab::d8_dense[l][q]); }
+                    for (int q = 6; q >= 0; --q) { wa = fma(wa, theta, s_coef[7 * l + q]); wb = fma(wb, theta, s_coef[98 + 7 * l + q]); }
                     wa *= theta; wb *= theta;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) { const double f = R[(14 + 3 * l + k) * NT]; accx[k] = fma(wa, f, accx[k]); accp[k] = fma(wb, f, accp[k]); }
                 }
                 double wsum = 0.0;
 #pragma unroll
-                for (int q = 6; q >= 0; --q) wsum = fma(wsum, theta, ssb_tab::d8_dense_sum[q]);
+                for (int q = 6; q >= 0; --q) wsum = fma(wsum, theta, s_coef[196 + q]);
                 wsum *= theta;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -253,6 +267,7 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
         // adjacent rows of one orbit are written by adjacent lanes.
         constexpr int NT = SSB_ORBIT_THREADS;
         double* myrec = srec + threadIdx.x;
+        const double* s_coef = srec + (14 + 3 * S) * NT;          // filled by the kernel (dense_coef_init)
         for (;;) {
             bool active = valid && status == 0 && tprev < T1;
             if (active && n_steps >= c.max_steps) { status = 1; active = false; }
@@ -326,7 +341,7 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
             }
             if (__any_sync(0xffffffffu, nsave > 0)) {
                 __syncwarp();
-                coop_dense<SOLVER>(srec, nsave, save_idx, tsp, ys, dir);
+                coop_dense<SOLVER>(srec, s_coef, nsave, save_idx, tsp, ys, dir);
                 __syncwarp();
                 if (nsave > 0) {           // reload the two look-ahead save times: not needed before the end of the next step
                     save_idx += nsave;
@@ -446,7 +461,8 @@ __global__ void __launch_bounds__(SSB_ORBIT_THREADS, MODE == 0 ? SSB_SNAP_MIN_BL
         if (valid) a.status[i] = status;
         return;
     }
-    extern __shared__ double s_steprec[];          // MODE 0: one published step record per thread (coop_dense), (14 + 3 S) x SSB_ORBIT_THREADS doubles
+    extern __shared__ double s_steprec[];          // MODE 0: one published step record per thread (coop_dense), (14 + 3 S) x SSB_ORBIT_THREADS doubles, + coefficient tables
+    if (MODE == 0) dense_coef_init<SOLVER>(s_steprec + (14 + 3 * Tab<SOLVER>::S) * SSB_ORBIT_THREADS);
     integrate_one<SOLVER, MODE, SIG, XS>(&sP, &Pin, a.w0 + ii * 6, a.t0[ii], a.t1[ii], tsp, a.M, a.ys + (size_t)ii * a.M * 6, a.c, valid,
                                      status, n_steps, n_acc, n_rej, nullptr, 0, sfx, HUGE_VAL, nullptr, 0, s_steprec);
     if (valid) {
@@ -1072,7 +1088,7 @@ int ssb_orbit_integrate_f64(const ssb_potential* pot, int64_t N, const double* w
     // XS = number of "fast extras" (linear-track moving perturbers / frame acceleration) next to a fused MW signature, final-state mode
     const int xs = (final_only && (sig == SIG_NHM || sig == SIG_NHHM)) ? ssb_fast_extras(&pc, sig == SIG_NHM ? 3 : 4) : 0;
     // MODE 0 (SaveAt with dense output): one step record of (14 + 3 stages) doubles per thread in dynamic shared memory (coop_dense)
-#define SSB_LAUNCH_ORBIT(S, MD, SG) do { const size_t shm = (MD) == 0 ? sizeof(double) * (14 + 3 * ((S) == 5 ? 7 : 14)) * SSB_ORBIT_THREADS : 0; \
+#define SSB_LAUNCH_ORBIT(S, MD, SG) do { const size_t shm = (MD) == 0 ? sizeof(double) * ((14 + 3 * ((S) == 5 ? 7 : 14)) * SSB_ORBIT_THREADS + 208) : 0; \
         if (shm > 48 * 1024) CK(cudaFuncSetAttribute(orbit_kernel<S, MD, SG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); \
         orbit_kernel<S, MD, SG, 0><<<grid, SSB_ORBIT_THREADS, shm, st>>>(pc, a); } while (0)
 #define SSB_LAUNCH_SIG(S, MD) do { switch (sig) { case SIG_N: SSB_LAUNCH_ORBIT(S, MD, SIG_N); break; case SIG_NHM: SSB_LAUNCH_ORBIT(S, MD, SIG_NHM); break; \

@@ -74,3 +74,31 @@ def test_short_integrations_agree_strictly():
             cand = mw3_oracle().integrate_orbits(w0, -60.0, 0.0, **kw)[0][:, 0]
         d = np.abs(cand - base) / (tol * (1 + np.abs(base)))
         assert d.max() < 10.0, (solver, tol, d.max())
+
+
+def test_dopri8_dense_output_error_on_the_headline_progenitor():
+    """A18 / VERDICT item 9.  diffrax's own Dopri8 interpolation coefficients cannot be reproduced here, so Dopri8 SaveAt rows between step
+    ends - the progenitor at every stripping time of a Dopri8 stream (main.py:289) - use our C1 5th-order continuous extension.  This bounds
+    what that costs on the headline configuration (C2 progenitor, 3 Gyr, rtol = atol = 1e-7): the interpolation-only error of the release
+    positions (dense row minus truth, minus the solver's own global error interpolated between the step ends) against the global error
+    of the solve itself, in units of tol.  Measured: interpolation <= 41 x tol (median 0.4) while the solve is off by up to 474 x tol -
+    and diffrax's exact Dopri5 quartic, the reference's default, interpolates WORSE on the same orbit (56 x tol, median 2.2)."""
+    orc = mw3_oracle()
+    w0 = orc.integrate_orbits([20.0, 0.0, 20.0, 0.0, 0.15, 0.0], 0.0, -3000.0)[0][0, 0]
+    ts = np.linspace(-3000.0, 0.0, 20001)
+    tol = 1e-7
+    out = {}
+    for solver in (5, 8):
+        ys = orc.integrate_orbits(w0, -3000.0, 0.0, ts=ts, solver=solver, rtol=tol, atol=tol)[0][0]
+        yt = orc.integrate_orbits(w0, -3000.0, 0.0, ts=ts, **{**TRUTH, "threads": 1})[0][0]
+        tg, yg = orc.orbit_steps(w0, -3000.0, 0.0, solver=solver, rtol=tol, atol=tol)
+        ytg = orc.integrate_orbits(w0, -3000.0, 0.0, ts=tg[1:], **{**TRUTH, "threads": 1})[0][0]
+        sc = tol * (1.0 + np.abs(yt))
+        glob = np.stack([np.interp(ts, tg[1:], (yg[1:] - ytg)[:, k]) for k in range(6)], axis=1)
+        e_interp = (np.abs(ys - yt - glob) / sc).max(axis=1)
+        e_glob = (np.abs(yg[1:] - ytg) / (tol * (1.0 + np.abs(ytg)))).max()
+        out[solver] = (e_interp.max(), np.median(e_interp), e_glob)
+    warnings.warn("dense-output error on the C2 progenitor, x tol (interpolation max, median | global error of the solve): "
+                  + "; ".join(f"Dopri{s}: {a:.1f}, {b:.2f} | {g:.0f}" for s, (a, b, g) in out.items()))
+    assert out[8][0] <= 100.0 and out[8][0] <= 0.25 * out[8][2]          # our Dopri8 extension: far inside the solver's own error
+    assert out[8][0] <= 1.5 * out[5][0]                                  # and no worse than diffrax's Dopri5 quartic on the same orbit
