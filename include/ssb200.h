@@ -56,7 +56,8 @@ typedef struct {
     int32_t type;   /* ssb_comp_type */
     int32_t track;  /* >= 0: evaluate at x - c(t), c = tracks[track] (TimeDepTranslatingPotential, potential.py:448-462); -1: static */
     int32_t sh;     /* SSB_SUBHALOS: which subhalo set */
-    int32_t _pad;
+    int32_t growth; /* GrowingPotential (potential.py:464-477): 0 = none, g > 0: the component's mass scale is multiplied by the FIRST column of
+                       tracks[g - 1] evaluated at t (a tabulated growth factor).  Not for SSB_UNIFORM_ACC / SSB_SUBHALOS components. */
     double p[8];
 } ssb_component;
 

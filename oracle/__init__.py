@@ -121,7 +121,12 @@ class Program:
     def _comp(self, typ, params, track=-1):
         p = np.zeros(8)
         p[: len(params)] = params
-        lib().orc_add_comp(self._h, typ, _p(p), int(track))
+        self._last_comp = lib().orc_add_comp(self._h, typ, _p(p), int(track))
+        return self
+
+    def growing(self, t, factor, kind=LINEAR):
+        """GrowingPotential (potential.py:464-477) around the component added LAST: Phi * growth_func(t), growth_func tabulated on (t, factor)."""
+        lib().orc_set_growth(self._h, int(self._last_comp), int(self.track(kind, t, np.asarray(factor, dtype=np.float64).reshape(-1, 1))))
         return self
 
     def nfw(self, m, r_s, track=-1, soft=0.0):

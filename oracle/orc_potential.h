@@ -97,6 +97,7 @@ struct Comp {
     double p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int track = -1;   // >=0: evaluate at x - c(t) (TimeDepTranslatingPotential, potential.py:448-462)
     int sh = -1;
+    int growth = -1;  // >=0: Phi * growth_func(t), growth_func = first column of that track (GrowingPotential, potential.py:464-477)
 };
 
 struct Program {
@@ -165,15 +166,17 @@ template <class T> inline T phi_total(const Program& P, const T* x, double t) {
             double ctr[3]; P.tracks[c.track].eval(t, ctr, nullptr);
             for (int k = 0; k < 3; ++k) xs[k] = x[k] - ctr[k];                        // potential.py:460-462
         }
+        double gf = 1.0;
+        if (c.growth >= 0) { double gv[3]; P.tracks[c.growth].eval(t, gv, nullptr); gf = gv[0]; }       // potential.py:476-477: pot.potential(xyz, t) * growth_factor
         switch (c.type) {
-            case C_NFW: acc += phi_nfw<T, double>(c.p[0], c.p[1], xs, c.p[2]); break;
-            case C_HERNQUIST: acc += phi_hernquist<T, double>(c.p[0], c.p[1], c.p[2], xs); break;
-            case C_MIYAMOTO: acc += phi_miyamoto<T, double>(c.p[0], c.p[1], c.p[2], xs); break;
-            case C_PLUMMER: acc += phi_plummer<T, double>(c.p[0], c.p[1], xs); break;
-            case C_ISOCHRONE: acc += phi_isochrone<T, double>(c.p[0], c.p[1], xs); break;
+            case C_NFW: acc += phi_nfw<T, double>(c.p[0], c.p[1], xs, c.p[2]) * gf; break;
+            case C_HERNQUIST: acc += phi_hernquist<T, double>(c.p[0], c.p[1], c.p[2], xs) * gf; break;
+            case C_MIYAMOTO: acc += phi_miyamoto<T, double>(c.p[0], c.p[1], c.p[2], xs) * gf; break;
+            case C_PLUMMER: acc += phi_plummer<T, double>(c.p[0], c.p[1], xs) * gf; break;
+            case C_ISOCHRONE: acc += phi_isochrone<T, double>(c.p[0], c.p[1], xs) * gf; break;
             case C_TRIAXNFW: {
                 T xq[3] = {xs[0] / c.p[2], xs[1] / c.p[3], xs[2] / c.p[4]};           // potential.py:94
-                acc += phi_nfw<T, double>(c.p[0], c.p[1], xq); break; }
+                acc += phi_nfw<T, double>(c.p[0], c.p[1], xq) * gf; break; }
             case C_SUBHALOS: {
                 const SubhaloSet& S = P.shs[c.sh];
                 for (int j = 0; j < S.n; ++j) acc += phi_subhalo<T>(S, j, xs, t);     // potential.py:830

@@ -264,6 +264,8 @@ int orc_add_comp(void* h, int type, const double* p, int track) {
     Program* P = (Program*)h; Comp c; c.type = type; std::memcpy(c.p, p, sizeof(c.p)); c.track = track;
     P->comps.push_back(c); return (int)P->comps.size() - 1;
 }
+// GrowingPotential (potential.py:464-477): component `comp` is multiplied by the first column of track `track` evaluated at t
+void orc_set_growth(void* h, int comp, int track) { Program* P = (Program*)h; P->comps[comp].growth = track; }
 int orc_add_subhalos(void* h, int profile, int dradius, double G, int n, const double* m, const double* rs,
                      const double* x0, const double* v, const double* t0, const double* tw, int track) {
     Program* P = (Program*)h; SubhaloSet S; S.n = n; S.profile = profile; S.dradius = dradius; S.G = G;

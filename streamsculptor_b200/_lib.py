@@ -23,7 +23,7 @@ _dp = C.c_void_p
 
 
 class Component(C.Structure):
-    _fields_ = [("type", C.c_int32), ("track", C.c_int32), ("sh", C.c_int32), ("_pad", C.c_int32), ("p", C.c_double * 8)]
+    _fields_ = [("type", C.c_int32), ("track", C.c_int32), ("sh", C.c_int32), ("growth", C.c_int32), ("p", C.c_double * 8)]
 
 
 class Track(C.Structure):

@@ -140,6 +140,7 @@ class Program:
 
     def __init__(self):
         self.comps, self.tracks, self.shs = [], [], []
+        self.growth = 0          # > 0 while the components of a GrowingPotential are being added: index + 1 of its growth-factor track
 
     def add_track(self, track):
         for i, t in enumerate(self.tracks):
@@ -153,7 +154,9 @@ class Program:
     def add(self, typ, params, track=-1, sh=-1):
         if len(self.comps) >= _lib.MAX_COMP:
             raise NotImplementedError(f"more than {_lib.MAX_COMP} components in one potential")
-        self.comps.append((int(typ), [float(p) for p in params], int(track), int(sh)))
+        if self.growth and int(typ) in (_lib.UNIFORM_ACC, _lib.SUBHALOS):
+            raise NotImplementedError("GrowingPotential around a force-only (UniformAcceleration) or subhalo-ensemble component is not supported")
+        self.comps.append((int(typ), [float(p) for p in params], int(track), int(sh), int(self.growth)))
 
     def add_subhalos(self, arrays, track=-1):
         if len(self.shs) >= _lib.MAX_SH:
@@ -164,8 +167,8 @@ class Program:
     def struct(self):
         P = _lib.Potential()
         P.n_comp, P.n_track, P.n_sh = len(self.comps), len(self.tracks), len(self.shs)
-        for i, (typ, params, track, sh) in enumerate(self.comps):
-            P.comp[i].type, P.comp[i].track, P.comp[i].sh = typ, track, sh
+        for i, (typ, params, track, sh, growth) in enumerate(self.comps):
+            P.comp[i].type, P.comp[i].track, P.comp[i].sh, P.comp[i].growth = typ, track, sh, growth
             for k, v in enumerate(params):
                 P.comp[i].p[k] = v
         for i, t in enumerate(self.tracks):

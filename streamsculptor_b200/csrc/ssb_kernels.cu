@@ -977,6 +977,8 @@ int ssb_validate_potential(const ssb_potential* p) {
         const ssb_component& c = p->comp[i];
         if (c.type < SSB_NFW || c.type > SSB_SUBHALOS) return ssb_set_error(SSB_ERR_UNSUPPORTED, "potential: unknown component type");
         if (c.track >= p->n_track) return ssb_set_error(SSB_ERR_ARG, "potential: component references a missing track");
+        if (c.growth < 0 || c.growth > p->n_track) return ssb_set_error(SSB_ERR_ARG, "potential: component references a missing growth track");
+        if (c.growth > 0 && (c.type == SSB_UNIFORM_ACC || c.type == SSB_SUBHALOS)) return ssb_set_error(SSB_ERR_UNSUPPORTED, "growth factor on a force-only / subhalo component");
         if (c.type == SSB_UNIFORM_ACC && c.track < 0) return ssb_set_error(SSB_ERR_ARG, "uniform acceleration needs a velocity track");
         if (c.type == SSB_SUBHALOS && (c.sh < 0 || c.sh >= p->n_sh)) return ssb_set_error(SSB_ERR_ARG, "subhalo component references a missing set");
     }

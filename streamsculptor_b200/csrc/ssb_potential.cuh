@@ -259,36 +259,43 @@ __device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x
             else track_eval<false>(Pt.track[c.track], t, ctr, ctr);
             xs[0] -= ctr[0]; xs[1] -= ctr[1]; xs[2] -= ctr[2];
         }
+        double gm = c.p[0];                                         // G m, times the tabulated growth factor (potential.py:474-477)
+        if (c.growth > 0) {
+            double gf[3];
+            if (frozen) gf[0] = frozen[6 * (c.growth - 1)];
+            else track_eval<false>(Pt.track[c.growth - 1], t, gf, gf);
+            gm *= gf[0];
+        }
         double phi = 0, q = 0, w = 0;
         switch (type) {
             case SSB_NFW: {
                 const double r2 = fma(xs[0], xs[0], fma(xs[1], xs[1], xs[2] * xs[2]));
-                nfw_terms<MODE>(c.p[0], c.p[1], r2, phi, q, w);
+                nfw_terms<MODE>(gm, c.p[1], r2, phi, q, w);
                 add_spherical<MODE>(xs, phi, q, w, P, g, H);
             } break;
             case SSB_HERNQUIST: {
                 const double r2 = fma(xs[0], xs[0], fma(xs[1], xs[1], fma(xs[2], xs[2], c.p[2])));
-                hernquist_terms<MODE>(c.p[0], c.p[1], r2, phi, q, w);
+                hernquist_terms<MODE>(gm, c.p[1], r2, phi, q, w);
                 add_spherical<MODE>(xs, phi, q, w, P, g, H);
             } break;
             case SSB_PLUMMER: {
                 const double r2 = fma(xs[0], xs[0], fma(xs[1], xs[1], xs[2] * xs[2]));
-                plummer_terms<MODE>(c.p[0], c.p[1], r2, phi, q, w);
+                plummer_terms<MODE>(gm, c.p[1], r2, phi, q, w);
                 add_spherical<MODE>(xs, phi, q, w, P, g, H);
             } break;
             case SSB_ISOCHRONE: {
                 const double r2 = fma(xs[0], xs[0], fma(xs[1], xs[1], xs[2] * xs[2]));
-                isochrone_terms<MODE>(c.p[0], c.p[1], r2, phi, q, w);
+                isochrone_terms<MODE>(gm, c.p[1], r2, phi, q, w);
                 add_spherical<MODE>(xs, phi, q, w, P, g, H);
             } break;
             case SSB_MIYAMOTO:
-                add_miyamoto<MODE>(c.p[0], c.p[1], c.p[2], xs, P, g, H);
+                add_miyamoto<MODE>(gm, c.p[1], c.p[2], xs, P, g, H);
                 break;
             case SSB_TRIAXNFW: {                                    // potential.py:94: x_i / q_i
                 const double i1 = frcp(c.p[2]), i2 = frcp(c.p[3]), i3 = frcp(c.p[4]);
                 const double xq[3] = {xs[0] * i1, xs[1] * i2, xs[2] * i3};
                 const double r2 = fma(xq[0], xq[0], fma(xq[1], xq[1], xq[2] * xq[2]));
-                nfw_terms<MODE>(c.p[0], c.p[1], r2, phi, q, w);
+                nfw_terms<MODE>(gm, c.p[1], r2, phi, q, w);
                 if (MODE & WANT_PHI) P += phi;
                 if (MODE & WANT_GRAD) { g[0] = fma(q * i1, xq[0], g[0]); g[1] = fma(q * i2, xq[1], g[1]); g[2] = fma(q * i3, xq[2], g[2]); }
                 if (MODE & WANT_HESS) {
@@ -368,7 +375,7 @@ static inline int ssb_fast_extras(const ssb_potential* p, int nf) {
     for (int i = nf; i < p->n_comp; ++i) {
         const ssb_component& c = p->comp[i];
         const bool kind_ok = c.type == SSB_NFW || c.type == SSB_HERNQUIST || c.type == SSB_PLUMMER || c.type == SSB_ISOCHRONE || c.type == SSB_UNIFORM_ACC;
-        if (!kind_ok || c.track < 0 || p->track[c.track].kind != SSB_TRACK_LINEAR) return 0;
+        if (!kind_ok || c.growth != 0 || c.track < 0 || p->track[c.track].kind != SSB_TRACK_LINEAR) return 0;
     }
     return nx;
 }
@@ -431,21 +438,23 @@ __device__ inline void pot_third(const ssb_potential& Pt, const double x[3], dou
         }
         const double r2 = xs[0] * xs[0] + xs[1] * xs[1] + xs[2] * xs[2];
         double w, u3;
+        double gm = c.p[0];
+        if (c.growth > 0) { double gf[3]; track_eval<false>(Pt.track[c.growth - 1], t, gf, gf); gm *= gf[0]; }
         switch (c.type) {
-            case SSB_NFW: nfw_wu(c.p[0], c.p[1], r2, w, u3); add_spherical_third(xs, w, u3, 1, 1, 1, T); break;
-            case SSB_HERNQUIST: hernquist_wu(c.p[0], c.p[1], r2 + c.p[2], w, u3); add_spherical_third(xs, w, u3, 1, 1, 1, T); break;
-            case SSB_PLUMMER: plummer_wu(c.p[0], c.p[1], r2, w, u3); add_spherical_third(xs, w, u3, 1, 1, 1, T); break;
-            case SSB_ISOCHRONE: hernquist_wu(c.p[0], c.p[1], r2 + c.p[1] * c.p[1], w, u3); add_spherical_third(xs, w, u3, 1, 1, 1, T); break;
+            case SSB_NFW: nfw_wu(gm, c.p[1], r2, w, u3); add_spherical_third(xs, w, u3, 1, 1, 1, T); break;
+            case SSB_HERNQUIST: hernquist_wu(gm, c.p[1], r2 + c.p[2], w, u3); add_spherical_third(xs, w, u3, 1, 1, 1, T); break;
+            case SSB_PLUMMER: plummer_wu(gm, c.p[1], r2, w, u3); add_spherical_third(xs, w, u3, 1, 1, 1, T); break;
+            case SSB_ISOCHRONE: hernquist_wu(gm, c.p[1], r2 + c.p[1] * c.p[1], w, u3); add_spherical_third(xs, w, u3, 1, 1, 1, T); break;
             case SSB_TRIAXNFW: {
                 const double i1 = 1.0 / c.p[2], i2 = 1.0 / c.p[3], i3 = 1.0 / c.p[4];
                 const double xq[3] = {xs[0] * i1, xs[1] * i2, xs[2] * i3};
-                nfw_wu(c.p[0], c.p[1], xq[0] * xq[0] + xq[1] * xq[1] + xq[2] * xq[2], w, u3);
+                nfw_wu(gm, c.p[1], xq[0] * xq[0] + xq[1] * xq[1] + xq[2] * xq[2], w, u3);
                 add_spherical_third(xq, w, u3, i1, i2, i3, T);
             } break;
             case SSB_MIYAMOTO: {
                 // Phi = f(D), f = -GM D^(-1/2), D = x^2 + y^2 + (a + zeta)^2, zeta = sqrt(z^2 + b^2):
                 // Phi_ijk = f''' D_i D_j D_k + f'' (D_ij D_k + D_ik D_j + D_jk D_i) + f' D_ijk
-                const double GM = c.p[0], a = c.p[1], b = c.p[2];
+                const double GM = gm, a = c.p[1], b = c.p[2];
                 const double zeta = sqrt(xs[2] * xs[2] + b * b), az = a + zeta;
                 const double D = xs[0] * xs[0] + xs[1] * xs[1] + az * az;
                 const double sD = sqrt(D);
@@ -559,7 +568,7 @@ static inline int ssb_canonicalize(const ssb_potential* in, ssb_potential* out) 
     int idx_n = -1, idx_m = -1, idx_h[2] = {-1, -1}, nh = 0, nn = 0, nm = 0;
     for (int i = 0; i < in->n_comp; ++i) {
         const ssb_component& c = in->comp[i];
-        if (c.track >= 0) continue;
+        if (c.track >= 0 || c.growth != 0) continue;
         if (c.type == SSB_NFW) { if (nn++ == 0) idx_n = i; }
         else if (c.type == SSB_HERNQUIST && c.p[2] == 0.0) { if (nh < 2) idx_h[nh] = i; nh++; }
         else if (c.type == SSB_MIYAMOTO) { if (nm++ == 0) idx_m = i; }

@@ -38,8 +38,8 @@ def flatten_program(pot):
     pot._lower(prog, -1)
     P = FfiProgram()
     P.n_comp, P.n_track, P.n_sh = len(prog.comps), len(prog.tracks), len(prog.shs)
-    for i, (typ, params, track, sh) in enumerate(prog.comps):
-        P.comp[i].type, P.comp[i].track, P.comp[i].sh = typ, track, sh
+    for i, (typ, params, track, sh, growth) in enumerate(prog.comps):
+        P.comp[i].type, P.comp[i].track, P.comp[i].sh, P.comp[i].growth = typ, track, sh, growth
         for k, v in enumerate(params):
             P.comp[i].p[k] = v
     tables = []

@@ -357,4 +357,35 @@ CustomPotential = _out_of_scope("CustomPotential", "arbitrary Python potential f
 ZhaoPotential = _out_of_scope("ZhaoPotential", "needs incomplete beta functions")
 PowerLawCutoffPotential = _out_of_scope("PowerLawCutoffPotential", "needs incomplete gamma functions")
 BovyMWPotential2014 = _out_of_scope("BovyMWPotential2014", "contains PowerLawCutoffPotential")
-GrowingPotential = _out_of_scope("GrowingPotential", "growth_func is an arbitrary Python callable")
+class GrowingPotential(Potential):                    # potential.py:464-477
+    """pot.potential(xyz, t) * growth_func(t).  growth_func must be TABULATED: a LinearTrack / CubicTrack whose first column is the growth
+    factor, an interpax-like object with .x / .f (1-D), or a pair (t, factor) of arrays (linear interpolation).  The wrapped potential may be
+    any sum of the analytic components (and translating ones); force-only and subhalo-ensemble components are not supported inside it."""
+
+    def __init__(self, pot, growth_func, units=None):
+        super().__init__(units, {'pot': pot, 'growth_func': growth_func})
+        self._gtrack = _scalar_track(growth_func)
+
+    def _lower(self, prog, track):
+        if prog.growth:
+            raise NotImplementedError("nested GrowingPotential is not implemented")
+        prog.growth = prog.add_track(self._gtrack) + 1
+        try:
+            self.pot._lower(prog, track)
+        finally:
+            prog.growth = 0
+
+
+def _scalar_track(f):
+    """Tabulated scalar function of time -> a Track whose first column carries it."""
+    if isinstance(f, rt.Track):
+        return f
+    if isinstance(f, (tuple, list)) and len(f) == 2:
+        t, y = np.asarray(f[0], dtype=np.float64), np.asarray(f[1], dtype=np.float64)
+        return rt.Track(_lib.TRACK_LINEAR, t, np.stack([y, np.zeros_like(y), np.zeros_like(y)], axis=1))
+    if hasattr(f, "x") and hasattr(f, "f"):
+        y = np.asarray(f.f, dtype=np.float64).reshape(len(np.asarray(f.x)), -1)[:, 0]
+        kind = _lib.TRACK_LINEAR if getattr(f, "method", "cubic") == "linear" else _lib.TRACK_CUBIC
+        return rt.Track(kind, np.asarray(f.x), np.stack([y, np.zeros_like(y), np.zeros_like(y)], axis=1))
+    raise NotImplementedError("growth_func must be tabulated (LinearTrack / CubicTrack, an interpax-like object, or a (t, factor) pair); "
+                              "arbitrary Python callables cannot run inside the CUDA kernels")

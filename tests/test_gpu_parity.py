@@ -1008,3 +1008,41 @@ def test_reference_printed_batch_of_orbits_through_the_product_api(cuda):
     warnings.warn(f"CUDA orbits vs the reference's printed values: {np.mean(d < 1e-9):.3f} within 1e-9, median {np.median(d):.1e}, max {d.max():.1e}")
     assert np.mean(d < 1e-9) >= 0.99 and d.max() < 5e-9         # measured: 1.000 within 1e-9, max 4.8e-10 (the 9 printed digits); x10 margin
 
+
+
+def test_growing_potential_matches_oracle(cuda):
+    """A10: GrowingPotential (potential.py:464-477) with a tabulated growth factor - field values against the oracle's autodiff of
+    Phi * growth_func(t), fixed-step orbits to 1e-10, and the fused-galaxy recognition must skip growing components."""
+    import streamsculptor_b200 as ssc
+    P = ssc.potential
+    tg = np.linspace(-3000.0, 0.0, 31)
+    gf = 0.6 + 0.4 * (tg + 3000.0) / 3000.0 + 0.05 * np.sin(tg / 400.0)
+    t, y = lmc_track()
+    orc = O.Program().hernquist(5e9, 1.0).miyamoto(6.8e10, 3.0, 0.28).nfw(5.4e11, 15.62).growing(tg, gf)
+    tr = orc.track(O.LINEAR, t, y)
+    orc.plummer(1.5e11, 10.8, track=tr).growing(tg, gf, kind=O.CUBIC)
+    prod = P.Potential_Combine([
+        P.HernquistPotential(m=5e9, r_s=1.0, units=ssc.usys), P.MiyamotoNagaiDisk(m=6.8e10, a=3.0, b=0.28, units=ssc.usys),
+        P.GrowingPotential(P.NFWPotential(m=5.4e11, r_s=15.62, units=ssc.usys), (tg, gf), units=ssc.usys),
+        P.GrowingPotential(P.TimeDepTranslatingPotential(P.PlummerPotential(m=1.5e11, r_s=10.8, units=ssc.usys), ssc.LinearTrack(t, y), units=ssc.usys),
+                           ssc.CubicTrack(tg, np.stack([gf, 0 * gf, 0 * gf], axis=1)), units=ssc.usys)], units=ssc.usys)
+    rng = np.random.default_rng(5)
+    xyz = rng.normal(size=(200, 3)) * np.array([15, 15, 8.0])
+    tt = rng.uniform(-2990, -10, 200)
+    assert relerr(prod.potential(xyz, tt), orc.potential(xyz, tt)) < 1e-12
+    assert relerr(prod.gradient(xyz, tt), orc.gradient(xyz, tt)) < 1e-11
+    assert relerr(prod.jacobian_force(xyz, tt), orc.hessian(xyz, tt)) < 1e-10
+    assert relerr(prod.third_derivative(xyz, tt), orc.third(xyz, tt)) < 1e-9
+    w0 = halo_orbits(64, seed=9)
+    t0 = np.linspace(-2900, -100, 64)
+    for solver in (5, 8):
+        ys_o, _, ns_o = orc.integrate_orbits(w0, t0, 0.0, solver=solver, dtmin=1.0, dtmax=1.0, threads=8)
+        sol = prod.integrate_orbit_batch_vmapped(w0=w0, ts=np.zeros((64, 1)), t0=t0, t1=0.0, solver=ssc.Dopri8() if solver == 8 else ssc.Dopri5(), dtmin=1.0, dtmax=1.0)
+        assert np.array_equal(sol.stats["num_steps"], ns_o[:, 0]) and relerr(sol.ys[:, 0], ys_o[:, 0]) < 1e-10
+    # the whole stream pipeline in a growing halo (fixed steps): release uses the grown Hessian as well
+    ts = np.linspace(-2000.0, 0.0, 201)
+    nr = np.random.Generator(np.random.PCG64(1)).standard_normal((201, 4))
+    w_prog = orc.integrate_orbits([20.0, 0.0, 20.0, 0.0, 0.15, 0.0], 0.0, -2000.0, dtmin=1.0, dtmax=1.0)[0][0, 0]
+    lo, to, _, _ = orc.gen_stream(ts, w_prog, 1e4, 583, solver=8, normals=nr, dtmin=1.0, dtmax=1.0)
+    lf, tf = prod.gen_stream_vmapped(ts=ts, prog_w0=w_prog, Msat=1e4, seed_num=583, solver=ssc.Dopri8(), normals=nr, dtmin=1.0, dtmax=1.0)
+    assert relerr(lf, lo) < 1e-9 and relerr(tf, to) < 1e-9

@@ -84,9 +84,20 @@ def test_lowering_flattens_the_object_tree():
     with pytest.raises(NotImplementedError):
         P.SubhaloLinePotentialCustom_fromFunc(func=P.Isochrone, m=[1.0], r_s=[1.0], subhalo_x0=np.zeros((1, 3)), subhalo_v=np.zeros((1, 3)),
                                               subhalo_t0=[0.0], t_window=1.0, units=ssc.usys)
-    for name in ("CustomPotential", "ZhaoPotential", "GrowingPotential"):
+    for name in ("CustomPotential", "ZhaoPotential"):
         with pytest.raises(NotImplementedError):
             getattr(P, name)()
+    with pytest.raises(NotImplementedError):            # GrowingPotential: the growth factor must be tabulated (potential.py:464-477 takes any callable)
+        P.GrowingPotential(P.NFWPotential(m=1.0, r_s=1.0, units=ssc.usys), growth_func=lambda t: 1.0, units=ssc.usys)
+    from streamsculptor_b200 import _lib, _runtime as rt
+    grow = P.GrowingPotential(P.Potential_Combine([P.NFWPotential(m=1e12, r_s=20.0, units=ssc.usys), P.PlummerPotential(m=1e10, r_s=1.0, units=ssc.usys)],
+                                                  units=ssc.usys), growth_func=(np.linspace(-3000.0, 0.0, 11), np.linspace(0.5, 1.0, 11)), units=ssc.usys)
+    prog = rt.Program()
+    P.Potential_Combine([P.HernquistPotential(m=5e9, r_s=1.0, units=ssc.usys), grow], units=ssc.usys)._lower(prog, -1)
+    assert [c[0] for c in prog.comps] == [_lib.HERNQUIST, _lib.NFW, _lib.PLUMMER] and [c[4] for c in prog.comps] == [0, 1, 1] and len(prog.tracks) == 1
+    with pytest.raises(NotImplementedError):            # no growth factor on force-only components
+        P.GrowingPotential(P.UniformAcceleration(ssc.LinearTrack(np.array([0.0, 1.0]), np.zeros((2, 3))), units=ssc.usys),
+                           growth_func=(np.array([0.0, 1.0]), np.ones(2)), units=ssc.usys)._lower(rt.Program(), -1)
 
 
 def test_no_cpu_fallback():
