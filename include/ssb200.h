@@ -27,10 +27,11 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 1
+#define SSB_ABI_VERSION 2
 #define SSB_MAX_COMP 12
 #define SSB_MAX_TRACK 4
 #define SSB_MAX_SUBHALO_SETS 2
+#define SSB_MAX_PSETS 1
 
 typedef enum {
     SSB_OK = 0,
@@ -49,7 +50,10 @@ typedef enum {
     SSB_ISOCHRONE = 4,    /* potential.py:114-122  p = {G*m, a}                        */
     SSB_TRIAXNFW = 5,     /* potential.py:86-97    p = {G*m, r_s, q1, q2, q3}          */
     SSB_UNIFORM_ACC = 6,  /* potential.py:480-502  gradient = d(velocity track)/dt ; track = velocity table */
-    SSB_SUBHALOS = 7      /* potential.py:802-850, 1161-1213  sh = index into ssb_potential.sh              */
+    SSB_SUBHALOS = 7,     /* potential.py:802-850, 1161-1213  sh = index into ssb_potential.sh              */
+    SSB_PERTURBERS = 8    /* a SET of moving spheres on tabulated tracks (sum of TimeDepTranslatingPotential components,
+                             potential.py:448-462, as the restricted N-body / LMC set-ups build them - BASELINE config 5:
+                             100 live perturbers); sh = index into ssb_potential.pset                        */
 } ssb_comp_type;
 
 typedef struct {
@@ -91,11 +95,27 @@ typedef struct {
     const double* tw;   /* [n]   t_window per subhalo (broadcast a scalar on the host side) */
 } ssb_subhalos;
 
+/* n moving spheres of one profile whose centres share ONE time grid (linear interpolation, linear extrapolation outside, as
+ * SSB_TRACK_LINEAR): one packed table instead of n components + n tracks, so that programs are not limited to SSB_MAX_COMP /
+ * SSB_MAX_TRACK moving bodies, and kernels whose particles share the stage times (ssb_shared_step_orbits_f64) interpolate every
+ * centre once per stage and CTA. */
 typedef struct {
-    int32_t n_comp, n_track, n_sh, _pad;
+    int32_t n;          /* perturbers */
+    int32_t n_knots;    /* knots of the shared time grid (>= 2) */
+    int32_t profile;    /* ssb_profile of every perturber */
+    int32_t _pad;
+    const double* t;    /* [n_knots] increasing (device) */
+    const double* y;    /* [n_knots, n, 3] centres */
+    const double* GM;   /* [n] G m */
+    const double* rs;   /* [n] scale radii */
+} ssb_perturbers;
+
+typedef struct {
+    int32_t n_comp, n_track, n_sh, n_pset;
     ssb_component comp[SSB_MAX_COMP];
     ssb_track track[SSB_MAX_TRACK];
     ssb_subhalos sh[SSB_MAX_SUBHALO_SETS];
+    ssb_perturbers pset[SSB_MAX_PSETS];
 } ssb_potential;
 
 /* ---- solver control: diffrax.PIDController(rtol, atol, dtmin, dtmax, force_dtmin=True) + max_steps (main.py:144-162) */

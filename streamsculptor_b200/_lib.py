@@ -13,9 +13,9 @@ _OUT = os.path.join(_HERE, "_lib", "libssb200.so")
 _SOURCES = ["ssb_kernels.cu", "ssb_response.cu", "ssb_response2.cu", "ssb_shared.cu", "ssb_variational.cu", "ssb_host.cu"]
 _HEADERS = ["ssb_common.cuh", "ssb_potential.cuh", "ssb_rk.cuh", "ssb_fastmath.cuh", "ssb_tableau.h", "ssb_logtab.h", "../../include/ssb200.h"]
 
-MAX_COMP, MAX_TRACK, MAX_SH = 12, 4, 2
+MAX_COMP, MAX_TRACK, MAX_SH, MAX_PSET = 12, 4, 2, 1
 
-NFW, HERNQUIST, MIYAMOTO, PLUMMER, ISOCHRONE, TRIAXNFW, UNIFORM_ACC, SUBHALOS = range(8)
+NFW, HERNQUIST, MIYAMOTO, PLUMMER, ISOCHRONE, TRIAXNFW, UNIFORM_ACC, SUBHALOS, PERTURBERS = range(9)
 TRACK_LINEAR, TRACK_CUBIC = 0, 1
 PROFILE_PLUMMER, PROFILE_HERNQUIST, PROFILE_NFW = 0, 1, 2
 
@@ -35,9 +35,13 @@ class Subhalos(C.Structure):
                 ("v", _dp), ("t0", _dp), ("tw", _dp)]
 
 
+class Perturbers(C.Structure):
+    _fields_ = [("n", C.c_int32), ("n_knots", C.c_int32), ("profile", C.c_int32), ("_pad", C.c_int32), ("t", _dp), ("y", _dp), ("GM", _dp), ("rs", _dp)]
+
+
 class Potential(C.Structure):
-    _fields_ = [("n_comp", C.c_int32), ("n_track", C.c_int32), ("n_sh", C.c_int32), ("_pad", C.c_int32),
-                ("comp", Component * MAX_COMP), ("track", Track * MAX_TRACK), ("sh", Subhalos * MAX_SH)]
+    _fields_ = [("n_comp", C.c_int32), ("n_track", C.c_int32), ("n_sh", C.c_int32), ("n_pset", C.c_int32),
+                ("comp", Component * MAX_COMP), ("track", Track * MAX_TRACK), ("sh", Subhalos * MAX_SH), ("pset", Perturbers * MAX_PSET)]
 
 
 class Ctrl(C.Structure):
@@ -133,7 +137,7 @@ def lib():
         for name, (args, res) in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes, fn.restype = args, res
-        if L.ssb_abi_version() != 1:
+        if L.ssb_abi_version() != 2:
             raise SSBError("libssb200 ABI mismatch")
         _LIB = L
     return _LIB

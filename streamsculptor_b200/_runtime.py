@@ -135,25 +135,83 @@ class SubhaloArrays:
                              v=d["v"].data_ptr(), t0=d["t0"].data_ptr(), tw=d["tw"].data_ptr())
 
 
+class PerturberArrays:
+    """n moving spheres of one profile on a shared time grid (ssb_perturbers): GM[n], rs[n], t[nk], centres y[nk, n, 3]."""
+
+    def __init__(self, profile, GM, rs, t, y):
+        self.profile = int(profile)
+        self.host = dict(GM=np.ascontiguousarray(np.asarray(GM, dtype=np.float64).reshape(-1)), rs=None, t=np.ascontiguousarray(np.asarray(t, dtype=np.float64).reshape(-1)), y=None)
+        self.n, self.n_knots = len(self.host["GM"]), len(self.host["t"])
+        self.host["rs"] = np.ascontiguousarray(np.broadcast_to(np.asarray(rs, dtype=np.float64), (self.n,)).copy())
+        self.host["y"] = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(self.n_knots, self.n, 3))
+        if self.n_knots < 2:
+            raise ValueError("a perturber set needs at least 2 knots")
+        self._dev = None
+
+    def struct(self):
+        if self._dev is None:
+            self._dev = {k: to_dev(v) for k, v in self.host.items()}
+        d = self._dev
+        return _lib.Perturbers(n=self.n, n_knots=self.n_knots, profile=self.profile, t=d["t"].data_ptr(), y=d["y"].data_ptr(), GM=d["GM"].data_ptr(),
+                               rs=d["rs"].data_ptr())
+
+
+_PROFILE_OF_COMP = {}          # filled below: component type -> subhalo / perturber profile id
+
+
 class Program:
-    """Flat potential program under construction."""
+    """Flat potential program under construction.  Component / track limits are enforced when the struct is built, after moving
+    spheres that share a time grid have been packed into a perturber set (pack_perturbers) if the program would not fit otherwise."""
 
     def __init__(self):
-        self.comps, self.tracks, self.shs = [], [], []
+        self.comps, self.tracks, self.shs, self.psets = [], [], [], []
         self.growth = 0          # > 0 while the components of a GrowingPotential are being added: index + 1 of its growth-factor track
 
     def add_track(self, track):
         for i, t in enumerate(self.tracks):
             if t is track:
                 return i
-        if len(self.tracks) >= _lib.MAX_TRACK:
-            raise NotImplementedError(f"more than {_lib.MAX_TRACK} tabulated tracks in one potential")
         self.tracks.append(track)
         return len(self.tracks) - 1
 
+    def add_perturbers(self, arrays):
+        if len(self.psets) >= _lib.MAX_PSET:
+            raise NotImplementedError(f"more than {_lib.MAX_PSET} perturber set(s) in one potential")
+        self.psets.append(arrays)
+        self.add(_lib.PERTURBERS, [], sh=len(self.psets) - 1)
+
+    def pack_perturbers(self):
+        """Move the largest group of translating spherical components (same type, linear tracks on one time grid, no growth factor) into
+        a perturber set: what a Potential_Combine of many TimeDepTranslatingPotential objects (the reference's way to write N moving
+        perturbers, potential.py:448-462) lowers to when it exceeds the component / track limits."""
+        if len(self.psets) >= _lib.MAX_PSET:
+            return False
+        groups = {}
+        for i, (typ, params, track, sh, growth) in enumerate(self.comps):
+            if typ not in _PROFILE_OF_COMP or track < 0 or growth or self.tracks[track].kind != _lib.TRACK_LINEAR:
+                continue
+            if typ == _lib.HERNQUIST and params[2] != 0.0:
+                continue
+            t = self.tracks[track].t_host
+            groups.setdefault((typ, len(t), float(t[0]), float(t[-1])), []).append(i)
+        groups = {k: [i for i in v if np.array_equal(self.tracks[self.comps[i][2]].t_host, self.tracks[self.comps[v[0]][2]].t_host)] for k, v in groups.items()}
+        if not groups:
+            return False
+        key, members = max(groups.items(), key=lambda kv: len(kv[1]))
+        if len(members) < 2:
+            return False
+        tr = [self.tracks[self.comps[i][2]] for i in members]
+        arrays = PerturberArrays(_PROFILE_OF_COMP[key[0]], [self.comps[i][1][0] for i in members], [self.comps[i][1][1] for i in members], tr[0].t_host,
+                                 np.stack([t.y_host for t in tr], axis=1))
+        keep = [c for i, c in enumerate(self.comps) if i not in set(members)]
+        used = sorted({c[2] for c in keep if c[2] >= 0} | {c[4] - 1 for c in keep if c[4] > 0})
+        remap = {old: new for new, old in enumerate(used)}
+        self.tracks = [self.tracks[o] for o in used]
+        self.comps = [(typ, params, remap.get(track, -1), sh, (remap[growth - 1] + 1) if growth > 0 else 0) for typ, params, track, sh, growth in keep]
+        self.add_perturbers(arrays)
+        return True
+
     def add(self, typ, params, track=-1, sh=-1):
-        if len(self.comps) >= _lib.MAX_COMP:
-            raise NotImplementedError(f"more than {_lib.MAX_COMP} components in one potential")
         if self.growth and int(typ) in (_lib.UNIFORM_ACC, _lib.SUBHALOS):
             raise NotImplementedError("GrowingPotential around a force-only (UniformAcceleration) or subhalo-ensemble component is not supported")
         self.comps.append((int(typ), [float(p) for p in params], int(track), int(sh), int(self.growth)))
@@ -165,8 +223,16 @@ class Program:
         self.add(_lib.SUBHALOS, [], track=track, sh=len(self.shs) - 1)
 
     def struct(self):
+        if len(self.comps) > _lib.MAX_COMP or len(self.tracks) > _lib.MAX_TRACK:
+            self.pack_perturbers()
+        if len(self.comps) > _lib.MAX_COMP:
+            raise NotImplementedError(f"more than {_lib.MAX_COMP} components in one potential (after packing moving spheres into a perturber set)")
+        if len(self.tracks) > _lib.MAX_TRACK:
+            raise NotImplementedError(f"more than {_lib.MAX_TRACK} tabulated tracks in one potential (after packing moving spheres into a perturber set)")
         P = _lib.Potential()
-        P.n_comp, P.n_track, P.n_sh = len(self.comps), len(self.tracks), len(self.shs)
+        P.n_comp, P.n_track, P.n_sh, P.n_pset = len(self.comps), len(self.tracks), len(self.shs), len(self.psets)
+        for i, s in enumerate(self.psets):
+            P.pset[i] = s.struct()
         for i, (typ, params, track, sh, growth) in enumerate(self.comps):
             P.comp[i].type, P.comp[i].track, P.comp[i].sh, P.comp[i].growth = typ, track, sh, growth
             for k, v in enumerate(params):
@@ -176,6 +242,9 @@ class Program:
         for i, s in enumerate(self.shs):
             P.sh[i] = s.struct()
         return P
+
+
+_PROFILE_OF_COMP.update({_lib.PLUMMER: _lib.PROFILE_PLUMMER, _lib.HERNQUIST: _lib.PROFILE_HERNQUIST, _lib.NFW: _lib.PROFILE_NFW})
 
 
 def lower(pot):

@@ -89,6 +89,16 @@ int upload_potential(const ssb_potential* h, ssb_potential* d, Pool& pool) {
     }
     for (int i = 0; i < h->n_sh; ++i)
         if (int e = upload_subhalos(&h->sh[i], &d->sh[i], pool)) return e;
+    if (h->n_pset < 0 || h->n_pset > SSB_MAX_PSETS) return ssb_set_error(SSB_ERR_ARG, "potential: perturber-set count out of range");
+    for (int i = 0; i < h->n_pset; ++i) {
+        const ssb_perturbers& s = h->pset[i];
+        const size_t n = (size_t)(s.n > 0 ? s.n : 0), nk = (size_t)(s.n_knots > 0 ? s.n_knots : 0);
+        if (n && (!s.t || !s.y || !s.GM || !s.rs)) return ssb_set_error(SSB_ERR_ARG, "perturber set: NULL host array");
+        if (int e = pool.up(s.t, 8 * nk, (const void**)&d->pset[i].t)) return e;
+        if (int e = pool.up(s.y, 24 * nk * n, (const void**)&d->pset[i].y)) return e;
+        if (int e = pool.up(s.GM, 8 * n, (const void**)&d->pset[i].GM)) return e;
+        if (int e = pool.up(s.rs, 8 * n, (const void**)&d->pset[i].rs)) return e;
+    }
     return 0;
 }
 

@@ -971,11 +971,18 @@ int ssb_cuda_check(cudaError_t e, const char* what) {
 int ssb_validate_potential(const ssb_potential* p) {
     if (!p) return ssb_set_error(SSB_ERR_ARG, "potential is NULL");
     if (p->n_comp < 0 || p->n_comp > SSB_MAX_COMP || p->n_track < 0 || p->n_track > SSB_MAX_TRACK || p->n_sh < 0 ||
-        p->n_sh > SSB_MAX_SUBHALO_SETS)
-        return ssb_set_error(SSB_ERR_ARG, "potential: component/track/subhalo-set count out of range");
+        p->n_sh > SSB_MAX_SUBHALO_SETS || p->n_pset < 0 || p->n_pset > SSB_MAX_PSETS)
+        return ssb_set_error(SSB_ERR_ARG, "potential: component/track/subhalo-set/perturber-set count out of range");
+    for (int i = 0; i < p->n_pset; ++i) {
+        const ssb_perturbers& s = p->pset[i];
+        if (s.n < 0 || s.n_knots < 2 || (s.n > 0 && (!s.t || !s.y || !s.GM || !s.rs))) return ssb_set_error(SSB_ERR_ARG, "perturber set: NULL array or < 2 knots");
+        if (s.profile < SSB_PROFILE_PLUMMER || s.profile > SSB_PROFILE_NFW) return ssb_set_error(SSB_ERR_UNSUPPORTED, "perturber set: unknown profile");
+    }
     for (int i = 0; i < p->n_comp; ++i) {
         const ssb_component& c = p->comp[i];
-        if (c.type < SSB_NFW || c.type > SSB_SUBHALOS) return ssb_set_error(SSB_ERR_UNSUPPORTED, "potential: unknown component type");
+        if (c.type < SSB_NFW || c.type > SSB_PERTURBERS) return ssb_set_error(SSB_ERR_UNSUPPORTED, "potential: unknown component type");
+        if (c.type == SSB_PERTURBERS && (c.sh < 0 || c.sh >= p->n_pset || c.track >= 0 || c.growth != 0))
+            return ssb_set_error(SSB_ERR_ARG, "perturber-set component: missing set, or combined with a translation / growth factor");
         if (c.track >= p->n_track) return ssb_set_error(SSB_ERR_ARG, "potential: component references a missing track");
         if (c.growth < 0 || c.growth > p->n_track) return ssb_set_error(SSB_ERR_ARG, "potential: component references a missing growth track");
         if (c.growth > 0 && (c.type == SSB_UNIFORM_ACC || c.type == SSB_SUBHALOS)) return ssb_set_error(SSB_ERR_UNSUPPORTED, "growth factor on a force-only / subhalo component");

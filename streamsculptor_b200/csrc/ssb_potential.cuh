@@ -228,6 +228,49 @@ __device__ __forceinline__ void add_subhalos(const ssb_subhalos& S, const double
     }
 }
 
+// a set of moving spheres on one shared time grid (ssb_perturbers).  `pc` (optional): the n centres ALREADY interpolated at this t
+// ([n][3]; kernels whose particles share the stage times prepare them once per stage and CTA).
+#define SSB_PSET_FROZEN_MAX 104
+__device__ __forceinline__ void pset_segment(const ssb_perturbers& S, double t, int& i, double& w) {
+    const double* __restrict__ a = S.t;
+    const int n = S.n_knots;
+    const double a0 = __ldg(a), a1 = __ldg(a + n - 1);
+    int g = (int)((t - a0) * ((double)(n - 1) / (a1 - a0)));
+    g = min(max(g, 0), n - 2);
+    double ta = __ldg(a + g), tb = __ldg(a + g + 1);
+    int walk = 0;                                       // searchsorted(t, v, 'left') - 1 clipped to [0, n-2], as the linear tracks
+    while (g > 0 && ta >= t && walk < 4) { --g; tb = ta; ta = __ldg(a + g); ++walk; }
+    while (g < n - 2 && tb < t && walk < 4) { ++g; ta = tb; tb = __ldg(a + g + 1); ++walk; }
+    if (walk >= 4) { g = min(max(lower_bound_d(a, n, t) - 1, 0), n - 2); ta = __ldg(a + g); tb = __ldg(a + g + 1); }
+    i = g;
+    w = (t - ta) * frcp(tb - ta);
+}
+__device__ __forceinline__ void pset_centres(const ssb_perturbers& S, double t, int j0, int j1, double* out /*[(j1-j0)][3]*/) {
+    int i; double w;
+    pset_segment(S, t, i, w);
+    const double* __restrict__ y0 = S.y + (size_t)i * S.n * 3;
+    const double* __restrict__ y1 = y0 + (size_t)S.n * 3;
+    for (int j = j0; j < j1; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) out[3 * (j - j0) + k] = (1.0 - w) * __ldg(y0 + 3 * j + k) + w * __ldg(y1 + 3 * j + k);
+}
+template <int MODE>
+__device__ __forceinline__ void add_perturbers(const ssb_perturbers& S, const double x[3], double t, double& P, double g[3], Sym3& H, const double* pc) {
+    int i = 0; double w = 0.0;
+    const double* __restrict__ y0 = nullptr; const double* __restrict__ y1 = nullptr;
+    if (!pc) { pset_segment(S, t, i, w); y0 = S.y + (size_t)i * S.n * 3; y1 = y0 + (size_t)S.n * 3; }
+    const double w1 = 1.0 - w;
+    for (int j = 0; j < S.n; ++j) {
+        double rel[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) rel[k] = x[k] - (pc ? pc[3 * j + k] : (w1 * __ldg(y0 + 3 * j + k) + w * __ldg(y1 + 3 * j + k)));
+        const double r2 = fma(rel[0], rel[0], fma(rel[1], rel[1], rel[2] * rel[2]));
+        double phi = 0, q = 0, ww = 0;
+        profile_terms<MODE>(S.profile, __ldg(S.GM + j), __ldg(S.rs + j), r2, phi, q, ww);
+        add_spherical<MODE>(rel, phi, q, ww, P, g, H);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // total field: sum over the program (Potential_Combine.gradient_func, potential.py:1291-1296)
 // ---------------------------------------------------------------------------------------------
@@ -235,7 +278,7 @@ __device__ __forceinline__ void add_subhalos(const ssb_subhalos& S, const double
 // evaluation points share one time (the shared-step kernels), so that the segment search and interpolation run once per stage, not per tracer.
 template <int MODE>
 __device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x[3], double t, double& P, double g[3], Sym3& H, int first = 0,
-                                         const double* frozen = nullptr) {
+                                         const double* frozen = nullptr, const double* frozen_pc = nullptr) {
     if (MODE & WANT_PHI) P = 0.0;
     if (MODE & WANT_GRAD) { g[0] = g[1] = g[2] = 0.0; }
     if (MODE & WANT_HESS) { H.xx = H.yy = H.zz = H.xy = H.xz = H.yz = 0.0; }
@@ -243,6 +286,10 @@ __device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x
     for (int ic = first; ic < nc; ++ic) {
         const ssb_component& c = Pt.comp[ic];
         const int type = c.type;
+        if (type == SSB_PERTURBERS) {
+            add_perturbers<MODE>(Pt.pset[c.sh], x, t, P, g, H, frozen_pc);
+            continue;
+        }
         if (type == SSB_UNIFORM_ACC) {                              // potential.py:497-499
             if (MODE & WANT_GRAD) {
                 double cv[3], dv[3];
@@ -430,6 +477,17 @@ __device__ inline void pot_third(const ssb_potential& Pt, const double x[3], dou
     for (int ic = 0; ic < Pt.n_comp; ++ic) {
         const ssb_component& c = Pt.comp[ic];
         if (c.type == SSB_UNIFORM_ACC) continue;
+        if (c.type == SSB_PERTURBERS) {
+            const ssb_perturbers& S = Pt.pset[c.sh];
+            for (int j = 0; j < S.n; ++j) {
+                double ctr[3], rel[3], w, u3;
+                pset_centres(S, t, j, j + 1, ctr);
+                for (int k = 0; k < 3; ++k) rel[k] = x[k] - ctr[k];
+                profile_wu(S.profile, S.GM[j], S.rs[j], rel[0] * rel[0] + rel[1] * rel[1] + rel[2] * rel[2], w, u3);
+                add_spherical_third(rel, w, u3, 1, 1, 1, T);
+            }
+            continue;
+        }
         double xs[3] = {x[0], x[1], x[2]};
         if (c.track >= 0) {
             double ctr[3];

@@ -1106,7 +1106,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
             double esq = (tid == 0) ? s_besq[q] : 0.0;          // same summation order as response_kernel, whatever the slot
             int bad_local = 0;
             sweep_items<SOLVER, PROFILE>(&sb[q], sPhiE[q], a.sorted, n_sh, n_items, slot[q].n_ret, n_act, cur, nxt, slot[q].tnext - slot[q].tprev, c, esq,
-                                         bad_local, a.retire ? (int)(slot[q].part & 3) : 0);
+                                         bad_local, slot[q].retire_on ? (int)(slot[q].part & 3) : 0);
             if (bad_local) s_bad[q] = 1;
             if (slot[q].n_ret > slot[q].n_dead && wid == (nw > 1 ? 1 : 0) && lane < 6) {
                 // retired items: sum over them of (E y)_k^2 = (E C E^T)_kk, scale atol (see the header); always by the same lanes, whatever the

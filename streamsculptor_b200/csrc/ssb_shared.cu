@@ -116,27 +116,30 @@ __global__ void shared_init_ctl2(int64_t N, SharedCtl* ctl, CtrlDev c) {
 // Force of the step-attempt kernel.  Every tracer is at the SAME time in every stage, so the time-dependent part of the program
 // (track centres of translating components, frame accelerations) is evaluated once per stage and CTA into `frozen` and the
 // tracers only subtract a centre; the static galaxy in front of the program (SIG != 0) is the fused inline signature of K1.
-__device__ __noinline__ double3 shared_accel_frozen(const ssb_potential* P, int first, double x, double y, double z, double t, const double* frozen) {
+__device__ __noinline__ double3 shared_accel_frozen(const ssb_potential* P, int first, double x, double y, double z, double t, const double* frozen,
+                                                    const double* frozen_pc) {
     const double X[3] = {x, y, z};
     double phi, g[3];
     Sym3 H;
-    pot_eval<WANT_GRAD>(*P, X, t, phi, g, H, first, frozen);
+    pot_eval<WANT_GRAD>(*P, X, t, phi, g, H, first, frozen, frozen_pc);
     return make_double3(-g[0], -g[1], -g[2]);
 }
 template <int SIG>
 struct SharedStageForce {
     const ssb_potential* P; const ssb_potential* Pc; double dir; const double* frozen; int stage; bool extra;
+    const double* frozen_pc;      // centres of the perturber set at every stage time [S][3 SSB_PSET_FROZEN_MAX], or nullptr (no set / too large)
     __device__ __forceinline__ void operator()(const double X[3], double tau, double A[3]) {
         const double* fz = frozen + stage * (6 * SSB_MAX_TRACK);
+        const double* fp = frozen_pc ? frozen_pc + stage * (3 * SSB_PSET_FROZEN_MAX) : nullptr;
         if (SIG == SIG_GENERIC) {
-            const double3 a = shared_accel_frozen(P, 0, X[0], X[1], X[2], tau * dir, fz);
+            const double3 a = shared_accel_frozen(P, 0, X[0], X[1], X[2], tau * dir, fz, fp);
             A[0] = a.x; A[1] = a.y; A[2] = a.z;
         } else {
             double g[3];
             fused_grad<SIG>(*Pc, X, g);
             A[0] = -g[0]; A[1] = -g[1]; A[2] = -g[2];
             if (extra) {
-                const double3 a = shared_accel_frozen(P, SigInfo<SIG>::NF, X[0], X[1], X[2], tau * dir, fz);
+                const double3 a = shared_accel_frozen(P, SigInfo<SIG>::NF, X[0], X[1], X[2], tau * dir, fz, fp);
                 A[0] += a.x; A[1] += a.y; A[2] += a.z;
             }
         }
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(128) shared_attempt(const __grid_constant__ ss
     constexpr int S = T::S;
     __shared__ ssb_potential sP;
     __shared__ double s_frozen[S][6 * SSB_MAX_TRACK];
+    __shared__ double s_pc[S][3 * SSB_PSET_FROZEN_MAX];           // perturber-set centres at the stage times (BASELINE config 5: 100 moving perturbers)
     stage_potential(&sP, &Pin);
     logtab_init();
     if (ctl->done) return;
@@ -165,13 +169,21 @@ __global__ void __launch_bounds__(128) shared_attempt(const __grid_constant__ ss
 #pragma unroll
         for (int m = 0; m < 3; ++m) { s_frozen[st][6 * k + m] = cv[m]; s_frozen[st][6 * k + 3 + m] = dv[m]; }
     }
+    const bool pc_frozen = sP.n_pset == 1 && sP.pset[0].n <= SSB_PSET_FROZEN_MAX;
+    if (pc_frozen) {              // every centre of the set at every stage time, once per CTA: (stage, perturber) pairs dealt out over the threads
+        const int np = sP.pset[0].n;
+        for (int q = threadIdx.x; q < S * np; q += blockDim.x) {
+            const int st = q / np, j = q - st * np;
+            pset_centres(sP.pset[0], (tprev + T::c(st) * dt) * dir, j, j + 1, &s_pc[st][3 * j]);
+        }
+    }
     __syncthreads();
     const double* cur = ctl->which ? buf1 : buf0;
     double* nxt = ctl->which ? buf0 : buf1;
     double esq = 0.0;
     int bad = 0;
     if (i < N) {
-        SharedStageForce<SIG> f{&sP, &Pin, dir, &s_frozen[0][0], 1, Pin.n_comp > SigInfo<SIG>::NF};
+        SharedStageForce<SIG> f{&sP, &Pin, dir, &s_frozen[0][0], 1, Pin.n_comp > SigInfo<SIG>::NF, pc_frozen ? &s_pc[0][0] : nullptr};
         double x[3], p[3], F[S][3], x1[3], p1[3], ex[3], ep[3];
         for (int k = 0; k < 3; ++k) { x[k] = cur[3 * i + k]; p[k] = cur[3 * N + 3 * i + k]; F[0][k] = cur[6 * N + 3 * i + k]; }
         rk_stages<SOLVER>(f, x, p, tprev, dt, F);

@@ -13,6 +13,7 @@
 // handler's fixed operands - per track: t[n], y[n,3], s[n,3] (knot slopes; ignored for linear tracks); per subhalo set: m[n], r_s[n],
 // x0[n,3], v[n,3], t0[n], t_window[n].  The handler assembles the ssb_potential that points at them.  Time-dependent potentials
 // (moving perturbers, subhalo ensembles) therefore work with traced arrays, which the previous attribute-only design could not carry.
+// Packed perturber sets (ssb_perturbers) are not carried yet: express them as translating components (<= SSB_MAX_TRACK) under jax.
 #if __has_include("xla/ffi/api/ffi.h")
 #include <cstring>
 

@@ -36,6 +36,8 @@ def flatten_program(pot):
     from . import _runtime as rt
     prog = rt.Program()
     pot._lower(prog, -1)
+    if prog.psets or len(prog.comps) > _lib.MAX_COMP or len(prog.tracks) > _lib.MAX_TRACK:
+        raise NotImplementedError("the FFI shim carries components, tracks and subhalo sets within the program limits; packed perturber sets are not carried yet")
     P = FfiProgram()
     P.n_comp, P.n_track, P.n_sh = len(prog.comps), len(prog.tracks), len(prog.shs)
     for i, (typ, params, track, sh, growth) in enumerate(prog.comps):

@@ -147,6 +147,26 @@ class TimeDepTranslatingPotential(Potential):         # potential.py:448-462
         self.pot._lower(prog, prog.add_track(self._track))
 
 
+class PerturberSetPotential(Potential):
+    """N moving spheres of one profile (func = PlummerPotential / HernquistPotential / NFWPotential) whose centres are tabulated on ONE time
+    grid: m[N], r_s[N] (or scalars), t[nk], centers[nk, N, 3]; linear interpolation in time (linear extrapolation outside, like the
+    reference's RegularGridInterpolator tables, potential.py:581-600).  The same field as Potential_Combine of N
+    TimeDepTranslatingPotential(func(m_i, r_s_i), LinearTrack(t, centers[:, i])) objects (potential.py:448-462) - which is also lowered to
+    this form automatically when it would exceed the component / track limits of a program - without the limit of 12 components / 4 tracks:
+    BASELINE config 5 (tracers in the field of 100 moving perturbers)."""
+
+    def __init__(self, func, m, r_s, t, centers, units=None):
+        super().__init__(units, {'func': func, 'm': m, 'r_s': r_s, 't': t, 'centers': centers})
+        m = np.atleast_1d(np.asarray(m, dtype=np.float64))
+        self._arrays = rt.PerturberArrays(_profile_of(func), self._G * m, np.broadcast_to(np.asarray(r_s, dtype=np.float64), m.shape), t, centers)
+
+    def _lower(self, prog, track):
+        _no_nested(track)
+        if prog.growth:
+            raise NotImplementedError("GrowingPotential around a perturber set is not supported")
+        prog.add_perturbers(self._arrays)
+
+
 class UniformAcceleration(Potential):                 # potential.py:480-502
     """Spatially uniform acceleration: gradient = d velocity_func / dt (slope of the tabulated velocity track)."""
 

@@ -343,3 +343,36 @@ def test_jax_plugin_flattens_programs_without_jax_or_cuda():
     assert np.allclose(s[0], (y[1] - y[0]) / (t[1] - t[0])) and np.allclose(s[10], 0.5 * ((y[10] - y[9]) / (t[10] - t[9]) + (y[11] - y[10]) / (t[11] - t[10])))
     with pytest.raises(ImportError):
         jp.register("libssb200_ffi.so")
+
+
+def test_many_moving_perturbers_pack_into_a_perturber_set():
+    """BASELINE config 5 needs 100 moving perturbers; a program holds 12 components / 4 tracks.  A Potential_Combine of many
+    TimeDepTranslatingPotential objects on one time grid (the reference's way to write them, potential.py:448-462) is lowered to ONE
+    perturber-set component; other tracks and growth factors keep working and are re-indexed."""
+    import numpy as np
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import _lib, _runtime as rt
+    P = ssc.potential
+    t = np.linspace(-3000.0, 0.0, 64)
+    rng = np.random.default_rng(0)
+    n = 30
+    cen = rng.normal(size=(64, n, 3)) * 20.0
+    ms, rs = 10 ** rng.uniform(8, 10, n), rng.uniform(0.5, 3.0, n)
+    other = ssc.LinearTrack(np.linspace(-3000.0, 0.0, 17), rng.normal(size=(17, 3)))
+    comps = [P.HernquistPotential(m=5e9, r_s=1.0, units=ssc.usys), P.MiyamotoNagaiDisk(m=6.8e10, a=3.0, b=0.28, units=ssc.usys),
+             P.GrowingPotential(P.NFWPotential(m=5.4e11, r_s=15.62, units=ssc.usys), (np.array([-3000.0, 0.0]), np.array([0.5, 1.0])), units=ssc.usys),
+             P.TimeDepTranslatingPotential(P.HernquistPotential(m=1e11, r_s=8.0, units=ssc.usys), other, units=ssc.usys)]
+    comps += [P.TimeDepTranslatingPotential(P.PlummerPotential(m=ms[i], r_s=rs[i], units=ssc.usys), ssc.LinearTrack(t, cen[:, i]), units=ssc.usys) for i in range(n)]
+    prog = rt.Program()
+    P.Potential_Combine(comps, units=ssc.usys)._lower(prog, -1)
+    assert len(prog.comps) == 4 + n and len(prog.tracks) == 2 + n
+    assert prog.pack_perturbers()
+    assert [c[0] for c in prog.comps] == [_lib.HERNQUIST, _lib.MIYAMOTO, _lib.NFW, _lib.HERNQUIST, _lib.PERTURBERS] and len(prog.tracks) == 2 and len(prog.psets) == 1
+    assert prog.comps[2][4] == 1 and prog.comps[3][2] == 1          # growth track first (index 0 -> growth = 1), the lone translating Hernquist on track 1
+    ps = prog.psets[0]
+    assert ps.n == n and ps.n_knots == 64 and ps.profile == _lib.PROFILE_PLUMMER and ps.host["y"].shape == (64, n, 3)
+    G = comps[0]._G
+    assert np.allclose(ps.host["GM"], G * ms) and np.allclose(ps.host["rs"], rs) and np.array_equal(ps.host["y"][:, 7], cen[:, 7])
+    # the explicit class gives the same arrays
+    direct = P.PerturberSetPotential(P.PlummerPotential, ms, rs, t, cen, units=ssc.usys)
+    assert np.allclose(direct._arrays.host["GM"], ps.host["GM"]) and np.array_equal(direct._arrays.host["y"], ps.host["y"])
