@@ -246,6 +246,12 @@ size_t ssb_response_saveat_scratch_bytes(int32_t n_sh);
 int ssb_second_order_response_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0, const double* D0,
                                   const double* E0, const double* t0, double t1, ssb_ctrl ctrl, double* wout, double* Dout, double* Eout,
                                   int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream);
+/* The same solve with PER-PARTICLE end times t1[N] (t1[i] < t0[i] integrates backwards): N copies of the progenitor, each integrated from
+ * the observed position back to one stripping time, give the backward-integrated progenitor field at every stripping time that
+ * GenerateMassRadiusPerturbation_CustomBase_SecondOrder maps into its perturbation ICs (perturbative.py:519-552). */
+int ssb_second_order_response_ends_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0, const double* D0,
+                                       const double* E0, const double* t0, const double* t1, ssb_ctrl ctrl, double* wout, double* Dout,
+                                       double* Eout, int32_t* status, int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream);
 size_t ssb_second_order_scratch_bytes(int32_t n_sh);
 /* RHS of the second-order field at one state y = [w(6), D(n_sh,12), E(n_sh,6)] (fields.py:289-320), for unit tests */
 int ssb_second_order_term_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, double t, const double* y, double* dy, void* stream);

@@ -107,6 +107,7 @@ _SIGNATURES = {
     "ssb_linear_response_saveat_f64": ([_PP, _SP, _dp, _dp, _dp, _dbl, _dp, _i32, Ctrl, _dp, _dp, _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
     "ssb_response_saveat_scratch_bytes": ([_i32], C.c_size_t),
     "ssb_second_order_response_f64": ([_PP, _SP, _i64, _dp, _dp, _dp, _dp, _dbl, Ctrl, _dp, _dp, _dp, _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
+    "ssb_second_order_response_ends_f64": ([_PP, _SP, _i64, _dp, _dp, _dp, _dp, _dp, Ctrl, _dp, _dp, _dp, _dp, _dp, _dp, C.c_size_t, _dp], C.c_int),
     "ssb_second_order_scratch_bytes": ([_i32], C.c_size_t),
     "ssb_second_order_term_f64": ([_PP, _SP, _dbl, _dp, _dp, _dp], C.c_int),
     "ssb_response_term_f64": ([_PP, _SP, _dbl, _dp, _dp, _dp], C.c_int),

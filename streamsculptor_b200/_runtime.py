@@ -426,8 +426,12 @@ def second_order_response(pot_base, sharrays, w0, D0, E0, t0, t1, ctrl):
     status, nsteps = empty((N,), tt.int32), empty((N, 3), tt.int32)
     nbytes = _lib.lib().ssb_second_order_scratch_bytes(sharrays.n)
     scratch = empty(((nbytes + 7) // 8,))
-    _lib.check(_lib.lib().ssb_second_order_response_f64(C.byref(P), C.byref(S), N, ptr(w0), ptr(D0), ptr(E0), ptr(t0), float(t1), ctrl, ptr(wout),
-                                                        ptr(Dout), ptr(Eout), ptr(status), ptr(nsteps), ptr(scratch), nbytes, stream_ptr()))
+    if is_dev(t1):            # per-particle end times
+        _lib.check(_lib.lib().ssb_second_order_response_ends_f64(C.byref(P), C.byref(S), N, ptr(w0), ptr(D0), ptr(E0), ptr(t0), ptr(t1), ctrl, ptr(wout),
+                                                                 ptr(Dout), ptr(Eout), ptr(status), ptr(nsteps), ptr(scratch), nbytes, stream_ptr()))
+    else:
+        _lib.check(_lib.lib().ssb_second_order_response_f64(C.byref(P), C.byref(S), N, ptr(w0), ptr(D0), ptr(E0), ptr(t0), float(t1), ctrl, ptr(wout),
+                                                            ptr(Dout), ptr(Eout), ptr(status), ptr(nsteps), ptr(scratch), nbytes, stream_ptr()))
     return wout, Dout, Eout, status, nsteps
 
 

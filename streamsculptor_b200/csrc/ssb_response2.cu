@@ -23,6 +23,7 @@ struct R2Args {
     int64_t N;
     const double *w0, *D0, *E0, *t0;
     double t1;
+    const double* t1v;        // optional per-particle end times (ssb_second_order_response_ends_f64); NULL: the common end time t1
     CtrlDev c;
     double *wout, *Dout, *Eout;
     int32_t *status, *nsteps;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(SSB_R2_THREADS, 1) response2_kernel(const __gr
         __syncthreads();
         const long long part = s_part;
         if (part >= a.N) break;
-        const double t0_in = a.t0[part], t1_in = a.t1;
+        const double t0_in = a.t0[part], t1_in = a.t1v ? a.t1v[part] : a.t1;
         const double dir = (t0_in < t1_in) ? 1.0 : -1.0;
         const double T0 = t0_in * dir, T1 = t1_in * dir;
         double* cur = buf0;
@@ -386,9 +387,23 @@ size_t ssb_second_order_scratch_bytes(int32_t n_sh) {
     return 256 + sizeof(double) * 2 * 18 * (size_t)(n_sh > 0 ? n_sh : 1) * SSB_R2_MAX_CTAS;
 }
 
+static int second_order_impl(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0, const double* D0, const double* E0,
+                             const double* t0, double t1, const double* t1v, ssb_ctrl ctrl, double* wout, double* Dout, double* Eout, int32_t* status,
+                             int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream);
 int ssb_second_order_response_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0, const double* D0, const double* E0,
                                   const double* t0, double t1, ssb_ctrl ctrl, double* wout, double* Dout, double* Eout, int32_t* status,
                                   int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream) {
+    return second_order_impl(pot_base, sh, N, w0, D0, E0, t0, t1, nullptr, ctrl, wout, Dout, Eout, status, nsteps, scratch, scratch_bytes, stream);
+}
+int ssb_second_order_response_ends_f64(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0, const double* D0, const double* E0,
+                                       const double* t0, const double* t1, ssb_ctrl ctrl, double* wout, double* Dout, double* Eout, int32_t* status,
+                                       int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream) {
+    if (!t1) return ssb_set_error(SSB_ERR_ARG, "second_order_response_ends: NULL end times");
+    return second_order_impl(pot_base, sh, N, w0, D0, E0, t0, 0.0, t1, ctrl, wout, Dout, Eout, status, nsteps, scratch, scratch_bytes, stream);
+}
+static int second_order_impl(const ssb_potential* pot_base, const ssb_subhalos* sh, int64_t N, const double* w0, const double* D0, const double* E0,
+                             const double* t0, double t1, const double* t1v, ssb_ctrl ctrl, double* wout, double* Dout, double* Eout, int32_t* status,
+                             int32_t* nsteps, void* scratch, size_t scratch_bytes, void* stream) {
     if (int e = ssb_validate_potential(pot_base)) return e;
     if (int e = ssb_validate_ctrl(ctrl)) return e;
     if (!sh || sh->n < 0 || sh->profile < SSB_PROFILE_PLUMMER || sh->profile > SSB_PROFILE_NFW) return ssb_set_error(SSB_ERR_ARG, "second_order_response: bad subhalo set");
@@ -403,7 +418,7 @@ int ssb_second_order_response_f64(const ssb_potential* pot_base, const ssb_subha
     int grid = sms < SSB_R2_MAX_CTAS ? sms : SSB_R2_MAX_CTAS;
     if (N < grid) grid = (int)N;
     R2Args a;
-    a.N = N; a.w0 = w0; a.D0 = D0; a.E0 = E0; a.t0 = t0; a.t1 = t1;
+    a.N = N; a.w0 = w0; a.D0 = D0; a.E0 = E0; a.t0 = t0; a.t1 = t1; a.t1v = t1v;
     a.c.rtol = ctrl.rtol; a.c.atol = ctrl.atol; a.c.dtmin = ctrl.dtmin; a.c.dtmax = ctrl.dtmax; a.c.max_steps = ctrl.max_steps;
     a.wout = wout; a.Dout = Dout; a.Eout = Eout; a.status = status; a.nsteps = nsteps;
     a.counter = (unsigned long long*)scratch;

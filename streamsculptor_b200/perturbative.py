@@ -171,6 +171,62 @@ class GenerateMassRadiusPerturbation_CustomBase(_ResponseGenerator):      # pert
         return np.dstack([np.einsum('ijk,ilk->ilj', J, F[:, :, :6]), np.einsum('ijk,ilk->ilj', J, F[:, :, 6:])])
 
 
+class GenerateMassRadiusPerturbation_CustomBase_SecondOrder(_ResponseGenerator):      # perturbative.py:491-585
+    """Custom-base perturbation generator up to SECOND order in the subhalo mass (+ first-order radius response): state per particle
+    [w(6), D(N_sh,12), E(N_sh,6)], field MassRadiusPerturbation_OTF_SecondOrder (fields.py:260-320).
+
+    Perturbation ICs (perturbative.py:519-552): the progenitor's own first- and second-order response, integrated BACKWARDS from the observed
+    position, evaluated at every stripping time and mapped through the release Jacobian.  The reference obtains all stripping times from ONE
+    backward solve with SaveAt(ts); here every stripping time is its own backward solve ending at ts[i] (N copies of the progenitor in one
+    launch of the second-order kernel, per-particle end times) - the same quantities to within the solver tolerance, without the dense
+    output of a 6 + 18 N_sh dimensional state."""
+
+    def __init__(self, potential_base, potential_perturbation, potential_structural=None, BaseStreamModel=None, units=None, solver=Dopri8(scan_kind='bounded'),
+                 rtol=1e-7, atol=1e-7, dtmin=0.05, dtmax=None, max_steps=1_000, **kwargs):
+        super().__init__(units, {'potential_base': potential_base, 'potential_perturbation': potential_perturbation,
+                                 'potential_structural': potential_structural, 'BaseStreamModel': BaseStreamModel})
+        self._init_common(potential_base, potential_perturbation)
+        self.base_stream = BaseStreamModel
+        ts = np.asarray(BaseStreamModel.ts, dtype=np.float64)
+        n, nsh = len(ts), self.num_pert
+        w_obs = np.asarray(BaseStreamModel.prog_loc_fwd)[-1]
+        self.field_wobs = [w_obs, np.zeros((nsh, 12)), np.zeros((nsh, 6))]                              # perturbative.py:515
+        ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
+        w0 = rt.to_dev(np.broadcast_to(w_obs, (n - 1, 6)).copy())
+        t_start = rt.to_dev(np.full(n - 1, ts[-1]))
+        _, D, E, status, _ = rt.second_order_response(self.potential_base_total, self.subhalo_arrays, w0, None, None, t_start, rt.to_dev(ts[:-1].copy()), ctrl)
+        if bool((status != 0).any()):
+            raise RuntimeError("backward integration of the progenitor's second-order field failed (max_steps reached or non-finite state)")
+        # the last stripping time is the start of the backward solve: its row is the initial (zero) field
+        self.prog_fieldICs_first_order_mass = np.concatenate([D.cpu().numpy(), np.zeros((1, nsh, 12))])   # [N, N_sh, 12], time order of ts
+        self.prog_fieldICs_second_order_mass = np.concatenate([E.cpu().numpy(), np.zeros((1, nsh, 6))])   # [N, N_sh, 6]
+        self.perturbation_ICs = self.compute_perturbation_ICs()
+        self.base_realspace_ICs = self.base_stream.streamICs
+
+    def compute_base_stream(self, cpu=False):         # perturbative.py:530-535
+        return self.base_stream.gen_stream()
+
+    def compute_perturbation_ICs(self):               # perturbative.py:539-552: [N x N_sh x 12, N x N_sh x 6]
+        J = np.asarray(self.base_stream.dRel_dIC)
+        F1, F2 = self.prog_fieldICs_first_order_mass, self.prog_fieldICs_second_order_mass
+        first = np.dstack([np.einsum('ijk,ilk->ilj', J, F1[:, :, :6]), np.einsum('ijk,ilk->ilj', J, F1[:, :, 6:])])
+        return [first, np.einsum('ijk,ilk->ilj', J, F2)]
+
+    def compute_perturbation_OTF(self, cpu=False, solver=Dopri8(scan_kind='bounded'), rtol=1e-8, atol=1e-8, dtmin=0.05, max_steps=10_000, dtmax=None):
+        """[w (N-1,6), D (N-1,N_sh,12), E (N-1,N_sh,6)] (perturbative.py:556-585)."""
+        ts = np.asarray(self.base_stream.ts, dtype=np.float64)
+        n = len(ts) - 1
+        ctrl = rt.make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps)
+        D0, E0 = np.asarray(self.perturbation_ICs[0])[:n], np.asarray(self.perturbation_ICs[1])[:n]
+        wout, Dout, Eout, status, nsteps = rt.second_order_response(self.potential_base_total, self.subhalo_arrays,
+                                                                    rt.to_dev(np.asarray(self.base_realspace_ICs)[:n]), rt.to_dev(D0) if np.any(D0) else None,
+                                                                    rt.to_dev(E0) if np.any(E0) else None, rt.to_dev(ts[:n]), float(ts[-1]), ctrl)
+        self.last_status, self.last_nsteps = status.cpu().numpy(), nsteps.cpu().numpy()
+        if (self.last_status != 0).any():
+            raise RuntimeError("compute_perturbation_OTF: a particle failed (max_steps reached or non-finite state)")
+        return [wout.cpu().numpy(), Dout.cpu().numpy(), Eout.cpu().numpy()]
+
+
 class BaseStreamModelChen25(Potential):               # perturbative.py:588-658
     """Chen+25 base model (perturbative.py:588-658).  `key`: int seed (= jax.random.PRNGKey(seed)) or the two key words.
     Optionally the release can be supplied instead of drawn: stream_ics = (pos_lead, pos_trail, vel_lead, vel_trail) each [N,3]

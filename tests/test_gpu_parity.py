@@ -1092,3 +1092,43 @@ def test_perturber_set_matches_oracle(cuda):
     w_o, M_o, _, _, _ = O.variational(orc, w0[:16], t0[:16], 0.0, order=1, solver=8, rtol=1e-8, atol=1e-8, dtmin=2.0, dtmax=2.0, max_steps=5000)
     assert int((st_v != 0).sum()) == 0 and relerr(w_v.cpu().numpy(), w_o) < 1e-10
     assert np.abs(M_v.cpu().numpy() - M_o).max() <= 1e-9 * np.abs(M_o).max()
+
+
+def test_custom_base_second_order_generator(cuda):
+    """GenerateMassRadiusPerturbation_CustomBase_SecondOrder (perturbative.py:491-585): the progenitor's backward-integrated first- and
+    second-order field at every stripping time (here: one backward solve per stripping time, per-particle end times of the second-order
+    kernel) mapped into the particles' perturbation ICs, then the second-order responses.  Fixed steps: against the oracle's second-order
+    solves started and ended at the same times."""
+    import streamsculptor_b200 as ssc
+    P, pt = ssc.potential, ssc.perturbative
+    nsh, nts = 5, 13
+    sh = subhalo_set(nsh, seed=29, t_lo=-500.0)
+    sh["x0"] = sh["x0"] * 0.3 + np.array([12.0, 3.0, -6.0])
+    sh["M"] = np.ones(nsh)
+    base, orc_base = mw3_product(), mw3_oracle()
+    ts = np.linspace(-600.0, 0.0, nts)
+    prog_w0 = [12.0, 3.0, -6.0, -0.05, 0.15, 0.03]
+    rng = np.random.default_rng(5)
+    pos_rel, vel_rel = rng.normal(size=(nts, 3)) * 0.05, rng.normal(size=(nts, 3)) * 1e-3
+    pert = P.SubhaloLinePotentialCustom_fromFunc(func=P.HernquistPotential, m=sh["m"], r_s=sh["rs"], subhalo_x0=sh["x0"], subhalo_v=sh["v"],
+                                                 subhalo_t0=sh["t0"], t_window=150.0, units=ssc.usys)
+    orc_sh = O.Program().subhalos(O.PR_HERNQUIST, sh["m"], sh["rs"], sh["x0"], sh["v"], sh["t0"], 150.0)
+    fixed = dict(rtol=1e-8, atol=1e-8, dtmin=2.0, dtmax=2.0)
+    model = pt.CustomBaseStreamModel(potential_base=base, prog_w0=prog_w0, ts=ts, pos_rel=pos_rel, vel_rel=vel_rel, solver=ssc.Dopri8(), units=ssc.usys, **fixed)
+    gen = pt.GenerateMassRadiusPerturbation_CustomBase_SecondOrder(potential_base=base, potential_perturbation=pert, BaseStreamModel=model, units=ssc.usys,
+                                                                   solver=ssc.Dopri8(), max_steps=5000, **fixed)
+    assert gen.perturbation_ICs[0].shape == (nts, nsh, 12) and gen.perturbation_ICs[1].shape == (nts, nsh, 6)
+    prog_o, _, _ = orc_base.integrate_orbits(prog_w0, ts[0], ts[-1], ts=ts, solver=8, **fixed)
+    w_obs = prog_o[0, -1]
+    for i in (0, 3, 7, nts - 2):                      # the progenitor's field at a few stripping times: oracle backward solves ending there
+        _, D_o, E_o, st_o, _ = O.second_order_response(orc_base, orc_sh, w_obs, ts[-1], ts[i], solver=8, max_steps=5000, **fixed)
+        assert st_o[0] == 0
+        assert np.abs(gen.prog_fieldICs_first_order_mass[i] - D_o[0]).max() <= 1e-9 * np.abs(D_o).max() + 1e-300
+        assert np.abs(gen.prog_fieldICs_second_order_mass[i] - E_o[0]).max() <= 1e-8 * np.abs(E_o).max() + 1e-300
+    assert not gen.prog_fieldICs_first_order_mass[-1].any()           # observation time: the field starts from zero
+    w, D, E = gen.compute_perturbation_OTF(cpu=False, solver=ssc.Dopri8(), **fixed)
+    ics = np.hstack([prog_o[0][:, :3] + pos_rel, prog_o[0][:, 3:] + vel_rel])
+    w_o, D_o, E_o, _, _ = O.second_order_response(orc_base, orc_sh, ics[:-1], ts[:-1], 0.0, D0=gen.perturbation_ICs[0][:-1], E0=gen.perturbation_ICs[1][:-1],
+                                                  solver=8, **fixed)
+    assert scaled_err(w, w_o, 1e-9).max() < 1.0
+    assert np.abs(D - D_o).max() <= 1e-8 * np.abs(D_o).max() and np.abs(E - E_o).max() <= 1e-7 * np.abs(E_o).max()
