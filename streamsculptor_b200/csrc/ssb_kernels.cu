@@ -1378,8 +1378,9 @@ static int gen_stream_impl(const ssb_potential* pot, const ssb_potential* pot_re
         memcpy(a.kv, kvals, sizeof(a.kv));
         a.w0_packed = w0; a.t0_packed = t0; a.t1_packed = t1; a.t_end = ts_last;
         CK(cudaEventRecord(ax->e0, st));                                   // the inputs are ready in the caller's stream order
-        // the parts with the longest serial prefix are enqueued first; part 0 runs on the caller's stream
-        for (int k = SSB_STREAM_PARTS - 1; k >= 0; --k) {
+        // part 0 (shortest serial prefix, longest orbits) is enqueued first, on the caller's stream: its kernels reach the GPU while the
+        // host is still enqueuing the other parts
+        for (int k = 0; k < SSB_STREAM_PARTS; ++k) {
             const int64_t p0 = b[k], cnt = b[k + 1] - b[k];
             if (cnt <= 0) continue;
             cudaStream_t sk = k == 0 ? st : ax->s[k - 1];
