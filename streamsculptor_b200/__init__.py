@@ -16,6 +16,8 @@ from . import fields  # noqa: F401
 from .fields import integrate_field  # noqa: F401
 from . import perturbative  # noqa: F401
 from . import RestrictedNbody  # noqa: F401
+from . import GenerateImpactParams, generate_derivs  # noqa: F401
+from .GenerateImpactParams import ImpactGenerator  # noqa: F401
 from .RestrictedNbody import RestrictedNbody_generator, integrate_restricted_Nbody, initialize_prog_params  # noqa: F401
 
 __all__ = ["usys", "Potential", "potential", "fields", "perturbative", "integrate_field", "Dopri5", "Dopri8", "LinearTrack", "CubicTrack"]

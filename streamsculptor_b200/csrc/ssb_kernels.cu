@@ -16,6 +16,12 @@
 #include <limits>
 #include <vector>
 
+// tableau coefficients as immediates in this translation unit (the one-thread-per-orbit kernels); measured on B200, constant bank vs
+// immediates: orbit_kernel<8> final state 11.56 vs 11.30 ms, Dopri5 8.41 vs 8.00 ms (immediates win), saving kernel 21.7 vs 22.5 ms,
+// response kernel 31.4 vs 33.7 ms (constant bank wins: ssb_response.cu keeps the default)
+#ifndef SSB_TABLEAU_CONSTBANK
+#define SSB_TABLEAU_CONSTBANK 0
+#endif
 #include "ssb_common.cuh"
 
 using namespace ssb;

@@ -16,7 +16,27 @@
 #include <math.h>
 
 #define SSB_TABLEAU_QUAL static __device__ constexpr
+#include "ssb_tableau.h"                // ssb_tab::  compile-time values: zero tests while unrolling, rolled loops
+// ... and the same numbers once more in the constant bank (ssb_ctab::).  A 64-bit immediate cannot be encoded in DFMA: with the constexpr
+// copy every tableau coefficient of the unrolled stepper was materialised by two UMOVs into a uniform register pair before each use
+// (500 UMOV + ~700 moves beside 2224 FP64 instructions in orbit_kernel<8>); a __constant__ entry with a compile-time index is an operand.
+#undef SSB_TABLEAU_QUAL
+#define SSB_TABLEAU_QUAL static __constant__
+#define SSB_TABLEAU_NS ssb_ctab
+#define SSB_TABLEAU_AGAIN
 #include "ssb_tableau.h"
+#undef SSB_TABLEAU_AGAIN
+#undef SSB_TABLEAU_NS
+#undef SSB_TABLEAU_QUAL
+#define SSB_TABLEAU_QUAL static __device__ constexpr
+#ifndef SSB_TABLEAU_CONSTBANK
+#define SSB_TABLEAU_CONSTBANK 1      // 0: operands from the constexpr copy (immediates materialised by UMOV pairs), for A/B builds
+#endif
+#if SSB_TABLEAU_CONSTBANK
+#define SSB_CTAB ssb_ctab
+#else
+#define SSB_CTAB ssb_tab
+#endif
 #include "ssb_fastmath.cuh"
 
 namespace ssb {
@@ -31,6 +51,13 @@ template <> struct Tab<5> {
     static __device__ __forceinline__ constexpr double e(int i) { return ssb_tab::d5_e[i]; }
     static __device__ __forceinline__ constexpr double ea(int i) { return ssb_tab::d5_ea[i]; }
     static __device__ __forceinline__ constexpr double esum() { return ssb_tab::d5_esum; }
+    // operands from the constant bank (same values)
+    static __device__ __forceinline__ double av(int i, int j) { return SSB_CTAB::d5_a[i][j]; }
+    static __device__ __forceinline__ double aav(int i, int j) { return SSB_CTAB::d5_aa[i][j]; }
+    static __device__ __forceinline__ double rsv(int i) { return SSB_CTAB::d5_rs[i]; }
+    static __device__ __forceinline__ double ev(int i) { return SSB_CTAB::d5_e[i]; }
+    static __device__ __forceinline__ double eav(int i) { return SSB_CTAB::d5_ea[i]; }
+    static __device__ __forceinline__ double esumv() { return SSB_CTAB::d5_esum; }
 };
 template <> struct Tab<8> {
     static constexpr int S = 14, ORDER = 8;
@@ -41,6 +68,12 @@ template <> struct Tab<8> {
     static __device__ __forceinline__ constexpr double e(int i) { return ssb_tab::d8_e[i]; }
     static __device__ __forceinline__ constexpr double ea(int i) { return ssb_tab::d8_ea[i]; }
     static __device__ __forceinline__ constexpr double esum() { return ssb_tab::d8_esum; }
+    static __device__ __forceinline__ double av(int i, int j) { return SSB_CTAB::d8_a[i][j]; }
+    static __device__ __forceinline__ double aav(int i, int j) { return SSB_CTAB::d8_aa[i][j]; }
+    static __device__ __forceinline__ double rsv(int i) { return SSB_CTAB::d8_rs[i]; }
+    static __device__ __forceinline__ double ev(int i) { return SSB_CTAB::d8_e[i]; }
+    static __device__ __forceinline__ double eav(int i) { return SSB_CTAB::d8_ea[i]; }
+    static __device__ __forceinline__ double esumv() { return SSB_CTAB::d8_esum; }
 };
 
 struct CtrlDev { double rtol, atol, dtmin, dtmax; int max_steps; };
@@ -65,8 +98,8 @@ __device__ __forceinline__ void rk_stages(Force& force, const double (&x)[D], co
             double acc = 0.0;
 #pragma unroll
             for (int l = 0; l < i; ++l)
-                if (T::aa(i, l) != 0.0) acc = fma(T::aa(i, l), F[l][k], acc);
-            X[k] = fma(h2, acc, fma(T::rs(i), hp[k], x[k]));            // x + c_i h p + h^2 sum_l (A.A)_il F_l
+                if (T::aa(i, l) != 0.0) acc = fma(T::aav(i, l), F[l][k], acc);
+            X[k] = fma(h2, acc, fma(T::rsv(i), hp[k], x[k]));            // x + c_i h p + h^2 sum_l (A.A)_il F_l
         }
         force(X, t + T::c(i) * h, F[i]);
     }
@@ -84,8 +117,8 @@ __device__ __forceinline__ void rk_candidate(const double (&x)[D], const double 
         double ax = 0.0, ap = 0.0;
 #pragma unroll
         for (int l = 0; l < L; ++l) {
-            if (T::aa(L, l) != 0.0) ax = fma(T::aa(L, l), F[l][k], ax);
-            if (T::a(L, l) != 0.0) ap = fma(T::a(L, l), F[l][k], ap);
+            if (T::aa(L, l) != 0.0) ax = fma(T::aav(L, l), F[l][k], ax);
+            if (T::a(L, l) != 0.0) ap = fma(T::av(L, l), F[l][k], ap);
         }
         x1[k] = fma(h2, ax, fma(T::rs(L) * h, p[k], x[k]));
         p1[k] = fma(h, ap, p[k]);
@@ -101,10 +134,10 @@ __device__ __forceinline__ void rk_error(const double (&p)[D], double h, const d
         double bx = 0.0, bp = 0.0;
 #pragma unroll
         for (int l = 0; l < T::S; ++l) {
-            if (T::ea(l) != 0.0) bx = fma(T::ea(l), F[l][k], bx);
-            if (T::e(l) != 0.0) bp = fma(T::e(l), F[l][k], bp);
+            if (T::ea(l) != 0.0) bx = fma(T::eav(l), F[l][k], bx);
+            if (T::e(l) != 0.0) bp = fma(T::ev(l), F[l][k], bp);
         }
-        ex[k] = h * fma(h, bx, T::esum() * p[k]);
+        ex[k] = h * fma(h, bx, T::esumv() * p[k]);
         ep[k] = h * bp;
     }
 }

@@ -1132,3 +1132,93 @@ def test_custom_base_second_order_generator(cuda):
                                                   solver=8, **fixed)
     assert scaled_err(w, w_o, 1e-9).max() < 1.0
     assert np.abs(D - D_o).max() <= 1e-8 * np.abs(D_o).max() and np.abs(E - E_o).max() <= 1e-7 * np.abs(E_o).max()
+
+
+def _small_driver_setup():
+    import streamsculptor_b200 as ssc
+    pot = mw3_product()
+    prog_today = np.array([12.0, 3.0, -6.0, -0.05, 0.15, 0.03])
+
+    def phi1(stream):                                   # stand-in for the observer-frame transform the user supplies (degrees along the orbit plane)
+        stream = np.asarray(stream)
+        return np.degrees(np.arctan2(stream[:, 1], stream[:, 0]))
+    return ssc, pot, prog_today, phi1
+
+
+@pytest.mark.gpu
+def test_impact_generator(cuda):
+    """ImpactGenerator (GenerateImpactParams.py:9-215): window means against masked passes over the stream, the sampled parameters inside
+    their bounds, and the impact geometry of get_subhalo_ImpactParams (GenerateImpactParams.py:186-211): the subhalo sits at distance b from
+    the patch, perpendicular to the patch's velocity; its velocity along the stream is the sampled parallel component."""
+    ssc, pot, prog_today, phi1 = _small_driver_setup()
+    from streamsculptor_b200 import GenerateImpactParams as G
+    t_age, n_arm = 1500.0, 400
+    IC = np.asarray(pot.integrate_orbit(w0=prog_today, t0=0.0, t1=-t_age, ts=np.array([-t_age])).ys[0])
+    ts = np.hstack([np.linspace(-t_age, -1.0, n_arm), [0.0]])
+    l, t = ssc.gen_stream_vmapped_Chen25(pot_base=pot, prog_w0=IC, ts=ts, key=3, Msat=3e4, atol=1e-7, rtol=1e-7, solver=ssc.Dopri8())
+    stream = np.vstack([np.asarray(l), np.asarray(t)])
+    ph = phi1(stream)
+    strip = np.hstack([ts[:-1], ts[:-1]])
+    lo, hi = np.percentile(ph, [10, 90])
+    n = 64
+    rs = np.linspace(0.1, 1.0, n)
+    gen = ssc.ImpactGenerator(pot=pot, tobs=0.0, stream=stream, stream_phi1=ph, phi1_bounds=[lo, hi], tImpactBounds=[-t_age, 0.0], phi1window=1.0,
+                              NumImpacts=n, bImpact_bounds=[0, 10.0 * rs], stripping_times=strip, phi1_exclude=[-0.5, 0.5], prog_today=prog_today, seednum=77)
+    q = np.linspace(lo, hi, 9)
+    m, tm = gen.get_particle_mean(q)
+    for i, c in enumerate(q):
+        sel = np.abs(ph - c) < 1.0
+        assert sel.sum() > 0
+        assert np.abs(m[i].cpu().numpy() - stream[sel].mean(axis=0)).max() < 1e-11 and abs(float(tm[i]) - strip[sel].mean()) < 1e-9
+    out = gen.get_subhalo_ImpactParams()
+    par, cart, patch = out["ImpactFrameParams"], out["CartesianImpactParams"], out["StreamPatch"]
+    assert not out["status"].any() and np.isfinite(cart).all()
+    assert (par["bImpact"] >= 0).all() and (par["bImpact"] <= 10.0 * rs).all()
+    assert (par["tImpact"] >= -t_age).all() and (par["tImpact"] <= 0.0).all()
+    assert ((par["phi1_samples"] >= lo) & (par["phi1_samples"] <= hi)).all() and not ((par["phi1_samples"] > -0.5) & (par["phi1_samples"] < 0.5)).any()
+    d = cart[:, :3] - patch[:, :3]
+    T = patch[:, 3:] / np.linalg.norm(patch[:, 3:], axis=1)[:, None]
+    assert np.abs(np.linalg.norm(d, axis=1) - par["bImpact"]).max() < 1e-12
+    assert np.abs((d * T).sum(1)).max() < 1e-12
+    assert np.abs((cart[:, 3:] * T).sum(1) - G.jax_normal(gen.keys[0], n) * gen.sigma).max() < 1e-12
+    # the patches really are the window means taken back to the impact times: the oracle's orbit from the same mean
+    m0, _ = gen.get_particle_mean(par["phi1_samples"][:4])
+    for i in range(4):
+        y, st, _ = mw3_oracle().integrate_orbits(m0[i].cpu().numpy(), 0.0, par["tImpact"][i], solver=8, rtol=1e-7, atol=1e-7, dtmin=0.1)
+        assert st[0] == 0 and scaled_err(patch[i], y[0], 1e-5).max() < 1.0
+    # same seed, same draw
+    gen2 = ssc.ImpactGenerator(pot=pot, tobs=0.0, stream=stream, stream_phi1=ph, phi1_bounds=[lo, hi], tImpactBounds=[-t_age, 0.0], phi1window=1.0,
+                               NumImpacts=n, bImpact_bounds=[0, 10.0 * rs], stripping_times=strip, phi1_exclude=[-0.5, 0.5], prog_today=prog_today, seednum=77)
+    assert np.array_equal(gen2.get_subhalo_ImpactParams()["CartesianImpactParams"], cart)
+
+
+@pytest.mark.gpu
+def test_production_driver_get_derivs(cuda, tmp_path):
+    """get_derivs (generate_derivs.py:24-216) at a small size: the files it writes hold what the reference's hold, the derivatives equal a
+    direct response solve over the same sampled subhaloes, and the device summary equals its numpy restatement."""
+    ssc, pot, prog_today, phi1 = _small_driver_setup()
+    from streamsculptor_b200.generate_derivs import get_derivs
+    kw = dict(prog_wtoday=prog_today, t_age=1500.0, t_dissolve=-1.0, log10_min_mass=5.0, log10_max_mass=8.0, phi1_bounds=[-60.0, 60.0], phi1_exclude=[-0.5, 0.5],
+              stream_seednum=3, key=21, Msat=3e4, r_s=0.004, target_num=24, phi1_function=phi1, pot=pot, N_batch=12, atol=1e-9, rtol=1e-9, phi1window=2.0,
+              N_arm=150)
+    get_derivs(path=str(tmp_path), save_iter_start=5, **kw)
+    files = sorted(p.name for p in tmp_path.iterdir())
+    assert files == ["5.npy", "6.npy"]
+    rec = np.load(tmp_path / "5.npy", allow_pickle=True).item()
+    assert set(rec) == {"pert_out", "r_s_root", "ImpactFrameParams"}
+    w, D = np.asarray(rec["pert_out"][0]), np.asarray(rec["pert_out"][1])
+    assert w.shape == (301, 6) and D.shape == (301, 12, 12) and np.isfinite(D).all() and np.abs(D).max() > 0     # lead and trail interleaved by release time
+    edges = np.linspace(-60.0, 60.0, 13)
+    out = get_derivs(path=None, save=False, summaries=edges, **kw)
+    assert len(out) == 2
+    w2, D2 = out[0]["pert_out"]
+    assert np.array_equal(out[0]["ImpactFrameParams"]["tImpact"], rec["ImpactFrameParams"]["tImpact"])          # same keys -> same draws
+    assert np.array_equal(np.asarray(w2).reshape(w.shape), w) and np.array_equal(np.asarray(D2).reshape(D.shape), D)
+    ph = phi1(np.asarray(w2).reshape(-1, 6))
+    disp = np.einsum("s,nsk->nk", out[0]["masses"], np.asarray(D2).reshape(-1, 12, 12)[:, :, :6])
+    idx = np.searchsorted(edges, ph, side="left") - 1
+    for b in range(12):
+        sel = idx == b
+        want = disp[sel].mean(axis=0) if sel.any() else np.zeros(6)
+        assert np.abs(out[0]["binned"][b] - want).max() <= 1e-12 * max(np.abs(disp).max(), 1e-300)
+    assert not np.array_equal(out[1]["ImpactFrameParams"]["tImpact"], out[0]["ImpactFrameParams"]["tImpact"])   # a fresh key per batch

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/ssb200.h but not exported"
     assert set(_lib.EXPORTED) == declared
-    assert L.ssb_abi_version() == 1
+    assert L.ssb_abi_version() == 2          # round 2: growth factors, perturber sets
 
 
 def test_struct_layouts_match_header():
@@ -32,7 +32,8 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Component) == 16 + 64
     assert C.sizeof(_lib.Track) == 8 + 3 * 8 + 2 * 8
     assert C.sizeof(_lib.Subhalos) == 16 + 6 * 8
-    assert C.sizeof(_lib.Potential) == 16 + 12 * 80 + 4 * 48 + 2 * 64
+    assert C.sizeof(_lib.Perturbers) == 16 + 4 * 8
+    assert C.sizeof(_lib.Potential) == 16 + 12 * 80 + 4 * 48 + 2 * 64 + 48
     assert C.sizeof(_lib.Ctrl) == 8 + 4 * 8
     # the CUDA side agrees (scratch sizes are computed from the same constants)
     L = _lib.lib()
@@ -376,3 +377,24 @@ def test_many_moving_perturbers_pack_into_a_perturber_set():
     # the explicit class gives the same arrays
     direct = P.PerturberSetPotential(P.PlummerPotential, ms, rs, t, cen, units=ssc.usys)
     assert np.allclose(direct._arrays.host["GM"], ps.host["GM"]) and np.array_equal(direct._arrays.host["y"], ps.host["y"])
+
+
+def test_impact_generator_random_recipes():
+    """jax.random on the host for the production driver's sampler (GenerateImpactParams.py:44,87-147): split + randint against the oracle's
+    recipe (the one golden D8 hangs on), normal against the oracle's, choice and uniform by their distributions."""
+    import numpy as np
+    import oracle as O
+    from streamsculptor_b200 import GenerateImpactParams as G
+    for seed in (0, 493, 583, 9302, 2**33 + 5):
+        assert np.array_equal(G.jax_randint(seed, 5, 0, 1000), O.randint5(seed, 0, 1000))
+        assert abs(G.jax_normal(seed, 1)[0] - O.normal1(seed)) < 1e-14
+    k = G.jax_split(11, 7)
+    assert k.shape == (7, 2) and k.dtype == np.uint32 and len({tuple(r) for r in k}) == 7
+    assert np.array_equal(G.jax_split(11, 7), k) and not np.array_equal(G.jax_split(12, 7), k)
+    z = G.jax_normal(k[0], 20000)
+    assert abs(z.mean()) < 0.03 and abs(z.std() - 1.0) < 0.03
+    u = G.jax_uniform_range(k[1], 20000, -2.0, np.full(20000, 3.0))
+    assert u.min() >= -2.0 and u.max() < 3.0 and abs(u.mean() - 0.5) < 0.05
+    a = np.arange(4.0)
+    c = G.jax_choice(k[2], a, 40000, [0.1, 0.2, 0.3, 0.4])
+    assert np.abs(np.bincount(c.astype(int), minlength=4) / 40000 - [0.1, 0.2, 0.3, 0.4]).max() < 0.01
