@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _OUT = os.path.join(_HERE, "_lib", "libssb200.so")
 _SOURCES = ["ssb_kernels.cu", "ssb_response.cu", "ssb_response2.cu", "ssb_shared.cu", "ssb_variational.cu", "ssb_host.cu"]
-_HEADERS = ["ssb_common.cuh", "ssb_potential.cuh", "ssb_rk.cuh", "ssb_fastmath.cuh", "ssb_tableau.h", "ssb_logtab.h", "../../include/ssb200.h"]
+_HEADERS = ["ssb_common.cuh", "ssb_response_wa.cuh", "ssb_potential.cuh", "ssb_rk.cuh", "ssb_fastmath.cuh", "ssb_tableau.h", "ssb_logtab.h", "../../include/ssb200.h"]
 
 MAX_COMP, MAX_TRACK, MAX_SH, MAX_PSET = 12, 4, 2, 1
 

@@ -1170,6 +1170,15 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
     }
 }
 
+// warp-autonomous form of the kernel: measured slower (51.9 vs 31.4 ms) and therefore not built by default;
+// -DSSB_RESP_WA=1 (tools/build_variants.sh) adds it, SSB_RESP_KERNEL=wa selects it, the bit-identity test covers it (SSB_TEST_RESP_WA=1)
+#ifndef SSB_RESP_WA
+#define SSB_RESP_WA 0
+#endif
+#if SSB_RESP_WA
+#include "ssb_response_wa.cuh"
+#endif
+
 // RHS of the coupled field at one state (fields.py:175-206): y = [w(6), D(n_sh,12)]
 __global__ void response_term_kernel(const __grid_constant__ ssb_potential Pin, const ssb_subhalos Sh, double t, const double* y, double* dy) {
     __shared__ ssb_potential sP;
@@ -1308,7 +1317,21 @@ static int response_impl(const ssb_potential* pot_base, const ssb_subhalos* sh, 
         case SIG_NHHM: SSB_LAUNCH_MP(S, SIG_NHHM, PR); break; default: SSB_LAUNCH_MP(S, SIG_GENERIC, PR); } } while (0)
 #define SSB_LAUNCH_MP_PR(S) do { switch (sh->profile) { case SSB_PROFILE_PLUMMER: SSB_LAUNCH_MP_SIG(S, SSB_PROFILE_PLUMMER); break; \
         case SSB_PROFILE_HERNQUIST: SSB_LAUNCH_MP_SIG(S, SSB_PROFILE_HERNQUIST); break; default: SSB_LAUNCH_MP_SIG(S, SSB_PROFILE_NFW); } } while (0)
-        if (ctrl.solver == 5) SSB_LAUNCH_MP_PR(5); else SSB_LAUNCH_MP_PR(8);
+#if SSB_RESP_WA
+        // the warp-autonomous form (ssb_response_wa.cuh): only on request, SSB_RESP_KERNEL=wa (A/B, tests)
+#define SSB_LAUNCH_WA(S, SG, PR) do { const size_t shm = (sizeof(BaseShared<((S) == 5 ? 7 : 14)>) * 2 + sizeof(double) * (72 + 36)) * SSB_RESP_MAX_NP \
+                                                        + sizeof(double) * 36 * (SSB_RESP_THREADS / 32); \
+        CK(cudaFuncSetAttribute(response_kernel_wa<S, SG, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); \
+        response_kernel_wa<S, SG, PR><<<grid, SSB_RESP_THREADS, shm, st>>>(sig == SG ? pc : *pot_base, *sh, a); } while (0)
+#define SSB_LAUNCH_WA_SIG(S, PR) do { switch (sig) { case SIG_NHM: SSB_LAUNCH_WA(S, SIG_NHM, PR); break; \
+        case SIG_NHHM: SSB_LAUNCH_WA(S, SIG_NHHM, PR); break; default: SSB_LAUNCH_WA(S, SIG_GENERIC, PR); } } while (0)
+#define SSB_LAUNCH_WA_PR(S) do { switch (sh->profile) { case SSB_PROFILE_PLUMMER: SSB_LAUNCH_WA_SIG(S, SSB_PROFILE_PLUMMER); break; \
+        case SSB_PROFILE_HERNQUIST: SSB_LAUNCH_WA_SIG(S, SSB_PROFILE_HERNQUIST); break; default: SSB_LAUNCH_WA_SIG(S, SSB_PROFILE_NFW); } } while (0)
+        const char* kern = getenv("SSB_RESP_KERNEL");
+        if (kern && kern[0] == 'w') { if (ctrl.solver == 5) SSB_LAUNCH_WA_PR(5); else SSB_LAUNCH_WA_PR(8); }
+        else
+#endif
+        { if (ctrl.solver == 5) SSB_LAUNCH_MP_PR(5); else SSB_LAUNCH_MP_PR(8); }
     } else {
         if (ctrl.solver == 5) SSB_LAUNCH_RESP_PR(5); else SSB_LAUNCH_RESP_PR(8);
     }

@@ -22,12 +22,13 @@ from .units import usys
 
 
 def binned_response(stream_phi1, D, M_sh, edges):
-    """Device summary of one batch: mean first-order displacement sum_sh M_sh D[:, sh, :6] of the stream in phi1 bins -> [n_bins, 6] (torch)."""
+    """Device summary of one batch: mean first-order displacement sum_sh M_sh D[:, sh, :6] of the stream in phi1 bins -> [n_bins, 6] (torch).
+    Particles without a result (+inf rows: zero-length integration, as diffrax's SaveAt leaves them) are left out."""
     tt = rt.torch()
     disp = tt.einsum("s,nsk->nk", tt.as_tensor(M_sh, dtype=D.dtype, device=D.device), D[:, :, :6])
     idx = tt.bucketize(stream_phi1, tt.as_tensor(edges, dtype=D.dtype, device=D.device)) - 1
     nb = len(edges) - 1
-    ok = (idx >= 0) & (idx < nb)
+    ok = (idx >= 0) & (idx < nb) & tt.isfinite(disp).all(dim=1) & tt.isfinite(stream_phi1)    # a particle released at the final time has +inf rows (diffrax)
     out = tt.zeros((nb, 6), dtype=D.dtype, device=D.device)
     cnt = tt.zeros((nb,), dtype=D.dtype, device=D.device)
     out.index_add_(0, idx[ok], disp[ok])

@@ -312,12 +312,18 @@ def test_response_multi_slot_kernel_bit_identical(cuda):
         for solver, tol, d0, t1, max_steps in cases:
             ctrl = rt.make_ctrl(solver, tol, tol, 0.01, None, max_steps)
             out = {}
+            wa_out = {}                                         # the warp-autonomous form of the kernel (csrc/ssb_response_wa.cuh)
             for retire in (0, 1):
                 os.environ["SSB_RESP_RETIRE"] = str(retire)
                 for np_slots in (0, 1, 2, 4, 8, 16):
                     os.environ["SSB_RESP_NP"] = str(np_slots)
-                    w, D, st, ns = rt.linear_response(base, pert._arrays, rt.to_dev(w0), None if d0 is None else rt.to_dev(d0), rt.to_dev(t0), t1, ctrl)
-                    out[retire, np_slots] = (w.cpu().numpy(), D.cpu().numpy(), st.cpu().numpy(), ns.cpu().numpy())
+                    for kern in ("mp", "wa") if (np_slots and os.environ.get("SSB_TEST_RESP_WA") == "1") else ("mp",):   # wa: variant builds only
+                        os.environ["SSB_RESP_KERNEL"] = kern
+                        w, D, st, ns = rt.linear_response(base, pert._arrays, rt.to_dev(w0), None if d0 is None else rt.to_dev(d0), rt.to_dev(t0), t1, ctrl)
+                        (out if kern == "mp" else wa_out)[retire, np_slots] = (w.cpu().numpy(), D.cpu().numpy(), st.cpu().numpy(), ns.cpu().numpy())
+            for key, res in wa_out.items():                     # same arithmetic in the same order: the same bits, retired items or not
+                for a, b in zip(res, out[key]):
+                    assert np.array_equal(a, b), f"warp-autonomous kernel differs from the CTA-wide one at (retire, slots) = {key}"
             ref = out[0, 0]
             if max_steps == 40:
                 assert (ref[2] == 1).any() and (ref[2] == 0).any()
@@ -346,6 +352,7 @@ def test_response_multi_slot_kernel_bit_identical(cuda):
     finally:
         os.environ.pop("SSB_RESP_NP", None)
         os.environ.pop("SSB_RESP_RETIRE", None)
+        os.environ.pop("SSB_RESP_KERNEL", None)
     # default slot count at a batch large enough to use it: same bits as the one-particle kernel
     N2 = 1200
     w0b = halo_orbits(N2, seed=12); t0b = np.linspace(-1000.0, -5.0, N2)
@@ -1198,25 +1205,39 @@ def test_production_driver_get_derivs(cuda, tmp_path):
     direct response solve over the same sampled subhaloes, and the device summary equals its numpy restatement."""
     ssc, pot, prog_today, phi1 = _small_driver_setup()
     from streamsculptor_b200.generate_derivs import get_derivs
-    kw = dict(prog_wtoday=prog_today, t_age=1500.0, t_dissolve=-1.0, log10_min_mass=5.0, log10_max_mass=8.0, phi1_bounds=[-60.0, 60.0], phi1_exclude=[-0.5, 0.5],
-              stream_seednum=3, key=21, Msat=3e4, r_s=0.004, target_num=24, phi1_function=phi1, pot=pot, N_batch=12, atol=1e-9, rtol=1e-9, phi1window=2.0,
-              N_arm=150)
+    # where the small stream lies in phi1 (the user of the reference knows it from the data): bounds well inside it, windows of a few degrees
+    IC = np.asarray(pot.integrate_orbit(w0=prog_today, t0=0.0, t1=-1500.0, ts=np.array([-1500.0])).ys[0])
+    ts = np.hstack([np.linspace(-1500.0, -1.0, 150), [0.0]])
+    l, t = ssc.gen_stream_vmapped_Chen25(pot_base=pot, prog_w0=IC, ts=ts, key=3, Msat=3e4, atol=1e-7, rtol=1e-7, solver=ssc.Dopri8(),
+                                         prog_pot=ssc.potential.PlummerPotential(m=3e4, r_s=0.004, units=ssc.usys))
+    ph_all = phi1(np.vstack([np.asarray(l), np.asarray(t)]))
+    ph_prog = float(phi1(prog_today[None])[0])
+    lo, hi = np.percentile(ph_all, [15, 85])
+    assert lo < ph_prog - 0.5 and hi > ph_prog + 0.5
+    window = 0.25 * (hi - lo)
+    kw = dict(prog_wtoday=prog_today, t_age=1500.0, t_dissolve=-1.0, log10_min_mass=5.0, log10_max_mass=8.0, phi1_bounds=[lo, hi],
+              phi1_exclude=[ph_prog - 0.5, ph_prog + 0.5], stream_seednum=3, key=21, Msat=3e4, r_s=0.004, target_num=24, phi1_function=phi1, pot=pot, N_batch=12,
+              atol=1e-9, rtol=1e-9, phi1window=window, N_arm=150)
     get_derivs(path=str(tmp_path), save_iter_start=5, **kw)
     files = sorted(p.name for p in tmp_path.iterdir())
     assert files == ["5.npy", "6.npy"]
     rec = np.load(tmp_path / "5.npy", allow_pickle=True).item()
     assert set(rec) == {"pert_out", "r_s_root", "ImpactFrameParams"}
     w, D = np.asarray(rec["pert_out"][0]), np.asarray(rec["pert_out"][1])
-    assert w.shape == (301, 6) and D.shape == (301, 12, 12) and np.isfinite(D).all() and np.abs(D).max() > 0     # lead and trail interleaved by release time
-    edges = np.linspace(-60.0, 60.0, 13)
+    assert w.shape == (301, 6) and D.shape == (301, 12, 12)                 # lead and trail interleaved by release time
+    # the last kept particle is released AT the final time: nothing to integrate, diffrax's SaveAt(ts) leaves its rows +inf (perturbative.py:733-749)
+    assert np.isfinite(D[:-1]).all() and np.isinf(D[-1]).all() and np.abs(D[:-1]).max() > 0
+    edges = np.linspace(ph_all.min() - 1e-9, ph_all.max() + 1e-9, 13)
     out = get_derivs(path=None, save=False, summaries=edges, **kw)
     assert len(out) == 2
     w2, D2 = out[0]["pert_out"]
     assert np.array_equal(out[0]["ImpactFrameParams"]["tImpact"], rec["ImpactFrameParams"]["tImpact"])          # same keys -> same draws
     assert np.array_equal(np.asarray(w2).reshape(w.shape), w) and np.array_equal(np.asarray(D2).reshape(D.shape), D)
-    ph = phi1(np.asarray(w2).reshape(-1, 6))
-    disp = np.einsum("s,nsk->nk", out[0]["masses"], np.asarray(D2).reshape(-1, 12, 12)[:, :, :6])
+    fin = np.isfinite(np.asarray(w2)).all(axis=1)
+    ph = phi1(np.asarray(w2)[fin])
+    disp = np.einsum("s,nsk->nk", out[0]["masses"], np.asarray(D2)[fin][:, :, :6])
     idx = np.searchsorted(edges, ph, side="left") - 1
+    assert fin.sum() == 300
     for b in range(12):
         sel = idx == b
         want = disp[sel].mean(axis=0) if sel.any() else np.zeros(6)
