@@ -17,6 +17,11 @@
 #ifndef SSB_SNAP_MIN_BLOCKS
 #define SSB_SNAP_MIN_BLOCKS 3   // saving kernel (MODE 0): CTAs per SM the register budget is set for (A/B: 2 = 255 registers, no spills)
 #endif
+// bit 0: saving kernel (K1 MODE 0), bit 1: final-state kernel (MODE 2): one CTA-wide vote per step-loop iteration keeps the four warps of a
+// CTA on the same iteration, so that they fetch the (larger-than-cache) loop body together
+#ifndef SSB_ORBIT_CTA_ALIGN
+#define SSB_ORBIT_CTA_ALIGN 1
+#endif
 #ifndef SSB_FUSED_INLINE
 #define SSB_FUSED_INLINE 1
 #endif

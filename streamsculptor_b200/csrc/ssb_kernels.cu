@@ -277,7 +277,8 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
         for (;;) {
             bool active = valid && status == 0 && tprev < T1;
             if (active && n_steps >= c.max_steps) { status = 1; active = false; }
-            if (!__any_sync(0xffffffffu, active)) break;
+            if (SSB_ORBIT_CTA_ALIGN & 1) { if (!__syncthreads_or(active)) break; }          // the CTA's warps stay on the same iteration: shared instruction fetch
+            else if (!__any_sync(0xffffffffu, active)) break;
             int nsave = 0;
             if (active) {
                 const double dt = tnext - tprev;
@@ -368,7 +369,8 @@ __device__ __forceinline__ void integrate_one(const ssb_potential* P, const ssb_
         bool active = valid && status == 0 && tprev < T1;
         if (MODE == 1) active = active && tprev < t_stop;            // K0 part runs (t_stop in mirrored time): same steps as the full solve, cut short
         if (active && n_steps >= c.max_steps) { status = 1; active = false; }
-        if (!__any_sync(0xffffffffu, active)) break;
+        if (MODE == 2 && (SSB_ORBIT_CTA_ALIGN & 2)) { if (!__syncthreads_or(active)) break; }
+        else if (!__any_sync(0xffffffffu, active)) break;
         if (!active) continue;
         const double dt = tnext - tprev;
         double x1[3], p1[3], ex[3], ep[3];
