@@ -1,6 +1,7 @@
-"""Small invocations of the kernels touched in session 3, sized for compute-sanitizer (memcheck / racecheck):
-response_kernel_mp with 4 particle slots per CTA, the zero-copy host outputs of the orbit kernel, the shared-step attempt kernel
-with once-per-stage track evaluation.  Usage: compute-sanitizer --tool racecheck python tools/sanitize_new_kernels.py"""
+"""Small invocations of the kernels touched in rounds 1-2, sized for compute-sanitizer (memcheck / racecheck):
+response_kernel_mp with 4 and 16 particle slots per CTA and retired items, the zero-copy host outputs of the orbit kernel, the shared-step
+attempt kernel with once-per-stage track evaluation, the saving orbit kernel (warp-cooperative dense output), the four-part stream pipeline,
+a perturber set and a growth factor.  Usage: compute-sanitizer --tool racecheck python tools/sanitize_new_kernels.py"""
 import os, sys
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tools"))
 import ctypes as C
@@ -47,3 +48,38 @@ wt = np.hstack([yk[0, :3] + rng.normal(size=(300, 3)) * 0.02, yk[0, 3:] + rng.no
 sol = ssc.integrate_field(w0=wt, ts=np.array([-60.0, -40.0]), solver=ssc.Dopri8(), field=field, rtol=1e-8, atol=1e-8, dtmin=0.05, max_steps=500)
 assert np.isfinite(sol.ys).all()
 print("shared-step kernels ok", int(sol.stats["num_steps"]))
+
+# ---- round 2 ----
+# (4) K3-mp with 16 slots per CTA and retired items (long spans: windows close for good, chunks of 16 retire, logs are applied at the end)
+os.environ["SSB_RESP_NP"] = "16"
+nsh = 48
+sh = subhalo_set(nsh, seed=7, t_lo=-900.0, tw=40.0)
+pert = P.SubhaloLinePotentialCustom_fromFunc(func=P.HernquistPotential, m=sh["m"], r_s=sh["rs"], subhalo_x0=sh["x0"], subhalo_v=sh["v"],
+                                             subhalo_t0=sh["t0"], t_window=sh["tw"], units=ssc.usys)
+N = 40
+w0, t0 = halo_orbits(N, seed=13), np.linspace(-1000.0, -5.0, N)
+ctrl = rt.make_ctrl(ssc.Dopri8(), 1e-7, 1e-7, 0.01, None, 10_000)
+w, D, st, ns = rt.linear_response(base, pert._arrays, rt.to_dev(w0), None, rt.to_dev(t0), 0.0, ctrl)
+assert int((st != 0).sum().item()) == 0 and bool(torch.isfinite(D).all())
+os.environ.pop("SSB_RESP_NP")
+print("response_kernel_mp, 16 slots + retired items ok")
+# (5) saving orbit kernel: per-orbit save times, warp-cooperative dense output (both solvers)
+wq = halo_orbits(200, seed=3)
+for solver in (ssc.Dopri8(), ssc.Dopri5()):
+    tsq = np.sort(np.random.default_rng(1).uniform(-400.0, 0.0, size=(200, 9)), axis=1)
+    tsq[:, 0] = -400.0
+    sol = base.integrate_orbit_batch_vmapped(w0=wq, ts=tsq, solver=solver, rtol=1e-7, atol=1e-7, dtmin=0.3)
+    assert np.isfinite(np.asarray(sol.ys)).all()
+print("saving orbit kernel ok")
+# (6) four-part stream pipeline (>= 32768 particles per arm), perturber set and growth factor in the orbit kernel
+ts4 = np.linspace(-400.0, 0.0, 33001)
+lead, trail = base.gen_stream_vmapped(ts=ts4, prog_w0=[-3.0, 14.0, 8.0, 0.14, 0.02, -0.07], Msat=1e4, seed_num=5, solver=ssc.Dopri8())
+assert np.isfinite(lead).all() and np.isfinite(trail).all()
+tkp = np.linspace(-400.0, 0.0, 41)
+cen = np.random.default_rng(4).normal(size=(41, 20, 3)) * 30.0
+pset = P.PerturberSetPotential(P.PlummerPotential, np.full(20, 1e8), np.full(20, 0.5), tkp, cen, units=ssc.usys)
+grow = P.GrowingPotential(P.PlummerPotential(m=1e10, r_s=2.0, units=ssc.usys), (tkp, 1.0 + 1e-3 * (tkp + 400.0)), units=ssc.usys)
+pot6 = P.Potential_Combine([base, pset, grow], units=ssc.usys)
+sol = pot6.integrate_orbit_batch_vmapped(w0=wq, ts=np.array([-400.0, 0.0]), solver=ssc.Dopri8(), rtol=1e-7, atol=1e-7, dtmin=0.3)
+assert np.isfinite(np.asarray(sol.ys)).all()
+print("four-part pipeline, perturber set, growth factor ok")
