@@ -51,9 +51,11 @@ typedef enum {
     SSB_TRIAXNFW = 5,     /* potential.py:86-97    p = {G*m, r_s, q1, q2, q3}          */
     SSB_UNIFORM_ACC = 6,  /* potential.py:480-502  gradient = d(velocity track)/dt ; track = velocity table */
     SSB_SUBHALOS = 7,     /* potential.py:802-850, 1161-1213  sh = index into ssb_potential.sh              */
-    SSB_PERTURBERS = 8    /* a SET of moving spheres on tabulated tracks (sum of TimeDepTranslatingPotential components,
+    SSB_PERTURBERS = 8,   /* a SET of moving spheres on tabulated tracks (sum of TimeDepTranslatingPotential components,
                              potential.py:448-462, as the restricted N-body / LMC set-ups build them - BASELINE config 5:
                              100 live perturbers); sh = index into ssb_potential.pset                        */
+    SSB_BAR = 9,          /* potential.py:178-198  Long & Murali bar rotating with Omega: p = {G*m, a, b, c, Omega}       */
+    SSB_DEHNEN_BAR = 10   /* potential.py:200-222  p = {alpha, v0, R0, Rb, phib, Omega}                                    */
 } ssb_comp_type;
 
 typedef struct {

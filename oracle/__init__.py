@@ -22,6 +22,7 @@ _LIB = None
 G_KPC_MYR_MSUN = 4.498502151469553e-12  # astropy G in kpc^3 Msun^-1 Myr^-2 (main.py:18,30; pinned by golden G1)
 
 NFW, HERNQUIST, MIYAMOTO, PLUMMER, ISOCHRONE, TRIAXNFW, UNIFORM_ACC, SUBHALOS = range(8)
+BAR, DEHNEN_BAR = 9, 10
 LINEAR, CUBIC = 0, 1
 PR_PLUMMER, PR_HERNQUIST, PR_NFW = 0, 1, 2
 
@@ -147,6 +148,14 @@ class Program:
 
     def triaxnfw(self, m, r_s, q1, q2, q3, track=-1):
         return self._comp(TRIAXNFW, [self.G * m, r_s, q1, q2, q3], track)
+
+    def bar(self, m, a, b, c, Omega, track=-1):
+        """BarPotential (potential.py:178-198)."""
+        return self._comp(BAR, [self.G * m, a, b, c, Omega], track)
+
+    def dehnen_bar(self, alpha, v0, R0, Rb, phib, Omega, track=-1):
+        """DehnenBarPotential (potential.py:200-222)."""
+        return self._comp(DEHNEN_BAR, [alpha, v0, R0, Rb, phib, Omega], track)
 
     def uniform_acc(self, t, vel):
         return self._comp(UNIFORM_ACC, [], self.track(LINEAR, t, vel))

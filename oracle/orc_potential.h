@@ -22,6 +22,8 @@ enum CompType {
     C_TRIAXNFW = 5,     // potential.py:86-97   p = {G*m, r_s, q1, q2, q3}
     C_UNIFORM_ACC = 6,  // potential.py:480-502 gradient = d velocity_func/dt ; track = velocity table
     C_SUBHALOS = 7,     // potential.py:802-904, 1161-1268 ; sh = index of the subhalo set
+    C_BAR = 9,          // potential.py:178-198 Long & Murali bar rotating with Omega: p = {G*m, a, b, c, Omega}
+    C_DEHNEN_BAR = 10,  // potential.py:200-222 p = {alpha, v0, R0, Rb, phib, Omega}
 };
 enum TrackKind { TK_LINEAR = 0, TK_CUBIC = 1 };
 enum Profile { PR_PLUMMER = 0, PR_HERNQUIST = 1, PR_NFW = 2 };
@@ -131,6 +133,28 @@ template <class T, class P> inline T phi_isochrone(const P& GM, const P& a, cons
     T r2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];                       // potential.py:121 (r = norm)
     return -GM / (a + sqrt(r2 + a * a));                                  // potential.py:122
 }
+// BarPotential (potential.py:178-198): the point is rotated by ang = -Omega t about z into the bar's frame
+template <class T> inline T phi_bar(double GM, double a, double b, double c, double Omega, const T* x, double t) {
+    const double ang = -Omega * t, cs = std::cos(ang), sn = std::sin(ang);                 // potential.py:187-188
+    T xr = x[0] * cs - x[1] * sn, yr = x[0] * sn + x[1] * cs;                             // potential.py:190: matmul(Rot_mat, xyz)
+    T zz = sqrt(x[2] * x[2] + c * c) + b;
+    T Tp = sqrt(sq(xr + a) + yr * yr + zz * zz);                                          // potential.py:192
+    T Tm = sqrt(sq(a - xr) + yr * yr + zz * zz);                                          // potential.py:193
+    return (GM / (2.0 * a)) * log((xr - a + Tm) / (xr + a + Tp));                         // potential.py:195
+}
+// DehnenBarPotential (potential.py:200-222).  cos(2 (phi - phib - Omega t)) R^2 is written as (x^2 - y^2) cos 2 beta + 2 x y sin 2 beta
+// (beta = phib + Omega t): the same function without arctan2 of a dual number.
+template <class T> inline T phi_dehnen_bar(double alpha, double v0, double R0, double Rb, double phib, double Omega, const T* x, double t) {
+    const double beta = phib + Omega * t, c2 = std::cos(2.0 * beta), s2 = std::sin(2.0 * beta);
+    T R2 = x[0] * x[0] + x[1] * x[1];
+    T r2 = R2 + x[2] * x[2];
+    T r = sqrt(r2);
+    T q = r / Rb;
+    T U = (val(r) >= Rb) ? -1.0 / (q * q * q) : q * q * q - 2.0;                           // potential.py:210-216
+    const double pref = alpha * (v0 * v0 / 3.0) * (R0 / Rb) * (R0 / Rb) * (R0 / Rb);       // potential.py:219
+    T ang = (x[0] * x[0] - x[1] * x[1]) * c2 + x[0] * x[1] * (2.0 * s2);
+    return pref * (ang / r2) * U;                                                          // potential.py:220
+}
 template <class T, class P> inline T phi_profile(int profile, const P& GM, const P& rs, const T* x) {
     switch (profile) {
         case PR_PLUMMER: return phi_plummer<T, P>(GM, rs, x);
@@ -177,6 +201,8 @@ template <class T> inline T phi_total(const Program& P, const T* x, double t) {
             case C_TRIAXNFW: {
                 T xq[3] = {xs[0] / c.p[2], xs[1] / c.p[3], xs[2] / c.p[4]};           // potential.py:94
                 acc += phi_nfw<T, double>(c.p[0], c.p[1], xq) * gf; break; }
+            case C_BAR: acc += phi_bar<T>(c.p[0], c.p[1], c.p[2], c.p[3], c.p[4], xs, t) * gf; break;
+            case C_DEHNEN_BAR: acc += phi_dehnen_bar<T>(c.p[0], c.p[1], c.p[2], c.p[3], c.p[4], c.p[5], xs, t) * gf; break;
             case C_SUBHALOS: {
                 const SubhaloSet& S = P.shs[c.sh];
                 for (int j = 0; j < S.n; ++j) acc += phi_subhalo<T>(S, j, xs, t);     // potential.py:830

@@ -11,11 +11,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _OUT = os.path.join(_HERE, "_lib", "libssb200.so")
 _SOURCES = ["ssb_kernels.cu", "ssb_response.cu", "ssb_response2.cu", "ssb_shared.cu", "ssb_variational.cu", "ssb_host.cu"]
-_HEADERS = ["ssb_common.cuh", "ssb_response_wa.cuh", "ssb_potential.cuh", "ssb_rk.cuh", "ssb_fastmath.cuh", "ssb_tableau.h", "ssb_logtab.h", "../../include/ssb200.h"]
+_HEADERS = ["ssb_common.cuh", "ssb_response_wa.cuh", "ssb_jet.cuh", "ssb_potential.cuh", "ssb_rk.cuh", "ssb_fastmath.cuh", "ssb_tableau.h", "ssb_logtab.h", "../../include/ssb200.h"]
 
 MAX_COMP, MAX_TRACK, MAX_SH, MAX_PSET = 12, 4, 2, 1
 
-NFW, HERNQUIST, MIYAMOTO, PLUMMER, ISOCHRONE, TRIAXNFW, UNIFORM_ACC, SUBHALOS, PERTURBERS = range(9)
+NFW, HERNQUIST, MIYAMOTO, PLUMMER, ISOCHRONE, TRIAXNFW, UNIFORM_ACC, SUBHALOS, PERTURBERS, BAR, DEHNEN_BAR = range(11)
 TRACK_LINEAR, TRACK_CUBIC = 0, 1
 PROFILE_PLUMMER, PROFILE_HERNQUIST, PROFILE_NFW = 0, 1, 2
 

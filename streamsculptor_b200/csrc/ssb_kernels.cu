@@ -988,7 +988,7 @@ int ssb_validate_potential(const ssb_potential* p) {
     }
     for (int i = 0; i < p->n_comp; ++i) {
         const ssb_component& c = p->comp[i];
-        if (c.type < SSB_NFW || c.type > SSB_PERTURBERS) return ssb_set_error(SSB_ERR_UNSUPPORTED, "potential: unknown component type");
+        if (c.type < SSB_NFW || c.type > SSB_DEHNEN_BAR) return ssb_set_error(SSB_ERR_UNSUPPORTED, "potential: unknown component type");
         if (c.type == SSB_PERTURBERS && (c.sh < 0 || c.sh >= p->n_pset || c.track >= 0 || c.growth != 0))
             return ssb_set_error(SSB_ERR_ARG, "perturber-set component: missing set, or combined with a translation / growth factor");
         if (c.track >= p->n_track) return ssb_set_error(SSB_ERR_ARG, "potential: component references a missing track");

@@ -11,6 +11,7 @@
 
 #include "../../include/ssb200.h"
 #include "ssb_fastmath.cuh"
+#include "ssb_jet.cuh"
 
 namespace ssb {
 
@@ -353,6 +354,18 @@ __device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x
             case SSB_SUBHALOS:
                 add_subhalos<MODE>(Pt.sh[c.sh], xs, t, P, g, H);
                 break;
+            case SSB_BAR:
+            case SSB_DEHNEN_BAR: {                                  // rotating bars: derivatives by jets (ssb_jet.cuh), out of line
+                constexpr int ORD = (MODE & WANT_HESS) ? 2 : 1;
+                double J[jet_n(ORD)];
+                if (type == SSB_BAR) bar_jet<ORD>(c.p, gm, xs[0], xs[1], xs[2], t, J);
+                else dehnen_bar_jet<ORD>(c.p, gm, xs[0], xs[1], xs[2], t, J);
+                if (MODE & WANT_PHI) P += J[0];
+                if (MODE & WANT_GRAD) { g[0] += J[1]; g[1] += J[2]; g[2] += J[3]; }
+                if (MODE & WANT_HESS) {                             // Taylor coefficients -> derivatives: xx, yy, zz carry 1/2!
+                    H.xx += 2.0 * J[4]; H.xy += J[5]; H.xz += J[6]; H.yy += 2.0 * J[7]; H.yz += J[8]; H.zz += 2.0 * J[9];
+                }
+            } break;
             default: break;
         }
     }
@@ -530,6 +543,15 @@ __device__ inline void pot_third(const ssb_potential& Pt, const double x[3], dou
                 T.xzz += f3 * Dx * Dz * Dz + f2 * Dzz * Dx;
                 T.yzz += f3 * Dy * Dz * Dz + f2 * Dzz * Dy;
                 T.xyz += f3 * Dx * Dy * Dz;
+            } break;
+            case SSB_BAR:
+            case SSB_DEHNEN_BAR: {
+                double J[20];
+                if (c.type == SSB_BAR) bar_jet<3>(c.p, gm, xs[0], xs[1], xs[2], t, J);
+                else dehnen_bar_jet<3>(c.p, gm, xs[0], xs[1], xs[2], t, J);
+                // xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz at 10..19; derivative = alpha! x coefficient
+                T.xxx += 6.0 * J[10]; T.xxy += 2.0 * J[11]; T.xxz += 2.0 * J[12]; T.xyy += 2.0 * J[13]; T.xyz += J[14];
+                T.xzz += 2.0 * J[15]; T.yyy += 6.0 * J[16]; T.yyz += 2.0 * J[17]; T.yzz += 2.0 * J[18]; T.zzz += 6.0 * J[19];
             } break;
             case SSB_SUBHALOS: {
                 const ssb_subhalos& S = Pt.sh[c.sh];

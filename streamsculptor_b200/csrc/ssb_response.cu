@@ -816,6 +816,7 @@ __global__ void __launch_bounds__(SSB_RESP_THREADS, SSB_RESP_CTAS_PER_SM) respon
                 }
                 __syncwarp();
             }
+            __syncwarp();                                      // every lane has read the slot's counters (racecheck: read-before-write inside the warp)
             if (lane == 0) {
                 slot[q].n_ret = n_ret; slot[q].log_len = len;
                 if (len >= a.log_cap && !slot[q].finishing) { slot[q].need_flush = 1; s_service = 1; }

@@ -81,6 +81,25 @@ class HernquistPotential(Potential):                  # potential.py:132-138
         prog.add(_lib.HERNQUIST, [self._G * self.m, self.r_s, self.soft], track)
 
 
+class BarPotential(Potential):                        # potential.py:178-198
+    """Long & Murali (1992) bar rotating about z with pattern speed Omega.  Derivatives on the device by Taylor jets (csrc/ssb_jet.cuh), as the
+    reference obtains them by autodiff; the component runs on the interpreter path (not in a fused signature)."""
+
+    def __init__(self, m, a, b, c, Omega, units=None):
+        super().__init__(units, {'m': m, 'a': a, 'b': b, 'c': c, 'Omega': Omega})
+
+    def _lower(self, prog, track):
+        prog.add(_lib.BAR, [self._G * self.m, self.a, self.b, self.c, self.Omega], track)
+
+
+class DehnenBarPotential(Potential):                  # potential.py:200-222
+    def __init__(self, alpha, v0, R0, Rb, phib, Omega, units=None):
+        super().__init__(units, {'alpha': alpha, 'v0': v0, 'R0': R0, 'Rb': Rb, 'phib': phib, 'Omega': Omega})
+
+    def _lower(self, prog, track):
+        prog.add(_lib.DEHNEN_BAR, [self.alpha, self.v0, self.R0, self.Rb, self.phib, self.Omega], track)
+
+
 class MN3ExponentialDiskPotential(Potential):         # potential.py:224-280 (sum of three Miyamoto-Nagai disks)
     _K_pos_dens = np.array([
         [0.0036, -0.0330, 0.1117, -0.1335, 0.1749], [-0.0131, 0.1090, -0.3035, 0.2921, -5.7976],

@@ -1243,3 +1243,51 @@ def test_production_driver_get_derivs(cuda, tmp_path):
         want = disp[sel].mean(axis=0) if sel.any() else np.zeros(6)
         assert np.abs(out[0]["binned"][b] - want).max() <= 1e-12 * max(np.abs(disp).max(), 1e-300)
     assert not np.array_equal(out[1]["ImpactFrameParams"]["tImpact"], out[0]["ImpactFrameParams"]["tImpact"])   # a fresh key per batch
+
+
+@pytest.mark.gpu
+def test_rotating_bars_match_oracle(cuda):
+    """N4: BarPotential (potential.py:178-198) and DehnenBarPotential (potential.py:200-222).  The device evaluates their gradient, Hessian and
+    third derivatives with Taylor jets through the scalar formula (csrc/ssb_jet.cuh); the oracle differentiates its own restatement with
+    nested dual numbers.  Field values at random points and times, fixed-step orbits (1e-10), a translating growing bar, and a stream whose
+    release needs the bar's Hessian."""
+    import streamsculptor_b200 as ssc
+    P = ssc.potential
+    bar_kw = dict(m=1e10, a=3.5, b=0.5, c=0.6, Omega=0.04)
+    deh_kw = dict(alpha=0.01, v0=0.22, R0=8.0, Rb=3.4, phib=0.4, Omega=0.05)
+    mw, omw = mw3_product(), mw3_oracle
+    for name, prod, orc in (
+            ("bar", P.Potential_Combine([mw, P.BarPotential(units=ssc.usys, **bar_kw)], units=ssc.usys),
+             omw().bar(bar_kw["m"], bar_kw["a"], bar_kw["b"], bar_kw["c"], bar_kw["Omega"])),
+            ("dehnen", P.Potential_Combine([mw, P.DehnenBarPotential(units=ssc.usys, **deh_kw)], units=ssc.usys),
+             omw().dehnen_bar(deh_kw["alpha"], deh_kw["v0"], deh_kw["R0"], deh_kw["Rb"], deh_kw["phib"], deh_kw["Omega"]))):
+        rng = np.random.default_rng(11)
+        xyz = rng.normal(size=(300, 3)) * np.array([6.0, 6.0, 2.0])            # inside and outside Rb, near and far from the bar's ends
+        t = rng.uniform(-3000.0, 0.0, 300)
+        assert relerr(prod.potential(xyz, t), orc.potential(xyz, t)) < 1e-12, name
+        assert relerr(prod.gradient(xyz, t), orc.gradient(xyz, t)) < 1e-11, name
+        assert relerr(prod.jacobian_force(xyz, t), orc.hessian(xyz, t)) < 1e-10, name
+        assert relerr(prod.third_derivative(xyz[:64], t[:64]), orc.third(xyz[:64], t[:64])) < 1e-9, name
+        # the bar alone, so that a wrong bar cannot hide behind the galaxy's larger numbers
+        alone = prod.potential_list[1]
+        o_alone = (O.Program().bar(**{k: bar_kw[k] for k in ("m", "a", "b", "c", "Omega")}) if name == "bar"
+                   else O.Program().dehnen_bar(**deh_kw))
+        assert relerr(alone.gradient(xyz, t), o_alone.gradient(xyz, t)) < 1e-10, name
+        assert relerr(alone.jacobian_force(xyz, t), o_alone.hessian(xyz, t)) < 1e-9, name
+        assert relerr(alone.third_derivative(xyz[:64], t[:64]), o_alone.third(xyz[:64], t[:64])) < 1e-8, name
+        # fixed-step orbits through the rotating field
+        w0 = halo_orbits(40, seed=21) * np.array([0.4, 0.4, 0.2, 1.0, 1.0, 0.5])
+        for solver in (5, 8):
+            sol = prod.integrate_orbit_batch_vmapped(w0=w0, ts=np.array([-400.0, -200.0, 0.0]), solver=ssc.Dopri8() if solver == 8 else ssc.Dopri5(),
+                                                     rtol=1e-8, atol=1e-8, dtmin=1.0, dtmax=1.0)
+            yo, st, _ = orc.integrate_orbits(w0, -400.0, 0.0, ts=np.array([-400.0, -200.0, 0.0]), solver=solver, rtol=1e-8, atol=1e-8, dtmin=1.0, dtmax=1.0)
+            assert not st.any() and relerr(np.asarray(sol.ys), yo) < 1e-10, (name, solver)
+    # a stream in MW3 + bar: release (Hessian of the bar) + orbits, fixed steps, against the oracle
+    prod = P.Potential_Combine([mw, P.BarPotential(units=ssc.usys, **bar_kw)], units=ssc.usys)
+    orc = omw().bar(bar_kw["m"], bar_kw["a"], bar_kw["b"], bar_kw["c"], bar_kw["Omega"])
+    ts = np.linspace(-600.0, 0.0, 41)
+    w0 = [8.0, 0.5, 3.0, -0.02, 0.2, 0.05]
+    nr = np.random.Generator(np.random.PCG64(3)).standard_normal((41, 4))
+    lead, trail = prod.gen_stream_vmapped(ts=ts, prog_w0=w0, Msat=1e4, seed_num=5, solver=ssc.Dopri8(), normals=nr, rtol=1e-8, atol=1e-8, dtmin=2.0, dtmax=2.0)
+    lo, to, st, _ = orc.gen_stream(ts, w0, 1e4, 5, solver=8, normals=nr, rtol=1e-8, atol=1e-8, dtmin=2.0, dtmax=2.0)
+    assert relerr(lead, lo) < 1e-9 and relerr(trail, to) < 1e-9

@@ -398,3 +398,73 @@ def test_impact_generator_random_recipes():
     a = np.arange(4.0)
     c = G.jax_choice(k[2], a, 40000, [0.1, 0.2, 0.3, 0.4])
     assert np.abs(np.bincount(c.astype(int), minlength=4) / 40000 - [0.1, 0.2, 0.3, 0.4]).max() < 0.01
+
+
+def test_oracle_rotating_bars_against_the_formulas():
+    """The oracle's BarPotential / DehnenBarPotential (potential.py:178-222) against a direct numpy evaluation of the reference's formulas
+    (rotation matrix, arctan2 and all), and its autodiff gradient against central differences of that."""
+    import numpy as np
+    import oracle as O
+    G = O.Program().G
+
+    def bar(x, t, m=1e10, a=3.5, b=0.5, c=0.6, Om=0.04):
+        ang = -Om * t
+        R = np.array([[np.cos(ang), -np.sin(ang), 0.0], [np.sin(ang), np.cos(ang), 0.0], [0.0, 0.0, 1.0]])
+        xc = R @ x
+        zz = b + np.sqrt(c ** 2 + xc[2] ** 2)
+        Tp = np.sqrt((a + xc[0]) ** 2 + xc[1] ** 2 + zz ** 2)
+        Tm = np.sqrt((a - xc[0]) ** 2 + xc[1] ** 2 + zz ** 2)
+        return G * m / (2.0 * a) * np.log((xc[0] - a + Tm) / (xc[0] + a + Tp))
+
+    def dehnen(x, t, alpha=0.01, v0=0.22, R0=8.0, Rb=3.4, phib=0.4, Om=0.05):
+        phi = np.arctan2(x[1], x[0]); R = np.hypot(x[0], x[1]); r = np.linalg.norm(x)
+        U = -(r / Rb) ** (-3) if r >= Rb else (r / Rb) ** 3 - 2.0
+        return alpha * (v0 ** 2 / 3) * (R0 / Rb) ** 3 * (R ** 2 / r ** 2) * U * np.cos(2 * (phi - phib - Om * t))
+
+    rng = np.random.default_rng(4)
+    xyz = rng.normal(size=(60, 3)) * np.array([6.0, 6.0, 2.0])
+    t = rng.uniform(-3000.0, 0.0, 60)
+    for f, prog in ((bar, O.Program().bar(1e10, 3.5, 0.5, 0.6, 0.04)), (dehnen, O.Program().dehnen_bar(0.01, 0.22, 8.0, 3.4, 0.4, 0.05))):
+        want = np.array([f(x, tt) for x, tt in zip(xyz, t)])
+        got = prog.potential(xyz, t)
+        assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+        g = prog.gradient(xyz, t)
+        h = 1e-5
+        fd = np.array([[(f(x + h * e, tt) - f(x - h * e, tt)) / (2 * h) for e in np.eye(3)] for x, tt in zip(xyz, t)])
+        assert np.abs(g - fd).max() <= 1e-7 * np.abs(fd).max()
+
+
+def test_device_jet_algebra_against_oracle_autodiff(tmp_path):
+    """csrc/ssb_jet.cuh (the Taylor jets the kernels use for the rotating bars) compiles as plain C++ too: potential, gradient, Hessian and
+    third derivatives of both bars from one order-3 jet, against the oracle's nested dual numbers - the device algebra checked without a GPU."""
+    import itertools
+    import subprocess
+    from math import factorial
+    import numpy as np
+    import oracle as O
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "jet_host_check")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "streamsculptor_b200", "csrc"), os.path.join(root, "tests", "jet_host_check.cpp"), "-o", exe],
+                   check=True)
+    G = O.Program().G
+    ex = [(3, 0, 0), (2, 1, 0), (2, 0, 1), (1, 2, 0), (1, 1, 1), (1, 0, 2), (0, 3, 0), (0, 2, 1), (0, 1, 2), (0, 0, 3)]
+    rng = np.random.default_rng(1)
+    for kind, prog in ((0, O.Program().bar(1e10, 3.5, 0.5, 0.6, 0.04)), (1, O.Program().dehnen_bar(0.01, 0.22, 8.0, 3.4, 0.4, 0.05))):
+        for _ in range(12):
+            x = rng.normal(size=3) * np.array([6.0, 6.0, 2.0])
+            t = rng.uniform(-3000.0, 0.0)
+            out = np.array(subprocess.run([exe, str(kind), *[repr(float(v)) for v in x], repr(float(t))], capture_output=True, text=True, check=True).stdout.split(),
+                           dtype=float)
+            J3, J2, J1 = out[:20], out[20:30], out[30:]
+            assert np.allclose(J3[:10], J2, rtol=1e-13, atol=0) and np.allclose(J3[:4], J1, rtol=1e-13, atol=0)     # orders 1 and 2 are prefixes of order 3
+            if kind == 0:
+                J3 = J3 * (G / 4.498502151469554e-12)          # the check program hard-codes G
+            tq = np.array([t])
+            H = np.array([[2 * J3[4], J3[5], J3[6]], [J3[5], 2 * J3[7], J3[8]], [J3[6], J3[8], 2 * J3[9]]])
+            T = np.zeros((3, 3, 3))
+            for c, e in zip(J3[10:], ex):
+                for perm in set(itertools.permutations([0] * e[0] + [1] * e[1] + [2] * e[2])):
+                    T[perm] = c * factorial(e[0]) * factorial(e[1]) * factorial(e[2])
+            for got, want, tol in ((J3[0], prog.potential(x[None], tq)[0], 1e-13), (J3[1:4], prog.gradient(x[None], tq)[0], 1e-12),
+                                   (H, prog.hessian(x[None], tq)[0], 1e-11), (T, np.asarray(prog.third(x[None], tq)[0]), 1e-10)):
+                assert np.abs(got - want).max() <= tol * np.abs(want).max()
