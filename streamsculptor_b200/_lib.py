@@ -64,7 +64,10 @@ def build(force=False, verbose=False, out=None):
         return _OUT
     os.makedirs(os.path.dirname(_OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr", "--threads", "0", "-split-compile", "0",
+    # -split-compile 1 (no parallel split of a translation unit): 3 minutes instead of 1, but the split changes inlining / FMA-contraction
+    # decisions inside the hot kernels - measured on one B200 box with the same source (profiles/r2_split_compile_ab.txt): stream kernel
+    # 11.39 -> 10.84 ms, response 34.2 -> 31.7 ms (production batch 38.1 -> 33.9 ms), saving kernel 20.5 -> 19.5 ms.  SSB_NVCC_SPLIT=0 for quick builds.
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr", "--threads", "0", "-split-compile", os.environ.get("SSB_NVCC_SPLIT", "1"),
            "-Xptxas", "-v" if verbose else "-O3", "-shared", "-Xcompiler", "-fPIC", "-o", _OUT] + os.environ.get("SSB_NVCC_FLAGS", "").split() + srcs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

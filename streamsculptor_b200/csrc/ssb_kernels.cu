@@ -31,11 +31,12 @@ using namespace ssb;
 // =============================================================================================
 // The force is a real function call (not inlined 13x into the unrolled stepper): the stepper body stays inside
 // the instruction cache and ptxas allocates the stage registers once.
+template <bool BARS>
 __device__ __noinline__ double3 accel_call(const ssb_potential* P, int first, double x, double y, double z, double t) {
     const double X[3] = {x, y, z};
     double phi, g[3];
     Sym3 H;
-    pot_eval<WANT_GRAD>(*P, X, t, phi, g, H, first);
+    pot_eval<WANT_GRAD, BARS>(*P, X, t, phi, g, H, first);
     return make_double3(-g[0], -g[1], -g[2]);
 }
 template <int SIG>
@@ -56,7 +57,7 @@ struct OrbitForce {
     const FastX* fx;             // XS > 0: the XS extras are "fast extras" (ssb_potential.cuh), evaluated inline
     __device__ __forceinline__ void operator()(const double X[3], double tau, double A[3]) const {
         if (SIG == SIG_GENERIC) {
-            const double3 a = accel_call(P, 0, X[0], X[1], X[2], tau * dir);
+            const double3 a = accel_call<true>(P, 0, X[0], X[1], X[2], tau * dir);
             A[0] = a.x; A[1] = a.y; A[2] = a.z;
         } else {
             if (INL) {         // 13 inlined copies of the fused force: fastest while the unrolled step loop still fits the instruction cache (final-state kernel)
@@ -74,7 +75,7 @@ struct OrbitForce {
                     for (int e = 0; e < XS; ++e) fastx_grad(fx[e], X, tau * dir, g2);
                     A[0] -= g2[0]; A[1] -= g2[1]; A[2] -= g2[2];
                 } else {
-                    const double3 a = accel_call(P, SigInfo<SIG>::NF, X[0], X[1], X[2], tau * dir);
+                    const double3 a = accel_call<false>(P, SigInfo<SIG>::NF, X[0], X[1], X[2], tau * dir);
                     A[0] += a.x; A[1] += a.y; A[2] += a.z;
                 }
             }

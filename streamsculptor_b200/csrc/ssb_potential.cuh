@@ -277,7 +277,11 @@ __device__ __forceinline__ void add_perturbers(const ssb_perturbers& S, const do
 // ---------------------------------------------------------------------------------------------
 // `frozen` (optional): [SSB_MAX_TRACK][6] = value c[3] and derivative dc[3] of every track ALREADY evaluated at this t - used where many
 // evaluation points share one time (the shared-step kernels), so that the segment search and interpolation run once per stage, not per tracer.
-template <int MODE>
+// BARS = false: the instantiation contains no code for the rotating bars (jets, out-of-line calls).  The interpreter TAILS of the fused-signature
+// kernels use it - their hot force functions stay as they were (a call inside them costs prologue spills on every evaluation: measured
+// +23 % on the production response batch) - and ssb_canonicalize gives a program with a bar no fused signature, so it runs on the generic
+// kernels, which carry the bar code.
+template <int MODE, bool BARS = true>
 __device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x[3], double t, double& P, double g[3], Sym3& H, int first = 0,
                                          const double* frozen = nullptr, const double* frozen_pc = nullptr) {
     if (MODE & WANT_PHI) P = 0.0;
@@ -355,7 +359,7 @@ __device__ __forceinline__ void pot_eval(const ssb_potential& Pt, const double x
                 add_subhalos<MODE>(Pt.sh[c.sh], xs, t, P, g, H);
                 break;
             case SSB_BAR:
-            case SSB_DEHNEN_BAR: {                                  // rotating bars: derivatives by jets (ssb_jet.cuh), out of line
+            case SSB_DEHNEN_BAR: if constexpr (BARS) {              // rotating bars: derivatives by jets (ssb_jet.cuh), out of line
                 constexpr int ORD = (MODE & WANT_HESS) ? 2 : 1;
                 double J[jet_n(ORD)];
                 if (type == SSB_BAR) bar_jet<ORD>(c.p, gm, xs[0], xs[1], xs[2], t, J);
@@ -654,6 +658,8 @@ static inline int ssb_canonicalize(const ssb_potential* in, ssb_potential* out) 
         else if (c.type == SSB_MIYAMOTO) { if (nm++ == 0) idx_m = i; }
     }
     int sig = SIG_GENERIC, order[4], nf = 0;
+    for (int i = 0; i < in->n_comp; ++i)
+        if (in->comp[i].type == SSB_BAR || in->comp[i].type == SSB_DEHNEN_BAR) return sig;   // bars: generic kernels only (pot_eval<.., BARS>)
     if (nn >= 1 && nh >= 2 && nm >= 1) { sig = SIG_NHHM; order[0] = idx_n; order[1] = idx_h[0]; order[2] = idx_h[1]; order[3] = idx_m; nf = 4; }
     else if (nn >= 1 && nh >= 1 && nm >= 1) { sig = SIG_NHM; order[0] = idx_n; order[1] = idx_h[0]; order[2] = idx_m; nf = 3; }
     else if (nn >= 1) { sig = SIG_N; order[0] = idx_n; nf = 1; }

@@ -116,12 +116,13 @@ __global__ void shared_init_ctl2(int64_t N, SharedCtl* ctl, CtrlDev c) {
 // Force of the step-attempt kernel.  Every tracer is at the SAME time in every stage, so the time-dependent part of the program
 // (track centres of translating components, frame accelerations) is evaluated once per stage and CTA into `frozen` and the
 // tracers only subtract a centre; the static galaxy in front of the program (SIG != 0) is the fused inline signature of K1.
+template <bool BARS>
 __device__ __noinline__ double3 shared_accel_frozen(const ssb_potential* P, int first, double x, double y, double z, double t, const double* frozen,
                                                     const double* frozen_pc) {
     const double X[3] = {x, y, z};
     double phi, g[3];
     Sym3 H;
-    pot_eval<WANT_GRAD>(*P, X, t, phi, g, H, first, frozen, frozen_pc);
+    pot_eval<WANT_GRAD, BARS>(*P, X, t, phi, g, H, first, frozen, frozen_pc);
     return make_double3(-g[0], -g[1], -g[2]);
 }
 template <int SIG>
@@ -132,14 +133,14 @@ struct SharedStageForce {
         const double* fz = frozen + stage * (6 * SSB_MAX_TRACK);
         const double* fp = frozen_pc ? frozen_pc + stage * (3 * SSB_PSET_FROZEN_MAX) : nullptr;
         if (SIG == SIG_GENERIC) {
-            const double3 a = shared_accel_frozen(P, 0, X[0], X[1], X[2], tau * dir, fz, fp);
+            const double3 a = shared_accel_frozen<true>(P, 0, X[0], X[1], X[2], tau * dir, fz, fp);
             A[0] = a.x; A[1] = a.y; A[2] = a.z;
         } else {
             double g[3];
             fused_grad<SIG>(*Pc, X, g);
             A[0] = -g[0]; A[1] = -g[1]; A[2] = -g[2];
             if (extra) {
-                const double3 a = shared_accel_frozen(P, SigInfo<SIG>::NF, X[0], X[1], X[2], tau * dir, fz, fp);
+                const double3 a = shared_accel_frozen<false>(P, SigInfo<SIG>::NF, X[0], X[1], X[2], tau * dir, fz, fp);
                 A[0] += a.x; A[1] += a.y; A[2] += a.z;
             }
         }

@@ -51,7 +51,7 @@ __device__ __noinline__ void var_field_eval(const ssb_potential* P, const ssb_po
         if (Pc->n_comp > SigInfo<SIG>::NF) {
             double g2[3];
             Sym3 H2;
-            pot_eval<WANT_GRAD | WANT_HESS>(*P, X, t, phi, g2, H2, SigInfo<SIG>::NF);
+            pot_eval<WANT_GRAD | WANT_HESS, false>(*P, X, t, phi, g2, H2, SigInfo<SIG>::NF);
             g[0] += g2[0]; g[1] += g2[1]; g[2] += g2[2];
             H->xx += H2.xx; H->yy += H2.yy; H->zz += H2.zz; H->xy += H2.xy; H->xz += H2.xz; H->yz += H2.yz;
         }
