@@ -114,10 +114,15 @@ class Program:
             pass
 
     # ---- builders -------------------------------------------------------------------------
-    def track(self, kind, t, y):
+    def track(self, kind, t, y, slopes=None):
+        """slopes: knot derivatives of a cubic track given by the caller (Hermite data of any C1 piecewise cubic, e.g. the not-a-knot spline the
+        reference builds with InterpolatedUnivariateSpline, potential.py:47-49) instead of interpax's 'cubic' slopes."""
         t, y = _d(t), _d(y)
         y = y.reshape(len(t), -1)
-        return lib().orc_add_track(self._h, int(kind), len(t), _p(t), _p(y), y.shape[1])
+        idx = lib().orc_add_track(self._h, int(kind), len(t), _p(t), _p(y), y.shape[1])
+        if slopes is not None:
+            lib().orc_set_track_slopes(self._h, idx, _p(_d(slopes).reshape(len(t), -1)))
+        return idx
 
     def _comp(self, typ, params, track=-1):
         p = np.zeros(8)

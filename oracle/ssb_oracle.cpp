@@ -260,6 +260,12 @@ int orc_add_track(void* h, int kind, int n, const double* t, const double* y, in
     T.t.assign(t, t + n); T.y.assign(y, y + (size_t)n * dim); T.finalize();
     P->tracks.push_back(T); return (int)P->tracks.size() - 1;
 }
+// knot slopes of a cubic track supplied by the caller (any C1 piecewise cubic through the knots, e.g. a not-a-knot spline) instead of the
+// interpax 'cubic' slopes Track::finalize computes
+void orc_set_track_slopes(void* h, int track, const double* s) {
+    Program* P = (Program*)h; Track& T = P->tracks[track];
+    T.s.assign(s, s + (size_t)T.n * T.dim);
+}
 int orc_add_comp(void* h, int type, const double* p, int track) {
     Program* P = (Program*)h; Comp c; c.type = type; std::memcpy(c.p, p, sizeof(c.p)); c.track = track;
     P->comps.push_back(c); return (int)P->comps.size() - 1;

@@ -67,19 +67,28 @@ def make_ctrl(solver, rtol, atol, dtmin, dtmax, max_steps):
 class Track:
     """A tabulated 3-vector function of time living on the device."""
 
-    def __init__(self, kind, t, y):
+    def __init__(self, kind, t, y, slopes=None):
+        """slopes (cubic tracks only): knot derivatives [n, 3] of ANY C1 piecewise-cubic through the knots (Hermite data), e.g. a not-a-knot
+        spline; None: interpax's 'cubic' slopes, computed on the device (ssb_track_slopes_f64)."""
         self.kind = int(kind)
         self.t_host = np.ascontiguousarray(np.asarray(t, dtype=np.float64)).reshape(-1)
         self.y_host = np.ascontiguousarray(np.asarray(y, dtype=np.float64)).reshape(len(self.t_host), 3)
         if len(self.t_host) < 2:
             raise ValueError("a track needs at least 2 knots")
+        self.s_host = None
+        if slopes is not None:
+            if self.kind != _lib.TRACK_CUBIC:
+                raise ValueError("knot slopes belong to cubic tracks")
+            self.s_host = np.ascontiguousarray(np.asarray(slopes, dtype=np.float64)).reshape(len(self.t_host), 3)
         self._dev = None
 
     def dev(self):
         if self._dev is None:
             t, y = to_dev(self.t_host), to_dev(self.y_host)
             s = None
-            if self.kind == _lib.TRACK_CUBIC:
+            if self.kind == _lib.TRACK_CUBIC and self.s_host is not None:
+                s = to_dev(self.s_host)
+            elif self.kind == _lib.TRACK_CUBIC:
                 s = empty((len(self.t_host), 3))
                 _lib.check(_lib.lib().ssb_track_slopes_f64(len(self.t_host), ptr(t), ptr(y), ptr(s), stream_ptr()))
             self._dev = (t, y, s)

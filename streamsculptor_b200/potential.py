@@ -28,9 +28,34 @@ def CubicTrack(t, y):
     return rt.Track(_lib.TRACK_CUBIC, t, y)
 
 
+def NotAKnotTrack(t, y):
+    """C2 cubic spline through the knots with not-a-knot end conditions - what jax_cosmo's InterpolatedUnivariateSpline(k=3) builds, the spline the
+    reference uses for the LMC orbit (potential.py:47-49) and the progenitor track of the restricted N-body driver (RestrictedNbody.py:34).  The
+    spline is solved once on the host (scipy, O(n)); the kernels evaluate it exactly, as the cubic Hermite segments it consists of (knot values
+    + knot slopes).  NaN outside the knots, like CubicTrack (the reference's spline extrapolates there)."""
+    from scipy.interpolate import CubicSpline
+    t = np.asarray(t, dtype=np.float64).reshape(-1)
+    y = np.asarray(y, dtype=np.float64).reshape(len(t), 3)
+    return rt.Track(_lib.TRACK_CUBIC, t, y, slopes=CubicSpline(t, y, axis=0, bc_type='not-a-knot')(t, 1))
+
+
 def _no_nested(track):
     if track >= 0:
         raise NotImplementedError("nested time-dependent translations are not implemented")
+
+
+class LMCPotential(Potential):                        # potential.py:40-63
+    """NFW sphere (LMC_internal['m_NFW'], ['r_s_NFW']) translating along a cubic spline through LMC_orbit = {'x', 'y', 'z', 't'}."""
+
+    def __init__(self, LMC_internal, LMC_orbit, units=None):
+        super().__init__(units, {'LMC_internal': LMC_internal, 'LMC_orbit': LMC_orbit})
+        self._track = NotAKnotTrack(LMC_orbit['t'], np.stack([np.asarray(LMC_orbit[k], dtype=np.float64) for k in ('x', 'y', 'z')], axis=1))
+
+    def _lower(self, prog, track):
+        _no_nested(track)
+        from .units import usys, resolve_G
+        G = resolve_G(usys)                            # potential.py:57: the inner NFW is built with units=usys, whatever `units` is
+        prog.add(_lib.NFW, [G * self.LMC_internal['m_NFW'], self.LMC_internal['r_s_NFW']], prog.add_track(self._track))
 
 
 class MiyamotoNagaiDisk(Potential):                   # potential.py:66-72

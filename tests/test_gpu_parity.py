@@ -1291,3 +1291,32 @@ def test_rotating_bars_match_oracle(cuda):
     lead, trail = prod.gen_stream_vmapped(ts=ts, prog_w0=w0, Msat=1e4, seed_num=5, solver=ssc.Dopri8(), normals=nr, rtol=1e-8, atol=1e-8, dtmin=2.0, dtmax=2.0)
     lo, to, st, _ = orc.gen_stream(ts, w0, 1e4, 5, solver=8, normals=nr, rtol=1e-8, atol=1e-8, dtmin=2.0, dtmax=2.0)
     assert relerr(lead, lo) < 1e-9 and relerr(trail, to) < 1e-9
+
+
+@pytest.mark.gpu
+def test_lmc_potential_and_not_a_knot_track(cuda):
+    """LMCPotential (potential.py:40-63): NFW on a cubic spline through the tabulated LMC orbit.  The track evaluates scipy's not-a-knot
+    spline (value and derivative); field values and fixed-step orbits against the oracle built with the same Hermite data."""
+    from scipy.interpolate import CubicSpline
+    import streamsculptor_b200 as ssc
+    P = ssc.potential
+    t, y = lmc_track(n=41)                                             # 41 knots over 3 Gyr: the spline matters between them
+    cs = CubicSpline(t, y, axis=0, bc_type="not-a-knot")
+    tq = np.random.default_rng(1).uniform(t[0], t[-1], 300)
+    trk = P.NotAKnotTrack(t, y)
+    assert np.abs(trk(tq) - cs(tq)).max() <= 1e-12 * np.abs(y).max()
+    assert np.abs(trk(tq, derivative=True) - cs(tq, 1)).max() <= 1e-11 * np.abs(cs(tq, 1)).max()
+    lmc = P.LMCPotential({"m_NFW": 1.5e11, "r_s_NFW": 10.0}, {"t": t, "x": y[:, 0], "y": y[:, 1], "z": y[:, 2]}, units=ssc.usys)
+    prod = P.Potential_Combine([mw3_product(), lmc], units=ssc.usys)
+    orc = mw3_oracle()
+    orc.nfw(1.5e11, 10.0, track=orc.track(O.CUBIC, t, y, slopes=cs(t, 1)))
+    rng = np.random.default_rng(6)
+    xyz = rng.normal(size=(200, 3)) * np.array([30.0, 30.0, 30.0])
+    tt = rng.uniform(t[0], t[-1], 200)
+    assert relerr(prod.potential(xyz, tt), orc.potential(xyz, tt)) < 1e-12
+    assert relerr(prod.gradient(xyz, tt), orc.gradient(xyz, tt)) < 1e-11
+    assert relerr(prod.jacobian_force(xyz, tt), orc.hessian(xyz, tt)) < 1e-10
+    w0 = halo_orbits(30, seed=4)
+    sol = prod.integrate_orbit_batch_vmapped(w0=w0, ts=np.array([-500.0, 0.0]), solver=ssc.Dopri8(), rtol=1e-8, atol=1e-8, dtmin=1.0, dtmax=1.0)
+    yo, st, _ = orc.integrate_orbits(w0, -500.0, 0.0, ts=np.array([-500.0, 0.0]), solver=8, rtol=1e-8, atol=1e-8, dtmin=1.0, dtmax=1.0)
+    assert not st.any() and relerr(np.asarray(sol.ys), yo) < 1e-10

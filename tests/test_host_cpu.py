@@ -468,3 +468,26 @@ def test_device_jet_algebra_against_oracle_autodiff(tmp_path):
             for got, want, tol in ((J3[0], prog.potential(x[None], tq)[0], 1e-13), (J3[1:4], prog.gradient(x[None], tq)[0], 1e-12),
                                    (H, prog.hessian(x[None], tq)[0], 1e-11), (T, np.asarray(prog.third(x[None], tq)[0]), 1e-10)):
                 assert np.abs(got - want).max() <= tol * np.abs(want).max()
+
+
+def test_not_a_knot_spline_as_hermite_segments():
+    """LMCPotential / the restricted N-body progenitor track use a C2 not-a-knot cubic spline in the reference (jax_cosmo
+    InterpolatedUnivariateSpline(k=3), potential.py:47-49).  A cubic spline IS its knot values + knot slopes: a cubic track fed with those slopes
+    reproduces scipy's not-a-knot spline (value and derivative) to rounding - checked on the oracle's track, the device evaluates the same
+    Hermite form (tests/test_gpu_parity.py)."""
+    import numpy as np
+    from scipy.interpolate import CubicSpline
+    import oracle as O
+    rng = np.random.default_rng(2)
+    t = np.sort(rng.uniform(-3000.0, 0.0, 40)); t[0], t[-1] = -3000.0, 0.0
+    y = np.cumsum(rng.normal(size=(40, 3)), axis=0) * 5.0
+    cs = CubicSpline(t, y, axis=0, bc_type="not-a-knot")
+    prog = O.Program()
+    tr = prog.track(O.CUBIC, t, y, slopes=cs(t, 1))
+    tq = np.concatenate([rng.uniform(-3000.0, 0.0, 500), t])
+    val, der = prog.track_eval(tr, tq)
+    assert np.abs(val - cs(tq)).max() <= 1e-12 * np.abs(y).max()
+    assert np.abs(der - cs(tq, 1)).max() <= 1e-11 * np.abs(cs(tq, 1)).max()
+    # and it is NOT what the default (interpax 'cubic') slopes give
+    tr2 = prog.track(O.CUBIC, t, y)
+    assert np.abs(prog.track_eval(tr2, tq)[0] - cs(tq)).max() > 1e-3
