@@ -149,8 +149,11 @@ struct SharedStageForce {
 };
 
 // one step attempt for every tracer
+#ifndef SSB_SHARED_MIN_BLOCKS
+#define SSB_SHARED_MIN_BLOCKS 3          // CTAs per SM the register budget is set for (3: 168 registers, 2: 240 and no spills)
+#endif
 template <int SOLVER, int SIG>
-__global__ void __launch_bounds__(128) shared_attempt(const __grid_constant__ ssb_potential Pin, int64_t N, double* buf0, double* buf1, SharedCtl* ctl, CtrlDev c) {
+__global__ void __launch_bounds__(128, SSB_SHARED_MIN_BLOCKS) shared_attempt(const __grid_constant__ ssb_potential Pin, int64_t N, double* buf0, double* buf1, SharedCtl* ctl, CtrlDev c) {
     typedef Tab<SOLVER> T;
     constexpr int S = T::S;
     __shared__ ssb_potential sP;
@@ -159,7 +162,6 @@ __global__ void __launch_bounds__(128) shared_attempt(const __grid_constant__ ss
     stage_potential(&sP, &Pin);
     logtab_init();
     if (ctl->done) return;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const double tprev = ctl->tprev, dt = ctl->tnext - ctl->tprev, dir = ctl->dir;
     // tracks at the S stage times of this attempt (the same expressions rk_stages / the last-stage call below hand to the force)
     for (int q = threadIdx.x; q < S * sP.n_track; q += blockDim.x) {
@@ -183,7 +185,9 @@ __global__ void __launch_bounds__(128) shared_attempt(const __grid_constant__ ss
     double* nxt = ctl->which ? buf0 : buf1;
     double esq = 0.0;
     int bad = 0;
-    if (i < N) {
+    // persistent CTAs: the prologue above (program, log table, 14 x tracks, perturber centres) and the atomic below are paid once per CTA
+    // and attempt, not once per 128 tracers (1e7 tracers: 78 k CTAs before, each with a prologue as long as its step)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
         SharedStageForce<SIG> f{&sP, &Pin, dir, &s_frozen[0][0], 1, Pin.n_comp > SigInfo<SIG>::NF, pc_frozen ? &s_pc[0][0] : nullptr};
         double x[3], p[3], F[S][3], x1[3], p1[3], ex[3], ep[3];
         for (int k = 0; k < 3; ++k) { x[k] = cur[3 * i + k]; p[k] = cur[3 * N + 3 * i + k]; F[0][k] = cur[6 * N + 3 * i + k]; }
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(128) shared_attempt(const __grid_constant__ ss
         rk_error<SOLVER>(p, dt, F, ex, ep);
         bool nanc = false;
         for (int k = 0; k < 3; ++k) { nanc |= isnan(x1[k]) | isnan(p1[k]); if (!isfinite(x1[k]) || !isfinite(p1[k])) bad = 1; }
-        esq = err_sq6(x, p, x1, p1, ex, ep, c.rtol, c.atol, nanc);
+        esq += err_sq6(x, p, x1, p1, ex, ep, c.rtol, c.atol, nanc);
         for (int k = 0; k < 3; ++k) { nxt[3 * i + k] = x1[k]; nxt[3 * N + 3 * i + k] = p1[k]; nxt[6 * N + 3 * i + k] = F[S - 1][k]; }
     }
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(&ctl->bad, 1);
@@ -466,7 +470,12 @@ int ssb_shared_step_orbits_f64(const ssb_potential* pot, int64_t N, const double
     const int batch = N >= 1000000 ? 4 : 32;
     ssb_potential pc;
     const int sig = ssb_canonicalize(pot, &pc);          // fused static galaxy in front (as in K1), the rest through the interpreter
-#define SSB_LAUNCH_ATT(S, SG) shared_attempt<S, SG><<<grid, 128, 0, st>>>(sig == SG ? pc : *pot, N, buf0, buf1, ctl, c)
+    // persistent grid for the attempts: SSB_SHARED_MIN_BLOCKS 128-thread CTAs per SM (44 KB of shared memory each), every CTA loops over tiles
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid_att = grid < (unsigned)(SSB_SHARED_MIN_BLOCKS * sms) ? grid : (unsigned)(SSB_SHARED_MIN_BLOCKS * sms);
+#define SSB_LAUNCH_ATT(S, SG) shared_attempt<S, SG><<<grid_att, 128, 0, st>>>(sig == SG ? pc : *pot, N, buf0, buf1, ctl, c)
 #define SSB_LAUNCH_ATT_SIG(S) do { switch (sig) { case SIG_NHM: SSB_LAUNCH_ATT(S, SIG_NHM); break; case SIG_NHHM: SSB_LAUNCH_ATT(S, SIG_NHHM); break; \
         default: SSB_LAUNCH_ATT(S, SIG_GENERIC); } } while (0)
     for (int64_t launched = 0; launched <= (int64_t)ctrl.max_steps + batch;) {
