@@ -125,10 +125,14 @@ __device__ __noinline__ double3 shared_accel_frozen(const ssb_potential* P, int 
     pot_eval<WANT_GRAD, BARS>(*P, X, t, phi, g, H, first, frozen, frozen_pc);
     return make_double3(-g[0], -g[1], -g[2]);
 }
-template <int SIG>
+template <int SIG, bool PS>
 struct SharedStageForce {
     const ssb_potential* P; const ssb_potential* Pc; double dir; const double* frozen; int stage; bool extra;
     const double* frozen_pc;      // centres of the perturber set at every stage time [S][3 SSB_PSET_FROZEN_MAX], or nullptr (no set / too large)
+    int one;                      // > 0: index + 1 of an extra that is a Plummer sphere on a track (the progenitor of the restricted N-body field,
+                                  // RestrictedNbody.py:93-106): its centre is frozen per stage, so the term is 20 inline instructions
+    int nps;                      // > 0: the only other extra is a set of `nps` Plummer perturbers with frozen centres: inline loop, four
+    const double* ps_par;         //      independent accumulators; ps_par = {GM[j], rs[j]} pairs in shared memory
     __device__ __forceinline__ void operator()(const double X[3], double tau, double A[3]) {
         const double* fz = frozen + stage * (6 * SSB_MAX_TRACK);
         const double* fp = frozen_pc ? frozen_pc + stage * (3 * SSB_PSET_FROZEN_MAX) : nullptr;
@@ -138,6 +142,35 @@ struct SharedStageForce {
         } else {
             double g[3];
             fused_grad<SIG>(*Pc, X, g);
+            if (one | (PS ? nps : 0)) {
+                if (one) {                                      // same operations as pot_eval's SSB_PLUMMER case
+                    const ssb_component& c = P->comp[one - 1];
+                    const double* ctr = fz + 6 * c.track;
+                    const double xs[3] = {X[0] - ctr[0], X[1] - ctr[1], X[2] - ctr[2]};
+                    const double r2 = fma(xs[0], xs[0], fma(xs[1], xs[1], xs[2] * xs[2]));
+                    double phi, q, w;
+                    plummer_terms<WANT_GRAD>(c.p[0], c.p[1], r2, phi, q, w);
+                    g[0] = fma(q, xs[0], g[0]); g[1] = fma(q, xs[1], g[1]); g[2] = fma(q, xs[2], g[2]);
+                }
+                if (PS && nps) {                                // sum over the perturbers: lane-independent work, four accumulator sets for ILP
+                    double a0[3] = {0, 0, 0}, a1[3] = {0, 0, 0}, a2[3] = {0, 0, 0}, a3[3] = {0, 0, 0};
+                    auto term = [&](int j, double (&acc)[3]) {
+                        const double xs[3] = {X[0] - fp[3 * j], X[1] - fp[3 * j + 1], X[2] - fp[3 * j + 2]};
+                        const double r2 = fma(xs[0], xs[0], fma(xs[1], xs[1], xs[2] * xs[2]));
+                        double phi, q, w;
+                        plummer_terms<WANT_GRAD>(ps_par[2 * j], ps_par[2 * j + 1], r2, phi, q, w);
+                        acc[0] = fma(q, xs[0], acc[0]); acc[1] = fma(q, xs[1], acc[1]); acc[2] = fma(q, xs[2], acc[2]);
+                    };
+                    int j = 0;
+                    for (; j + 4 <= nps; j += 4) { term(j, a0); term(j + 1, a1); term(j + 2, a2); term(j + 3, a3); }
+                    for (; j < nps; ++j) term(j, a0);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) g[k] += (a0[k] + a1[k]) + (a2[k] + a3[k]);
+                }
+                A[0] = -g[0]; A[1] = -g[1]; A[2] = -g[2];
+                stage++;
+                return;
+            }
             A[0] = -g[0]; A[1] = -g[1]; A[2] = -g[2];
             if (extra) {
                 const double3 a = shared_accel_frozen<false>(P, SigInfo<SIG>::NF, X[0], X[1], X[2], tau * dir, fz, fp);
@@ -152,12 +185,13 @@ struct SharedStageForce {
 #ifndef SSB_SHARED_MIN_BLOCKS
 #define SSB_SHARED_MIN_BLOCKS 3          // CTAs per SM the register budget is set for (3: 168 registers, 2: 240 and no spills)
 #endif
-template <int SOLVER, int SIG>
+template <int SOLVER, int SIG, bool PS>
 __global__ void __launch_bounds__(128, SSB_SHARED_MIN_BLOCKS) shared_attempt(const __grid_constant__ ssb_potential Pin, int64_t N, double* buf0, double* buf1, SharedCtl* ctl, CtrlDev c) {
     typedef Tab<SOLVER> T;
     constexpr int S = T::S;
     __shared__ ssb_potential sP;
     __shared__ double s_frozen[S][6 * SSB_MAX_TRACK];
+    __shared__ double s_ppar[2 * SSB_PSET_FROZEN_MAX];            // {G m, r_s} of the set's perturbers
     __shared__ double s_pc[S][3 * SSB_PSET_FROZEN_MAX];           // perturber-set centres at the stage times (BASELINE config 5: 100 moving perturbers)
     stage_potential(&sP, &Pin);
     logtab_init();
@@ -175,6 +209,7 @@ __global__ void __launch_bounds__(128, SSB_SHARED_MIN_BLOCKS) shared_attempt(con
     const bool pc_frozen = sP.n_pset == 1 && sP.pset[0].n <= SSB_PSET_FROZEN_MAX;
     if (pc_frozen) {              // every centre of the set at every stage time, once per CTA: (stage, perturber) pairs dealt out over the threads
         const int np = sP.pset[0].n;
+        for (int j = threadIdx.x; j < np; j += blockDim.x) { s_ppar[2 * j] = sP.pset[0].GM[j]; s_ppar[2 * j + 1] = sP.pset[0].rs[j]; }
         for (int q = threadIdx.x; q < S * np; q += blockDim.x) {
             const int st = q / np, j = q - st * np;
             pset_centres(sP.pset[0], (tprev + T::c(st) * dt) * dir, j, j + 1, &s_pc[st][3 * j]);
@@ -185,10 +220,23 @@ __global__ void __launch_bounds__(128, SSB_SHARED_MIN_BLOCKS) shared_attempt(con
     double* nxt = ctl->which ? buf0 : buf1;
     double esq = 0.0;
     int bad = 0;
+    // extras the force functor evaluates inline: at most one Plummer sphere on a track and (PS) one frozen set of Plummer perturbers,
+    // nothing else (shared_inline_extras on the host decides PS with the same rule)
+    int one_plummer = 0, n_inline_ps = 0;
+    if (SIG != SIG_GENERIC) {
+        int n_pl = 0, i_pl = 0, n_set = 0, n_other = 0;
+        for (int ic = SigInfo<SIG>::NF; ic < sP.n_comp; ++ic) {
+            const ssb_component& cx = sP.comp[ic];
+            if (cx.type == SSB_PLUMMER && cx.track >= 0 && cx.growth == 0) { n_pl++; i_pl = ic + 1; }
+            else if (cx.type == SSB_PERTURBERS && pc_frozen && sP.pset[0].profile == SSB_PROFILE_PLUMMER) n_set++;
+            else n_other++;
+        }
+        if (n_other == 0 && n_pl <= 1 && n_set <= (PS ? 1 : 0) && n_pl + n_set > 0) { one_plummer = n_pl ? i_pl : 0; n_inline_ps = n_set ? sP.pset[0].n : 0; }
+    }
     // persistent CTAs: the prologue above (program, log table, 14 x tracks, perturber centres) and the atomic below are paid once per CTA
     // and attempt, not once per 128 tracers (1e7 tracers: 78 k CTAs before, each with a prologue as long as its step)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
-        SharedStageForce<SIG> f{&sP, &Pin, dir, &s_frozen[0][0], 1, Pin.n_comp > SigInfo<SIG>::NF, pc_frozen ? &s_pc[0][0] : nullptr};
+        SharedStageForce<SIG, PS> f{&sP, &Pin, dir, &s_frozen[0][0], 1, Pin.n_comp > SigInfo<SIG>::NF, pc_frozen ? &s_pc[0][0] : nullptr, one_plummer, n_inline_ps, s_ppar};
         double x[3], p[3], F[S][3], x1[3], p1[3], ex[3], ep[3];
         for (int k = 0; k < 3; ++k) { x[k] = cur[3 * i + k]; p[k] = cur[3 * N + 3 * i + k]; F[0][k] = cur[6 * N + 3 * i + k]; }
         rk_stages<SOLVER>(f, x, p, tprev, dt, F);
@@ -475,7 +523,21 @@ int ssb_shared_step_orbits_f64(const ssb_potential* pot, int64_t N, const double
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid_att = grid < (unsigned)(SSB_SHARED_MIN_BLOCKS * sms) ? grid : (unsigned)(SSB_SHARED_MIN_BLOCKS * sms);
-#define SSB_LAUNCH_ATT(S, SG) shared_attempt<S, SG><<<grid_att, 128, 0, st>>>(sig == SG ? pc : *pot, N, buf0, buf1, ctl, c)
+    // a frozen set of Plummer perturbers as the only extra besides an optional moving Plummer: the kernel variant with the inline perturber loop
+    bool ps = false;
+    if (sig != SIG_GENERIC && pot->n_pset == 1 && pot->pset[0].n <= SSB_PSET_FROZEN_MAX && pot->pset[0].profile == SSB_PROFILE_PLUMMER) {
+        const int nf = sig == SIG_N ? 1 : sig == SIG_NHM ? 3 : 4;
+        int n_pl = 0, n_set = 0, n_other = 0;
+        for (int ic = nf; ic < pc.n_comp; ++ic) {
+            const ssb_component& cx = pc.comp[ic];
+            if (cx.type == SSB_PLUMMER && cx.track >= 0 && cx.growth == 0) n_pl++;
+            else if (cx.type == SSB_PERTURBERS) n_set++;
+            else n_other++;
+        }
+        ps = n_other == 0 && n_pl <= 1 && n_set == 1;
+    }
+#define SSB_LAUNCH_ATT(S, SG) do { if (ps) shared_attempt<S, SG, true><<<grid_att, 128, 0, st>>>(sig == SG ? pc : *pot, N, buf0, buf1, ctl, c); \
+        else shared_attempt<S, SG, false><<<grid_att, 128, 0, st>>>(sig == SG ? pc : *pot, N, buf0, buf1, ctl, c); } while (0)
 #define SSB_LAUNCH_ATT_SIG(S) do { switch (sig) { case SIG_NHM: SSB_LAUNCH_ATT(S, SIG_NHM); break; case SIG_NHHM: SSB_LAUNCH_ATT(S, SIG_NHHM); break; \
         default: SSB_LAUNCH_ATT(S, SIG_GENERIC); } } while (0)
     for (int64_t launched = 0; launched <= (int64_t)ctrl.max_steps + batch;) {
