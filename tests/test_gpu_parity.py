@@ -1320,3 +1320,59 @@ def test_lmc_potential_and_not_a_knot_track(cuda):
     sol = prod.integrate_orbit_batch_vmapped(w0=w0, ts=np.array([-500.0, 0.0]), solver=ssc.Dopri8(), rtol=1e-8, atol=1e-8, dtmin=1.0, dtmax=1.0)
     yo, st, _ = orc.integrate_orbits(w0, -500.0, 0.0, ts=np.array([-500.0, 0.0]), solver=8, rtol=1e-8, atol=1e-8, dtmin=1.0, dtmax=1.0)
     assert not st.any() and relerr(np.asarray(sol.ys), yo) < 1e-10
+
+
+@pytest.mark.gpu
+def test_response_with_moving_progenitor_base_potential(cuda):
+    """The production driver's base potential (perturbative.py:642-644): galaxy + the progenitor's Plummer sphere on a cubic track, plus a second
+    moving sphere on a linear track (interpreter tail behind the fused galaxy in the serial base-orbit phase).  The multi-slot kernel against
+    the one-particle kernel bit for bit, and fixed steps against the oracle.  (The progenitor is softer than the production one - r_s 0.05
+    instead of 0.004 kpc - so that a 2 Myr fixed step resolves its core: inside a 0.004 kpc core the dynamical time is 0.7 Myr and a fixed-step
+    comparison only measures how rounding differences are amplified.)"""
+    import os
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import _runtime as rt
+    P = ssc.potential
+    mw = mw3_product()
+    tk = np.linspace(-1000.0, 0.0, 201)
+    yk = np.asarray(mw.integrate_orbit(w0=[12.0, 3.0, -6.0, -0.05, 0.15, 0.03], ts=tk[::-1].copy(), t0=0.0, t1=-1000.0).ys)[::-1].copy()
+    tl, yl = lmc_track(n=60, t_lo=-1000.0)
+    base = P.Potential_Combine([mw, P.TimeDepTranslatingPotential(P.PlummerPotential(m=3e4, r_s=0.05, units=ssc.usys), ssc.CubicTrack(tk, yk[:, :3].copy()), units=ssc.usys),
+                                P.TimeDepTranslatingPotential(P.HernquistPotential(m=1e10, r_s=8.0, units=ssc.usys), ssc.LinearTrack(tl, yl), units=ssc.usys)],
+                               units=ssc.usys)
+    orc = mw3_oracle()
+    orc.plummer(3e4, 0.05, track=orc.track(O.CUBIC, tk, yk[:, :3]))
+    orc.hernquist(1e10, 8.0, track=orc.track(O.LINEAR, tl, yl))
+    nsh = 24
+    sh = subhalo_set(nsh, seed=9, t_lo=-900.0, tw=150.0)
+    pert = P.SubhaloLinePotentialCustom_fromFunc(func=P.HernquistPotential, m=sh["m"], r_s=sh["rs"], subhalo_x0=sh["x0"], subhalo_v=sh["v"],
+                                                 subhalo_t0=sh["t0"], t_window=sh["tw"], units=ssc.usys)
+    orc_sh = O.Program().subhalos(O.PR_HERNQUIST, sh["m"], sh["rs"], sh["x0"], sh["v"], sh["t0"], sh["tw"])
+    N = 45
+    rng = np.random.default_rng(3)
+    t0 = np.linspace(-950.0, -20.0, N)
+    prog = np.stack([np.interp(t0, tk, yk[:, k]) for k in range(6)], axis=1)
+    w0 = prog + np.hstack([rng.normal(size=(N, 3)) * 0.05, rng.normal(size=(N, 3)) * 1e-3])
+    try:
+        for solver, tol, fixed in ((ssc.Dopri8(), 1e-8, None), (ssc.Dopri5(), 1e-7, None), (ssc.Dopri8(), 1e-8, 2.0)):
+            ctrl = rt.make_ctrl(solver, tol, tol, fixed or 0.01, fixed, 10_000)
+            out = {}
+            for retire in (0, 1):
+                os.environ["SSB_RESP_RETIRE"] = str(retire)
+                for np_slots in (0, 4, 16):
+                    os.environ["SSB_RESP_NP"] = str(np_slots)
+                    w, D, st, ns = rt.linear_response(base, pert._arrays, rt.to_dev(w0), None, rt.to_dev(t0), 0.0, ctrl)
+                    out[retire, np_slots] = (w.cpu().numpy(), D.cpu().numpy(), st.cpu().numpy(), ns.cpu().numpy())
+            assert not out[0, 0][2].any()
+            for np_slots in (4, 16):
+                for a, b in zip(out[0, np_slots], out[0, 0]):
+                    assert np.array_equal(a, b), f"{np_slots} slots differ from the one-particle kernel with moving components in the base potential"
+                for a, b in zip(out[1, np_slots], out[1, 4]):
+                    assert np.array_equal(a, b)
+            if fixed:
+                w_o, D_o, st_o, _ = O.linear_response(orc, orc_sh, w0, t0, 0.0, solver=8, rtol=tol, atol=tol, dtmin=fixed, dtmax=fixed)
+                assert not st_o.any() and scaled_err(out[0, 16][0], w_o, 1e-10).max() < 1.0
+                assert np.abs(out[0, 16][1] - D_o).max() <= 1e-9 * np.abs(D_o).max()
+    finally:
+        os.environ.pop("SSB_RESP_NP", None)
+        os.environ.pop("SSB_RESP_RETIRE", None)

@@ -29,6 +29,14 @@ x0 = prog_at[:, :3] + b[:, None] * d
 v = rng.normal(size=(n_sh, 3)) * 0.184
 pert = P.SubhaloLinePotentialCustom_fromFunc(func=P.HernquistPotential, m=np.ones(n_sh), r_s=rs, subhalo_x0=x0, subhalo_v=v, subhalo_t0=t_imp,
                                              t_window=150.0, units=ssc.usys)
+if len(sys.argv) > 4 and sys.argv[4] == "prog":          # the production driver's base potential: galaxy + the progenitor's moving Plummer (perturbative.py:642-644)
+    tk = np.linspace(-3000.0, 0.0, 2001)
+    yk = pot.integrate_orbit(w0=back, ts=tk, t0=-3000.0, t1=0.0).ys
+    rs_prog = float(sys.argv[5]) if len(sys.argv) > 5 else 0.004
+    mk = ssc.LinearTrack if (len(sys.argv) > 6 and sys.argv[6] == "linear") else ssc.CubicTrack
+    pot = P.Potential_Combine([pot, P.TimeDepTranslatingPotential(P.PlummerPotential(m=1e4, r_s=rs_prog, units=ssc.usys), mk(tk, yk[:, :3].copy()),
+                                                                  units=ssc.usys)], units=ssc.usys)
+    print(f"base potential: MW3 + moving Plummer progenitor (r_s = {rs_prog}) on a {mk.__name__}")
 ctrl = rt.make_ctrl(ssc.Dopri8(), tol, tol, 0.01, None, 10_000)
 w0_d, t0_d = rt.to_dev(w0), rt.to_dev(t0)
 for it in range(3):
@@ -38,5 +46,6 @@ for it in range(3):
     e.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(e)
 steps = int(ns[:, 0].sum().item())
+print(f"max |D| = {float(D[torch.isfinite(D)].abs().max()):.3e}; steps acc/rej {int(ns[:, 1].sum())}/{int(ns[:, 2].sum())}")
 print(f"C4: {len(w0)} particles x {n_sh} subhalos, Dopri8 tol={tol}: {ms:.1f} ms, particle-steps {steps}, pair-steps/s {steps * n_sh / ms * 1e3:.3e}, "
       f"status!=0: {int((st != 0).sum().item())}, mean steps {steps / len(w0):.1f}, flop/s (2.85 kflop/pair-step) {2850.0 * steps * n_sh / ms * 1e3 / 1e12:.2f} TF")
