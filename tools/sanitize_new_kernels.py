@@ -83,3 +83,9 @@ pot6 = P.Potential_Combine([base, pset, grow], units=ssc.usys)
 sol = pot6.integrate_orbit_batch_vmapped(w0=wq, ts=np.array([-400.0, 0.0]), solver=ssc.Dopri8(), rtol=1e-7, atol=1e-7, dtmin=0.3)
 assert np.isfinite(np.asarray(sol.ys)).all()
 print("four-part pipeline, perturber set, growth factor ok")
+# (7) shared-step kernel with both inline extras: the progenitor's moving Plummer and a frozen set of Plummer perturbers (kernel variant PS)
+field7 = RN.RestrictedNbody_generator(potential=P.Potential_Combine([base, pset], units=ssc.usys), progenitor_potential=P.PlummerPotential,
+                                      interp_prog=ssc.CubicTrack(tk, yk[:, :3].copy()), init_mass=2e4, init_rs=0.01, r_esc=0.05)
+sol = ssc.integrate_field(w0=wt, ts=np.array([-60.0, -40.0]), solver=ssc.Dopri8(), field=field7, rtol=1e-8, atol=1e-8, dtmin=0.05, max_steps=500)
+assert np.isfinite(sol.ys).all()
+print("shared-step kernel with inline perturber set ok", int(sol.stats["num_steps"]))
