@@ -63,7 +63,9 @@ def jax_choice(key, a, n, p):
 
 class ImpactGenerator:
     def __init__(self, pot, tobs, stream, stream_phi1, stripping_times, prog_today, phi1window=0.1, NumImpacts=1, tImpactBounds=None,
-                 bImpact_bounds=(0, 1.0), sigma=SIGMA_180_KMS, phi1_bounds=None, phi1_exclude=(1.0, 1.0), stream_length=None, seednum=0):
+                 bImpact_bounds=(0, 1.0), sigma=SIGMA_180_KMS, phi1_bounds=None, phi1_exclude=(1.0, 1.0), stream_length=None, seednum=0, shared=None):
+        """shared: a dict the caller keeps between generators built on the SAME stream (the production driver builds one per batch): the
+        stream's device copy, its sorted prefix sums and the length-oscillation table are computed by the first one and reused."""
         self.pot = pot
         self.tobs = float(tobs)
         self.NumImpacts = int(NumImpacts)
@@ -72,11 +74,12 @@ class ImpactGenerator:
         self.phi1_exclude = [float(phi1_exclude[0]), float(phi1_exclude[1])]
         self.keys = jax_split(self.seednum, 7)                                                     # GenerateImpactParams.py:44
         tt = rt.torch()
-        self.stream = rt.to_dev(stream).reshape(-1, 6)
-        self.stream_phi1 = rt.to_dev(stream_phi1).reshape(-1)
-        self.stripping_times = rt.to_dev(stripping_times).reshape(-1)
-        phi1_h = self.stream_phi1.cpu().numpy()
-        self.tImpactBounds = [float(self.stripping_times.min()), 0.0] if tImpactBounds is None else [float(tImpactBounds[0]), float(tImpactBounds[1])]
+        cache = shared if shared is not None else {}
+        if "stream" not in cache:
+            cache["stream"] = (rt.to_dev(stream).reshape(-1, 6), rt.to_dev(stream_phi1).reshape(-1), rt.to_dev(stripping_times).reshape(-1))
+        self.stream, self.stream_phi1, self.stripping_times = cache["stream"]
+        phi1_h = np.asarray(stream_phi1, dtype=np.float64).reshape(-1) if not rt.is_dev(stream_phi1) else self.stream_phi1.cpu().numpy()
+        self.tImpactBounds = [float(np.min(np.asarray(stripping_times.cpu() if rt.is_dev(stripping_times) else stripping_times))), 0.0] if tImpactBounds is None else [float(tImpactBounds[0]), float(tImpactBounds[1])]
         self.phi1_bounds = [float(phi1_h.min()), float(phi1_h.max())] if phi1_bounds is None else [float(phi1_bounds[0]), float(phi1_bounds[1])]
         if len(bImpact_bounds) == 2 and np.ndim(bImpact_bounds[0]) == 0 and np.ndim(bImpact_bounds[1]) == 0:
             self.b_low, self.b_high = float(bImpact_bounds[0]), float(bImpact_bounds[1])
@@ -86,17 +89,21 @@ class ImpactGenerator:
         else:                                                # N_impacts x 2
             bb = np.asarray(bImpact_bounds, dtype=np.float64)
             self.b_low, self.b_high = bb[:, 0], bb[:, 1]
-        stream_h = self.stream.cpu().numpy()
-        length = compute_stream_length(stream=stream_h, phi1=phi1_h) if stream_length is None else stream_length    # GenerateImpactParams.py:64-68
-        ind_break = len(self.stripping_times) // 2
-        self.length_osc = compute_length_oscillations(pot=self.pot, prog_today=self.prog_today, first_stripped_lead=stream_h[0],
-                                                      first_stripped_trail=stream_h[ind_break], t_age=abs(min(self.tImpactBounds)),
-                                                      length_today=length)                        # GenerateImpactParams.py:74-83
-        # sorted copy + prefix sums: window means in O(log N) per sample
-        order = tt.argsort(self.stream_phi1)
-        self._phi1_sorted = self.stream_phi1[order].contiguous()
-        zero = tt.zeros((1, 7), dtype=tt.float64, device=self.stream.device)
-        self._cum = tt.cat([zero, tt.cumsum(tt.cat([self.stream[order], self.stripping_times[order, None]], dim=1), dim=0)])
+        osc_key = ("length_osc", abs(min(self.tImpactBounds)), None if stream_length is None else float(stream_length))
+        if osc_key not in cache:
+            stream_h = np.asarray(stream, dtype=np.float64).reshape(-1, 6) if not rt.is_dev(stream) else self.stream.cpu().numpy()
+            length = compute_stream_length(stream=stream_h, phi1=phi1_h) if stream_length is None else stream_length    # GenerateImpactParams.py:64-68
+            ind_break = len(self.stripping_times) // 2
+            cache[osc_key] = compute_length_oscillations(pot=self.pot, prog_today=self.prog_today, first_stripped_lead=stream_h[0],
+                                                         first_stripped_trail=stream_h[ind_break], t_age=abs(min(self.tImpactBounds)),
+                                                         length_today=length)                     # GenerateImpactParams.py:74-83
+        self.length_osc = cache[osc_key]
+        if "sorted" not in cache:                                # sorted copy + prefix sums: window means in O(log N) per sample
+            order = tt.argsort(self.stream_phi1)
+            zero = tt.zeros((1, 7), dtype=tt.float64, device=self.stream.device)
+            cache["sorted"] = (self.stream_phi1[order].contiguous(),
+                               tt.cat([zero, tt.cumsum(tt.cat([self.stream[order], self.stripping_times[order, None]], dim=1), dim=0)]))
+        self._phi1_sorted, self._cum = cache["sorted"]
 
     # GenerateImpactParams.py:87-105
     def w_parallel_sample(self, vs):

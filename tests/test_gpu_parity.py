@@ -1243,6 +1243,14 @@ def test_production_driver_get_derivs(cuda, tmp_path):
         want = disp[sel].mean(axis=0) if sel.any() else np.zeros(6)
         assert np.abs(out[0]["binned"][b] - want).max() <= 1e-12 * max(np.abs(disp).max(), 1e-300)
     assert not np.array_equal(out[1]["ImpactFrameParams"]["tImpact"], out[0]["ImpactFrameParams"]["tImpact"])   # a fresh key per batch
+    # batches in flight on their own CUDA streams (the default) against one batch at a time: the same results, batch by batch
+    kw4 = dict(kw, target_num=48)
+    ser = get_derivs(path=None, save=False, pipeline=1, **kw4)
+    par = get_derivs(path=None, save=False, pipeline=3, **kw4)
+    assert len(ser) == len(par) == 4
+    for a, b in zip(ser, par):
+        assert np.array_equal(a["pert_out"][0], b["pert_out"][0]) and np.array_equal(a["pert_out"][1], b["pert_out"][1])
+        assert np.array_equal(a["ImpactFrameParams"]["bImpact"], b["ImpactFrameParams"]["bImpact"])
 
 
 @pytest.mark.gpu
