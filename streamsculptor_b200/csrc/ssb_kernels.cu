@@ -105,8 +105,16 @@ __device__ __forceinline__ void dense_coef_init(double* s_coef) {
     }
     __syncthreads();
 }
+#ifndef SSB_COOP_INLINE
+#define SSB_COOP_INLINE 0          // 1: the cooperative dense output inlined into the step loop (A/B: no call, but the loop body grows)
+#endif
+#if SSB_COOP_INLINE
+#define SSB_COOP_QUAL __device__ __forceinline__
+#else
+#define SSB_COOP_QUAL __device__ __noinline__
+#endif
 template <int SOLVER>
-__device__ __noinline__ void coop_dense(const double* __restrict__ srec, const double* __restrict__ s_coef, int nsave, int save_idx, const double* tsp, double* ys,
+SSB_COOP_QUAL void coop_dense(const double* __restrict__ srec, const double* __restrict__ s_coef, int nsave, int save_idx, const double* tsp, double* ys,
                                         double dir) {
     constexpr int NT = SSB_ORBIT_THREADS;
     constexpr int S = Tab<SOLVER>::S;
