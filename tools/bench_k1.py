@@ -12,11 +12,11 @@ solver = ssc.Dopri5() if (len(sys.argv) > 2 and sys.argv[2] == "5") else ssc.Dop
 mw3 = mw3_product()
 base = mw3
 back = mw3.integrate_orbit(w0=[20.0, 0.0, 20.0, 0.0, 0.15, 0.0], ts=np.array([0.0, -3000.0]), t0=0.0, t1=-3000.0).ys[-1]
-if len(sys.argv) > 3 and sys.argv[3] == "c3":      # C3: MW3 + translating Plummer on a 1000-knot linear track (its own orbit in MW3)
+if len(sys.argv) > 3 and sys.argv[3] in ("c3", "c3cubic"):      # C3: MW3 + translating Plummer on a 1000-knot linear (or cubic) track (its own orbit in MW3)
     P = ssc.potential
     tk = np.linspace(-3000.0, 0.0, 1000)
     lmc = base.integrate_orbit(w0=[-1.0, -41.0, -28.0, -0.058, -0.23, 0.23], ts=tk[::-1].copy(), t0=0.0, t1=-3000.0).ys[::-1, :3].copy()
-    mw3 = P.Potential_Combine([base, P.TimeDepTranslatingPotential(P.PlummerPotential(m=1.5e11, r_s=10.8, units=ssc.usys), ssc.LinearTrack(tk, lmc),
+    mw3 = P.Potential_Combine([base, P.TimeDepTranslatingPotential(P.PlummerPotential(m=1.5e11, r_s=10.8, units=ssc.usys), (ssc.CubicTrack if sys.argv[3] == "c3cubic" else ssc.LinearTrack)(tk, lmc),
                                                                     units=ssc.usys)], units=ssc.usys)
 ts = rt.to_dev(np.linspace(-3000.0, 0.0, n // 2 + 1))
 pw = rt.to_dev(back)
