@@ -71,8 +71,12 @@ struct OrbitForce {
             if (extra) {
                 if (XS > 0) {
                     double g2[3] = {0.0, 0.0, 0.0};
+                    if (XS == 3) {                                                   // one extra on a cubic track
+                        fastx_grad_cubic(fx[0], X, tau * dir, g2);
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < XS; ++e) fastx_grad(fx[e], X, tau * dir, g2);
+                        for (int e = 0; e < (XS == 3 ? 0 : XS); ++e) fastx_grad(fx[e], X, tau * dir, g2);
+                    }
                     A[0] -= g2[0]; A[1] -= g2[1]; A[2] -= g2[2];
                 } else {
                     const double3 a = accel_call<false>(P, SigInfo<SIG>::NF, X[0], X[1], X[2], tau * dir);
@@ -441,9 +445,10 @@ __global__ void __launch_bounds__(SSB_ORBIT_THREADS, MODE == 0 ? SSB_SNAP_MIN_BL
     __shared__ ssb_potential sP;
     stage_potential(&sP, &Pin);
     logtab_init();
-    __shared__ FastX sfx[XS > 0 ? XS : 1];
+    constexpr int NX = XS == 3 ? 1 : XS;         // XS: 1, 2 = that many fast extras on linear tracks; 3 = one on a cubic track
+    __shared__ FastX sfx[NX > 0 ? NX : 1];
     if (XS > 0) {
-        if ((int)threadIdx.x < XS) fastx_fill(&sfx[threadIdx.x], sP, SigInfo<SIG>::NF + threadIdx.x);
+        if ((int)threadIdx.x < NX) fastx_fill(&sfx[threadIdx.x], sP, SigInfo<SIG>::NF + threadIdx.x);
         __syncthreads();
     }
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1112,7 +1117,8 @@ int ssb_orbit_integrate_f64(const ssb_potential* pot, int64_t N, const double* w
     ssb_potential pc;
     const int sig = ssb_canonicalize(pot, &pc);
     // XS = number of "fast extras" (linear-track moving perturbers / frame acceleration) next to a fused MW signature, final-state mode
-    const int xs = (final_only && (sig == SIG_NHM || sig == SIG_NHHM)) ? ssb_fast_extras(&pc, sig == SIG_NHM ? 3 : 4) : 0;
+    int xs = (final_only && (sig == SIG_NHM || sig == SIG_NHHM)) ? ssb_fast_extras(&pc, sig == SIG_NHM ? 3 : 4) : 0;
+    if (!xs && final_only && (sig == SIG_NHM || sig == SIG_NHHM) && ssb_fast_extra_cubic(&pc, sig == SIG_NHM ? 3 : 4)) xs = 3;
     // MODE 0 (SaveAt with dense output): one step record of (14 + 3 stages) doubles per thread in dynamic shared memory (coop_dense)
 #define SSB_LAUNCH_ORBIT(S, MD, SG) do { const size_t shm = (MD) == 0 ? sizeof(double) * ((14 + 3 * ((S) == 5 ? 7 : 14)) * SSB_ORBIT_THREADS + 208) : 0; \
         if (shm > 48 * 1024) CK(cudaFuncSetAttribute(orbit_kernel<S, MD, SG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); \
@@ -1120,9 +1126,11 @@ int ssb_orbit_integrate_f64(const ssb_potential* pot, int64_t N, const double* w
 #define SSB_LAUNCH_SIG(S, MD) do { switch (sig) { case SIG_N: SSB_LAUNCH_ORBIT(S, MD, SIG_N); break; case SIG_NHM: SSB_LAUNCH_ORBIT(S, MD, SIG_NHM); break; \
         case SIG_NHHM: SSB_LAUNCH_ORBIT(S, MD, SIG_NHHM); break; default: SSB_LAUNCH_ORBIT(S, MD, SIG_GENERIC); } } while (0)
 #define SSB_LAUNCH_XS(S) do { if (sig == SIG_NHM) { if (xs == 1) orbit_kernel<S, 2, SIG_NHM, 1><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
-                                                      else orbit_kernel<S, 2, SIG_NHM, 2><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); } \
+                                                      else if (xs == 2) orbit_kernel<S, 2, SIG_NHM, 2><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
+                                                      else orbit_kernel<S, 2, SIG_NHM, 3><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); } \
         else { if (xs == 1) orbit_kernel<S, 2, SIG_NHHM, 1><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
-               else orbit_kernel<S, 2, SIG_NHHM, 2><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); } } while (0)
+               else if (xs == 2) orbit_kernel<S, 2, SIG_NHHM, 2><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
+               else orbit_kernel<S, 2, SIG_NHHM, 3><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); } } while (0)
     if (ctrl.solver == 5) { if (xs) SSB_LAUNCH_XS(5); else if (final_only) SSB_LAUNCH_SIG(5, 2); else SSB_LAUNCH_SIG(5, 0); }
     else { if (xs) SSB_LAUNCH_XS(8); else if (final_only) SSB_LAUNCH_SIG(8, 2); else SSB_LAUNCH_SIG(8, 0); }
     CKL("orbit_kernel");

@@ -384,6 +384,7 @@ struct FastX {
     double t_first, inv_dt, GM, a, soft;
     const double* t; const double* y;
     int n, type;
+    const double* s; double t_last;       // cubic tracks (fastx_grad_cubic): knot slopes, last knot
 };
 static __device__ __noinline__ void fastx_slow(const double* __restrict__ t, const double* __restrict__ y, int n, double v, double* out /*ta, tb, y0[3], y1[3]*/) {
     const int i = min(max(lower_bound_d(t, n, v) - 1, 0), n - 2);
@@ -395,6 +396,7 @@ __device__ __forceinline__ void fastx_fill(FastX* fx, const ssb_potential& Pt, i
     const ssb_track& T = Pt.track[c.track];
     fx->t_first = T.t_first; fx->inv_dt = T.inv_dt; fx->t = T.t; fx->y = T.y; fx->n = T.n; fx->type = c.type;
     fx->GM = c.p[0]; fx->a = c.p[1]; fx->soft = c.type == SSB_HERNQUIST ? c.p[2] : 0.0;
+    fx->s = T.s; fx->t_last = T.t[T.n - 1];
 }
 __device__ __forceinline__ void fastx_grad(const FastX& fx, const double x[3], double v, double g[3]) {
     const int n = fx.n;
@@ -431,6 +433,69 @@ __device__ __forceinline__ void fastx_grad(const FastX& fx, const double x[3], d
     else if (fx.type == SSB_NFW) nfw_terms<WANT_GRAD>(fx.GM, fx.a, r2, phi, q, wq);
     else isochrone_terms<WANT_GRAD>(fx.GM, fx.a, r2, phi, q, wq);
     g[0] = fma(q, xs[0], g[0]); g[1] = fma(q, xs[1], g[1]); g[2] = fma(q, xs[2], g[2]);
+}
+// The same for ONE spherical component on a CUBIC track (interpax 'cubic': the progenitor's own potential in the Chen25 stream models,
+// streamhelpers.py:520; NotAKnotTrack): segment guess, one round of 14 loads, the Hermite form of track_eval, rare out-of-line fix-up.
+static __device__ __noinline__ void fastx_slow_cubic(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ s, int n, double v,
+                                                     double* out /*ta, tb, y0[3], y1[3], s0[3], s1[3]*/) {
+    const int i = min(max(upper_bound_d(t, n, v), 1), n - 1) - 1;
+    out[0] = __ldg(t + i); out[1] = __ldg(t + i + 1);
+    for (int k = 0; k < 3; ++k) {
+        out[2 + k] = __ldg(y + 3 * i + k); out[5 + k] = __ldg(y + 3 * i + 3 + k);
+        out[8 + k] = __ldg(s + 3 * i + k); out[11 + k] = __ldg(s + 3 * i + 3 + k);
+    }
+}
+__device__ __forceinline__ void fastx_grad_cubic(const FastX& fx, const double x[3], double v, double g[3]) {
+    const int n = fx.n;
+    if (!(v >= fx.t_first && v <= fx.t_last)) {                    // interpax extrap=False: NaN outside the knots
+        const double qn = __longlong_as_double(0x7ff8000000000000LL);
+        g[0] = g[1] = g[2] = qn;
+        return;
+    }
+    int i = (int)((v - fx.t_first) * fx.inv_dt);
+    i = min(max(i, 0), n - 2);
+    const double* __restrict__ tp = fx.t + i;
+    double ta = __ldg(tp), tb = __ldg(tp + 1);
+    double y0[3], y1[3], s0[3], s1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        y0[k] = __ldg(fx.y + 3 * i + k); y1[k] = __ldg(fx.y + 3 * i + 3 + k);
+        s0[k] = __ldg(fx.s + 3 * i + k); s1[k] = __ldg(fx.s + 3 * i + 3 + k);
+    }
+    // searchsorted(t, v, 'right') clipped to [1, n-1], minus 1: t[i] <= v < t[i+1] inside the table
+    const bool ok = (ta <= v || i == 0) && (v < tb || i == n - 2);
+    if (!ok) {
+        double o[14];
+        fastx_slow_cubic(fx.t, fx.y, fx.s, n, v, o);
+        ta = o[0]; tb = o[1];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { y0[k] = o[2 + k]; y1[k] = o[5 + k]; s0[k] = o[8 + k]; s1[k] = o[11 + k]; }
+    }
+    const double dx = tb - ta, dxi = dx == 0.0 ? 0.0 : frcp(dx);
+    const double u = (v - ta) * dxi;
+    double xs[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {                                  // the Hermite form of track_eval
+        const double f0 = y0[k], f1 = y1[k];
+        const double m0 = s0[k] * dx, m1 = s1[k] * dx;
+        const double c2 = 3.0 * (f1 - f0) - 2.0 * m0 - m1;
+        const double c3 = 2.0 * (f0 - f1) + m0 + m1;
+        xs[k] = x[k] - (f0 + u * (m0 + u * (c2 + u * c3)));
+    }
+    const double r2 = fma(xs[0], xs[0], fma(xs[1], xs[1], fma(xs[2], xs[2], fx.soft)));
+    double phi, q, wq;
+    if (fx.type == SSB_PLUMMER) plummer_terms<WANT_GRAD>(fx.GM, fx.a, r2, phi, q, wq);
+    else if (fx.type == SSB_HERNQUIST) hernquist_terms<WANT_GRAD>(fx.GM, fx.a, r2, phi, q, wq);
+    else if (fx.type == SSB_NFW) nfw_terms<WANT_GRAD>(fx.GM, fx.a, r2, phi, q, wq);
+    else isochrone_terms<WANT_GRAD>(fx.GM, fx.a, r2, phi, q, wq);
+    g[0] = fma(q, xs[0], g[0]); g[1] = fma(q, xs[1], g[1]); g[2] = fma(q, xs[2], g[2]);
+}
+// host side: exactly one extra, spherical, on a cubic track -> 1
+static inline int ssb_fast_extra_cubic(const ssb_potential* p, int nf) {
+    if (p->n_comp - nf != 1) return 0;
+    const ssb_component& c = p->comp[nf];
+    const bool kind_ok = c.type == SSB_NFW || c.type == SSB_HERNQUIST || c.type == SSB_PLUMMER || c.type == SSB_ISOCHRONE;
+    return (kind_ok && c.growth == 0 && c.track >= 0 && p->track[c.track].kind == SSB_TRACK_CUBIC) ? 1 : 0;
 }
 // host side: do the components beyond the first `nf` qualify?  returns their number (1 or 2) or 0
 static inline int ssb_fast_extras(const ssb_potential* p, int nf) {
