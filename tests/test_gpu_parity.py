@@ -1384,3 +1384,43 @@ def test_response_with_moving_progenitor_base_potential(cuda):
     finally:
         os.environ.pop("SSB_RESP_NP", None)
         os.environ.pop("SSB_RESP_RETIRE", None)
+
+
+@pytest.mark.gpu
+def test_saving_kernel_ragged_save_lists(cuda):
+    """Edge cases of the warp-cooperative dense output (K1 MODE 0): a batch size that is no multiple of a warp, save lists with MANY times
+    inside one step (gallop + bisection), duplicate save times, save times equal to t0 and to t1, one save time only, orbits that hit max_steps
+    half-way (later rows stay +inf, earlier rows are written) and zero-length orbits - fixed steps, against the oracle to 1e-10, and row by
+    row the same +inf pattern."""
+    import streamsculptor_b200 as ssc
+    orc, prod = mw3_oracle(), mw3_product()
+    N, M = 77, 41
+    rng = np.random.default_rng(8)
+    w0 = halo_orbits(N, seed=6)
+    t0 = rng.uniform(-900.0, -600.0, N)
+    t1 = rng.uniform(-100.0, 0.0, N)
+    ts = np.sort(rng.uniform(0.0, 1.0, (N, M)), axis=1) * (t1 - t0)[:, None] + t0[:, None]
+    ts[:, 0] = t0; ts[:, -1] = t1                                   # first row = y0 exactly, last row = the final state
+    ts[::5, 10:30] = ts[::5, 10:11] + np.linspace(0.0, 3.0, 20)     # twenty save times inside two 2-Myr steps
+    ts[::7, 5] = ts[::7, 4]                                         # duplicates
+    ts = np.sort(ts, axis=1)
+    t1z = t1.copy(); t1z[3] = t0[3]                                 # a zero-length orbit: nothing is saved
+    for solver in (5, 8):
+        sv = ssc.Dopri8() if solver == 8 else ssc.Dopri5()
+        for max_steps in (10_000, 150):                             # 150 fixed steps of 2 Myr end before t1 for every orbit
+            ys_o, st_o, ns_o = orc.integrate_orbits(w0, t0, t1z, ts=ts, solver=solver, dtmin=2.0, dtmax=2.0, max_steps=max_steps, threads=8)
+            sol = prod.integrate_orbit_batch_vmapped(w0=w0, ts=ts, t0=t0, t1=t1z, solver=sv, dtmin=2.0, dtmax=2.0, max_steps=max_steps)
+            ys = np.asarray(sol.ys)
+            assert np.array_equal(np.asarray(sol.result), st_o) and np.array_equal(sol.stats["num_steps"], ns_o[:, 0])
+            assert np.array_equal(np.isinf(ys), np.isinf(ys_o))
+            fin = np.isfinite(ys_o)
+            assert np.abs(ys[fin] - ys_o[fin]).max() <= 1e-10 * (1.0 + np.abs(ys_o[fin]).max())
+            assert np.isinf(ys[3]).all()
+            if max_steps == 150:
+                assert (st_o[np.arange(N) != 3] == 1).all()
+                assert np.isinf(ys[0, -1]).all() and np.isfinite(ys[0, 0]).all()        # cut short: the end is missing, the start is there
+    # one save time only, per orbit, somewhere inside the span
+    ts1 = (0.5 * (t0 + t1))[:, None]
+    ys_o, _, _ = orc.integrate_orbits(w0, t0, t1, ts=ts1, solver=8, dtmin=2.0, dtmax=2.0, threads=8)
+    sol = prod.integrate_orbit_batch_vmapped(w0=w0, ts=ts1, t0=t0, t1=t1, solver=ssc.Dopri8(), dtmin=2.0, dtmax=2.0)
+    assert scaled_err(np.asarray(sol.ys), ys_o, 1e-10).max() < 1.0
