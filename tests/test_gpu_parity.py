@@ -1424,3 +1424,34 @@ def test_saving_kernel_ragged_save_lists(cuda):
     ys_o, _, _ = orc.integrate_orbits(w0, t0, t1, ts=ts1, solver=8, dtmin=2.0, dtmax=2.0, threads=8)
     sol = prod.integrate_orbit_batch_vmapped(w0=w0, ts=ts1, t0=t0, t1=t1, solver=ssc.Dopri8(), dtmin=2.0, dtmax=2.0)
     assert scaled_err(np.asarray(sol.ys), ys_o, 1e-10).max() < 1.0
+
+
+@pytest.mark.gpu
+def test_response_edge_sizes(cuda):
+    """Sizes at the edges of the response kernel's bookkeeping: one subhalo, counts around the retirement chunk of 16 positions (15, 16, 17,
+    33), a set larger than the in-kernel sort (4100 > 4096: identity order, nothing skipped or retired), one particle, and a particle count that
+    leaves slots empty - fixed steps, against the oracle, retirement on and off."""
+    import os
+    import streamsculptor_b200 as ssc
+    from streamsculptor_b200 import _runtime as rt
+    P = ssc.potential
+    base, orc_base = mw3_product(), mw3_oracle()
+    ctrl = rt.make_ctrl(ssc.Dopri8(), 1e-8, 1e-8, 2.0, 2.0, 10_000)
+    try:
+        for nsh, N in ((1, 5), (15, 19), (16, 3), (17, 1), (33, 40), (4100, 2)):
+            sh = subhalo_set(nsh, seed=nsh, t_lo=-700.0, tw=40.0)
+            pert = P.SubhaloLinePotentialCustom_fromFunc(func=P.HernquistPotential, m=sh["m"], r_s=sh["rs"], subhalo_x0=sh["x0"], subhalo_v=sh["v"],
+                                                         subhalo_t0=sh["t0"], t_window=sh["tw"], units=ssc.usys)
+            orc_sh = O.Program().subhalos(O.PR_HERNQUIST, sh["m"], sh["rs"], sh["x0"], sh["v"], sh["t0"], sh["tw"])
+            w0 = halo_orbits(N, seed=nsh + 1)
+            t0 = np.linspace(-800.0, -30.0, N)
+            w_o, D_o, st_o, ns_o = O.linear_response(orc_base, orc_sh, w0, t0, 0.0, solver=8, rtol=1e-8, atol=1e-8, dtmin=2.0, dtmax=2.0, threads=8)
+            assert not st_o.any()
+            for retire in (1, 0):
+                os.environ["SSB_RESP_RETIRE"] = str(retire)
+                w, D, st, ns = rt.linear_response(base, pert._arrays, rt.to_dev(w0), None, rt.to_dev(t0), 0.0, ctrl)
+                assert not bool(st.any()) and np.array_equal(ns.cpu().numpy()[:, 0], ns_o[:, 0]), (nsh, N, retire)
+                assert scaled_err(w.cpu().numpy(), w_o, 1e-10).max() < 1.0, (nsh, N, retire)
+                assert np.abs(D.cpu().numpy() - D_o).max() <= 1e-9 * np.abs(D_o).max() + 1e-300, (nsh, N, retire)
+    finally:
+        os.environ.pop("SSB_RESP_RETIRE", None)
