@@ -156,7 +156,19 @@ struct ItemForce {
             for (int k = 0; k < 3; ++k) rel[k] = X[k] - fma(ip->v[k], dt, ip->x0[k]);
             const double r2 = fma(rel[0], rel[0], fma(rel[1], rel[1], rel[2] * rel[2]));
             double ph, q, w = 0;
-            if (blk) profile_dradius(profile, ip->GM, ip->rs, r2, ph, q);                  // fields.py:200
+            if (PROFILE == SSB_PROFILE_HERNQUIST) {
+                // mass block (fields.py:191) and radius block (fields.py:200) share r, 1/(r + a) and G m/(r + a)^2: both factors from one copy of
+                // the code and a select instead of two inlined branches per stage (the sweep's 13-stage body is what the instruction cache
+                // cannot hold).  Same operations, same order as hernquist_terms / profile_dradius.
+                const double ir = frsqrt(r2), r = r2 * ir, ira = frcp(r + ip->rs);
+                const double t2 = ip->GM * ira * ira;
+                const double qm = t2 * ir, qr = -2.0 * t2 * ira * ir;
+                q = blk ? qr : qm;
+            } else if (PROFILE == SSB_PROFILE_PLUMMER) {
+                const double sI = frsqrt(fma(ip->rs, ip->rs, r2)), s2 = sI * sI;
+                const double qm = ip->GM * sI * s2, psi = ip->GM * ip->rs * sI * s2, qr = -3.0 * psi * s2;
+                q = blk ? qr : qm;
+            } else if (blk) profile_dradius(profile, ip->GM, ip->rs, r2, ph, q);           // fields.py:200
             else profile_terms<WANT_GRAD>(profile, ip->GM, ip->rs, r2, ph, q, w);          // fields.py:191
             g0 = -q * rel[0]; g1 = -q * rel[1]; g2 = -q * rel[2];
         }
