@@ -150,12 +150,14 @@ struct ItemForce {
         const double* T = sh->T[i];
         const double dt = sh->t[i] - ip->t0;
         double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-        if (fabs(dt) < ip->tw) {                                   // potential.py:826 / 846
+        if (PROFILE == SSB_PROFILE_HERNQUIST || PROFILE == SSB_PROFILE_PLUMMER) {
+            // the hot sweeps: no branch around the window gate either (an item on the 13-stage path is inside its window at most stages) -
+            // the force factor is computed and selected to zero outside the window; same operations inside it
             double rel[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) rel[k] = X[k] - fma(ip->v[k], dt, ip->x0[k]);
             const double r2 = fma(rel[0], rel[0], fma(rel[1], rel[1], rel[2] * rel[2]));
-            double ph, q, w = 0;
+            double q;
             if (PROFILE == SSB_PROFILE_HERNQUIST) {
                 // mass block (fields.py:191) and radius block (fields.py:200) share r, 1/(r + a) and G m/(r + a)^2: both factors from one copy of
                 // the code and a select instead of two inlined branches per stage (the sweep's 13-stage body is what the instruction cache
@@ -164,11 +166,20 @@ struct ItemForce {
                 const double t2 = ip->GM * ira * ira;
                 const double qm = t2 * ir, qr = -2.0 * t2 * ira * ir;
                 q = blk ? qr : qm;
-            } else if (PROFILE == SSB_PROFILE_PLUMMER) {
+            } else {
                 const double sI = frsqrt(fma(ip->rs, ip->rs, r2)), s2 = sI * sI;
                 const double qm = ip->GM * sI * s2, psi = ip->GM * ip->rs * sI * s2, qr = -3.0 * psi * s2;
                 q = blk ? qr : qm;
-            } else if (blk) profile_dradius(profile, ip->GM, ip->rs, r2, ph, q);           // fields.py:200
+            }
+            const bool inside = fabs(dt) < ip->tw;                  // potential.py:826 / 846
+            g0 = inside ? -q * rel[0] : 0.0; g1 = inside ? -q * rel[1] : 0.0; g2 = inside ? -q * rel[2] : 0.0;
+        } else if (fabs(dt) < ip->tw) {                            // potential.py:826 / 846
+            double rel[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rel[k] = X[k] - fma(ip->v[k], dt, ip->x0[k]);
+            const double r2 = fma(rel[0], rel[0], fma(rel[1], rel[1], rel[2] * rel[2]));
+            double ph, q, w = 0;
+            if (blk) profile_dradius(profile, ip->GM, ip->rs, r2, ph, q);                  // fields.py:200
             else profile_terms<WANT_GRAD>(profile, ip->GM, ip->rs, r2, ph, q, w);          // fields.py:191
             g0 = -q * rel[0]; g1 = -q * rel[1]; g2 = -q * rel[2];
         }
