@@ -68,7 +68,7 @@ struct OrbitForce {
                 const double3 f = fused_call<SIG>(Pc, X[0], X[1], X[2]);
                 A[0] = f.x; A[1] = f.y; A[2] = f.z;
             }
-            if (extra) {
+            if (XS != 4 && extra) {       // XS == 4: the program IS the fused signature (the headline stream): no extras path in the step loop at all
                 if (XS > 0) {
                     double g2[3] = {0.0, 0.0, 0.0};
                     if (XS == 3) {                                                   // one extra on a cubic track
@@ -445,9 +445,9 @@ __global__ void __launch_bounds__(SSB_ORBIT_THREADS, MODE == 0 ? SSB_SNAP_MIN_BL
     __shared__ ssb_potential sP;
     stage_potential(&sP, &Pin);
     logtab_init();
-    constexpr int NX = XS == 3 ? 1 : XS;         // XS: 1, 2 = that many fast extras on linear tracks; 3 = one on a cubic track
+    constexpr int NX = XS == 3 ? 1 : (XS == 4 ? 0 : XS);   // XS: 1, 2 = that many fast extras on linear tracks; 3 = one on a cubic track; 4 = no extras at all
     __shared__ FastX sfx[NX > 0 ? NX : 1];
-    if (XS > 0) {
+    if (NX > 0) {
         if ((int)threadIdx.x < NX) fastx_fill(&sfx[threadIdx.x], sP, SigInfo<SIG>::NF + threadIdx.x);
         __syncthreads();
     }
@@ -1101,6 +1101,12 @@ int ssb_track_eval_f64(const ssb_track* tr, int64_t nq, const double* tq, double
     return 0;
 }
 
+// SSB_ORBIT_NOEXTRAS=0: keep the general final-state kernel for programs that are exactly a fused signature (A/B)
+static bool orbit_noextras_enabled() {
+    const char* e = getenv("SSB_ORBIT_NOEXTRAS");
+    return !(e && e[0] == '0');
+}
+
 int ssb_orbit_integrate_f64(const ssb_potential* pot, int64_t N, const double* w0, const double* t0, const double* t1, const double* ts,
                             int32_t M, int32_t ts_per_orbit, ssb_ctrl ctrl, double* ys, int32_t* status, int32_t* nsteps, void* stream) {
     if (int e = ssb_validate_potential(pot)) return e;
@@ -1119,6 +1125,7 @@ int ssb_orbit_integrate_f64(const ssb_potential* pot, int64_t N, const double* w
     // XS = number of "fast extras" (linear-track moving perturbers / frame acceleration) next to a fused MW signature, final-state mode
     int xs = (final_only && (sig == SIG_NHM || sig == SIG_NHHM)) ? ssb_fast_extras(&pc, sig == SIG_NHM ? 3 : 4) : 0;
     if (!xs && final_only && (sig == SIG_NHM || sig == SIG_NHHM) && ssb_fast_extra_cubic(&pc, sig == SIG_NHM ? 3 : 4)) xs = 3;
+    if (!xs && final_only && (sig == SIG_NHM || sig == SIG_NHHM) && pc.n_comp == (sig == SIG_NHM ? 3 : 4) && orbit_noextras_enabled()) xs = 4;
     // MODE 0 (SaveAt with dense output): one step record of (14 + 3 stages) doubles per thread in dynamic shared memory (coop_dense)
 #define SSB_LAUNCH_ORBIT(S, MD, SG) do { const size_t shm = (MD) == 0 ? sizeof(double) * ((14 + 3 * ((S) == 5 ? 7 : 14)) * SSB_ORBIT_THREADS + 208) : 0; \
         if (shm > 48 * 1024) CK(cudaFuncSetAttribute(orbit_kernel<S, MD, SG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); \
@@ -1127,10 +1134,12 @@ int ssb_orbit_integrate_f64(const ssb_potential* pot, int64_t N, const double* w
         case SIG_NHHM: SSB_LAUNCH_ORBIT(S, MD, SIG_NHHM); break; default: SSB_LAUNCH_ORBIT(S, MD, SIG_GENERIC); } } while (0)
 #define SSB_LAUNCH_XS(S) do { if (sig == SIG_NHM) { if (xs == 1) orbit_kernel<S, 2, SIG_NHM, 1><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
                                                       else if (xs == 2) orbit_kernel<S, 2, SIG_NHM, 2><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
-                                                      else orbit_kernel<S, 2, SIG_NHM, 3><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); } \
+                                                      else if (xs == 3) orbit_kernel<S, 2, SIG_NHM, 3><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
+                                                      else orbit_kernel<S, 2, SIG_NHM, 4><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); } \
         else { if (xs == 1) orbit_kernel<S, 2, SIG_NHHM, 1><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
                else if (xs == 2) orbit_kernel<S, 2, SIG_NHHM, 2><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
-               else orbit_kernel<S, 2, SIG_NHHM, 3><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); } } while (0)
+               else if (xs == 3) orbit_kernel<S, 2, SIG_NHHM, 3><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
+               else orbit_kernel<S, 2, SIG_NHHM, 4><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); } } while (0)
     if (ctrl.solver == 5) { if (xs) SSB_LAUNCH_XS(5); else if (final_only) SSB_LAUNCH_SIG(5, 2); else SSB_LAUNCH_SIG(5, 0); }
     else { if (xs) SSB_LAUNCH_XS(8); else if (final_only) SSB_LAUNCH_SIG(8, 2); else SSB_LAUNCH_SIG(8, 0); }
     CKL("orbit_kernel");

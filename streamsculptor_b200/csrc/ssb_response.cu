@@ -272,12 +272,13 @@ __global__ void response_gather_kernel(const ssb_subhalos Sh, const int* order, 
 // cost 72 FMAs instead of 13 stages; algebraically identical to the staged evaluation, rounding differs at the 1e-16 level.
 __device__ __forceinline__ void item_finish(const double (&q)[3], const double (&pp)[3], const double (&q1)[3], const double (&pp1)[3], const double (&ex)[3],
                                             const double (&ep)[3], const CtrlDev& c, double* __restrict__ nxt, int n_items, int it, double& esq, int& bad_local) {
-    bool nan_cand = false;
+    bool nan_cand = false, fin = true;                        // no short-circuit branches in the sweep's tail either
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         nan_cand |= isnan(q1[k]) | isnan(pp1[k]);
-        if (!isfinite(q1[k]) || !isfinite(pp1[k])) bad_local = 1;
+        fin &= isfinite(q1[k]) & isfinite(pp1[k]);
     }
+    bad_local |= fin ? 0 : 1;
     esq += err_sq6(q, pp, q1, pp1, ex, ep, c.rtol, c.atol, nan_cand);
 #pragma unroll
     for (int k = 0; k < 3; ++k) { nxt[(size_t)k * n_items + it] = q1[k]; nxt[(size_t)(3 + k) * n_items + it] = pp1[k]; }
