@@ -1127,9 +1127,13 @@ int ssb_orbit_integrate_f64(const ssb_potential* pot, int64_t N, const double* w
     if (!xs && final_only && (sig == SIG_NHM || sig == SIG_NHHM) && ssb_fast_extra_cubic(&pc, sig == SIG_NHM ? 3 : 4)) xs = 3;
     if (!xs && final_only && (sig == SIG_NHM || sig == SIG_NHHM) && pc.n_comp == (sig == SIG_NHM ? 3 : 4) && orbit_noextras_enabled()) xs = 4;
     // MODE 0 (SaveAt with dense output): one step record of (14 + 3 stages) doubles per thread in dynamic shared memory (coop_dense)
-#define SSB_LAUNCH_ORBIT(S, MD, SG) do { const size_t shm = (MD) == 0 ? sizeof(double) * ((14 + 3 * ((S) == 5 ? 7 : 14)) * SSB_ORBIT_THREADS + 208) : 0; \
-        if (shm > 48 * 1024) CK(cudaFuncSetAttribute(orbit_kernel<S, MD, SG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); \
-        orbit_kernel<S, MD, SG, 0><<<grid, SSB_ORBIT_THREADS, shm, st>>>(pc, a); } while (0)
+#define SSB_LAUNCH_ORBIT_X(S, MD, SG, X) do { const size_t shm = (MD) == 0 ? sizeof(double) * ((14 + 3 * ((S) == 5 ? 7 : 14)) * SSB_ORBIT_THREADS + 208) : 0; \
+        if (shm > 48 * 1024) CK(cudaFuncSetAttribute(orbit_kernel<S, MD, SG, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); \
+        orbit_kernel<S, MD, SG, X><<<grid, SSB_ORBIT_THREADS, shm, st>>>(pc, a); } while (0)
+#define SSB_LAUNCH_ORBIT(S, MD, SG) SSB_LAUNCH_ORBIT_X(S, MD, SG, 0)
+    // saving mode for a program that is exactly a fused MW signature: the variant without any extras path in the step loop (as XS = 4 above)
+#define SSB_LAUNCH_SAVE_NOX(S) do { if (sig == SIG_NHM) SSB_LAUNCH_ORBIT_X(S, 0, SIG_NHM, 4); else SSB_LAUNCH_ORBIT_X(S, 0, SIG_NHHM, 4); } while (0)
+    const bool save_nox = !final_only && (sig == SIG_NHM || sig == SIG_NHHM) && pc.n_comp == (sig == SIG_NHM ? 3 : 4) && orbit_noextras_enabled();
 #define SSB_LAUNCH_SIG(S, MD) do { switch (sig) { case SIG_N: SSB_LAUNCH_ORBIT(S, MD, SIG_N); break; case SIG_NHM: SSB_LAUNCH_ORBIT(S, MD, SIG_NHM); break; \
         case SIG_NHHM: SSB_LAUNCH_ORBIT(S, MD, SIG_NHHM); break; default: SSB_LAUNCH_ORBIT(S, MD, SIG_GENERIC); } } while (0)
 #define SSB_LAUNCH_XS(S) do { if (sig == SIG_NHM) { if (xs == 1) orbit_kernel<S, 2, SIG_NHM, 1><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
@@ -1140,8 +1144,8 @@ int ssb_orbit_integrate_f64(const ssb_potential* pot, int64_t N, const double* w
                else if (xs == 2) orbit_kernel<S, 2, SIG_NHHM, 2><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
                else if (xs == 3) orbit_kernel<S, 2, SIG_NHHM, 3><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); \
                else orbit_kernel<S, 2, SIG_NHHM, 4><<<grid, SSB_ORBIT_THREADS, 0, st>>>(pc, a); } } while (0)
-    if (ctrl.solver == 5) { if (xs) SSB_LAUNCH_XS(5); else if (final_only) SSB_LAUNCH_SIG(5, 2); else SSB_LAUNCH_SIG(5, 0); }
-    else { if (xs) SSB_LAUNCH_XS(8); else if (final_only) SSB_LAUNCH_SIG(8, 2); else SSB_LAUNCH_SIG(8, 0); }
+    if (ctrl.solver == 5) { if (xs) SSB_LAUNCH_XS(5); else if (final_only) SSB_LAUNCH_SIG(5, 2); else if (save_nox) SSB_LAUNCH_SAVE_NOX(5); else SSB_LAUNCH_SIG(5, 0); }
+    else { if (xs) SSB_LAUNCH_XS(8); else if (final_only) SSB_LAUNCH_SIG(8, 2); else if (save_nox) SSB_LAUNCH_SAVE_NOX(8); else SSB_LAUNCH_SIG(8, 0); }
     CKL("orbit_kernel");
     return 0;
 }
