@@ -125,8 +125,12 @@ __device__ __noinline__ double3 shared_accel_frozen(const ssb_potential* P, int 
     pot_eval<WANT_GRAD, BARS>(*P, X, t, phi, g, H, first, frozen, frozen_pc);
     return make_double3(-g[0], -g[1], -g[2]);
 }
-template <int SIG, bool PS>
+// XM: 0 = general (extras through the interpreter call unless the inline Plummer applies), 1 = every extra is handled inline and there is no
+// perturber set, 2 = the same with a frozen perturber set; in 1 and 2 the step loop contains NO call site (a never-taken call costs spills
+// around it in every stage: -12 % on the orbit kernel, ssb_kernels.cu XS = 4)
+template <int SIG, int XM>
 struct SharedStageForce {
+    static constexpr bool PS = XM == 2;
     const ssb_potential* P; const ssb_potential* Pc; double dir; const double* frozen; int stage; bool extra;
     const double* frozen_pc;      // centres of the perturber set at every stage time [S][3 SSB_PSET_FROZEN_MAX], or nullptr (no set / too large)
     int one;                      // > 0: index + 1 of an extra that is a Plummer sphere on a track (the progenitor of the restricted N-body field,
@@ -172,7 +176,7 @@ struct SharedStageForce {
                 return;
             }
             A[0] = -g[0]; A[1] = -g[1]; A[2] = -g[2];
-            if (extra) {
+            if (XM == 0 && extra) {
                 const double3 a = shared_accel_frozen<false>(P, SigInfo<SIG>::NF, X[0], X[1], X[2], tau * dir, fz, fp);
                 A[0] += a.x; A[1] += a.y; A[2] += a.z;
             }
@@ -185,7 +189,7 @@ struct SharedStageForce {
 #ifndef SSB_SHARED_MIN_BLOCKS
 #define SSB_SHARED_MIN_BLOCKS 3          // CTAs per SM the register budget is set for (3: 168 registers, 2: 240 and no spills)
 #endif
-template <int SOLVER, int SIG, bool PS>
+template <int SOLVER, int SIG, int XM>
 __global__ void __launch_bounds__(128, SSB_SHARED_MIN_BLOCKS) shared_attempt(const __grid_constant__ ssb_potential Pin, int64_t N, double* buf0, double* buf1, SharedCtl* ctl, CtrlDev c) {
     typedef Tab<SOLVER> T;
     constexpr int S = T::S;
@@ -231,12 +235,12 @@ __global__ void __launch_bounds__(128, SSB_SHARED_MIN_BLOCKS) shared_attempt(con
             else if (cx.type == SSB_PERTURBERS && pc_frozen && sP.pset[0].profile == SSB_PROFILE_PLUMMER) n_set++;
             else n_other++;
         }
-        if (n_other == 0 && n_pl <= 1 && n_set <= (PS ? 1 : 0) && n_pl + n_set > 0) { one_plummer = n_pl ? i_pl : 0; n_inline_ps = n_set ? sP.pset[0].n : 0; }
+        if (n_other == 0 && n_pl <= 1 && n_set <= (XM == 2 ? 1 : 0) && n_pl + n_set > 0) { one_plummer = n_pl ? i_pl : 0; n_inline_ps = n_set ? sP.pset[0].n : 0; }
     }
     // persistent CTAs: the prologue above (program, log table, 14 x tracks, perturber centres) and the atomic below are paid once per CTA
     // and attempt, not once per 128 tracers (1e7 tracers: 78 k CTAs before, each with a prologue as long as its step)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
-        SharedStageForce<SIG, PS> f{&sP, &Pin, dir, &s_frozen[0][0], 1, Pin.n_comp > SigInfo<SIG>::NF, pc_frozen ? &s_pc[0][0] : nullptr, one_plummer, n_inline_ps, s_ppar};
+        SharedStageForce<SIG, XM> f{&sP, &Pin, dir, &s_frozen[0][0], 1, Pin.n_comp > SigInfo<SIG>::NF, pc_frozen ? &s_pc[0][0] : nullptr, one_plummer, n_inline_ps, s_ppar};
         double x[3], p[3], F[S][3], x1[3], p1[3], ex[3], ep[3];
         for (int k = 0; k < 3; ++k) { x[k] = cur[3 * i + k]; p[k] = cur[3 * N + 3 * i + k]; F[0][k] = cur[6 * N + 3 * i + k]; }
         rk_stages<SOLVER>(f, x, p, tprev, dt, F);
@@ -523,21 +527,24 @@ int ssb_shared_step_orbits_f64(const ssb_potential* pot, int64_t N, const double
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid_att = grid < (unsigned)(SSB_SHARED_MIN_BLOCKS * sms) ? grid : (unsigned)(SSB_SHARED_MIN_BLOCKS * sms);
-    // a frozen set of Plummer perturbers as the only extra besides an optional moving Plummer: the kernel variant with the inline perturber loop
-    bool ps = false;
-    if (sig != SIG_GENERIC && pot->n_pset == 1 && pot->pset[0].n <= SSB_PSET_FROZEN_MAX && pot->pset[0].profile == SSB_PROFILE_PLUMMER) {
+    // which extras-handling variant of the attempt kernel (SharedStageForce): 0 general, 1 / 2 everything inline (without / with a frozen set of
+    // Plummer perturbers) - the same rule as in the kernel
+    int xm = 0;
+    if (sig != SIG_GENERIC) {
         const int nf = sig == SIG_N ? 1 : sig == SIG_NHM ? 3 : 4;
+        const bool set_ok = pot->n_pset == 1 && pot->pset[0].n <= SSB_PSET_FROZEN_MAX && pot->pset[0].profile == SSB_PROFILE_PLUMMER;
         int n_pl = 0, n_set = 0, n_other = 0;
         for (int ic = nf; ic < pc.n_comp; ++ic) {
             const ssb_component& cx = pc.comp[ic];
             if (cx.type == SSB_PLUMMER && cx.track >= 0 && cx.growth == 0) n_pl++;
-            else if (cx.type == SSB_PERTURBERS) n_set++;
+            else if (cx.type == SSB_PERTURBERS && set_ok) n_set++;
             else n_other++;
         }
-        ps = n_other == 0 && n_pl <= 1 && n_set == 1;
+        if (n_other == 0 && n_pl <= 1 && n_set <= 1) xm = n_set ? 2 : 1;
     }
-#define SSB_LAUNCH_ATT(S, SG) do { if (ps) shared_attempt<S, SG, true><<<grid_att, 128, 0, st>>>(sig == SG ? pc : *pot, N, buf0, buf1, ctl, c); \
-        else shared_attempt<S, SG, false><<<grid_att, 128, 0, st>>>(sig == SG ? pc : *pot, N, buf0, buf1, ctl, c); } while (0)
+#define SSB_LAUNCH_ATT(S, SG) do { if (xm == 2) shared_attempt<S, SG, 2><<<grid_att, 128, 0, st>>>(sig == SG ? pc : *pot, N, buf0, buf1, ctl, c); \
+        else if (xm == 1) shared_attempt<S, SG, 1><<<grid_att, 128, 0, st>>>(sig == SG ? pc : *pot, N, buf0, buf1, ctl, c); \
+        else shared_attempt<S, SG, 0><<<grid_att, 128, 0, st>>>(sig == SG ? pc : *pot, N, buf0, buf1, ctl, c); } while (0)
 #define SSB_LAUNCH_ATT_SIG(S) do { switch (sig) { case SIG_NHM: SSB_LAUNCH_ATT(S, SIG_NHM); break; case SIG_NHHM: SSB_LAUNCH_ATT(S, SIG_NHHM); break; \
         default: SSB_LAUNCH_ATT(S, SIG_GENERIC); } } while (0)
     for (int64_t launched = 0; launched <= (int64_t)ctrl.max_steps + batch;) {
