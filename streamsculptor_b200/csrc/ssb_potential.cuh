@@ -386,7 +386,8 @@ struct FastX {
     int n, type;
     const double* s; double t_last;       // cubic tracks (fastx_grad_cubic): knot slopes, last knot
 };
-static __device__ __noinline__ void fastx_slow(const double* __restrict__ t, const double* __restrict__ y, int n, double v, double* out /*ta, tb, y0[3], y1[3]*/) {
+// (inlined: a call site in the step loop, even a rarely taken one, costs spills around it in every stage)
+static __device__ __forceinline__ void fastx_slow(const double* __restrict__ t, const double* __restrict__ y, int n, double v, double* out /*ta, tb, y0[3], y1[3]*/) {
     const int i = min(max(lower_bound_d(t, n, v) - 1, 0), n - 2);
     out[0] = __ldg(t + i); out[1] = __ldg(t + i + 1);
     for (int k = 0; k < 3; ++k) { out[2 + k] = __ldg(y + 3 * i + k); out[5 + k] = __ldg(y + 3 * i + 3 + k); }
@@ -436,7 +437,7 @@ __device__ __forceinline__ void fastx_grad(const FastX& fx, const double x[3], d
 }
 // The same for ONE spherical component on a CUBIC track (interpax 'cubic': the progenitor's own potential in the Chen25 stream models,
 // streamhelpers.py:520; NotAKnotTrack): segment guess, one round of 14 loads, the Hermite form of track_eval, rare out-of-line fix-up.
-static __device__ __noinline__ void fastx_slow_cubic(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ s, int n, double v,
+static __device__ __forceinline__ void fastx_slow_cubic(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ s, int n, double v,
                                                      double* out /*ta, tb, y0[3], y1[3], s0[3], s1[3]*/) {
     const int i = min(max(upper_bound_d(t, n, v), 1), n - 1) - 1;
     out[0] = __ldg(t + i); out[1] = __ldg(t + i + 1);
