@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(SSB_ORBIT_THREADS, SSB_ORBIT_MIN_BLOCKS) trace
 // K0: one orbit with dense output at M save times (progenitor at all stripping times, main.py:289)
 //   scratch layout: hdr[8] doubles {n_acc, status, n_steps, n_rej, dir}, then rec[max_steps][SSB_REC_STRIDE]
 // =============================================================================================
-template <int SOLVER, int SIG>
+template <int SOLVER, int SIG, int XS = 0>
 __global__ void __launch_bounds__(32) dense_step_kernel(const __grid_constant__ ssb_potential Pin, const double* w0, double t0, double t1,
                                                         const double* t0p, const double* t1p, CtrlDev c, double* scratch, int rec_cap,
                                                         int32_t* status_out, int32_t* nsteps_out, const double* tstop_p = nullptr) {
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(32) dense_step_kernel(const __grid_constant__ 
     int status, n_steps, n_acc, n_rej;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const double t_stop = tstop_p ? *tstop_p * ((t0 < t1) ? 1.0 : -1.0) : inf;      // mirrored time, as integrate_one runs
-    integrate_one<SOLVER, 1, SIG>(&sP, &Pin, w0, t0, t1, nullptr, 0, nullptr, c, valid, status, n_steps, n_acc, n_rej, scratch + 8, rec_cap, nullptr, t_stop);
+    integrate_one<SOLVER, 1, SIG, XS>(&sP, &Pin, w0, t0, t1, nullptr, 0, nullptr, c, valid, status, n_steps, n_acc, n_rej, scratch + 8, rec_cap, nullptr, t_stop);
     if (valid) {
         scratch[0] = (double)min(n_acc, rec_cap); scratch[1] = (double)status; scratch[4] = (t0 < t1) ? 1.0 : -1.0;
         if (status_out) *status_out = status;
@@ -1161,7 +1161,13 @@ static int dense_launch(const ssb_potential* pot, const double* w0, double t0, d
 #define SSB_LAUNCH_DENSE(S, SG) dense_step_kernel<S, SG><<<1, 32, 0, st>>>(pc, w0, t0, t1, t0p, t1p, c, scratch, ctrl.max_steps, status, nsteps, tstop_p)
 #define SSB_LAUNCH_DENSE_SIG(S) do { switch (sig) { case SIG_N: SSB_LAUNCH_DENSE(S, SIG_N); break; case SIG_NHM: SSB_LAUNCH_DENSE(S, SIG_NHM); break; \
         case SIG_NHHM: SSB_LAUNCH_DENSE(S, SIG_NHHM); break; default: SSB_LAUNCH_DENSE(S, SIG_GENERIC); } } while (0)
-    if (ctrl.solver == 5) SSB_LAUNCH_DENSE_SIG(5); else SSB_LAUNCH_DENSE_SIG(8);
+    // a program that is exactly a fused MW signature: the stepper without any extras path in its loop (XS = 4, as the orbit kernels) - this
+    // single-thread solve is pure latency, and the call site's spills are on its critical path
+#define SSB_LAUNCH_DENSE_NOX(S) do { if (sig == SIG_NHM) dense_step_kernel<S, SIG_NHM, 4><<<1, 32, 0, st>>>(pc, w0, t0, t1, t0p, t1p, c, scratch, ctrl.max_steps, status, nsteps, tstop_p); \
+        else dense_step_kernel<S, SIG_NHHM, 4><<<1, 32, 0, st>>>(pc, w0, t0, t1, t0p, t1p, c, scratch, ctrl.max_steps, status, nsteps, tstop_p); } while (0)
+    const bool nox = (sig == SIG_NHM || sig == SIG_NHHM) && pc.n_comp == (sig == SIG_NHM ? 3 : 4) && orbit_noextras_enabled();
+    if (nox) { if (ctrl.solver == 5) SSB_LAUNCH_DENSE_NOX(5); else SSB_LAUNCH_DENSE_NOX(8); }
+    else { if (ctrl.solver == 5) SSB_LAUNCH_DENSE_SIG(5); else SSB_LAUNCH_DENSE_SIG(8); }
     CKL("dense_step_kernel");
     if (M > 0) {
         if (ctrl.solver == 5) dense_eval_kernel<5><<<nblk(M, 128), 128, 0, st>>>(scratch, ts, M, ys, ts_begin, ts_stride);
